@@ -1,0 +1,21 @@
+#!/usr/bin/env bash
+# Builds the compiled-reference pieces of the oracle into oracle/_ref/ (git-ignored).
+# Reference sources are compiled where they lie under $TF2_REFERENCE (default /root/reference);
+# nothing is copied into the repo.  Safe to run when the reference is absent (does nothing).
+set -euo pipefail
+here="$(cd "$(dirname "$0")" && pwd)"
+ref="${TF2_REFERENCE:-/root/reference}"
+out="$here/_ref"
+[ -d "$ref/Runtime_Engine/cnn/host/src" ] || { echo "reference not present at $ref; skipping"; exit 0; }
+mkdir -p "$out"
+host="$ref/Runtime_Engine/cnn/host"
+common="$ref/Runtime_Engine/common/inc"
+for net in RESNET50 GOOGLENET RESNET50_PRUNED; do
+  lower=$(echo "$net" | tr 'A-Z' 'a-z')
+  g++ -std=c++11 -O1 -fPIC -shared -w -fopenmp -D"$net" -DPRINT_LEVEL_QUIET \
+      -I"$here/stub" -I"$common" -I"$host/inc" \
+      "$host/src/model_loader.cpp" "$host/src/quantization.cpp" "$host/src/input_loader.cpp" \
+      "$host/src/debug.cpp" "$here/ref_host_shim.cpp" \
+      -o "$out/libtf2ref_host_${lower}.so"
+done
+echo "built: $(ls "$out")"

@@ -1,0 +1,149 @@
+"""ctypes front-end of the CPU oracle (oracle/tf2_oracle.c) and of the compiled-reference host
+loaders (oracle/_ref/).  TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs — never by tf2_b200/."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from typing import List, Optional
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "libtf2oracle.so")
+
+
+class BiasBn(C.Structure):
+    _fields_ = [("bias", C.c_int32), ("alpha", C.c_int32), ("beta", C.c_int32)]
+
+
+class OLayer(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "C", "IH", "IW", "N", "k", "pad", "stride", "OH", "OW", "relu", "pool", "pool_stride", "pool_pad",
+        "PH", "PW", "add", "add_relu", "gap", "ipool")]
+
+
+_lib = None
+
+
+def build(force: bool = False) -> str:
+    if force or not os.path.exists(_LIB) or os.path.getmtime(_LIB) < os.path.getmtime(os.path.join(_HERE, "tf2_oracle.c")):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "libtf2oracle.so"])
+    return _LIB
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB):
+            build()
+        L = C.CDLL(_LIB)
+        L.tf2o_mul.argtypes = [C.c_int8, C.c_uint8]
+        L.tf2o_mul.restype = C.c_int32
+        L.tf2o_get_real.argtypes = [C.c_float, C.c_int8]
+        L.tf2o_get_real.restype = C.c_uint8
+        L.tf2o_quantize_input.argtypes = [C.c_float, C.c_int]
+        L.tf2o_quantize_input.restype = C.c_int8
+        L.tf2o_requant.argtypes = [C.c_int32, C.c_int32, C.c_int32]
+        L.tf2o_requant.restype = C.c_int8
+        L.tf2o_gap_finish.argtypes = [C.c_int32]
+        L.tf2o_gap_finish.restype = C.c_int8
+        L.tf2o_filter_trans.argtypes = [C.c_void_p, C.c_void_p]
+        L.tf2o_feature_trans.argtypes = [C.c_void_p, C.c_void_p]
+        L.tf2o_conv_acc.argtypes = [C.POINTER(OLayer), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.tf2o_layer_forward.argtypes = [C.POINTER(OLayer), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_void_p]
+        L.tf2o_run_network.argtypes = [C.c_int, C.POINTER(OLayer)] + [C.c_void_p] * 4 + [C.c_int] + \
+            [C.c_void_p] * 8 + [C.c_int, C.c_int, C.c_void_p, C.c_int]
+        L.tf2o_run_network.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def olayer(ld, tin) -> OLayer:
+    """LayerDesc (+ its input TensorDesc) -> oracle layer struct."""
+    o = OLayer()
+    o.C, o.IH, o.IW = (tin.C if ld.ipool else ld.C), tin.H, tin.W
+    o.N, o.k, o.pad, o.stride, o.OH, o.OW = ld.N, ld.k, ld.pad, ld.stride, ld.OH, ld.OW
+    o.relu, o.pool, o.pool_stride, o.pool_pad, o.PH, o.PW = ld.relu, ld.pool, ld.pool_stride, ld.pool_pad, ld.PH, ld.PW
+    o.add, o.add_relu, o.gap, o.ipool = (1 if ld.add_tensor >= 0 else 0), ld.add_relu, ld.gap, ld.ipool
+    return o
+
+
+def layer_forward(ld, tin, X, codes, params, R=None, want_acc=False):
+    """X int8 [C][IH][IW]; codes uint8 [N][C][k][k]; params int32 [N][3]; R int8 [N][PH][PW]."""
+    L = lib()
+    o = olayer(ld, tin)
+    X = np.ascontiguousarray(X, dtype=np.int8)
+    # the oracle reads only ld.C channels of a wider tensor when C < tin.C (never in shipped nets)
+    osz = (ld.N,) if ld.gap else (ld.N, ld.PH, ld.PW)
+    out = np.zeros(osz, dtype=np.int8)
+    acc = np.zeros((ld.N, ld.OH, ld.OW), dtype=np.int32) if want_acc else None
+    cptr = np.ascontiguousarray(codes, dtype=np.uint8).ctypes.data if codes is not None else None
+    pptr = np.ascontiguousarray(params, dtype=np.int32).ctypes.data if params is not None else None
+    if codes is not None:
+        codes = np.ascontiguousarray(codes, dtype=np.uint8)
+        params = np.ascontiguousarray(params, dtype=np.int32)
+        cptr, pptr = codes.ctypes.data, params.ctypes.data
+    Rc = np.ascontiguousarray(R, dtype=np.int8) if R is not None else None
+    L.tf2o_layer_forward(C.byref(o), X.ctypes.data, cptr, pptr, Rc.ctypes.data if Rc is not None else None,
+                         out.ctypes.data, acc.ctypes.data if acc is not None else None)
+    return (out, acc) if want_acc else out
+
+
+def run_network(net, model, t0_int8: np.ndarray, result_tensor: Optional[int] = None, n_threads: int = 0):
+    """t0_int8: [B][C0][H0][W0] int8 (tensor 0).  Returns int8 [B][C][H][W] of the result tensor."""
+    L = lib()
+    nl = net.num_layers
+    layers = (OLayer * nl)()
+    in_idx = np.zeros(nl, np.int32); out_idx = np.zeros(nl, np.int32)
+    out_ch0 = np.zeros(nl, np.int32); add_idx = np.zeros(nl, np.int32)
+    code_off = np.zeros(nl, np.int64); param_off = np.zeros(nl, np.int64)
+    code_chunks: List[np.ndarray] = []; param_chunks: List[np.ndarray] = []
+    co = po = 0
+    for l, ld in enumerate(net.layers):
+        layers[l] = olayer(ld, net.tensors[ld.in_tensor])
+        in_idx[l], out_idx[l], out_ch0[l], add_idx[l] = ld.in_tensor, ld.out_tensor, ld.out_ch0, ld.add_tensor
+        code_off[l], param_off[l] = co, po
+        codes, params = model[l]
+        if codes is not None:
+            c = np.ascontiguousarray(codes, dtype=np.uint8).reshape(-1)
+            p = np.ascontiguousarray(params, dtype=np.int32).reshape(-1, 3)
+            code_chunks.append(c); param_chunks.append(p)
+            co += c.size; po += p.shape[0]
+    codes_all = np.concatenate(code_chunks) if code_chunks else np.zeros(1, np.uint8)
+    params_all = np.concatenate(param_chunks) if param_chunks else np.zeros((1, 3), np.int32)
+    tC = np.array([t.C for t in net.tensors], np.int32)
+    tH = np.array([t.H for t in net.tensors], np.int32)
+    tW = np.array([t.W for t in net.tensors], np.int32)
+    rt = net.result_tensor() if result_tensor is None else result_tensor
+    x = np.ascontiguousarray(t0_int8, dtype=np.int8)
+    B = x.shape[0]
+    out = np.zeros((B, int(tC[rt]), int(tH[rt]), int(tW[rt])), np.int8)
+    rc = L.tf2o_run_network(nl, layers, in_idx.ctypes.data, out_idx.ctypes.data, out_ch0.ctypes.data,
+                            add_idx.ctypes.data, len(net.tensors), tC.ctypes.data, tH.ctypes.data, tW.ctypes.data,
+                            codes_all.ctypes.data, code_off.ctypes.data, params_all.ctypes.data,
+                            param_off.ctypes.data, x.ctypes.data, B, rt, out.ctypes.data, n_threads)
+    if rc != 0:
+        raise MemoryError("oracle run_network failed")
+    return out
+
+
+# ---- compiled reference host loaders (oracle/_ref/, built by oracle/build_ref.sh) --------------
+def ref_host_lib(net_name: str):
+    """Returns the ctypes handle of oracle/_ref/libtf2ref_host_<net>.so or None if not built."""
+    p = os.path.join(_HERE, "_ref", f"libtf2ref_host_{net_name}.so")
+    if not os.path.exists(p):
+        return None
+    L = C.CDLL(p)
+    L.ref_get_real.argtypes = [C.c_float, C.c_char]
+    L.ref_get_real.restype = C.c_char
+    L.ref_filter_layer_stride.restype = C.c_longlong
+    vp = C.c_void_p
+    L.ref_filter_trans.argtypes = [vp, vp]
+    L.ref_feature_trans.argtypes = [vp, vp]
+    L.ref_quantization.argtypes = [vp, C.c_char_p]
+    L.ref_load_model.argtypes = [C.c_char_p, vp, vp, vp]
+    L.ref_load_input_image.argtypes = [C.c_char_p, vp, vp]
+    return L

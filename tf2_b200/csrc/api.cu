@@ -1,0 +1,796 @@
+// api.cu — engine object, weight preparation, execution plan and the C ABI of libtf2b200.so.
+//
+// Host-side mirror of the reference's NetWork (Runtime_Engine/cnn/host/src/network.cpp:22-168:
+// owns filter / bias_bn / feature buffers) and Runner (runner.cpp:54-196: runs the layer
+// sequence), but for a CUDA device: tensors live in HBM as NHWC int8, layers run as kernel launches
+// on one stream.  See include/tf2b200.h for the contract of every entry point.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/tf2b200.h"
+#include "common.cuh"
+
+namespace tf2b {
+cudaError_t launch_conv_shift(const ConvParams& p, const int16_t* wgt, cudaStream_t stream);
+int conv_shift_bn();
+int conv_shift_kc();
+cudaError_t launch_chw_to_hwc(const int8_t*, int8_t*, int, int, int, int, int, cudaStream_t);
+cudaError_t launch_hwc_to_chw(const int8_t*, int8_t*, int, int, int, int, int, cudaStream_t);
+cudaError_t launch_hwc_repitch(const int8_t*, int8_t*, size_t, int, int, int, cudaStream_t);
+cudaError_t launch_raw224_to_s2d(const int8_t*, int8_t*, int, cudaStream_t);
+cudaError_t launch_maxpool3x3(const int8_t*, int8_t*, const int8_t*, int, int, int, int, int, int,
+                              int, int, int, int, int, int, cudaStream_t);
+cudaError_t launch_gap(const int8_t*, int8_t*, int, int, int, int, int, cudaStream_t);
+// tensor-core path (conv_mma.cu)
+bool mma_layer_supported(const tf2b_layer_desc& L, int in_pitch, int planes8);
+cudaError_t launch_conv_mma(const ConvParams& p, const int8_t* wgt8, int planes8,
+                            const int* plane8_shift, void* tmaps, cudaStream_t stream);
+size_t mma_tmap_bytes();
+int mma_build_tmaps(void* host_tmaps, const ConvParams& p, const int8_t* wgt8, int planes8,
+                    std::string* err);
+int mma_bn();
+int mma_bk();
+}  // namespace tf2b
+
+using tf2b::ConvParams;
+
+static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+struct LayerState {
+  tf2b_layer_desc d;
+  bool loaded = false;
+  int Cp = 0;  // reduction channels padded to 16
+  // --- shift kernel (int16 planes) ---
+  int Npad_s = 0, Kp_s = 0, planes_s = 0;
+  int plane_shift_s[tf2b::kMaxPlanes] = {0, 0, 0, 0};
+  int plane_neg_s[tf2b::kMaxPlanes] = {0, 0, 0, 0};
+  std::vector<int16_t> h_w16;
+  // --- mma kernel (int8 planes) ---
+  int Npad_m = 0, Kp_m = 0, planes_m = 0;
+  int plane_shift_m[tf2b::kMaxPlanes] = {0, 0, 0, 0};
+  std::vector<int8_t> h_w8;
+  bool mma_ok = false;
+  // --- per-channel params (padded to max(Npad_s, Npad_m)) ---
+  int Npar = 0;
+  std::vector<int32_t> h_bias, h_alpha, h_beta;
+  std::vector<uint8_t> h_nshift;
+  // device views inside the arena
+  size_t off_w16 = 0, off_w8 = 0, off_bias = 0, off_alpha = 0, off_beta = 0, off_nshift = 0;
+  int kernel = 0;  // 0 none (ipool), 1 shift, 2 mma
+  std::vector<unsigned char> h_tmaps;  // CUtensorMap blobs for the mma path (host copy)
+  size_t off_tmaps = 0;
+};
+
+struct BlobLayerMeta {  // fixed-size, trivially copyable: travels inside the weight blob
+  int32_t loaded, Cp, Npad_s, Kp_s, planes_s, plane_shift_s[4], plane_neg_s[4];
+  int32_t Npad_m, Kp_m, planes_m, plane_shift_m[4], mma_ok, Npar;
+  int64_t off_w16, off_w8, off_bias, off_alpha, off_beta, off_nshift;
+};
+
+struct tf2b_net {
+  int device = 0;
+  std::vector<tf2b_tensor_desc> tensors;
+  std::vector<int> tpitch;  // channel pitch of each tensor (C rounded up to 16)
+  std::vector<LayerState> layers;
+  int variant = TF2B_VARIANT_AUTO;
+  int max_images = 0;
+  bool finalized = false;
+  int result_tensor = -1;
+  // device memory
+  unsigned char* arena = nullptr;
+  size_t arena_bytes = 0;
+  std::vector<int8_t*> tbuf;
+  int8_t* scratch0 = nullptr;
+  int8_t* scratch1 = nullptr;
+  size_t scratch_bytes = 0;
+  int8_t* io_in = nullptr;   // staging for host-buffer entry points
+  int8_t* io_out = nullptr;
+  size_t io_in_bytes = 0, io_out_bytes = 0;
+  cudaStream_t own_stream = nullptr;
+  int last_launches = 0;
+  int last_images = 0;
+  std::string err;
+};
+
+static int fail(tf2b_net* n, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (n) n->err = buf;
+  return code;
+}
+
+#define CUDA_TRY(n, expr)                                                                  \
+  do {                                                                                     \
+    cudaError_t e__ = (expr);                                                              \
+    if (e__ != cudaSuccess)                                                                \
+      return fail(n, TF2B_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), \
+                  __FILE__, __LINE__);                                                     \
+  } while (0)
+
+static std::string g_create_err;
+
+// ------------------------------------------------------------------------------------------------
+// weight preparation: LoadModel codes -> per-channel base shift + power-of-two weight planes
+// ------------------------------------------------------------------------------------------------
+static int prepare_layer(tf2b_net* net, LayerState& S, const uint8_t* codes,
+                         const tf2b_bias_bn* params) {
+  const tf2b_layer_desc& d = S.d;
+  const int C = d.C, N = d.N, k = d.k;
+  S.Cp = round_up(C, 16);
+  const int Ktot = k * k * S.Cp;
+  // per-channel base shift = smallest shift among the channel's non-zero codes
+  std::vector<uint8_t> base(N, 0);
+  int max_rel = 0;
+  for (int n = 0; n < N; n++) {
+    int mn = 99, mx = -1;
+    const uint8_t* cn = codes + (size_t)n * C * k * k;
+    for (int i = 0; i < C * k * k; i++) {
+      if (cn[i] & 0x40) continue;
+      int s = cn[i] & 0x1f;
+      mn = std::min(mn, s);
+      mx = std::max(mx, s);
+    }
+    if (mx < 0) { mn = 0; mx = 0; }
+    base[n] = (uint8_t)mn;
+    max_rel = std::max(max_rel, mx - mn);
+  }
+  const bool quirk = d.in_may_be_m128 != 0;
+  // ---- shift kernel planes: int16 +-2^e, e in 0..14 ----
+  {
+    const int lv = 15;
+    const int np = max_rel / lv + 1;
+    S.planes_s = np * (quirk ? 2 : 1);
+    if (S.planes_s > tf2b::kMaxPlanes)
+      return fail(net, TF2B_ERR_ARG, "layer needs %d int16 planes (> %d)", S.planes_s, tf2b::kMaxPlanes);
+    S.Npad_s = round_up(N, tf2b::conv_shift_bn());
+    S.Kp_s = round_up(Ktot, tf2b::conv_shift_kc());
+    S.h_w16.assign((size_t)S.planes_s * S.Npad_s * S.Kp_s, 0);
+    for (int p = 0; p < np; p++) {
+      if (quirk) {
+        S.plane_shift_s[2 * p] = S.plane_shift_s[2 * p + 1] = lv * p;
+        S.plane_neg_s[2 * p] = 0;
+        S.plane_neg_s[2 * p + 1] = 1;
+      } else {
+        S.plane_shift_s[p] = lv * p;
+        S.plane_neg_s[p] = 0;
+      }
+    }
+    for (int n = 0; n < N; n++) {
+      for (int c = 0; c < C; c++) {
+        for (int t = 0; t < k * k; t++) {
+          uint8_t cd = codes[((size_t)n * C + c) * k * k + t];
+          if (cd & 0x40) continue;
+          int rel = (cd & 0x1f) - base[n];
+          int p = rel / lv, e = rel - p * lv;
+          bool negw = (cd & 0x80) != 0;
+          size_t kidx = (size_t)t * S.Cp + c;
+          if (quirk) {
+            int pl = 2 * p + (negw ? 1 : 0);
+            S.h_w16[((size_t)pl * S.Npad_s + n) * S.Kp_s + kidx] = (int16_t)(1 << e);
+          } else {
+            S.h_w16[((size_t)p * S.Npad_s + n) * S.Kp_s + kidx] = (int16_t)(negw ? -(1 << e) : (1 << e));
+          }
+        }
+      }
+    }
+  }
+  // ---- mma kernel planes: int8 +-2^e, e in 0..6 (only when the input cannot hold -128) ----
+  S.mma_ok = false;
+  S.planes_m = 0;
+  S.h_w8.clear();
+  if (!quirk) {
+    const int lv = 7;
+    const int np = max_rel / lv + 1;
+    const int in_pitch = net->tpitch[d.in_tensor];
+    if (np <= tf2b::kMaxPlanes && tf2b::mma_layer_supported(d, in_pitch, np)) {
+      S.planes_m = np;
+      S.Npad_m = round_up(N, tf2b::mma_bn());
+      S.Kp_m = k * k * round_up(S.Cp, tf2b::mma_bk());
+      const int Cpm = round_up(S.Cp, tf2b::mma_bk());
+      S.h_w8.assign((size_t)np * S.Npad_m * S.Kp_m, 0);
+      for (int p = 0; p < np; p++) S.plane_shift_m[p] = lv * p;
+      for (int n = 0; n < N; n++)
+        for (int c = 0; c < C; c++)
+          for (int t = 0; t < k * k; t++) {
+            uint8_t cd = codes[((size_t)n * C + c) * k * k + t];
+            if (cd & 0x40) continue;
+            int rel = (cd & 0x1f) - base[n];
+            int p = rel / lv, e = rel - p * lv;
+            int v = 1 << e;
+            if (cd & 0x80) v = -v;
+            S.h_w8[((size_t)p * S.Npad_m + n) * S.Kp_m + (size_t)t * Cpm + c] = (int8_t)v;
+          }
+      S.mma_ok = true;
+    }
+  }
+  S.Npar = std::max(S.Npad_s, S.Npad_m);
+  S.h_bias.assign(S.Npar, 0);
+  S.h_alpha.assign(S.Npar, 0);
+  S.h_beta.assign(S.Npar, 0);
+  S.h_nshift.assign(round_up(S.Npar, 16), 0);
+  for (int n = 0; n < N; n++) {
+    S.h_bias[n] = params[n].bias;
+    S.h_alpha[n] = params[n].alpha;
+    S.h_beta[n] = params[n].beta;
+    S.h_nshift[n] = base[n];
+  }
+  S.loaded = true;
+  return TF2B_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* tf2b_version(void) { return "tf2b200 0.1 (sm_100a)"; }
+
+const char* tf2b_last_error(tf2b_net* net) { return net ? net->err.c_str() : g_create_err.c_str(); }
+
+int tf2b_create(const tf2b_tensor_desc* tensors, int n_tensors, const tf2b_layer_desc* layers,
+                int n_layers, int device, tf2b_net** out) {
+  if (!tensors || !layers || !out || n_tensors <= 0 || n_layers <= 0) {
+    g_create_err = "tf2b_create: null/empty argument";
+    return TF2B_ERR_ARG;
+  }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {
+    g_create_err = std::string("tf2b_create: no usable CUDA device (") +
+                   (e != cudaSuccess ? cudaGetErrorString(e) : "device index out of range") +
+                   "); this engine has no CPU fallback";
+    return TF2B_ERR_CUDA;
+  }
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess) {
+    g_create_err = std::string("cudaSetDevice: ") + cudaGetErrorString(e);
+    return TF2B_ERR_CUDA;
+  }
+  tf2b_net* n = new tf2b_net();
+  n->device = device;
+  n->tensors.assign(tensors, tensors + n_tensors);
+  n->tpitch.resize(n_tensors);
+  for (int t = 0; t < n_tensors; t++) {
+    if (tensors[t].C <= 0 || tensors[t].H <= 0 || tensors[t].W <= 0) {
+      g_create_err = "tf2b_create: tensor with non-positive dimension";
+      delete n;
+      return TF2B_ERR_ARG;
+    }
+    n->tpitch[t] = round_up(tensors[t].C, 16);
+  }
+  n->layers.resize(n_layers);
+  for (int l = 0; l < n_layers; l++) {
+    const tf2b_layer_desc& d = layers[l];
+    auto bad = [&](const char* why) {
+      char b[256];
+      snprintf(b, sizeof b, "tf2b_create: layer %d: %s", l, why);
+      g_create_err = b;
+      delete n;
+      return TF2B_ERR_ARG;
+    };
+    if (d.in_tensor < 0 || d.in_tensor >= n_tensors || d.out_tensor < 0 || d.out_tensor >= n_tensors)
+      return bad("tensor id out of range");
+    if (d.add_tensor >= n_tensors) return bad("add_tensor out of range");
+    if (d.out_ch0 % 16 != 0) return bad("concat channel offset must be a multiple of 16");
+    if (d.out_ch0 + d.N > tensors[d.out_tensor].C) return bad("output channels exceed out_tensor");
+    const tf2b_tensor_desc& ti = tensors[d.in_tensor];
+    const tf2b_tensor_desc& to = tensors[d.out_tensor];
+    if (d.ipool) {
+      if (d.N != ti.C) return bad("ipool must keep the channel count");
+      if (d.PH != to.H || d.PW != to.W) return bad("ipool output size mismatch");
+    } else {
+      if (d.C > ti.C || d.C <= 0 || d.N <= 0 || d.k <= 0 || d.stride <= 0) return bad("bad conv geometry");
+      if ((ti.H + 2 * d.pad - d.k) / d.stride + 1 != d.OH || (ti.W + 2 * d.pad - d.k) / d.stride + 1 != d.OW)
+        return bad("OH/OW do not match (IH + 2*pad - k)/stride + 1");
+      int eh = d.gap ? 1 : d.PH, ew = d.gap ? 1 : d.PW;
+      if (eh != to.H || ew != to.W) return bad("output tensor size mismatch");
+      if (!d.pool && (d.PH != d.OH || d.PW != d.OW)) return bad("PH/PW must equal OH/OW without pool");
+    }
+    if (d.add_tensor >= 0) {
+      const tf2b_tensor_desc& tr = tensors[d.add_tensor];
+      if (tr.H != d.PH || tr.W != d.PW || tr.C < d.N) return bad("residual tensor shape mismatch");
+    }
+    n->layers[l].d = d;
+  }
+  n->result_tensor = layers[n_layers - 1].out_tensor;
+  e = cudaStreamCreateWithFlags(&n->own_stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    g_create_err = std::string("cudaStreamCreate: ") + cudaGetErrorString(e);
+    delete n;
+    return TF2B_ERR_CUDA;
+  }
+  *out = n;
+  return TF2B_OK;
+}
+
+int tf2b_load_layer(tf2b_net* net, int layer, const uint8_t* codes, const tf2b_bias_bn* params) {
+  if (!net) return TF2B_ERR_ARG;
+  if (layer < 0 || layer >= (int)net->layers.size()) return fail(net, TF2B_ERR_ARG, "layer %d out of range", layer);
+  if (net->finalized) return fail(net, TF2B_ERR_STATE, "tf2b_load_layer after tf2b_finalize");
+  LayerState& S = net->layers[layer];
+  if (S.d.ipool) return fail(net, TF2B_ERR_ARG, "layer %d is an ipool pseudo layer (no weights)", layer);
+  if (!codes || !params) return fail(net, TF2B_ERR_ARG, "null codes/params");
+  return prepare_layer(net, S, codes, params);
+}
+
+int tf2b_load_layer_packed4(tf2b_net* net, int layer, const uint8_t* nibbles, int min_exp,
+                            const int8_t* q_in, const int8_t* q_out, const tf2b_bias_bn* params) {
+  if (!net) return TF2B_ERR_ARG;
+  if (layer < 0 || layer >= (int)net->layers.size()) return fail(net, TF2B_ERR_ARG, "layer %d out of range", layer);
+  if (!nibbles || !q_in || !q_out || !params) return fail(net, TF2B_ERR_ARG, "null argument");
+  const tf2b_layer_desc& d = net->layers[layer].d;
+  if (d.ipool) return fail(net, TF2B_ERR_ARG, "layer %d is an ipool pseudo layer (no weights)", layer);
+  const size_t kk = (size_t)d.k * d.k;
+  std::vector<uint8_t> codes((size_t)d.N * d.C * kk);
+  for (int n = 0; n < d.N; n++)
+    for (int c = 0; c < d.C; c++) {
+      // model_loader.cpp:159-162: expand = INFLAT + q_in[c] - q_out[n] (kept in a char)
+      int8_t expand = (int8_t)(15 + q_in[c] - q_out[n]);
+      for (size_t t = 0; t < kk; t++) {
+        size_t i = ((size_t)n * d.C + c) * kk + t;
+        uint8_t nib = (nibbles[i >> 1] >> ((i & 1) * 4)) & 0xF;
+        uint8_t code;
+        int e = nib & 7;
+        if (e == 7) {
+          // 4bit_data_format.txt: e=7 with sign bit 0 is 0.0; 15 is invalid -> treated as zero
+          code = 0x40;
+        } else {
+          // value = +-2^(min_exp+e); Get_real finds i = -(min_exp+e) in 0..14, else i = 0
+          int i2 = -(min_exp + e);
+          if (i2 >= 17) {
+            code = 0x40;  // |w| = 2^-17 < 1e-5: Get_real's zero test (model_loader.cpp:101-102)
+          } else {
+            if (i2 < 0 || i2 > 14) i2 = 0;
+            int8_t sh = (int8_t)(expand - i2);
+            if (sh < 0) sh = 0;
+            code = (uint8_t)sh;
+            if (!(nib & 8)) code |= 0x80;  // bit3 set = positive
+          }
+        }
+        codes[i] = code;
+      }
+    }
+  return tf2b_load_layer(net, layer, codes.data(), params);
+}
+
+int tf2b_set_variant(tf2b_net* net, int variant) {
+  if (!net) return TF2B_ERR_ARG;
+  if (variant < 0 || variant > 2) return fail(net, TF2B_ERR_ARG, "unknown variant %d", variant);
+  net->variant = variant;
+  for (auto& S : net->layers) {
+    if (S.d.ipool) { S.kernel = 0; continue; }
+    S.kernel = (variant != TF2B_VARIANT_SHIFT && S.mma_ok) ? 2 : 1;
+  }
+  return TF2B_OK;
+}
+
+int tf2b_set_result(tf2b_net* net, int tensor) {
+  if (!net) return TF2B_ERR_ARG;
+  if (tensor < 0 || tensor >= (int)net->tensors.size()) return fail(net, TF2B_ERR_ARG, "tensor out of range");
+  net->result_tensor = tensor;
+  return TF2B_OK;
+}
+
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static size_t layout_arena(tf2b_net* net) {
+  size_t off = 0;
+  for (auto& S : net->layers) {
+    if (S.d.ipool || !S.loaded) continue;
+    S.off_w16 = off; off = align256(off + S.h_w16.size() * 2);
+    S.off_w8 = off; off = align256(off + S.h_w8.size());
+    S.off_bias = off; off = align256(off + (size_t)S.Npar * 4);
+    S.off_alpha = off; off = align256(off + (size_t)S.Npar * 4);
+    S.off_beta = off; off = align256(off + (size_t)S.Npar * 4);
+    S.off_nshift = off; off = align256(off + S.h_nshift.size());
+  }
+  return off;
+}
+
+static size_t blob_header_bytes(const tf2b_net* net) {
+  return align256(16 + net->layers.size() * sizeof(BlobLayerMeta));
+}
+
+int64_t tf2b_weight_blob_bytes(tf2b_net* net) {
+  if (!net) return TF2B_ERR_ARG;
+  if (!net->finalized) return fail(net, TF2B_ERR_STATE, "finalize first");
+  return (int64_t)(blob_header_bytes(net) + net->arena_bytes);
+}
+
+static int alloc_runtime(tf2b_net* net);
+
+int tf2b_finalize(tf2b_net* net, int max_images) {
+  if (!net) return TF2B_ERR_ARG;
+  if (net->finalized) return fail(net, TF2B_ERR_STATE, "already finalized");
+  if (max_images <= 0) return fail(net, TF2B_ERR_ARG, "max_images must be positive");
+  for (size_t l = 0; l < net->layers.size(); l++)
+    if (!net->layers[l].d.ipool && !net->layers[l].loaded)
+      return fail(net, TF2B_ERR_STATE, "layer %zu has no weights loaded", l);
+  CUDA_TRY(net, cudaSetDevice(net->device));
+  net->max_images = max_images;
+  net->arena_bytes = layout_arena(net);
+  CUDA_TRY(net, cudaMalloc(&net->arena, std::max<size_t>(net->arena_bytes, 256)));
+  for (auto& S : net->layers) {
+    if (S.d.ipool) continue;
+    auto up = [&](size_t off, const void* src, size_t bytes) -> cudaError_t {
+      if (!bytes) return cudaSuccess;
+      return cudaMemcpy(net->arena + off, src, bytes, cudaMemcpyHostToDevice);
+    };
+    CUDA_TRY(net, up(S.off_w16, S.h_w16.data(), S.h_w16.size() * 2));
+    CUDA_TRY(net, up(S.off_w8, S.h_w8.data(), S.h_w8.size()));
+    CUDA_TRY(net, up(S.off_bias, S.h_bias.data(), (size_t)S.Npar * 4));
+    CUDA_TRY(net, up(S.off_alpha, S.h_alpha.data(), (size_t)S.Npar * 4));
+    CUDA_TRY(net, up(S.off_beta, S.h_beta.data(), (size_t)S.Npar * 4));
+    CUDA_TRY(net, up(S.off_nshift, S.h_nshift.data(), S.h_nshift.size()));
+  }
+  int rc = alloc_runtime(net);
+  if (rc != TF2B_OK) return rc;
+  net->finalized = true;
+  return tf2b_set_variant(net, net->variant);
+}
+
+// Builds the ConvParams of a layer for `B` images (pointers into the arena and tensor buffers).
+static ConvParams conv_params(tf2b_net* net, const LayerState& S, int B, int8_t* dst, int dstC,
+                              const int8_t* res, int resC, bool mma) {
+  const tf2b_layer_desc& d = S.d;
+  ConvParams p;
+  memset(&p, 0, sizeof p);
+  const tf2b_tensor_desc& ti = net->tensors[d.in_tensor];
+  p.x = net->tbuf[d.in_tensor];
+  p.y = dst;
+  p.r = res;
+  p.bias = reinterpret_cast<const int32_t*>(net->arena + S.off_bias);
+  p.alpha = reinterpret_cast<const int32_t*>(net->arena + S.off_alpha);
+  p.beta = reinterpret_cast<const int32_t*>(net->arena + S.off_beta);
+  p.nshift = net->arena + S.off_nshift;
+  p.acc_dump = nullptr;
+  p.B = B; p.IH = ti.H; p.IW = ti.W; p.Cp = S.Cp; p.xC = net->tpitch[d.in_tensor];
+  p.OH = d.OH; p.OW = d.OW; p.N = d.N; p.yC = dstC; p.rC = resC;
+  p.k = d.k; p.pad = d.pad; p.stride = d.stride;
+  p.relu = d.relu; p.add_relu = d.add_relu;
+  if (mma) {
+    p.Npad = S.Npad_m; p.Kp = S.Kp_m; p.Ktot = S.Kp_m; p.planes = S.planes_m;
+    for (int i = 0; i < tf2b::kMaxPlanes; i++) { p.plane_shift[i] = S.plane_shift_m[i]; p.plane_neg[i] = 0; }
+  } else {
+    p.Npad = S.Npad_s; p.Kp = S.Kp_s; p.Ktot = d.k * d.k * S.Cp; p.planes = S.planes_s;
+    for (int i = 0; i < tf2b::kMaxPlanes; i++) { p.plane_shift[i] = S.plane_shift_s[i]; p.plane_neg[i] = S.plane_neg_s[i]; }
+  }
+  return p;
+}
+
+static int alloc_runtime(tf2b_net* net) {
+  const int B = net->max_images;
+  net->tbuf.assign(net->tensors.size(), nullptr);
+  for (size_t t = 0; t < net->tensors.size(); t++) {
+    size_t bytes = (size_t)B * net->tensors[t].H * net->tensors[t].W * net->tpitch[t];
+    CUDA_TRY(net, cudaMalloc(&net->tbuf[t], bytes));
+    CUDA_TRY(net, cudaMemset(net->tbuf[t], 0, bytes));
+  }
+  size_t sc = 256;
+  for (auto& S : net->layers) {
+    const tf2b_layer_desc& d = S.d;
+    if (d.ipool) continue;
+    if (d.pool || d.gap) sc = std::max(sc, (size_t)B * d.OH * d.OW * round_up(d.N, 16));
+  }
+  net->scratch_bytes = sc;
+  CUDA_TRY(net, cudaMalloc(&net->scratch0, sc));
+  CUDA_TRY(net, cudaMalloc(&net->scratch1, sc));
+  // staging for host entry points: largest of tensor 0 / raw image, and the result tensor
+  size_t in_b = std::max((size_t)3 * 224 * 224, (size_t)net->tensors[0].C * net->tensors[0].H * net->tensors[0].W) * B;
+  size_t out_b = 0;
+  for (auto& t : net->tensors) out_b = std::max(out_b, (size_t)t.C * t.H * t.W * B);
+  net->io_in_bytes = in_b;
+  net->io_out_bytes = out_b;
+  CUDA_TRY(net, cudaMalloc(&net->io_in, in_b));
+  CUDA_TRY(net, cudaMalloc(&net->io_out, out_b));
+  // tensor maps of the tensor-core path depend on buffer addresses: build them now
+  for (auto& S : net->layers) {
+    if (!S.mma_ok) continue;
+    const tf2b_layer_desc& d = S.d;
+    bool to_scratch = d.pool || d.gap;
+    int8_t* dst = to_scratch ? net->scratch0 : net->tbuf[d.out_tensor] + d.out_ch0;
+    int dstC = to_scratch ? round_up(d.N, 16) : net->tpitch[d.out_tensor];
+    ConvParams p = conv_params(net, S, B, dst, dstC, nullptr, 0, true);
+    S.h_tmaps.assign(tf2b::mma_tmap_bytes(), 0);
+    std::string err;
+    int rc = tf2b::mma_build_tmaps(S.h_tmaps.data(), p,
+                                   reinterpret_cast<const int8_t*>(net->arena + S.off_w8), S.planes_m, &err);
+    if (rc != 0) {
+      // not fatal: fall back to the shift kernel for this layer, remember why
+      S.mma_ok = false;
+      net->err = "mma tensor map: " + err;
+    }
+  }
+  return TF2B_OK;
+}
+
+static int run_layers(tf2b_net* net, int B, cudaStream_t st, int only_layer, int32_t* acc_dump) {
+  int launches = 0;
+  for (size_t l = 0; l < net->layers.size(); l++) {
+    if (only_layer >= 0 && (int)l != only_layer) continue;
+    LayerState& S = net->layers[l];
+    const tf2b_layer_desc& d = S.d;
+    const tf2b_tensor_desc& ti = net->tensors[d.in_tensor];
+    int8_t* out = net->tbuf[d.out_tensor] + d.out_ch0;
+    const int outC = net->tpitch[d.out_tensor];
+    const int8_t* res = d.add_tensor >= 0 ? net->tbuf[d.add_tensor] : nullptr;
+    const int resC = d.add_tensor >= 0 ? net->tpitch[d.add_tensor] : 0;
+    if (d.ipool) {
+      if (only_layer >= 0) return fail(net, TF2B_ERR_ARG, "ipool layer has no accumulators");
+      CUDA_TRY(net, tf2b::launch_maxpool3x3(net->tbuf[d.in_tensor], out, nullptr, B, ti.H, ti.W,
+                                            net->tpitch[d.in_tensor], d.PH, d.PW, outC, 0, d.N, 1, 1, 0, st));
+      launches++;
+      continue;
+    }
+    const bool to_scratch = d.pool || d.gap;
+    const int Np16 = round_up(d.N, 16);
+    int8_t* cdst = to_scratch ? net->scratch0 : out;
+    const int cdstC = to_scratch ? Np16 : outC;
+    // the residual add sits after the pool (pool_tail -> feature_writer): fuse it into the conv
+    // epilogue only when there is no pool
+    const int8_t* cres = d.pool ? nullptr : res;
+    bool use_mma = S.kernel == 2 && S.mma_ok && acc_dump == nullptr;
+    ConvParams p = conv_params(net, S, B, cdst, cdstC, cres, resC, use_mma);
+    p.acc_dump = acc_dump;
+    if (use_mma) {
+      CUDA_TRY(net, tf2b::launch_conv_mma(p, reinterpret_cast<const int8_t*>(net->arena + S.off_w8),
+                                          S.planes_m, S.plane_shift_m, S.h_tmaps.data(), st));
+    } else {
+      CUDA_TRY(net, tf2b::launch_conv_shift(p, reinterpret_cast<const int16_t*>(net->arena + S.off_w16), st));
+    }
+    launches++;
+    if (only_layer >= 0) break;
+    const int8_t* cur = cdst;
+    int curC = cdstC, curH = d.OH, curW = d.OW;
+    if (d.pool) {
+      int8_t* pdst = d.gap ? net->scratch1 : out;
+      int pdstC = d.gap ? Np16 : outC;
+      CUDA_TRY(net, tf2b::launch_maxpool3x3(cur, pdst, res, B, curH, curW, curC, d.PH, d.PW, pdstC, resC,
+                                            d.N, d.pool_stride, d.pool_pad, d.add_relu, st));
+      launches++;
+      cur = pdst; curC = pdstC; curH = d.PH; curW = d.PW;
+    }
+    if (d.gap) {
+      CUDA_TRY(net, tf2b::launch_gap(cur, out, B, curH * curW, curC, outC, d.N, st));
+      launches++;
+    }
+  }
+  net->last_launches += launches;
+  return TF2B_OK;
+}
+
+static int check_run(tf2b_net* net, int n_images) {
+  if (!net) return TF2B_ERR_ARG;
+  if (!net->finalized) return fail(net, TF2B_ERR_STATE, "tf2b_finalize has not been called");
+  if (n_images <= 0 || n_images > net->max_images)
+    return fail(net, TF2B_ERR_ARG, "n_images %d outside 1..%d", n_images, net->max_images);
+  return TF2B_OK;
+}
+
+static int write_result(tf2b_net* net, int tensor, int B, int8_t* out_dev, int layout, cudaStream_t st) {
+  const tf2b_tensor_desc& t = net->tensors[tensor];
+  const int Cp = net->tpitch[tensor];
+  if (layout == TF2B_LAYOUT_CHW) {
+    CUDA_TRY(net, tf2b::launch_hwc_to_chw(net->tbuf[tensor], out_dev, B, t.C, t.H, t.W, Cp, st));
+  } else if (layout == TF2B_LAYOUT_HWC) {
+    CUDA_TRY(net, tf2b::launch_hwc_repitch(net->tbuf[tensor], out_dev, (size_t)B * t.H * t.W, t.C, Cp, t.C, st));
+  } else {
+    return fail(net, TF2B_ERR_ARG, "unknown layout %d", layout);
+  }
+  net->last_launches++;
+  return TF2B_OK;
+}
+
+int tf2b_run(tf2b_net* net, const int8_t* in_dev, int in_layout, int n_images, int8_t* out_dev,
+             int out_layout, void* stream) {
+  int rc = check_run(net, n_images);
+  if (rc) return rc;
+  if (!in_dev || !out_dev) return fail(net, TF2B_ERR_ARG, "null device pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  CUDA_TRY(net, cudaSetDevice(net->device));
+  net->last_launches = 0;
+  net->last_images = n_images;
+  const tf2b_tensor_desc& t0 = net->tensors[0];
+  if (in_layout == TF2B_LAYOUT_CHW) {
+    CUDA_TRY(net, tf2b::launch_chw_to_hwc(in_dev, net->tbuf[0], n_images, t0.C, t0.H, t0.W, net->tpitch[0], st));
+  } else if (in_layout == TF2B_LAYOUT_HWC) {
+    CUDA_TRY(net, tf2b::launch_hwc_repitch(in_dev, net->tbuf[0], (size_t)n_images * t0.H * t0.W, t0.C, t0.C,
+                                           net->tpitch[0], st));
+  } else {
+    return fail(net, TF2B_ERR_ARG, "unknown layout %d", in_layout);
+  }
+  net->last_launches++;
+  rc = run_layers(net, n_images, st, -1, nullptr);
+  if (rc) return rc;
+  return write_result(net, net->result_tensor, n_images, out_dev, out_layout, st);
+}
+
+int tf2b_run_raw224(tf2b_net* net, const int8_t* raw_dev, int n_images, int8_t* out_dev, int out_layout,
+                    void* stream) {
+  int rc = check_run(net, n_images);
+  if (rc) return rc;
+  if (!raw_dev || !out_dev) return fail(net, TF2B_ERR_ARG, "null device pointer");
+  const tf2b_tensor_desc& t0 = net->tensors[0];
+  if (t0.C != 27 || t0.H != 114 || t0.W != 114)
+    return fail(net, TF2B_ERR_ARG, "tensor 0 is %dx%dx%d, not the 27x114x114 space-to-depth input", t0.C, t0.H, t0.W);
+  cudaStream_t st = (cudaStream_t)stream;
+  CUDA_TRY(net, cudaSetDevice(net->device));
+  net->last_launches = 0;
+  net->last_images = n_images;
+  CUDA_TRY(net, tf2b::launch_raw224_to_s2d(raw_dev, net->tbuf[0], n_images, st));
+  net->last_launches++;
+  rc = run_layers(net, n_images, st, -1, nullptr);
+  if (rc) return rc;
+  return write_result(net, net->result_tensor, n_images, out_dev, out_layout, st);
+}
+
+int tf2b_run_raw224_host(tf2b_net* net, const int8_t* raw_host, int n_images, int8_t* out_host, int out_layout) {
+  int rc = check_run(net, n_images);
+  if (rc) return rc;
+  if (!raw_host || !out_host) return fail(net, TF2B_ERR_ARG, "null host pointer");
+  cudaStream_t st = net->own_stream;
+  CUDA_TRY(net, cudaSetDevice(net->device));
+  const tf2b_tensor_desc& tr = net->tensors[net->result_tensor];
+  CUDA_TRY(net, cudaMemcpyAsync(net->io_in, raw_host, (size_t)n_images * 3 * 224 * 224, cudaMemcpyHostToDevice, st));
+  rc = tf2b_run_raw224(net, net->io_in, n_images, net->io_out, out_layout, st);
+  if (rc) return rc;
+  CUDA_TRY(net, cudaMemcpyAsync(out_host, net->io_out, (size_t)n_images * tr.C * tr.H * tr.W, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(net, cudaStreamSynchronize(st));
+  return TF2B_OK;
+}
+
+int tf2b_run_host(tf2b_net* net, const int8_t* in_host, int in_layout, int n_images, int8_t* out_host,
+                  int out_layout) {
+  int rc = check_run(net, n_images);
+  if (rc) return rc;
+  if (!in_host || !out_host) return fail(net, TF2B_ERR_ARG, "null host pointer");
+  cudaStream_t st = net->own_stream;
+  CUDA_TRY(net, cudaSetDevice(net->device));
+  const tf2b_tensor_desc& t0 = net->tensors[0];
+  const tf2b_tensor_desc& tr = net->tensors[net->result_tensor];
+  CUDA_TRY(net, cudaMemcpyAsync(net->io_in, in_host, (size_t)n_images * t0.C * t0.H * t0.W, cudaMemcpyHostToDevice, st));
+  rc = tf2b_run(net, net->io_in, in_layout, n_images, net->io_out, out_layout, st);
+  if (rc) return rc;
+  CUDA_TRY(net, cudaMemcpyAsync(out_host, net->io_out, (size_t)n_images * tr.C * tr.H * tr.W, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(net, cudaStreamSynchronize(st));
+  return TF2B_OK;
+}
+
+int tf2b_read_tensor(tf2b_net* net, int tensor, int n_images, int8_t* dst_dev, int layout, void* stream) {
+  int rc = check_run(net, n_images);
+  if (rc) return rc;
+  if (tensor < 0 || tensor >= (int)net->tensors.size() || !dst_dev) return fail(net, TF2B_ERR_ARG, "bad tensor/pointer");
+  CUDA_TRY(net, cudaSetDevice(net->device));
+  return write_result(net, tensor, n_images, dst_dev, layout, (cudaStream_t)stream);
+}
+
+int tf2b_dump_acc(tf2b_net* net, int layer, int n_images, int32_t* acc_dev, void* stream) {
+  int rc = check_run(net, n_images);
+  if (rc) return rc;
+  if (layer < 0 || layer >= (int)net->layers.size() || !acc_dev) return fail(net, TF2B_ERR_ARG, "bad layer/pointer");
+  CUDA_TRY(net, cudaSetDevice(net->device));
+  // the conv of this layer is recomputed from its (still resident) input tensor into scratch, so the
+  // feature maps of the last run are left untouched
+  LayerState& S = net->layers[layer];
+  if (S.d.ipool) return fail(net, TF2B_ERR_ARG, "ipool layer has no accumulators");
+  tf2b_layer_desc saved = S.d;
+  size_t need = (size_t)n_images * S.d.OH * S.d.OW * round_up(S.d.N, 16);
+  if (need > net->scratch_bytes) {
+    // layers that normally write straight to their tensor may exceed the scratch: grow it
+    CUDA_TRY(net, cudaFree(net->scratch0));
+    CUDA_TRY(net, cudaFree(net->scratch1));
+    net->scratch_bytes = need;
+    CUDA_TRY(net, cudaMalloc(&net->scratch0, need));
+    CUDA_TRY(net, cudaMalloc(&net->scratch1, need));
+  }
+  S.d.pool = 1;  // forces the convolution output into scratch0; only the conv launch runs
+  S.d.add_tensor = -1;
+  int rc2 = run_layers(net, n_images, (cudaStream_t)stream, layer, acc_dev);
+  S.d = saved;
+  return rc2;
+}
+
+int tf2b_export_weight_blob(tf2b_net* net, void* dev_dst, void* stream) {
+  if (!net || !dev_dst) return TF2B_ERR_ARG;
+  if (!net->finalized) return fail(net, TF2B_ERR_STATE, "finalize first");
+  CUDA_TRY(net, cudaSetDevice(net->device));
+  const size_t hb = blob_header_bytes(net);
+  std::vector<unsigned char> hdr(hb, 0);
+  uint64_t magic = 0x54463242424c4f42ull, nl = net->layers.size();
+  memcpy(hdr.data(), &magic, 8);
+  memcpy(hdr.data() + 8, &nl, 8);
+  for (size_t l = 0; l < net->layers.size(); l++) {
+    const LayerState& S = net->layers[l];
+    BlobLayerMeta m;
+    memset(&m, 0, sizeof m);
+    m.loaded = S.loaded; m.Cp = S.Cp; m.Npad_s = S.Npad_s; m.Kp_s = S.Kp_s; m.planes_s = S.planes_s;
+    m.Npad_m = S.Npad_m; m.Kp_m = S.Kp_m; m.planes_m = S.planes_m; m.mma_ok = S.planes_m > 0; m.Npar = S.Npar;
+    for (int i = 0; i < 4; i++) {
+      m.plane_shift_s[i] = S.plane_shift_s[i]; m.plane_neg_s[i] = S.plane_neg_s[i]; m.plane_shift_m[i] = S.plane_shift_m[i];
+    }
+    m.off_w16 = S.off_w16; m.off_w8 = S.off_w8; m.off_bias = S.off_bias; m.off_alpha = S.off_alpha;
+    m.off_beta = S.off_beta; m.off_nshift = S.off_nshift;
+    memcpy(hdr.data() + 16 + l * sizeof m, &m, sizeof m);
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  CUDA_TRY(net, cudaMemcpyAsync(dev_dst, hdr.data(), hb, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(net, cudaMemcpyAsync((unsigned char*)dev_dst + hb, net->arena, net->arena_bytes, cudaMemcpyDeviceToDevice, st));
+  CUDA_TRY(net, cudaStreamSynchronize(st));
+  return TF2B_OK;
+}
+
+// Import = the receiving side of the init-time NCCL broadcast: engine created from the same layer
+// tables, no model file read; call instead of tf2b_load_layer, then tf2b_finalize.
+int tf2b_import_weight_blob(tf2b_net* net, const void* dev_src, void* stream) {
+  if (!net || !dev_src) return TF2B_ERR_ARG;
+  if (net->finalized) return fail(net, TF2B_ERR_STATE, "import must precede tf2b_finalize");
+  CUDA_TRY(net, cudaSetDevice(net->device));
+  const size_t hb = blob_header_bytes(net);
+  std::vector<unsigned char> hdr(hb);
+  cudaStream_t st = (cudaStream_t)stream;
+  CUDA_TRY(net, cudaMemcpyAsync(hdr.data(), dev_src, hb, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(net, cudaStreamSynchronize(st));
+  uint64_t magic, nl;
+  memcpy(&magic, hdr.data(), 8);
+  memcpy(&nl, hdr.data() + 8, 8);
+  if (magic != 0x54463242424c4f42ull || nl != net->layers.size())
+    return fail(net, TF2B_ERR_ARG, "weight blob does not match this network");
+  for (size_t l = 0; l < net->layers.size(); l++) {
+    LayerState& S = net->layers[l];
+    BlobLayerMeta m;
+    memcpy(&m, hdr.data() + 16 + l * sizeof m, sizeof m);
+    if (S.d.ipool) continue;
+    if (!m.loaded) return fail(net, TF2B_ERR_ARG, "blob layer %zu has no weights", l);
+    S.loaded = true; S.Cp = m.Cp; S.Npad_s = m.Npad_s; S.Kp_s = m.Kp_s; S.planes_s = m.planes_s;
+    S.Npad_m = m.Npad_m; S.Kp_m = m.Kp_m; S.planes_m = m.planes_m; S.mma_ok = m.mma_ok != 0; S.Npar = m.Npar;
+    for (int i = 0; i < 4; i++) {
+      S.plane_shift_s[i] = m.plane_shift_s[i]; S.plane_neg_s[i] = m.plane_neg_s[i]; S.plane_shift_m[i] = m.plane_shift_m[i];
+    }
+    // pull the arrays back to the host so finalize() can lay out and upload them uniformly
+    auto pull = [&](auto& vec, size_t count, int64_t off) -> cudaError_t {
+      vec.resize(count);
+      if (!count) return cudaSuccess;
+      return cudaMemcpy(vec.data(), (const unsigned char*)dev_src + hb + off, count * sizeof(vec[0]), cudaMemcpyDeviceToHost);
+    };
+    CUDA_TRY(net, pull(S.h_w16, (size_t)S.planes_s * S.Npad_s * S.Kp_s, m.off_w16));
+    CUDA_TRY(net, pull(S.h_w8, (size_t)S.planes_m * S.Npad_m * S.Kp_m, m.off_w8));
+    CUDA_TRY(net, pull(S.h_bias, (size_t)S.Npar, m.off_bias));
+    CUDA_TRY(net, pull(S.h_alpha, (size_t)S.Npar, m.off_alpha));
+    CUDA_TRY(net, pull(S.h_beta, (size_t)S.Npar, m.off_beta));
+    CUDA_TRY(net, pull(S.h_nshift, (size_t)round_up(S.Npar, 16), m.off_nshift));
+  }
+  return TF2B_OK;
+}
+
+int tf2b_last_launches(tf2b_net* net) { return net ? net->last_launches : 0; }
+
+const char* tf2b_layer_kernel(tf2b_net* net, int layer) {
+  if (!net || layer < 0 || layer >= (int)net->layers.size()) return "none";
+  const LayerState& S = net->layers[layer];
+  if (S.d.ipool) return "none";
+  return (S.kernel == 2 && S.mma_ok) ? "mma" : "shift";
+}
+
+void tf2b_destroy(tf2b_net* net) {
+  if (!net) return;
+  cudaSetDevice(net->device);
+  for (auto p : net->tbuf) if (p) cudaFree(p);
+  if (net->arena) cudaFree(net->arena);
+  if (net->scratch0) cudaFree(net->scratch0);
+  if (net->scratch1) cudaFree(net->scratch1);
+  if (net->io_in) cudaFree(net->io_in);
+  if (net->io_out) cudaFree(net->io_out);
+  if (net->own_stream) cudaStreamDestroy(net->own_stream);
+  delete net;
+}
+
+}  // extern "C"
