@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""bench.py — images/sec of the TF2 quantised-convolution hot path on B200 (BASELINE.json metric).
+
+Workload (N=1): ResNet50 INT4-weight / INT8-feature, 224x224, batch 256 per GPU (BASELINE configs[1]
+with --variant shift, configs[2] with --variant mma; default `auto` = per-layer choice).  Synthetic
+INQ-style weights in the reference's param.bin format, the shipped per-channel Q table, synthetic
+int8 images.  One "step" = one batch through the whole network.
+
+  python bench.py --gpus N --steps K --warmup W [--variant auto|shift|mma] [--impl reference]
+For N>1 launch with torch.distributed.run (one rank per GPU); images shard across ranks (weak
+scaling, no data-path collective; one NCCL broadcast of the weight blob at init).
+
+Prints ONE JSON line (rank 0).  `value` is device-resident throughput (inputs already in HBM),
+`e2e` the same through the host-buffer C-ABI call (pinned host int8 images in, logits out, H2D/D2H
+inside the timed region).  `roofline` describes the dominant kernel family measured live with CUDA
+events on the launching stream; `cpu_baseline` is the CPU oracle on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from tf2_b200 import capi, formats, nets, synth  # noqa: E402
+
+BATCH = 256
+NET = "resnet50"
+METRIC = "images/sec ResNet50-INT4 224x224"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "src": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "src": "fallback"}
+
+
+def build_model(net_name=NET, seed=3):
+    net = nets.load(net_name)
+    q = formats.parse_q_file(net, os.path.join(ROOT, "tests", "golden", f"{net_name}_Q"))
+    blob = synth.synth_float_blob(net, seed=seed, q=q)
+    model = formats.load_float_blob(net, blob, q)
+    return net, q, model
+
+
+def algorithmic_bytes_per_image(net):
+    """Layer-by-layer int8 activation traffic (inputs + outputs + residual reads), SURVEY.md 8d."""
+    tot = 0
+    for ld in net.layers:
+        ti, to = net.tensors[ld.in_tensor], net.tensors[ld.out_tensor]
+        cin = ti.C if ld.ipool else ld.C
+        tot += cin * ti.H * ti.W
+        tot += ld.N * to.H * to.W
+        if ld.add_tensor >= 0:
+            tot += ld.N * ld.PH * ld.PW
+    return tot
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 7:
+                for i, nme in enumerate(names):
+                    if r[3 + i].lower().startswith("active"):
+                        reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_run(net, model, t0, n_threads):
+    from oracle import oracle as O
+    t = time.perf_counter()
+    O.run_network(net, model, t0, n_threads=n_threads)
+    return time.perf_counter() - t
+
+
+def cpu_baseline(net, q, model, target_s=12.0):
+    """CPU oracle (a C restatement = 'port') on a bounded sample of the same workload."""
+    cores = len(os.sched_getaffinity(0))
+    imgs = synth.synth_images(max(2, min(cores, 8)), seed=21)
+    _, t0 = formats.prepare_input(net, imgs, q)
+    dt = cpu_reference_run(net, model, t0, cores)           # warm-up + calibration
+    per_img = dt / t0.shape[0]
+    n = int(max(cores, min(256, target_s / max(per_img, 1e-6))))
+    imgs = synth.synth_images(n, seed=22)
+    _, t0 = formats.prepare_input(net, imgs, q)
+    dt = cpu_reference_run(net, model, t0, cores)
+    return {"value": n / dt, "unit": "images/sec", "cores": cores, "kind": "port",
+            "sample": f"{n} of the {BATCH} images of one batch, whole ResNet50, oracle/tf2_oracle.c with OpenMP"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--variant", default="auto", choices=["auto", "shift", "mma"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    workload = f"ResNet50 INT4/INT8 batch={args.batch} per GPU, 224x224, variant={args.variant}"
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        net, q, model = build_model()
+        cores = len(os.sched_getaffinity(0))
+        per_step = max(2, min(cores, 16))   # bounded sample: images per step
+        imgs = synth.synth_images(per_step, seed=5)
+        _, t0 = formats.prepare_input(net, imgs, q)
+        for _ in range(max(1, min(args.warmup, 1))):
+            cpu_reference_run(net, model, t0, cores)
+        t = time.perf_counter()
+        for _ in range(args.steps):
+            cpu_reference_run(net, model, t0, cores)
+        dt = time.perf_counter() - t
+        val = per_step * args.steps / dt
+        line = {"metric": METRIC, "value": val, "unit": "images/sec", "impl": "reference", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8xint4->int32",
+                "data": "synthetic", "config": {"workload": workload, "images_per_step": per_step},
+                "cpu_baseline": {"value": val, "unit": "images/sec", "cores": cores, "kind": "port",
+                                 "sample": f"{per_step} images per step, whole ResNet50, oracle/tf2_oracle.c (C restatement "
+                                           f"of the reference device kernels; the FPGA emulator path cannot run here)"},
+                "e2e": {"value": val, "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+        return 0
+
+    # ------------------------------------------------------------------ our arm (GPU)
+    import torch
+    from tf2_b200.network import NetWork, Runner
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: tf2_b200 has no CPU fallback")
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    dev = torch.device(f"cuda:{local_rank}")
+    torch.cuda.set_device(dev)
+    variant = {"auto": capi.VARIANT_AUTO, "shift": capi.VARIANT_SHIFT, "mma": capi.VARIANT_MMA}[args.variant]
+    B = args.batch
+
+    net = nets.load(NET)
+    nw = NetWork(net, device=local_rank)
+    q = None
+    if rank == 0:
+        net, q, model = build_model()
+        nw.InitFromCodes(model, q, max_images=B, variant=variant)
+    if world > 1:
+        # single NCCL broadcast of the packed weight blob at init
+        nbytes = torch.tensor([nw.weight_blob_bytes() if rank == 0 else 0], dtype=torch.int64, device=dev)
+        dist.broadcast(nbytes, 0)
+        blob = torch.empty(int(nbytes.item()), dtype=torch.uint8, device=dev)
+        if rank == 0:
+            nw.export_weight_blob(blob.data_ptr())
+        dist.broadcast(blob, 0)
+        if rank != 0:
+            nw.InitFromBlob(blob.data_ptr(), max_images=B, variant=variant)
+        del blob
+    runner = Runner(nw)
+
+    # synthetic int8 images; 4 distinct batches (154 MB > 126 MB L2) rotate so inputs are never L2-resident
+    g = torch.Generator(device="cpu").manual_seed(1234 + rank)
+    nrot = 4
+    host_batches = [torch.randint(-128, 128, (B, 3, 224, 224), dtype=torch.int8, generator=g).pin_memory()
+                    for _ in range(nrot)]
+    dev_batches = [hb.to(dev) for hb in host_batches]
+    out = torch.empty((B, 1000, 1, 1), dtype=torch.int8, device=dev)
+    out_host = torch.empty((B, 1000, 1, 1), dtype=torch.int8).pin_memory()
+    stream = torch.cuda.current_stream(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for i in range(args.warmup):
+        runner.run_device(dev_batches[i % nrot], out=out, raw224=True, stream=stream)
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for i in range(args.steps):
+        runner.run_device(dev_batches[i % nrot], out=out, raw224=True, stream=stream)
+    ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = nw.last_launches() * args.steps
+    clocks = sampler.stop() if sampler else None
+
+    # end to end through the host-buffer C-ABI call (H2D of the int8 images + D2H of the logits inside)
+    for i in range(min(args.warmup, 2)):
+        runner.run_host(host_batches[i % nrot], out_host, raw224=True)
+    barrier()
+    t = time.perf_counter()
+    for i in range(args.steps):
+        runner.run_host(host_batches[i % nrot], out_host, raw224=True)
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t
+
+    # per-layer device times of the conv kernels (live, CUDA events on the launching stream)
+    nw.set_profile(True)
+    conv_ms = np.zeros(net.num_layers)
+    layer_ms = np.zeros(net.num_layers)
+    nprof = 3
+    for i in range(nprof):
+        runner.run_device(dev_batches[i % nrot], out=out, raw224=True, stream=stream)
+        c, l = nw.get_profile()
+        conv_ms += c
+        layer_ms += l
+    conv_ms /= nprof
+    layer_ms /= nprof
+    nw.set_profile(False)
+    kernels = nw.layer_kernels()
+
+    if world > 1:
+        tt = torch.tensor([ms, e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms, e2e_s = float(tt[0]), float(tt[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    peaks = load_peaks()
+    total_images = B * world * args.steps
+    value = total_images / (ms * 1e-3)
+    macs = net.macs_per_image()
+    # dominant kernel family by device time
+    fam_time = {}
+    for l, kname in enumerate(kernels):
+        fam_time[kname] = fam_time.get(kname, 0.0) + float(conv_ms[l])
+    dom = max((k for k in fam_time if k != "none"), key=lambda k: fam_time[k])
+    dom_layers = [l for l, kname in enumerate(kernels) if kname == dom]
+    dom_ops = 2.0 * sum((net.layers[l].OH * net.layers[l].OW * net.layers[l].N * net.layers[l].C * net.layers[l].k ** 2
+                         if not net.layers[l].first_layer_7x7 else
+                         net.layers[l].OH * net.layers[l].OW * net.layers[l].N * 147) for l in dom_layers) * B
+    dom_s = fam_time[dom] * 1e-3
+    int8_peak = 2.0 * peaks["bf16_tflops_sustained"]   # INT8 tcgen05 rate = 2x bf16 on sm_100a
+    achieved = dom_ops / dom_s / 1e12
+    roofline = {"bound": "tensor", "kernel": f"conv_{dom}", "achieved": achieved, "peak": int8_peak, "unit": "TOP/s",
+                "frac": achieved / int8_peak,
+                "peak_source": f"2 x {peaks['src']} sustained bf16 cuBLAS TF/s (INT8 MMA issues at twice the bf16 rate)",
+                "launches_per_step": len(dom_layers), "share_of_step": dom_s / (float(layer_ms.sum()) * 1e-3),
+                "traffic": None,
+                "hbm_view": {"algorithmic_bytes_per_image": algorithmic_bytes_per_image(net),
+                             "achieved_gbs": algorithmic_bytes_per_image(net) * B / (float(layer_ms.sum()) * 1e-3) / 1e9,
+                             "peak_gbs": peaks["hbm_gbs"]}}
+
+    line = {"metric": METRIC, "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int8xint4->int32", "data": "synthetic",
+            "config": {"workload": workload, "global_batch": B * world, "parallelism": f"dp{world}",
+                       "kernels": {k: kernels.count(k) for k in sorted(set(kernels))},
+                       "l2": "inputs rotate over 4 distinct batches (154 MB) > 126 MB L2; activations per step are GBs",
+                       "gmac_per_image": macs / 1e9},
+            "clocks": clocks, "gpu_launches": launches,
+            "e2e": {"value": total_images / e2e_s, "unit": "images/sec",
+                    "h2d_bytes_per_step": B * 3 * 224 * 224, "d2h_bytes_per_step": B * 1000},
+            "roofline": roofline,
+            "frac_of_int8_mma_roofline": (value / world) * 2 * macs / 1e12 / int8_peak,
+            "frac_of_hbm_roofline": (value / world) * algorithmic_bytes_per_image(net) / 1e9 / peaks["hbm_gbs"]}
+    if world == 1 and not args.no_cpu_baseline:
+        if q is None:
+            net, q, model = build_model()
+        line["cpu_baseline"] = cpu_baseline(net, q, model)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -138,6 +138,13 @@ int tf2b_read_tensor(tf2b_net* net, int tensor, int n_images, int8_t* dst_dev, i
  * (bias + sum of shifted features, before requantisation) to acc_dev as [image][N][OH][OW]. */
 int tf2b_dump_acc(tf2b_net* net, int layer, int n_images, int32_t* acc_dev, void* stream);
 
+/* Per-layer device timing (the reference gets its latency from OpenCL event profiling of the
+ * sequencer kernel, runner.cpp:187-189).  With profiling on, every run records CUDA events on the
+ * launching stream around each layer and around its convolution kernel; tf2b_get_profile waits
+ * for the last run and returns milliseconds per layer (arrays of n_layers floats). */
+int tf2b_set_profile(tf2b_net* net, int on);
+int tf2b_get_profile(tf2b_net* net, float* conv_ms, float* layer_ms, int n_layers);
+
 /* Number of kernels the last tf2b_run* call launched (bench.py's gpu_launches). */
 int tf2b_last_launches(tf2b_net* net);
 /* Name of the convolution kernel the plan uses for a layer ("shift", "mma", "none"). */

@@ -1,0 +1,81 @@
+"""GPU parity for the whole ResNet50 INT4/INT8 network (BASELINE configs[1]/[2]) vs the CPU oracle,
+plus size-independent properties at the full batch size."""
+import os
+
+import numpy as np
+import pytest
+
+from tests import helpers as H
+from tests.conftest import GOLDEN
+from tf2_b200 import capi, formats, nets, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def resnet_model():
+    net = nets.resnet50()
+    q = formats.parse_q_file(net, os.path.join(GOLDEN, "resnet50_Q"))
+    blob = synth.synth_float_blob(net, seed=3, q=q)
+    model = formats.load_float_blob(net, blob, q)
+    return net, q, model
+
+
+@pytest.mark.parametrize("variant", [capi.VARIANT_SHIFT, capi.VARIANT_AUTO], ids=["shift", "auto"])
+def test_resnet50_matches_oracle(resnet_model, variant):
+    import torch
+    from oracle import oracle as O
+    from tf2_b200.network import NetWork, Runner
+    net, q, model = resnet_model
+    B = 2
+    imgs = synth.synth_images(B, seed=11)
+    raw, t0 = formats.prepare_input(net, imgs, q)
+    nw = NetWork(net, 0)
+    nw.InitFromCodes(model, q, max_images=B, variant=variant)
+    r = Runner(nw)
+    got = r.run_device(torch.from_numpy(raw).cuda(), raw224=True).cpu().numpy()
+    exp = O.run_network(net, model, t0)
+    assert got.shape == exp.shape == (B, 1000, 1, 1)
+    assert np.array_equal(got, exp), f"fc1000 int8 differs in {(got != exp).sum()} of {exp.size}"
+    # the device-side space-to-depth transform equals feature_trans
+    t0_dev = r.read_tensor(0, B).cpu().numpy()
+    assert np.array_equal(t0_dev, t0)
+    # every intermediate feature map and every INT32 accumulator of image 0
+    tens, accs = H.oracle_tensors(net, model, t0[0])
+    for t in range(1, len(net.tensors)):
+        g = r.read_tensor(t, B).cpu().numpy()[0]
+        assert np.array_equal(g, tens[t]), f"tensor {t} ({net.tensors[t].name}) differs in {(g != tens[t]).sum()}"
+    for l in (0, 1, 3, 4, 13, 26, 45, 52, 53):
+        g = r.dump_acc(l, B).cpu().numpy()[0]
+        assert np.array_equal(g, accs[l]), f"layer {l} accumulators differ"
+    # the reference-facing host call gives the same answer (Runner::Run, float images in)
+    got_host = r.Run(imgs)
+    assert np.array_equal(got_host, exp)
+    assert nw.last_launches() >= net.num_layers
+    nw.CleanUp()
+
+
+def test_resnet50_batch256_properties(resnet_model):
+    """Full BASELINE batch: results are independent of batch composition and order."""
+    import torch
+    from tf2_b200.network import NetWork, Runner
+    net, q, model = resnet_model
+    B = 256
+    rng = np.random.default_rng(0)
+    raw = rng.integers(-128, 128, size=(B, 3, 224, 224), dtype=np.int8)
+    raw[1] = raw[0]                      # duplicate images must give duplicate outputs
+    nw = NetWork(net, 0)
+    nw.InitFromCodes(model, q, max_images=B)
+    r = Runner(nw)
+    x = torch.from_numpy(raw).cuda()
+    a = r.run_device(x, raw224=True).cpu().numpy()
+    assert np.array_equal(a[0], a[1])
+    perm = rng.permutation(B)
+    b = r.run_device(x[torch.from_numpy(perm).cuda()].contiguous(), raw224=True).cpu().numpy()
+    assert np.array_equal(b, a[perm])    # permutation equivariance over images
+    c = r.run_device(x[:5].contiguous(), raw224=True).cpu().numpy()
+    assert np.array_equal(c, a[:5])      # a sub-batch reproduces the same images
+    a2 = r.run_device(x, raw224=True).cpu().numpy()
+    assert np.array_equal(a, a2)         # deterministic
+    assert a.std() > 1.0                 # the synthetic model keeps the logits alive
+    nw.CleanUp()

@@ -35,7 +35,7 @@ SYMBOLS = [
     "tf2b_create", "tf2b_load_layer", "tf2b_load_layer_packed4", "tf2b_finalize", "tf2b_set_variant",
     "tf2b_weight_blob_bytes", "tf2b_export_weight_blob", "tf2b_import_weight_blob", "tf2b_run",
     "tf2b_run_raw224", "tf2b_run_raw224_host", "tf2b_run_host", "tf2b_set_result", "tf2b_read_tensor",
-    "tf2b_dump_acc", "tf2b_last_launches", "tf2b_layer_kernel", "tf2b_last_error", "tf2b_version",
+    "tf2b_dump_acc", "tf2b_set_profile", "tf2b_get_profile", "tf2b_last_launches", "tf2b_layer_kernel", "tf2b_last_error", "tf2b_version",
     "tf2b_destroy",
 ]
 
@@ -73,6 +73,8 @@ def load() -> C.CDLL:
     lib.tf2b_set_result.argtypes = [vp, i32]
     lib.tf2b_read_tensor.argtypes = [vp, i32, i32, vp, i32, vp]
     lib.tf2b_dump_acc.argtypes = [vp, i32, i32, vp, vp]
+    lib.tf2b_set_profile.argtypes = [vp, i32]
+    lib.tf2b_get_profile.argtypes = [vp, vp, vp, i32]
     lib.tf2b_last_launches.argtypes = [vp]
     lib.tf2b_layer_kernel.argtypes = [vp, i32]
     lib.tf2b_layer_kernel.restype = C.c_char_p
@@ -84,7 +86,7 @@ def load() -> C.CDLL:
     for name in ("tf2b_create", "tf2b_load_layer", "tf2b_load_layer_packed4", "tf2b_finalize",
                  "tf2b_set_variant", "tf2b_export_weight_blob", "tf2b_import_weight_blob", "tf2b_run",
                  "tf2b_run_raw224", "tf2b_run_raw224_host", "tf2b_run_host", "tf2b_set_result",
-                 "tf2b_read_tensor", "tf2b_dump_acc", "tf2b_last_launches"):
+                 "tf2b_read_tensor", "tf2b_dump_acc", "tf2b_last_launches", "tf2b_set_profile", "tf2b_get_profile"):
         getattr(lib, name).restype = i32
     _lib = lib
     return lib

@@ -95,6 +95,8 @@ struct tf2b_net {
   cudaStream_t own_stream = nullptr;
   int last_launches = 0;
   int last_images = 0;
+  bool profile = false;
+  std::vector<cudaEvent_t> ev;  // 3 per layer: layer start, conv end, layer end
   std::string err;
 };
 
@@ -515,9 +517,11 @@ static int alloc_runtime(tf2b_net* net) {
 
 static int run_layers(tf2b_net* net, int B, cudaStream_t st, int only_layer, int32_t* acc_dump) {
   int launches = 0;
+  const bool prof = net->profile && only_layer < 0 && !net->ev.empty();
   for (size_t l = 0; l < net->layers.size(); l++) {
     if (only_layer >= 0 && (int)l != only_layer) continue;
     LayerState& S = net->layers[l];
+    if (prof) CUDA_TRY(net, cudaEventRecord(net->ev[3 * l], st));
     const tf2b_layer_desc& d = S.d;
     const tf2b_tensor_desc& ti = net->tensors[d.in_tensor];
     int8_t* out = net->tbuf[d.out_tensor] + d.out_ch0;
@@ -529,6 +533,10 @@ static int run_layers(tf2b_net* net, int B, cudaStream_t st, int only_layer, int
       CUDA_TRY(net, tf2b::launch_maxpool3x3(net->tbuf[d.in_tensor], out, nullptr, B, ti.H, ti.W,
                                             net->tpitch[d.in_tensor], d.PH, d.PW, outC, 0, d.N, 1, 1, 0, st));
       launches++;
+      if (prof) {
+        CUDA_TRY(net, cudaEventRecord(net->ev[3 * l + 1], st));
+        CUDA_TRY(net, cudaEventRecord(net->ev[3 * l + 2], st));
+      }
       continue;
     }
     const bool to_scratch = d.pool || d.gap;
@@ -548,6 +556,7 @@ static int run_layers(tf2b_net* net, int B, cudaStream_t st, int only_layer, int
       CUDA_TRY(net, tf2b::launch_conv_shift(p, reinterpret_cast<const int16_t*>(net->arena + S.off_w16), st));
     }
     launches++;
+    if (prof) CUDA_TRY(net, cudaEventRecord(net->ev[3 * l + 1], st));
     if (only_layer >= 0) break;
     const int8_t* cur = cdst;
     int curC = cdstC, curH = d.OH, curW = d.OW;
@@ -563,6 +572,7 @@ static int run_layers(tf2b_net* net, int B, cudaStream_t st, int only_layer, int
       CUDA_TRY(net, tf2b::launch_gap(cur, out, B, curH * curW, curC, outC, d.N, st));
       launches++;
     }
+    if (prof) CUDA_TRY(net, cudaEventRecord(net->ev[3 * l + 2], st));
   }
   net->last_launches += launches;
   return TF2B_OK;
@@ -771,6 +781,30 @@ int tf2b_import_weight_blob(tf2b_net* net, const void* dev_src, void* stream) {
   return TF2B_OK;
 }
 
+int tf2b_set_profile(tf2b_net* net, int on) {
+  if (!net) return TF2B_ERR_ARG;
+  CUDA_TRY(net, cudaSetDevice(net->device));
+  if (on && net->ev.empty()) {
+    net->ev.resize(3 * net->layers.size());
+    for (auto& e : net->ev) CUDA_TRY(net, cudaEventCreate(&e));
+  }
+  net->profile = on != 0;
+  return TF2B_OK;
+}
+
+int tf2b_get_profile(tf2b_net* net, float* conv_ms, float* layer_ms, int n_layers) {
+  if (!net || !conv_ms || !layer_ms) return TF2B_ERR_ARG;
+  if (n_layers != (int)net->layers.size()) return fail(net, TF2B_ERR_ARG, "n_layers mismatch");
+  if (net->ev.empty()) return fail(net, TF2B_ERR_STATE, "profiling was never enabled");
+  CUDA_TRY(net, cudaSetDevice(net->device));
+  CUDA_TRY(net, cudaEventSynchronize(net->ev.back()));
+  for (int l = 0; l < n_layers; l++) {
+    CUDA_TRY(net, cudaEventElapsedTime(&conv_ms[l], net->ev[3 * l], net->ev[3 * l + 1]));
+    CUDA_TRY(net, cudaEventElapsedTime(&layer_ms[l], net->ev[3 * l], net->ev[3 * l + 2]));
+  }
+  return TF2B_OK;
+}
+
 int tf2b_last_launches(tf2b_net* net) { return net ? net->last_launches : 0; }
 
 const char* tf2b_layer_kernel(tf2b_net* net, int layer) {
@@ -790,6 +824,7 @@ void tf2b_destroy(tf2b_net* net) {
   if (net->io_in) cudaFree(net->io_in);
   if (net->io_out) cudaFree(net->io_out);
   if (net->own_stream) cudaStreamDestroy(net->own_stream);
+  for (auto e : net->ev) cudaEventDestroy(e);
   delete net;
 }
 

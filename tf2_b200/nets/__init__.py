@@ -1,0 +1,105 @@
+"""Built-in network descriptions.
+
+`resnet50`, `googlenet`, `resnet50_pruned` are the reference's own layer tables
+(`Runtime_Engine/cnn/host/inc/{resnet50,googlenet,resnet50_pruned}.h`) resolved by
+`NetDesc.from_header` and stored as JSON by tools/gen_nets.py.  Any other TF2 header can be loaded
+at run time with `NetDesc.from_header(path)`.
+"""
+from __future__ import annotations
+
+import json
+import os
+from typing import List, Optional
+
+from ..netdesc import LayerDesc, NetDesc, TensorDesc
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def load(name: str) -> NetDesc:
+    p = os.path.join(_HERE, name + ".json")
+    if not os.path.exists(p):
+        raise KeyError(f"unknown built-in network {name!r}")
+    with open(p) as f:
+        return NetDesc.from_json(json.load(f))
+
+
+def resnet50() -> NetDesc:
+    return load("resnet50")
+
+
+def googlenet() -> NetDesc:
+    return load("googlenet")
+
+
+def resnet50_pruned() -> NetDesc:
+    return load("resnet50_pruned")
+
+
+def chain(input_chw, specs: List[dict], name: str = "chain") -> NetDesc:
+    """Small hand-made networks for tests: a list of layer specs applied in sequence.
+
+    spec keys: N, k=1, pad=0, stride=1, relu=1, pool=0, pool_stride=1, pool_pad=0, add=None (index
+    of an earlier layer whose output is the residual operand, -1 = the input), add_relu=0, gap=0,
+    ipool=0, src=None (index of the producing layer, default previous; -1 = input), bias_en=0,
+    bn_en=1, concat=None ((group id, channel offset, total channels))."""
+    C0, H0, W0 = input_chw
+    tensors = [TensorDesc(C0, H0, W0, 0, "input")]
+    layers: List[LayerDesc] = []
+    out_of = {-1: 0}
+    concat_t = {}
+    for i, s in enumerate(specs):
+        src = s.get("src", i - 1)
+        tin = out_of[src]
+        ti = tensors[tin]
+        k, pad, stride = s.get("k", 1), s.get("pad", 0), s.get("stride", 1)
+        ipool = s.get("ipool", 0)
+        if ipool:
+            N, C, k, pad, stride = ti.C, ti.C, 3, 1, 1
+            OH, OW, PH, PW = ti.H, ti.W, ti.H, ti.W
+            pool, ps, pp = 1, 1, 1
+        else:
+            N, C = s["N"], s.get("C", ti.C)
+            OH = (ti.H + 2 * pad - k) // stride + 1
+            OW = (ti.W + 2 * pad - k) // stride + 1
+            pool, ps, pp = s.get("pool", 0), s.get("pool_stride", 1), s.get("pool_pad", 0)
+            if pool:
+                PH = s.get("PH", (OH + 2 * pp - 3) // ps + 1)
+                PW = s.get("PW", (OW + 2 * pp - 3) // ps + 1)
+            else:
+                PH, PW = OH, OW
+        gap = s.get("gap", 0)
+        oh, ow = (1, 1) if gap else (PH, PW)
+        cc = s.get("concat")
+        if cc is not None:
+            gid, ch0, ctot = cc
+            if gid not in concat_t:
+                tensors.append(TensorDesc(ctot, oh, ow, -1, f"concat{gid}"))
+                concat_t[gid] = len(tensors) - 1
+            tout = concat_t[gid]
+        else:
+            ch0 = 0
+            tensors.append(TensorDesc(N, oh, ow, i + 1, f"out{i}"))
+            tout = len(tensors) - 1
+        out_of[i] = tout
+        add = s.get("add")
+        layers.append(LayerDesc(
+            name=f"layer{i}", in_tensor=tin, out_tensor=tout, out_ch0=ch0,
+            add_tensor=(out_of[add] if add is not None else -1), C=C, N=N, k=k, pad=pad, stride=stride,
+            OH=OH, OW=OW, relu=s.get("relu", 1), pool=pool, pool_stride=ps, pool_pad=pp, PH=PH, PW=PW,
+            add_relu=s.get("add_relu", 0), gap=gap, ipool=ipool, bias_en=s.get("bias_en", 0),
+            bn_en=s.get("bn_en", 1), q_in_row=0, q_out_row=i + 1))
+    may = [False] * len(tensors)
+    may[0] = True
+    for ld in layers:
+        if ld.ipool:
+            nonneg = not may[ld.in_tensor]
+        else:
+            nonneg = bool(ld.add_relu if ld.add_tensor >= 0 else ld.relu)
+        if not nonneg:
+            may[ld.out_tensor] = True
+    for ld in layers:
+        ld.in_may_be_m128 = 1 if may[ld.in_tensor] else 0
+    mo = max(max(t.C for t in tensors), 1)
+    return NetDesc(name=name, tensors=tensors, layers=layers, max_out_channel=mo,
+                   num_q_rows=len(layers) + 1, input_c=C0, input_h=H0, input_w=W0)

@@ -120,6 +120,17 @@ class NetWork:
     def export_weight_blob(self, dst_dev_ptr: int, stream: int = 0):
         self._check(self._lib.tf2b_export_weight_blob(self._h, dst_dev_ptr, stream))
 
+    def set_profile(self, on: bool):
+        self._check(self._lib.tf2b_set_profile(self._h, 1 if on else 0))
+
+    def get_profile(self):
+        """(conv_ms, layer_ms) float32 arrays of the last profiled run."""
+        n = self.net.num_layers
+        conv = np.zeros(n, np.float32)
+        layer = np.zeros(n, np.float32)
+        self._check(self._lib.tf2b_get_profile(self._h, conv.ctypes.data, layer.ctypes.data, n))
+        return conv, layer
+
     def last_launches(self) -> int:
         return int(self._lib.tf2b_last_launches(self._h))
 

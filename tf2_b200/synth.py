@@ -45,10 +45,16 @@ def synth_q_text(net: NetDesc, seed: int = 0, spread: int = 2) -> str:
     return "\n".join(str(v) for v in vals) + "\n"
 
 
-def synth_float_blob(net: NetDesc, seed: int = 0, zero_frac: float = 0.2) -> bytes:
-    """Random model in param.bin order (model_loader.cpp:154-213)."""
+def synth_float_blob(net: NetDesc, seed: int = 0, zero_frac: float = 0.2,
+                     q: Optional[np.ndarray] = None, target_rms: float = 20.0) -> bytes:
+    """Random model in param.bin order (model_loader.cpp:154-213).
+
+    When the Q table `q` (formats.parse_q_*) is given, the BatchNorm scale of every channel is
+    calibrated analytically so that the INT8 feature maps keep an rms of about `target_rms` at
+    every depth (otherwise a random net decays to a few LSBs and parity tests exercise few bits)."""
     rng = np.random.default_rng(seed)
     out = io.BytesIO()
+    lvl_p = np.array([1, 2, 4, 6, 6, 5, 4], dtype=np.float64) / 28.0
     for ld in net.layers:
         if ld.ipool:
             continue
@@ -61,7 +67,7 @@ def synth_float_blob(net: NetDesc, seed: int = 0, zero_frac: float = 0.2) -> byt
         # He-style scale -> largest magnitude level 2^max_exp, 7 levels below it
         std = np.sqrt(2.0 / fan_in)
         max_exp = int(np.clip(np.round(np.log2(std * 2.5)), -8, 0))
-        lv = rng.choice(7, size=(N, C, H, W), p=np.array([1, 2, 4, 6, 6, 5, 4], dtype=np.float64) / 28.0)
+        lv = rng.choice(7, size=(N, C, H, W), p=lvl_p)
         mag = np.exp2((max_exp - lv).astype(np.float32))
         sign = rng.choice(np.array([-1.0, 1.0], dtype=np.float32), size=(N, C, H, W))
         w = (mag * sign).astype(np.float32)
@@ -73,8 +79,23 @@ def synth_float_blob(net: NetDesc, seed: int = 0, zero_frac: float = 0.2) -> byt
             out.write(rng.normal(0, 0.05, N).astype("<f4").tobytes())          # mean
             out.write(rng.uniform(0.5, 1.5, N).astype("<f4").tobytes())        # variance
             out.write(np.array([1.0], dtype="<f4").tobytes())                  # scale_factor
-            # gamma keeps the int8 maps alive: the conv output std is ~ sqrt(fan_in*(1-zero))*E|w|*x
-            out.write(rng.uniform(0.4, 1.2, N).astype("<f4").tobytes())        # gamma
+            var = rng.uniform(0.5, 1.5, N)
+            if q is not None:
+                # real-domain rms of the input (post-ReLU ~ target/sqrt(2) LSBs of 2^-Q_in) and of
+                # the conv output; gamma/sqrt(var) maps it to target_rms LSBs of 2^-Q_out
+                Cq = net.input_c if ld.first_layer_7x7 else C
+                Qin = -q[ld.q_in_row, :Cq].astype(np.float64)
+                Qout = -q[ld.q_out_row, :N].astype(np.float64)
+                x_rms = (50.0 if ld.q_in_row == 0 else target_rms / np.sqrt(2.0)) * np.mean(np.exp2(-Qin))
+                ew2 = float(np.sum(lvl_p * np.exp2(2.0 * (max_exp - np.arange(7)))))
+                conv_rms = np.sqrt(fan_in * (1.0 - zero_frac) * ew2) * x_rms
+                gamma = (target_rms * np.exp2(-Qout) / conv_rms) * np.sqrt(var) * rng.uniform(0.8, 1.25, N)
+            else:
+                gamma = rng.uniform(0.4, 1.2, N)
+            out.seek(out.tell() - 4 * N - 4)   # rewrite variance with the values gamma was fitted to
+            out.write(var.astype("<f4").tobytes())
+            out.write(np.array([1.0], dtype="<f4").tobytes())
+            out.write(gamma.astype("<f4").tobytes())                           # gamma
             out.write(rng.normal(0, 0.2, N).astype("<f4").tobytes())           # beta
     return out.getvalue()
 
