@@ -35,7 +35,7 @@ size_t mma_tmap_bytes();
 int mma_build_tmaps(void* host_tmaps, const ConvParams& p, const int8_t* wgt8, int planes8,
                     std::string* err);
 int mma_bn();
-int mma_bk();
+int mma_pick_bk(int Cp);
 }  // namespace tf2b
 
 using tf2b::ConvParams;
@@ -196,8 +196,8 @@ static int prepare_layer(tf2b_net* net, LayerState& S, const uint8_t* codes,
     if (np <= tf2b::kMaxPlanes && tf2b::mma_layer_supported(d, in_pitch, np)) {
       S.planes_m = np;
       S.Npad_m = round_up(N, tf2b::mma_bn());
-      S.Kp_m = k * k * round_up(S.Cp, tf2b::mma_bk());
-      const int Cpm = round_up(S.Cp, tf2b::mma_bk());
+      const int Cpm = round_up(S.Cp, tf2b::mma_pick_bk(S.Cp));
+      S.Kp_m = k * k * Cpm;
       S.h_w8.assign((size_t)np * S.Npad_m * S.Kp_m, 0);
       for (int p = 0; p < np; p++) S.plane_shift_m[p] = lv * p;
       for (int n = 0; n < N; n++)

@@ -1,20 +1,533 @@
-// conv_mma.cu — kernel B (tcgen05 INT8 MMA path).  Placeholder until the tensor-core kernel lands:
-// reports every layer as unsupported so the plan uses the shift kernel.
+// conv_mma.cu — kernel B: INT8 x INT4->INT8 implicit-GEMM convolution on the 5th-gen tensor cores.
+//
+// Reference semantics are those of kernel A (pe.cl:27-49,144-203; relu.cl:54; feature_writer.cl:
+// 124-127).  The power-of-two weights make the shift-accumulate a true integer GEMM: a code with
+// shift s contributes feature * (+-2^s) mod 2^32.  Per output channel the smallest shift is factored
+// out (applied to the finished sum, exact mod 2^32); the remaining exponent e = s - base is split
+// into planes of 7 levels so every weight is an int8 +-2^(e mod 7).  tcgen05.mma kind::i8 multiplies
+// the int8 activation tile with each plane into its own int32 TMEM accumulator (|sum| <= 127*64*K
+// < 2^31, so nothing saturates or wraps inside the tensor core) and the epilogue recombines
+// sum_p acc_p << 7p, adds the bias seed and requantises exactly like pe.cl:185-203.
+//
+// Structure (one persistent CTA per SM, warp specialised):
+//   warp 0      TMA producer: activation tile (flat [pixels x BK] for 1x1, or a (BK, tw, th, tn) box
+//               of the NHWC tensor per filter tap with hardware zero fill = the conv padding) and
+//               one weight tile per plane, SWIZZLE_128B/64B, into an mbarrier ring
+//   warp 1      MMA issuer: tcgen05.mma cta_group::1 kind::i8, M=128, N=BN, K=32 per instruction,
+//               accumulators double-buffered in TMEM; tcgen05.commit frees smem stages
+//   warps 2..9  epilogue: tcgen05.ld -> plane recombination -> requant/ReLU/residual -> 16-byte stores
+#include <cuda.h>
+#include <cuda_runtime.h>
+
 #include <string>
 
 #include "../../include/tf2b200.h"
 #include "common.cuh"
 
 namespace tf2b {
-bool mma_layer_supported(const tf2b_layer_desc&, int, int) { return false; }
-cudaError_t launch_conv_mma(const ConvParams&, const int8_t*, int, const int*, void*, cudaStream_t) {
-  return cudaErrorNotSupported;
+
+namespace {
+
+constexpr int MMA_M = 128;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_THREADS = 32 * (2 + NUM_EPI_WARPS);
+constexpr int MAX_STAGES = 8;
+constexpr int TMEM_COLS = 512;
+
+struct MmaParams {
+  ConvParams c;
+  int mode;                 // 0 = flat (1x1, stride 1, pad 0), 1 = box (one TMA box per filter tap)
+  int tw, th, tn;           // box tile: output columns, rows, images (tw*th*tn <= 128)
+  int tiles_w, tiles_h, tiles_b;
+  int m_tiles, n_tiles;
+  int BK, BN, planes, stages;
+  int kchunks;              // channel chunks per tap = Cpm / BK
+  int Cpm;                  // input channels rounded up to BK (weight K layout: tap*Cpm + c)
+  int taps;                 // k*k
+  int a_bytes, b_bytes;     // bytes one TMA load delivers (A box, one B plane tile)
+  int plane8_shift[kMaxPlanes];
+  int Npad;                 // rows per weight plane
+  unsigned idesc;           // tcgen05 instruction descriptor
+  unsigned sbo16;           // stride byte offset >> 4 of the smem descriptors
+  unsigned layout_type;     // UMMA smem layout type (2 = SWIZZLE_128B, 4 = SWIZZLE_64B)
+};
+
+struct TmapPair {
+  CUtensorMap a;
+  CUtensorMap b;
+};
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
-size_t mma_tmap_bytes() { return 0; }
-int mma_build_tmaps(void*, const ConvParams&, const int8_t*, int, std::string* err) {
-  if (err) *err = "tensor-core path not built";
-  return -1;
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-int mma_bn() { return 64; }
-int mma_bk() { return 64; }
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait: a descriptor/protocol bug must trap, not hang the GPU
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000ll) __trap();
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(unsigned smem, const CUtensorMap* map, unsigned bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(unsigned smem, const CUtensorMap* map, unsigned bar, int c0, int c1,
+                                            int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(unsigned smem_dst, unsigned ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(unsigned taddr, unsigned ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(unsigned bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], int8 x int8 -> int32
+__device__ __forceinline__ void umma_i8(unsigned tmem_d, unsigned long long desc_a, unsigned long long desc_b,
+                                        unsigned idesc, unsigned accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(unsigned taddr, unsigned (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major smem matrix descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor): start address and
+// byte offsets in 16-byte units, version 1 (Blackwell), swizzle mode in bits 61..63.
+__device__ __forceinline__ unsigned long long make_smem_desc(unsigned saddr, unsigned sbo16, unsigned layout_type) {
+  unsigned long long d = 0;
+  d |= (unsigned long long)((saddr >> 4) & 0x3FFF);
+  d |= (unsigned long long)1 << 16;                       // leading byte offset (unused for swizzled K-major)
+  d |= (unsigned long long)(sbo16 & 0x3FFF) << 32;        // stride between 8-row groups
+  d |= (unsigned long long)1 << 46;                       // descriptor version
+  d |= (unsigned long long)(layout_type & 7) << 61;
+  return d;
+}
+
+struct TileCoord {
+  int n0;            // first output channel
+  int m0;            // flat: first pixel
+  int b0, oh0, ow0;  // box: first image / row / column
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const MmaParams& P, int tile) {
+  TileCoord t;
+  int nt = tile % P.n_tiles;
+  int mt = tile / P.n_tiles;
+  t.n0 = nt * P.BN;
+  t.m0 = mt * MMA_M;
+  t.b0 = t.oh0 = t.ow0 = 0;
+  if (P.mode == 1) {
+    int wt = mt % P.tiles_w;
+    int r = mt / P.tiles_w;
+    int ht = r % P.tiles_h;
+    int bt = r / P.tiles_h;
+    t.ow0 = wt * P.tw;
+    t.oh0 = ht * P.th;
+    t.b0 = bt * P.tn;
+  }
+  return t;
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ TmapPair maps) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  // carve: [stages][A | B planes] (1024-aligned), then barriers
+  const unsigned smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int a_stage = MMA_M * P.BK;
+  const int b_plane = P.BN * P.BK;
+  const int stage_bytes = a_stage + P.planes * b_plane;
+
+  __shared__ __align__(8) unsigned long long bars[2 * MAX_STAGES + 4];
+  __shared__ unsigned tmem_base_slot;
+  const unsigned full_bar = smem_u32(&bars[0]);                  // [stages]
+  const unsigned empty_bar = smem_u32(&bars[MAX_STAGES]);        // [stages]
+  const unsigned tfull_bar = smem_u32(&bars[2 * MAX_STAGES]);    // [2]
+  const unsigned tempty_bar = smem_u32(&bars[2 * MAX_STAGES + 2]);  // [2]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = P.m_tiles * P.n_tiles;
+  const int kiters = P.taps * P.kchunks;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&maps.a);
+    tma_prefetch_desc(&maps.b);
+    for (int s = 0; s < P.stages; s++) {
+      mbar_init(full_bar + 8 * s, 1);
+      mbar_init(empty_bar + 8 * s, 1);
+    }
+    for (int b = 0; b < 2; b++) {
+      mbar_init(tfull_bar + 8 * b, 1);
+      mbar_init(tempty_bar + 8 * b, NUM_EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_base_slot), TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const unsigned tmem_base = tmem_base_slot;
+  const int acc_cols = P.planes * P.BN;  // TMEM columns of one accumulator buffer
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      unsigned phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(P, tile);
+        for (int tap = 0; tap < P.taps; tap++) {
+          const int fh = tap / P.c.k, fw = tap - fh * P.c.k;
+          for (int kc = 0; kc < P.kchunks; kc++) {
+            mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+            const unsigned fb = full_bar + 8 * stage;
+            mbar_expect_tx(fb, (unsigned)(P.a_bytes + P.planes * P.b_bytes));
+            const unsigned sa = smem_base + stage * stage_bytes;
+            if (P.mode == 0) {
+              tma_load_2d(sa, &maps.a, fb, kc * P.BK, t.m0);
+            } else {
+              tma_load_4d(sa, &maps.a, fb, kc * P.BK, t.ow0 * P.c.stride - P.c.pad + fw,
+                          t.oh0 * P.c.stride - P.c.pad + fh, t.b0);
+            }
+            for (int pl = 0; pl < P.planes; pl++)
+              tma_load_2d(sa + a_stage + pl * b_plane, &maps.b, fb, tap * P.Cpm + kc * P.BK, pl * P.Npad + t.n0);
+            if (++stage == P.stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer (one thread)
+    if (lane == 0) {
+      int stage = 0;
+      unsigned phase = 0;
+      int buf = 0;
+      unsigned tphase[2] = {0, 0};
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar + 8 * buf, tphase[buf] ^ 1);   // epilogue has drained this accumulator
+        tc_fence_after();
+        const unsigned d_tmem = tmem_base + buf * acc_cols;
+        for (int it = 0; it < kiters; it++) {
+          mbar_wait(full_bar + 8 * stage, phase);
+          tc_fence_after();
+          const unsigned sa = smem_base + stage * stage_bytes;
+          const unsigned long long da = make_smem_desc(sa, P.sbo16, P.layout_type);
+          for (int pl = 0; pl < P.planes; pl++) {
+            const unsigned long long db = make_smem_desc(sa + a_stage + pl * b_plane, P.sbo16, P.layout_type);
+            for (int k4 = 0; k4 < P.BK / 32; k4++) {
+              // advance both descriptors by 32 bytes of K inside the swizzled row
+              umma_i8(d_tmem + pl * P.BN, da + (unsigned long long)(2 * k4), db + (unsigned long long)(2 * k4),
+                      P.idesc, (it > 0 || k4 > 0) ? 1u : 0u);
+            }
+          }
+          umma_commit(empty_bar + 8 * stage);               // frees the smem stage when the MMAs retire
+          if (++stage == P.stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(tfull_bar + 8 * buf);                   // accumulators complete -> epilogue
+        tphase[buf] ^= 1;
+        buf ^= 1;
+      }
+    }
+  } else {
+    // ===================================================== epilogue warps
+    const int ew = warp - 2;            // 0..7
+    const int quarter = warp & 3;       // TMEM lane quarter this warp may access
+    const int half = ew >> 2;           // which half of the BN columns
+    const int row = quarter * 32 + lane;
+    const ConvParams& c = P.c;
+    const int M = c.B * c.OH * c.OW;
+    int buf = 0;
+    unsigned tphase[2] = {0, 0};
+    const int cols_per_half = P.BN / 2;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(P, tile);
+      // which output pixel is this thread's row?
+      bool valid;
+      long long pix;
+      if (P.mode == 0) {
+        int m = t.m0 + row;
+        valid = m < M;
+        pix = m;
+      } else {
+        int wl = row % P.tw;
+        int r = row / P.tw;
+        int hl = r % P.th;
+        int nl = r / P.th;
+        int ow = t.ow0 + wl, oh = t.oh0 + hl, b = t.b0 + nl;
+        valid = (nl < P.tn) && (ow < c.OW) && (oh < c.OH) && (b < c.B);
+        pix = ((long long)b * c.OH + oh) * c.OW + ow;
+      }
+      mbar_wait(tfull_bar + 8 * buf, tphase[buf]);
+      tc_fence_after();
+      const unsigned t_row = tmem_base + ((unsigned)(quarter * 32) << 16) + buf * acc_cols;
+      for (int cc = 0; cc < cols_per_half; cc += 16) {
+        const int col = half * cols_per_half + cc;
+        const int n = t.n0 + col;
+        unsigned tot[16];
+        tmem_ld16(t_row + col, tot);
+        tmem_ld_wait();
+        for (int pl = 1; pl < P.planes; pl++) {
+          unsigned v[16];
+          tmem_ld16(t_row + pl * P.BN + col, v);
+          tmem_ld_wait();
+          const int sh = P.plane8_shift[pl];
+#pragma unroll
+          for (int j = 0; j < 16; j++) tot[j] += v[j] << sh;
+        }
+        if (valid && n < c.N) {
+          unsigned packed[4] = {0, 0, 0, 0};
+#pragma unroll
+          for (int j = 0; j < 16; j++) {
+            const int nn = n + j;   // < Npad (params are padded with zeros)
+            int a32 = (int)((unsigned)__ldg(c.bias + nn) + (tot[j] << __ldg(c.nshift + nn)));
+            int y = requant(a32, __ldg(c.alpha + nn), __ldg(c.beta + nn));
+            if (c.relu) y = max(y, 0);
+            packed[j >> 2] |= (unsigned)(y & 0xff) << (8 * (j & 3));
+          }
+          int8_t* dst = c.y + pix * c.yC + n;
+          const int nvalid = min(16, c.N - n);
+          if (nvalid == 16) {
+            uint4 v = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+            if (c.r != nullptr) {
+              uint4 rv = *reinterpret_cast<const uint4*>(c.r + pix * c.rC + n);
+              v.x = add_res4(v.x, rv.x, c.add_relu);
+              v.y = add_res4(v.y, rv.y, c.add_relu);
+              v.z = add_res4(v.z, rv.z, c.add_relu);
+              v.w = add_res4(v.w, rv.w, c.add_relu);
+            }
+            *reinterpret_cast<uint4*>(dst) = v;
+          } else {
+            for (int e = 0; e < nvalid; e++) {
+              int yv = (int)(signed char)((packed[e >> 2] >> (8 * (e & 3))) & 0xff);
+              if (c.r != nullptr) {
+                int s = yv + (int)c.r[pix * c.rC + n + e];
+                s = max(-128, min(127, s));
+                if (c.add_relu) s = max(s, 0);
+                yv = s;
+              }
+              dst[e] = (int8_t)yv;
+            }
+          }
+        }
+      }
+      // accumulator buffer drained: hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar + 8 * buf);
+      tphase[buf] ^= 1;
+      buf ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn(std::string* err) {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !p) {
+    if (err) *err = "cuTensorMapEncodeTiled entry point not available";
+    return nullptr;
+  }
+  fn = (EncodeTiledFn)p;
+  return fn;
+}
+
+int pick_bk(int Cp) { return (Cp % 128 == 0) ? 128 : 64; }
+
+// geometry shared by the support test, the tensor-map builder and the launcher
+void fill_geometry(MmaParams& P, const ConvParams& c, int planes8) {
+  P.c = c;
+  P.planes = planes8;
+  P.BK = pick_bk(c.Cp);
+  P.Cpm = (c.Cp + P.BK - 1) / P.BK * P.BK;
+  P.kchunks = P.Cpm / P.BK;
+  P.taps = c.k * c.k;
+  P.BN = (planes8 <= 2 && c.N >= 128) ? 128 : 64;
+  P.Npad = c.Npad;
+  P.n_tiles = (c.N + P.BN - 1) / P.BN;
+  P.mode = (c.k == 1 && c.stride == 1 && c.pad == 0) ? 0 : 1;
+  if (P.mode == 0) {
+    P.tw = P.th = P.tn = 0;
+    P.tiles_w = P.tiles_h = P.tiles_b = 0;
+    const long long M = (long long)c.B * c.OH * c.OW;
+    P.m_tiles = (int)((M + MMA_M - 1) / MMA_M);
+    P.a_bytes = MMA_M * P.BK;
+  } else {
+    P.tw = c.OW < MMA_M ? c.OW : MMA_M;
+    P.th = MMA_M / P.tw;
+    if (P.th > c.OH) P.th = c.OH;
+    // balance rows over the tiles of one image (14 rows -> 7+7 rather than 9+5)
+    int th_tiles = (c.OH + P.th - 1) / P.th;
+    P.th = (c.OH + th_tiles - 1) / th_tiles;
+    P.tn = (P.th == c.OH) ? (MMA_M / (P.tw * P.th)) : 1;
+    if (P.tn < 1) P.tn = 1;
+    // NB: tn must not depend on the batch size of a particular run (the tensor map is built once for
+    // max_images); images past the batch end are zero-filled / masked rows
+    P.tiles_w = (c.OW + P.tw - 1) / P.tw;
+    P.tiles_h = (c.OH + P.th - 1) / P.th;
+    P.tiles_b = (c.B + P.tn - 1) / P.tn;
+    P.m_tiles = P.tiles_w * P.tiles_h * P.tiles_b;
+    P.a_bytes = P.tw * P.th * P.tn * P.BK;
+  }
+  P.b_bytes = P.BN * P.BK;
+  const int stage_bytes = MMA_M * P.BK + planes8 * P.b_bytes;
+  int st = (200 * 1024) / stage_bytes;
+  P.stages = st > MAX_STAGES ? MAX_STAGES : (st < 2 ? 2 : st);
+  // instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): c_format S32 (2) at bit 4,
+  // a/b format signed int8 (1) at bits 7 / 10, K-major A and B, N>>3 at bit 17, M>>4 at bit 24,
+  // saturate (bit 3) off
+  P.idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(P.BN >> 3) << 17) | ((unsigned)(MMA_M >> 4) << 24);
+  P.layout_type = (P.BK == 128) ? 2u : 4u;
+  P.sbo16 = (unsigned)(8 * P.BK) >> 4;
+}
+
+}  // namespace
+
+int mma_bn() { return 128; }   // weight planes are padded to a multiple of this many rows
+int mma_pick_bk(int Cp) { return pick_bk(Cp); }
+
+bool mma_layer_supported(const tf2b_layer_desc& L, int in_pitch, int planes8) {
+  if (L.ipool) return false;
+  if (L.stride != 1) return false;            // strided taps stay on the shift kernel for now
+  if (planes8 < 1 || planes8 > kMaxPlanes) return false;
+  if (in_pitch % 16 != 0) return false;
+  if (L.OW > 256 || L.k > 7) return false;
+  // TMEM: two accumulator buffers of planes*BN columns
+  int BN = (planes8 <= 2 && L.N >= 128) ? 128 : 64;
+  if (2 * planes8 * BN > TMEM_COLS) return false;
+  return true;
+}
+
+size_t mma_tmap_bytes() { return sizeof(TmapPair); }
+
+int mma_build_tmaps(void* host_tmaps, const ConvParams& c, const int8_t* wgt8, int planes8, std::string* err) {
+  EncodeTiledFn enc = get_encode_fn(err);
+  if (!enc) return -1;
+  MmaParams P;
+  fill_geometry(P, c, planes8);
+  TmapPair* tp = reinterpret_cast<TmapPair*>(host_tmaps);
+  const CUtensorMapSwizzle sw = (P.BK == 128) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUresult r;
+  if (P.mode == 0) {
+    cuuint64_t dims[2] = {(cuuint64_t)c.Cp, (cuuint64_t)c.B * c.IH * c.IW};
+    cuuint64_t strides[1] = {(cuuint64_t)c.xC};
+    cuuint32_t box[2] = {(cuuint32_t)P.BK, (cuuint32_t)MMA_M};
+    cuuint32_t es[2] = {1, 1};
+    r = enc(&tp->a, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)c.x, dims, strides, box, es,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else {
+    cuuint64_t dims[4] = {(cuuint64_t)c.Cp, (cuuint64_t)c.IW, (cuuint64_t)c.IH, (cuuint64_t)c.B};
+    cuuint64_t strides[3] = {(cuuint64_t)c.xC, (cuuint64_t)c.xC * c.IW, (cuuint64_t)c.xC * c.IW * c.IH};
+    cuuint32_t box[4] = {(cuuint32_t)P.BK, (cuuint32_t)P.tw, (cuuint32_t)P.th, (cuuint32_t)P.tn};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    r = enc(&tp->a, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, (void*)c.x, dims, strides, box, es,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
+  if (r != CUDA_SUCCESS) {
+    if (err) *err = "cuTensorMapEncodeTiled(A) failed with CUresult " + std::to_string((int)r);
+    return -1;
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)c.Kp, (cuuint64_t)planes8 * c.Npad};
+    cuuint64_t strides[1] = {(cuuint64_t)c.Kp};
+    cuuint32_t box[2] = {(cuuint32_t)P.BK, (cuuint32_t)P.BN};
+    cuuint32_t es[2] = {1, 1};
+    r = enc(&tp->b, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)wgt8, dims, strides, box, es,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
+  if (r != CUDA_SUCCESS) {
+    if (err) *err = "cuTensorMapEncodeTiled(B) failed with CUresult " + std::to_string((int)r);
+    return -1;
+  }
+  return 0;
+}
+
+cudaError_t launch_conv_mma(const ConvParams& c, const int8_t* /*wgt8*/, int planes8, const int* plane8_shift,
+                            void* tmaps, cudaStream_t stream) {
+  static int num_sms = 0;
+  static bool attr_set = false;
+  if (!num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  MmaParams P;
+  fill_geometry(P, c, planes8);
+  for (int i = 0; i < kMaxPlanes; i++) P.plane8_shift[i] = plane8_shift[i];
+  const int stage_bytes = MMA_M * P.BK + planes8 * P.b_bytes;
+  const size_t smem = (size_t)P.stages * stage_bytes + 1024;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const int num_tiles = P.m_tiles * P.n_tiles;
+  const int grid = num_tiles < num_sms ? num_tiles : num_sms;
+  const TmapPair* tp = reinterpret_cast<const TmapPair*>(tmaps);
+  conv_mma_kernel<<<grid, NUM_THREADS, smem, stream>>>(P, *tp);
+  return cudaGetLastError();
+}
+
 }  // namespace tf2b
