@@ -135,6 +135,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--layers-out", default=None, help="write per-layer device times (JSON) to this file")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -260,6 +261,15 @@ def main():
     layer_ms /= nprof
     nw.set_profile(False)
     kernels = nw.layer_kernels()
+    if args.layers_out and rank == 0:
+        rows = []
+        for l, ld in enumerate(net.layers):
+            macs_l = 0 if ld.ipool else ld.OH * ld.OW * ld.N * ld.C * ld.k * ld.k * B
+            rows.append({"layer": l, "kernel": kernels[l], "C": ld.C, "N": ld.N, "k": ld.k, "stride": ld.stride,
+                         "OH": ld.OH, "conv_ms": float(conv_ms[l]), "layer_ms": float(layer_ms[l]),
+                         "tops": (2 * macs_l / (conv_ms[l] * 1e-3) / 1e12) if conv_ms[l] > 0 else None})
+        with open(args.layers_out, "w") as f:
+            json.dump(rows, f, indent=0)
 
     if world > 1:
         tt = torch.tensor([ms, e2e_s], dtype=torch.float64, device=dev)

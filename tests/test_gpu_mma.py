@@ -31,7 +31,39 @@ CASES = [
     ("bottleneck_residual", (256, 14, 14), [dict(N=64, k=1), dict(N=64, k=3, pad=1),
                                             dict(N=256, k=1, relu=0, add=-1, add_relu=1)], 3, {}),
     ("wide_map_112", (32, 112, 112), [dict(N=64, k=3, pad=1)], 1, {}),
+    ("s2_3x3_c128_56to28", (128, 56, 56), [dict(N=128, k=3, pad=1, stride=2)], 2, {}),
+    ("s2_3x3_c256_28to14", (256, 28, 28), [dict(N=256, k=3, pad=1, stride=2)], 3, {}),
+    ("s2_3x3_c512_14to7", (512, 14, 14), [dict(N=512, k=3, pad=1, stride=2)], 5, {}),
+    ("s2_1x1_c256_56to28", (256, 56, 56), [dict(N=512, k=1, stride=2, relu=0)], 2, {}),
+    ("s2_1x1_c1024_14to7", (1024, 14, 14), [dict(N=2048, k=1, stride=2, relu=0)], 3, {}),
+    ("s2_3x3_odd_15to8", (64, 15, 15), [dict(N=64, k=3, pad=1, stride=2)], 3, {}),
 ]
+
+
+def test_mma_first_layer_quirk():
+    """A layer fed by the network input (may hold -128) runs on the tensor cores through the
+    negated copy of tensor 0 and still reproduces pe.cl:32-34's int8 negate."""
+    import torch
+    from tf2_b200.network import NetWork, Runner
+    rng = np.random.default_rng(77)
+    for chw, spec in (((27, 30, 30), dict(N=64, k=3, pad=0)), ((3, 20, 20), dict(N=32, k=3, pad=1, relu=0)),
+                      ((40, 9, 9), dict(N=48, k=1))):
+        net = nets.chain(chw, [spec])
+        x = H.random_input(rng, *chw, nonneg=False, B=3)
+        x[0, :, :2, :] = -128
+        model = H.random_model(net, rng, x)
+        nw = NetWork(net, 0)
+        nw.InitFromCodes(model, None, max_images=3, variant=capi.VARIANT_MMA)
+        assert nw.layer_kernels() == ["mma"], nw.layer_kernels()
+        r = Runner(nw)
+        out = r.run_device(torch.from_numpy(x).cuda()).cpu().numpy()
+        xh = np.ascontiguousarray(x.transpose(0, 2, 3, 1))
+        out2 = r.run_device(torch.from_numpy(xh).cuda(), in_layout=capi.LAYOUT_HWC).cpu().numpy()
+        for b in range(3):
+            tens, _ = H.oracle_tensors(net, model, x[b])
+            assert np.array_equal(out[b], tens[1]), f"{chw}: image {b} differs in {(out[b] != tens[1]).sum()}"
+            assert np.array_equal(out2[b], tens[1])
+        nw.CleanUp()
 
 
 @pytest.mark.parametrize("name,chw,specs,B,ckw", CASES, ids=[c[0] for c in CASES])

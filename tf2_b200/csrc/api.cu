@@ -20,10 +20,10 @@ namespace tf2b {
 cudaError_t launch_conv_shift(const ConvParams& p, const int16_t* wgt, cudaStream_t stream);
 int conv_shift_bn();
 int conv_shift_kc();
-cudaError_t launch_chw_to_hwc(const int8_t*, int8_t*, int, int, int, int, int, cudaStream_t);
+cudaError_t launch_chw_to_hwc(const int8_t*, int8_t*, int, int, int, int, int, int, cudaStream_t);
 cudaError_t launch_hwc_to_chw(const int8_t*, int8_t*, int, int, int, int, int, cudaStream_t);
-cudaError_t launch_hwc_repitch(const int8_t*, int8_t*, size_t, int, int, int, cudaStream_t);
-cudaError_t launch_raw224_to_s2d(const int8_t*, int8_t*, int, cudaStream_t);
+cudaError_t launch_hwc_repitch(const int8_t*, int8_t*, size_t, int, int, int, int, cudaStream_t);
+cudaError_t launch_raw224_to_s2d(const int8_t*, int8_t*, int, int, cudaStream_t);
 cudaError_t launch_maxpool3x3(const int8_t*, int8_t*, const int8_t*, int, int, int, int, int, int,
                               int, int, int, int, int, int, cudaStream_t);
 cudaError_t launch_gap(const int8_t*, int8_t*, int, int, int, int, int, cudaStream_t);
@@ -46,6 +46,7 @@ struct LayerState {
   tf2b_layer_desc d;
   bool loaded = false;
   int Cp = 0;  // reduction channels padded to 16
+  int Cp_m = 0;  // reduction channels seen by the tensor-core path (2*Cp when it reads the negated copy)
   // --- shift kernel (int16 planes) ---
   int Npad_s = 0, Kp_s = 0, planes_s = 0;
   int plane_shift_s[tf2b::kMaxPlanes] = {0, 0, 0, 0};
@@ -68,7 +69,7 @@ struct LayerState {
 };
 
 struct BlobLayerMeta {  // fixed-size, trivially copyable: travels inside the weight blob
-  int32_t loaded, Cp, Npad_s, Kp_s, planes_s, plane_shift_s[4], plane_neg_s[4];
+  int32_t loaded, Cp, Cp_m, Npad_s, Kp_s, planes_s, plane_shift_s[4], plane_neg_s[4];
   int32_t Npad_m, Kp_m, planes_m, plane_shift_m[4], mma_ok, Npar;
   int64_t off_w16, off_w8, off_bias, off_alpha, off_beta, off_nshift;
 };
@@ -77,6 +78,7 @@ struct tf2b_net {
   int device = 0;
   std::vector<tf2b_tensor_desc> tensors;
   std::vector<int> tpitch;  // channel pitch of each tensor (C rounded up to 16)
+  int t0_neg_off = 0;       // channel offset of the negated copy inside tensor 0
   std::vector<LayerState> layers;
   int variant = TF2B_VARIANT_AUTO;
   int max_images = 0;
@@ -185,18 +187,23 @@ static int prepare_layer(tf2b_net* net, LayerState& S, const uint8_t* codes,
       }
     }
   }
-  // ---- mma kernel planes: int8 +-2^e, e in 0..6 (only when the input cannot hold -128) ----
+  // ---- mma kernel planes: int8 +-2^e, e in 0..6.  A layer whose input may hold -128 can use the
+  //      tensor cores only when that input is tensor 0 (which carries the negated copy): positive
+  //      weights multiply channel c, magnitudes of negative weights multiply channel Cp + c.
   S.mma_ok = false;
   S.planes_m = 0;
   S.h_w8.clear();
-  if (!quirk) {
+  S.Cp_m = S.Cp;
+  if (!quirk || d.in_tensor == 0) {
     const int lv = 7;
     const int np = max_rel / lv + 1;
     const int in_pitch = net->tpitch[d.in_tensor];
-    if (np <= tf2b::kMaxPlanes && tf2b::mma_layer_supported(d, in_pitch, np)) {
+    const bool dual = quirk;
+    if (dual) S.Cp_m = 2 * S.Cp;
+    if ((!dual || S.Cp == net->t0_neg_off) && np <= tf2b::kMaxPlanes && tf2b::mma_layer_supported(d, in_pitch, np)) {
       S.planes_m = np;
       S.Npad_m = round_up(N, tf2b::mma_bn());
-      const int Cpm = round_up(S.Cp, tf2b::mma_pick_bk(S.Cp));
+      const int Cpm = round_up(S.Cp_m, tf2b::mma_pick_bk(S.Cp_m));
       S.Kp_m = k * k * Cpm;
       S.h_w8.assign((size_t)np * S.Npad_m * S.Kp_m, 0);
       for (int p = 0; p < np; p++) S.plane_shift_m[p] = lv * p;
@@ -208,8 +215,11 @@ static int prepare_layer(tf2b_net* net, LayerState& S, const uint8_t* codes,
             int rel = (cd & 0x1f) - base[n];
             int p = rel / lv, e = rel - p * lv;
             int v = 1 << e;
-            if (cd & 0x80) v = -v;
-            S.h_w8[((size_t)p * S.Npad_m + n) * S.Kp_m + (size_t)t * Cpm + c] = (int8_t)v;
+            int cc = c;
+            if (cd & 0x80) {
+              if (dual) cc = S.Cp + c; else v = -v;
+            }
+            S.h_w8[((size_t)p * S.Npad_m + n) * S.Kp_m + (size_t)t * Cpm + cc] = (int8_t)v;
           }
       S.mma_ok = true;
     }
@@ -269,6 +279,11 @@ int tf2b_create(const tf2b_tensor_desc* tensors, int n_tensors, const tf2b_layer
     }
     n->tpitch[t] = round_up(tensors[t].C, 16);
   }
+  // Tensor 0 (the quantised image) can hold -128, where the reference negates inside int8
+  // (pe.cl:32-34).  It is stored with a second, int8-negated copy of its channels so that the
+  // tensor-core path can multiply the copy with the magnitudes of the negative weights.
+  n->t0_neg_off = round_up(tensors[0].C, 16);
+  n->tpitch[0] = 2 * n->t0_neg_off;
   n->layers.resize(n_layers);
   for (int l = 0; l < n_layers; l++) {
     const tf2b_layer_desc& d = layers[l];
@@ -455,7 +470,7 @@ static ConvParams conv_params(tf2b_net* net, const LayerState& S, int B, int8_t*
   p.beta = reinterpret_cast<const int32_t*>(net->arena + S.off_beta);
   p.nshift = net->arena + S.off_nshift;
   p.acc_dump = nullptr;
-  p.B = B; p.IH = ti.H; p.IW = ti.W; p.Cp = S.Cp; p.xC = net->tpitch[d.in_tensor];
+  p.B = B; p.IH = ti.H; p.IW = ti.W; p.Cp = mma ? S.Cp_m : S.Cp; p.xC = net->tpitch[d.in_tensor];
   p.OH = d.OH; p.OW = d.OW; p.N = d.N; p.yC = dstC; p.rC = resC;
   p.k = d.k; p.pad = d.pad; p.stride = d.stride;
   p.relu = d.relu; p.add_relu = d.add_relu;
@@ -592,7 +607,7 @@ static int write_result(tf2b_net* net, int tensor, int B, int8_t* out_dev, int l
   if (layout == TF2B_LAYOUT_CHW) {
     CUDA_TRY(net, tf2b::launch_hwc_to_chw(net->tbuf[tensor], out_dev, B, t.C, t.H, t.W, Cp, st));
   } else if (layout == TF2B_LAYOUT_HWC) {
-    CUDA_TRY(net, tf2b::launch_hwc_repitch(net->tbuf[tensor], out_dev, (size_t)B * t.H * t.W, t.C, Cp, t.C, st));
+    CUDA_TRY(net, tf2b::launch_hwc_repitch(net->tbuf[tensor], out_dev, (size_t)B * t.H * t.W, t.C, Cp, t.C, 0, st));
   } else {
     return fail(net, TF2B_ERR_ARG, "unknown layout %d", layout);
   }
@@ -611,10 +626,11 @@ int tf2b_run(tf2b_net* net, const int8_t* in_dev, int in_layout, int n_images, i
   net->last_images = n_images;
   const tf2b_tensor_desc& t0 = net->tensors[0];
   if (in_layout == TF2B_LAYOUT_CHW) {
-    CUDA_TRY(net, tf2b::launch_chw_to_hwc(in_dev, net->tbuf[0], n_images, t0.C, t0.H, t0.W, net->tpitch[0], st));
+    CUDA_TRY(net, tf2b::launch_chw_to_hwc(in_dev, net->tbuf[0], n_images, t0.C, t0.H, t0.W, net->tpitch[0],
+                                          net->t0_neg_off, st));
   } else if (in_layout == TF2B_LAYOUT_HWC) {
     CUDA_TRY(net, tf2b::launch_hwc_repitch(in_dev, net->tbuf[0], (size_t)n_images * t0.H * t0.W, t0.C, t0.C,
-                                           net->tpitch[0], st));
+                                           net->tpitch[0], net->t0_neg_off, st));
   } else {
     return fail(net, TF2B_ERR_ARG, "unknown layout %d", in_layout);
   }
@@ -636,7 +652,7 @@ int tf2b_run_raw224(tf2b_net* net, const int8_t* raw_dev, int n_images, int8_t* 
   CUDA_TRY(net, cudaSetDevice(net->device));
   net->last_launches = 0;
   net->last_images = n_images;
-  CUDA_TRY(net, tf2b::launch_raw224_to_s2d(raw_dev, net->tbuf[0], n_images, st));
+  CUDA_TRY(net, tf2b::launch_raw224_to_s2d(raw_dev, net->tbuf[0], n_images, 1, st));
   net->last_launches++;
   rc = run_layers(net, n_images, st, -1, nullptr);
   if (rc) return rc;
@@ -722,7 +738,7 @@ int tf2b_export_weight_blob(tf2b_net* net, void* dev_dst, void* stream) {
     const LayerState& S = net->layers[l];
     BlobLayerMeta m;
     memset(&m, 0, sizeof m);
-    m.loaded = S.loaded; m.Cp = S.Cp; m.Npad_s = S.Npad_s; m.Kp_s = S.Kp_s; m.planes_s = S.planes_s;
+    m.loaded = S.loaded; m.Cp = S.Cp; m.Cp_m = S.Cp_m; m.Npad_s = S.Npad_s; m.Kp_s = S.Kp_s; m.planes_s = S.planes_s;
     m.Npad_m = S.Npad_m; m.Kp_m = S.Kp_m; m.planes_m = S.planes_m; m.mma_ok = S.planes_m > 0; m.Npar = S.Npar;
     for (int i = 0; i < 4; i++) {
       m.plane_shift_s[i] = S.plane_shift_s[i]; m.plane_neg_s[i] = S.plane_neg_s[i]; m.plane_shift_m[i] = S.plane_shift_m[i];
@@ -760,7 +776,7 @@ int tf2b_import_weight_blob(tf2b_net* net, const void* dev_src, void* stream) {
     memcpy(&m, hdr.data() + 16 + l * sizeof m, sizeof m);
     if (S.d.ipool) continue;
     if (!m.loaded) return fail(net, TF2B_ERR_ARG, "blob layer %zu has no weights", l);
-    S.loaded = true; S.Cp = m.Cp; S.Npad_s = m.Npad_s; S.Kp_s = m.Kp_s; S.planes_s = m.planes_s;
+    S.loaded = true; S.Cp = m.Cp; S.Cp_m = m.Cp_m; S.Npad_s = m.Npad_s; S.Kp_s = m.Kp_s; S.planes_s = m.planes_s;
     S.Npad_m = m.Npad_m; S.Kp_m = m.Kp_m; S.planes_m = m.planes_m; S.mma_ok = m.mma_ok != 0; S.Npar = m.Npar;
     for (int i = 0; i < 4; i++) {
       S.plane_shift_s[i] = m.plane_shift_s[i]; S.plane_neg_s[i] = m.plane_neg_s[i]; S.plane_shift_m[i] = m.plane_shift_m[i];

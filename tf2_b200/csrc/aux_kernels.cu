@@ -9,8 +9,10 @@ namespace tf2b {
 namespace {
 
 // [B][C][H][W] -> [B][H][W][Cp]  (channels >= C are written as zero)
+// neg_off > 0: channels [neg_off, neg_off + C) receive the int8-negated copy (-(-128) = -128,
+// pe.cl:32-34) that the tensor-core path multiplies with the magnitudes of the negative weights
 __global__ void chw_to_hwc_kernel(const int8_t* __restrict__ src, int8_t* __restrict__ dst, int B,
-                                  int C, int H, int W, int Cp) {
+                                  int C, int H, int W, int Cp, int neg_off) {
   size_t total = (size_t)B * H * W * (Cp / 4);
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
        i += (size_t)gridDim.x * blockDim.x) {
@@ -24,8 +26,11 @@ __global__ void chw_to_hwc_kernel(const int8_t* __restrict__ src, int8_t* __rest
 #pragma unroll
     for (int e = 0; e < 4; e++) {
       int c = c4 * 4 + e;
+      bool ng = neg_off > 0 && c >= neg_off;
+      if (ng) c -= neg_off;
       if (c < C) {
         unsigned char x = (unsigned char)src[(((size_t)b * C + c) * H + h) * W + w];
+        if (ng) x = (unsigned char)(0u - x);
         v |= (unsigned)x << (8 * e);
       }
     }
@@ -51,13 +56,17 @@ __global__ void hwc_to_chw_kernel(const int8_t* __restrict__ src, int8_t* __rest
 
 // [B][H][W][Cs] (first C channels) -> [B][H][W][Cd] dense copy with re-pitch (zero fill)
 __global__ void hwc_repitch_kernel(const int8_t* __restrict__ src, int8_t* __restrict__ dst,
-                                   size_t npix, int C, int Cs, int Cd) {
+                                   size_t npix, int C, int Cs, int Cd, int neg_off) {
   size_t total = npix * Cd;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
        i += (size_t)gridDim.x * blockDim.x) {
     int c = (int)(i % Cd);
     size_t pix = i / Cd;
-    dst[i] = c < C ? src[pix * Cs + c] : (int8_t)0;
+    bool ng = neg_off > 0 && c >= neg_off;
+    if (ng) c -= neg_off;
+    unsigned char x = c < C ? (unsigned char)src[pix * Cs + c] : (unsigned char)0;
+    if (ng) x = (unsigned char)(0u - x);
+    dst[i] = (int8_t)x;
   }
 }
 
@@ -66,8 +75,9 @@ __global__ void hwc_repitch_kernel(const int8_t* __restrict__ src, int8_t* __res
 //   d <  6: P[2r + d%2][2c + d/2]     d >= 6: P[2r + 2][2c + d-6]      P = raw zero-padded by 3
 // channels 27..31 are zero.  Quantise-then-permute equals the reference's permute-then-quantise
 // (runner.cpp:158-164 is elementwise and maps the padding zeros to zero).
+// With dual != 0 the pixel is 64 bytes: channels 32..58 hold the int8-negated copy (pe.cl:32-34).
 __global__ void raw224_to_s2d_kernel(const int8_t* __restrict__ raw, int8_t* __restrict__ dst,
-                                     int B) {
+                                     int B, int dual) {
   const int OD = 114, ID = 224;
   size_t total = (size_t)B * OD * OD;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
@@ -93,9 +103,15 @@ __global__ void raw224_to_s2d_kernel(const int8_t* __restrict__ raw, int8_t* __r
         out[ci * 9 + d] = v;
       }
     }
-    uint4* o = reinterpret_cast<uint4*>(dst + i * 32);
-    o[0] = *reinterpret_cast<const uint4*>(out);
-    o[1] = *reinterpret_cast<const uint4*>(out + 16);
+    uint4* o = reinterpret_cast<uint4*>(dst + i * (dual ? 64 : 32));
+    uint4 v0 = *reinterpret_cast<const uint4*>(out);
+    uint4 v1 = *reinterpret_cast<const uint4*>(out + 16);
+    o[0] = v0;
+    o[1] = v1;
+    if (dual) {
+      o[2] = make_uint4(__vneg4(v0.x), __vneg4(v0.y), __vneg4(v0.z), __vneg4(v0.w));
+      o[3] = make_uint4(__vneg4(v1.x), __vneg4(v1.y), __vneg4(v1.z), __vneg4(v1.w));
+    }
   }
 }
 
@@ -178,9 +194,9 @@ inline int grid_for(size_t total, int block) {
 }  // namespace
 
 cudaError_t launch_chw_to_hwc(const int8_t* src, int8_t* dst, int B, int C, int H, int W, int Cp,
-                              cudaStream_t s) {
+                              int neg_off, cudaStream_t s) {
   size_t total = (size_t)B * H * W * (Cp / 4);
-  chw_to_hwc_kernel<<<grid_for(total, 256), 256, 0, s>>>(src, dst, B, C, H, W, Cp);
+  chw_to_hwc_kernel<<<grid_for(total, 256), 256, 0, s>>>(src, dst, B, C, H, W, Cp, neg_off);
   return cudaGetLastError();
 }
 cudaError_t launch_hwc_to_chw(const int8_t* src, int8_t* dst, int B, int C, int H, int W, int Cp,
@@ -190,14 +206,14 @@ cudaError_t launch_hwc_to_chw(const int8_t* src, int8_t* dst, int B, int C, int 
   return cudaGetLastError();
 }
 cudaError_t launch_hwc_repitch(const int8_t* src, int8_t* dst, size_t npix, int C, int Cs, int Cd,
-                               cudaStream_t s) {
+                               int neg_off, cudaStream_t s) {
   size_t total = npix * Cd;
-  hwc_repitch_kernel<<<grid_for(total, 256), 256, 0, s>>>(src, dst, npix, C, Cs, Cd);
+  hwc_repitch_kernel<<<grid_for(total, 256), 256, 0, s>>>(src, dst, npix, C, Cs, Cd, neg_off);
   return cudaGetLastError();
 }
-cudaError_t launch_raw224_to_s2d(const int8_t* raw, int8_t* dst, int B, cudaStream_t s) {
+cudaError_t launch_raw224_to_s2d(const int8_t* raw, int8_t* dst, int B, int dual, cudaStream_t s) {
   size_t total = (size_t)B * 114 * 114;
-  raw224_to_s2d_kernel<<<grid_for(total, 128), 128, 0, s>>>(raw, dst, B);
+  raw224_to_s2d_kernel<<<grid_for(total, 128), 128, 0, s>>>(raw, dst, B, dual);
   return cudaGetLastError();
 }
 cudaError_t launch_maxpool3x3(const int8_t* src, int8_t* dst, const int8_t* res, int B, int H, int W,

@@ -40,6 +40,15 @@ __device__ __forceinline__ int requant(int32_t acc, int32_t alpha, int32_t beta)
   return max(-128, min(127, y));
 }
 
+// Same with the ReLU of relu.cl:54 folded into the lower clamp bound (lo = 0 with ReLU, else -128).
+__device__ __forceinline__ int requant_clamped(int32_t acc, int32_t alpha, int32_t beta, int lo) {
+  long long t = (long long)acc * (long long)alpha;
+  int a = (int)(t >> 20);
+  int s = (int)((unsigned)a + (unsigned)beta);
+  int y = ((s >> 14) + 1) >> 1;
+  return max(lo, min(127, y));
+}
+
 // feature_writer.cl:124-127 on 4 packed int8 lanes: saturating add, optional ReLU.
 __device__ __forceinline__ unsigned add_res4(unsigned y, unsigned r, int add_relu) {
   unsigned s = __vaddss4(y, r);

@@ -19,6 +19,8 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <cstdio>
+#include <cstdlib>
 #include <string>
 
 #include "../../include/tf2b200.h"
@@ -29,10 +31,11 @@ namespace tf2b {
 namespace {
 
 constexpr int MMA_M = 128;
-constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_EPI_WARPS = 16;
 constexpr int NUM_THREADS = 32 * (2 + NUM_EPI_WARPS);
 constexpr int MAX_STAGES = 8;
 constexpr int TMEM_COLS = 512;
+constexpr int EPI_ROW = 48;   // bytes per staging row: 32 data + 16 pad (conflict-free 16-byte accesses)
 
 struct MmaParams {
   ConvParams c;
@@ -50,6 +53,7 @@ struct MmaParams {
   unsigned idesc;           // tcgen05 instruction descriptor
   unsigned sbo16;           // stride byte offset >> 4 of the smem descriptors
   unsigned layout_type;     // UMMA smem layout type (2 = SWIZZLE_128B, 4 = SWIZZLE_64B)
+  long long* dbg;           // optional per-CTA cycle counters [grid][8] (TF2B_MMA_DEBUG), else nullptr
 };
 
 struct TmapPair {
@@ -87,6 +91,13 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > 4000000000ll) __trap();
   }
+}
+// same, accumulating the cycles spent waiting (role breakdown for TF2B_MMA_DEBUG)
+__device__ __forceinline__ void mbar_wait_timed(unsigned bar, unsigned parity, long long& acc, bool on) {
+  if (!on) { mbar_wait(bar, parity); return; }
+  long long t0 = clock64();
+  mbar_wait(bar, parity);
+  acc += clock64() - t0;
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -139,6 +150,21 @@ __device__ __forceinline__ void tmem_ld16(unsigned taddr, unsigned (&v)[16]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// One elected lane of a converged warp (the form CUTLASS uses: keeps the surrounding code
+// warp-uniform so descriptors live in uniform registers and UTCIMMA/UTMALDG issue back to back).
+__device__ __forceinline__ bool elect_one() {
+  unsigned pred = 0;
+  unsigned laneid = 0;
+  asm volatile(
+      "{\n\t.reg .b32 %%rx;\n\t.reg .pred %%px;\n\t"
+      "elect.sync %%rx|%%px, %2;\n\t"
+      "@%%px mov.s32 %1, 1;\n\t"
+      "mov.s32 %0, %%rx;\n\t}"
+      : "+r"(laneid), "+r"(pred)
+      : "r"(0xFFFFFFFF));
+  return pred != 0;
+}
+
 // K-major smem matrix descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor): start address and
 // byte offsets in 16-byte units, version 1 (Blackwell), swizzle mode in bits 61..63.
 __device__ __forceinline__ unsigned long long make_smem_desc(unsigned saddr, unsigned sbo16, unsigned layout_type) {
@@ -187,6 +213,8 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
 
   __shared__ __align__(8) unsigned long long bars[2 * MAX_STAGES + 4];
   __shared__ unsigned tmem_base_slot;
+  __shared__ __align__(16) unsigned char epi_stage[NUM_EPI_WARPS][32 * EPI_ROW];  // int8 staging tiles
+  __shared__ __align__(16) int epi_params[NUM_EPI_WARPS][4 * 32];                 // bias/alpha/beta/2^nshift
   const unsigned full_bar = smem_u32(&bars[0]);                  // [stages]
   const unsigned empty_bar = smem_u32(&bars[MAX_STAGES]);        // [stages]
   const unsigned tfull_bar = smem_u32(&bars[2 * MAX_STAGES]);    // [2]
@@ -218,152 +246,228 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
   const int acc_cols = P.planes * P.BN;  // TMEM columns of one accumulator buffer
 
   if (warp == 0) {
-    // ===================================================== TMA producer
-    if (lane == 0) {
+    // ===================================================== TMA producer (whole warp, one elected lane issues)
+    {
       int stage = 0;
       unsigned phase = 0;
+      const bool dbg = P.dbg != nullptr;
+      long long w_empty = 0, t_start = clock64();
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const TileCoord t = decode_tile(P, tile);
         for (int tap = 0; tap < P.taps; tap++) {
           const int fh = tap / P.c.k, fw = tap - fh * P.c.k;
           for (int kc = 0; kc < P.kchunks; kc++) {
-            mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+            mbar_wait_timed(empty_bar + 8 * stage, phase ^ 1, w_empty, dbg);
             const unsigned fb = full_bar + 8 * stage;
-            mbar_expect_tx(fb, (unsigned)(P.a_bytes + P.planes * P.b_bytes));
             const unsigned sa = smem_base + stage * stage_bytes;
-            if (P.mode == 0) {
-              tma_load_2d(sa, &maps.a, fb, kc * P.BK, t.m0);
-            } else {
-              tma_load_4d(sa, &maps.a, fb, kc * P.BK, t.ow0 * P.c.stride - P.c.pad + fw,
-                          t.oh0 * P.c.stride - P.c.pad + fh, t.b0);
+            if (elect_one()) {
+              mbar_expect_tx(fb, (unsigned)(P.a_bytes + P.planes * P.b_bytes));
+              if (P.mode == 0) {
+                tma_load_2d(sa, &maps.a, fb, kc * P.BK, t.m0);
+              } else {
+                tma_load_4d(sa, &maps.a, fb, kc * P.BK, t.ow0 * P.c.stride - P.c.pad + fw,
+                            t.oh0 * P.c.stride - P.c.pad + fh, t.b0);
+              }
+              for (int pl = 0; pl < P.planes; pl++)
+                tma_load_2d(sa + a_stage + pl * b_plane, &maps.b, fb, tap * P.Cpm + kc * P.BK, pl * P.Npad + t.n0);
             }
-            for (int pl = 0; pl < P.planes; pl++)
-              tma_load_2d(sa + a_stage + pl * b_plane, &maps.b, fb, tap * P.Cpm + kc * P.BK, pl * P.Npad + t.n0);
+            __syncwarp();
             if (++stage == P.stages) { stage = 0; phase ^= 1; }
           }
         }
       }
+      if (dbg && lane == 0) {
+        P.dbg[blockIdx.x * 8 + 0] = w_empty;
+        P.dbg[blockIdx.x * 8 + 1] = clock64() - t_start;
+      }
     }
   } else if (warp == 1) {
-    // ===================================================== MMA issuer (one thread)
-    if (lane == 0) {
+    // ===================================================== MMA issuer (whole warp, one elected lane issues)
+    {
       int stage = 0;
       unsigned phase = 0;
       int buf = 0;
       unsigned tphase[2] = {0, 0};
+      const bool dbg = P.dbg != nullptr;
+      long long w_full = 0, w_tempty = 0, t_start = clock64();
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait(tempty_bar + 8 * buf, tphase[buf] ^ 1);   // epilogue has drained this accumulator
+        mbar_wait_timed(tempty_bar + 8 * buf, tphase[buf] ^ 1, w_tempty, dbg);   // epilogue has drained this accumulator
         tc_fence_after();
         const unsigned d_tmem = tmem_base + buf * acc_cols;
         for (int it = 0; it < kiters; it++) {
-          mbar_wait(full_bar + 8 * stage, phase);
+          mbar_wait_timed(full_bar + 8 * stage, phase, w_full, dbg);
           tc_fence_after();
           const unsigned sa = smem_base + stage * stage_bytes;
           const unsigned long long da = make_smem_desc(sa, P.sbo16, P.layout_type);
-          for (int pl = 0; pl < P.planes; pl++) {
-            const unsigned long long db = make_smem_desc(sa + a_stage + pl * b_plane, P.sbo16, P.layout_type);
-            for (int k4 = 0; k4 < P.BK / 32; k4++) {
-              // advance both descriptors by 32 bytes of K inside the swizzled row
-              umma_i8(d_tmem + pl * P.BN, da + (unsigned long long)(2 * k4), db + (unsigned long long)(2 * k4),
-                      P.idesc, (it > 0 || k4 > 0) ? 1u : 0u);
+          if (elect_one()) {
+            for (int pl = 0; pl < P.planes; pl++) {
+              const unsigned long long db = make_smem_desc(sa + a_stage + pl * b_plane, P.sbo16, P.layout_type);
+              for (int k4 = 0; k4 < P.BK / 32; k4++) {
+                // advance both descriptors by 32 bytes of K inside the swizzled row
+                umma_i8(d_tmem + pl * P.BN, da + (unsigned long long)(2 * k4), db + (unsigned long long)(2 * k4),
+                        P.idesc, (it > 0 || k4 > 0) ? 1u : 0u);
+              }
             }
+            umma_commit(empty_bar + 8 * stage);             // frees the smem stage when the MMAs retire
+            if (it == kiters - 1) umma_commit(tfull_bar + 8 * buf);   // accumulators complete -> epilogue
           }
-          umma_commit(empty_bar + 8 * stage);               // frees the smem stage when the MMAs retire
+          __syncwarp();
           if (++stage == P.stages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(tfull_bar + 8 * buf);                   // accumulators complete -> epilogue
         tphase[buf] ^= 1;
         buf ^= 1;
+      }
+      if (dbg && lane == 0) {
+        P.dbg[blockIdx.x * 8 + 2] = w_full;
+        P.dbg[blockIdx.x * 8 + 3] = w_tempty;
+        P.dbg[blockIdx.x * 8 + 4] = clock64() - t_start;
       }
     }
   } else {
     // ===================================================== epilogue warps
-    const int ew = warp - 2;            // 0..7
+    // Warp (quarter q, half h) owns rows 32q..32q+31 (its TMEM lane quarter) x W = BN/2 columns.
+    // Per tile: (1) before the accumulators are ready, fetch its per-channel params into its private
+    // smem slice and prefetch its residual operand with the coalesced mapping; (2) tcgen05.ld ->
+    // recombine planes -> requantise -> 16-byte st.shared into a private [32][W] staging tile;
+    // (3) re-read the staging tile with lanes along the channel dimension so every global access
+    // covers whole 32-byte sectors: residual add, 16-byte stores.  No cross-warp synchronisation.
+    const int ew = warp - 2;            // 0..15
     const int quarter = warp & 3;       // TMEM lane quarter this warp may access
-    const int half = ew >> 2;           // which half of the BN columns
-    const int row = quarter * 32 + lane;
+    const int slice = ew >> 2;          // which quarter of the BN columns
     const ConvParams& c = P.c;
     const int M = c.B * c.OH * c.OW;
+    const int W = P.BN / 4;             // 16 or 32 columns per warp
+    const int segs = W / 16;            // 16-byte segments per row (1 or 2)
+    const int rows_per_it = 32 / segs;  // rows covered by one warp-wide 16-byte access
+    const int nit = segs;               // iterations that cover the 32 x W tile
+    const int lo_clamp = c.relu ? 0 : -128;   // relu.cl:54 folded into the clamp of pe.cl:194
+    unsigned char* stage = epi_stage[ew];
+    int* prm = epi_params[ew];          // [4][32]: bias, alpha, beta, 2^nshift
     int buf = 0;
     unsigned tphase[2] = {0, 0};
-    const int cols_per_half = P.BN / 2;
+    const bool dbg = P.dbg != nullptr && warp == 2;
+    long long w_tfull = 0, t_start = clock64();
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(P, tile);
-      // which output pixel is this thread's row?
-      bool valid;
-      long long pix;
-      if (P.mode == 0) {
-        int m = t.m0 + row;
-        valid = m < M;
-        pix = m;
-      } else {
-        int wl = row % P.tw;
-        int r = row / P.tw;
-        int hl = r % P.th;
-        int nl = r / P.th;
-        int ow = t.ow0 + wl, oh = t.oh0 + hl, b = t.b0 + nl;
-        valid = (nl < P.tn) && (ow < c.OW) && (oh < c.OH) && (b < c.B);
-        pix = ((long long)b * c.OH + oh) * c.OW + ow;
+      const int ncol0 = t.n0 + slice * W;         // first output channel of this warp
+      // ---- (1a) params of this warp's W channels -> smem (padded arrays: always in bounds)
+      __syncwarp();
+      if (lane < W) {
+        const int n = ncol0 + lane;
+        prm[lane] = __ldg(c.bias + n);
+        prm[32 + lane] = __ldg(c.alpha + n);
+        prm[64 + lane] = __ldg(c.beta + n);
+        prm[96 + lane] = 1 << (int)__ldg(c.nshift + n);   // (x << s) == x * 2^s  (mod 2^32)
       }
-      mbar_wait(tfull_bar + 8 * buf, tphase[buf]);
+      // ---- (1b) coalesced mapping: iteration it, lane -> (row, seg); pixel + residual prefetch
+      long long pixs[2];
+      uint4 resv[2];
+#pragma unroll
+      for (int it = 0; it < 2; it++) {
+        pixs[it] = -1;
+        resv[it] = make_uint4(0, 0, 0, 0);
+        if (it < nit) {
+          const int rl = it * rows_per_it + lane / segs;   // row inside the warp's 32 rows
+          const int row = quarter * 32 + rl;
+          bool valid;
+          long long pix;
+          if (P.mode == 0) {
+            int m = t.m0 + row;
+            valid = m < M;
+            pix = m;
+          } else {
+            int wl = row % P.tw;
+            int r = row / P.tw;
+            int hl = r % P.th;
+            int nl = r / P.th;
+            int ow = t.ow0 + wl, oh = t.oh0 + hl, b = t.b0 + nl;
+            valid = (nl < P.tn) && (ow < c.OW) && (oh < c.OH) && (b < c.B);
+            pix = ((long long)b * c.OH + oh) * c.OW + ow;
+          }
+          const int n = ncol0 + (lane % segs) * 16;
+          if (valid && n < c.N) {
+            pixs[it] = pix;
+            if (c.r != nullptr && n + 16 <= c.N)
+              resv[it] = __ldg(reinterpret_cast<const uint4*>(c.r + pix * c.rC + n));
+          }
+        }
+      }
+      __syncwarp();
+      // ---- (2) accumulators -> int8 staging tile
+      mbar_wait_timed(tfull_bar + 8 * buf, tphase[buf], w_tfull, dbg);
       tc_fence_after();
-      const unsigned t_row = tmem_base + ((unsigned)(quarter * 32) << 16) + buf * acc_cols;
-      for (int cc = 0; cc < cols_per_half; cc += 16) {
-        const int col = half * cols_per_half + cc;
-        const int n = t.n0 + col;
+      const unsigned t_row = tmem_base + ((unsigned)(quarter * 32) << 16) + buf * acc_cols + slice * W;
+      for (int cc = 0; cc < W; cc += 16) {
         unsigned tot[16];
-        tmem_ld16(t_row + col, tot);
+        tmem_ld16(t_row + cc, tot);
         tmem_ld_wait();
         for (int pl = 1; pl < P.planes; pl++) {
           unsigned v[16];
-          tmem_ld16(t_row + pl * P.BN + col, v);
+          tmem_ld16(t_row + pl * P.BN + cc, v);
           tmem_ld_wait();
-          const int sh = P.plane8_shift[pl];
+          const unsigned mulp = 1u << P.plane8_shift[pl];
 #pragma unroll
-          for (int j = 0; j < 16; j++) tot[j] += v[j] << sh;
+          for (int j = 0; j < 16; j++) tot[j] += v[j] * mulp;
         }
-        if (valid && n < c.N) {
-          unsigned packed[4] = {0, 0, 0, 0};
+        unsigned packed[4];
 #pragma unroll
-          for (int j = 0; j < 16; j++) {
-            const int nn = n + j;   // < Npad (params are padded with zeros)
-            int a32 = (int)((unsigned)__ldg(c.bias + nn) + (tot[j] << __ldg(c.nshift + nn)));
-            int y = requant(a32, __ldg(c.alpha + nn), __ldg(c.beta + nn));
-            if (c.relu) y = max(y, 0);
-            packed[j >> 2] |= (unsigned)(y & 0xff) << (8 * (j & 3));
-          }
-          int8_t* dst = c.y + pix * c.yC + n;
+        for (int j4 = 0; j4 < 4; j4++) {
+          const int4 pb = *reinterpret_cast<const int4*>(prm + cc + 4 * j4);
+          const int4 pa = *reinterpret_cast<const int4*>(prm + 32 + cc + 4 * j4);
+          const int4 pe = *reinterpret_cast<const int4*>(prm + 64 + cc + 4 * j4);
+          const int4 pm = *reinterpret_cast<const int4*>(prm + 96 + cc + 4 * j4);
+          const int y0 = requant_clamped((int)(tot[4 * j4 + 0] * (unsigned)pm.x + (unsigned)pb.x), pa.x, pe.x, lo_clamp);
+          const int y1 = requant_clamped((int)(tot[4 * j4 + 1] * (unsigned)pm.y + (unsigned)pb.y), pa.y, pe.y, lo_clamp);
+          const int y2 = requant_clamped((int)(tot[4 * j4 + 2] * (unsigned)pm.z + (unsigned)pb.z), pa.z, pe.z, lo_clamp);
+          const int y3 = requant_clamped((int)(tot[4 * j4 + 3] * (unsigned)pm.w + (unsigned)pb.w), pa.w, pe.w, lo_clamp);
+          // byte 0 of each value -> one packed word
+          packed[j4] = __byte_perm(__byte_perm(y0, y1, 0x0040), __byte_perm(y2, y3, 0x0040), 0x5410);
+        }
+        *reinterpret_cast<uint4*>(stage + lane * EPI_ROW + cc) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+      }
+      // accumulator buffer drained: hand it back to the MMA warp as early as possible
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar + 8 * buf);
+      tphase[buf] ^= 1;
+      buf ^= 1;
+      // ---- (3) coalesced residual add + store
+#pragma unroll
+      for (int it = 0; it < 2; it++) {
+        if (it < nit && pixs[it] >= 0) {
+          const int rl = it * rows_per_it + lane / segs;
+          const int sg = lane % segs;
+          const int n = ncol0 + sg * 16;
+          uint4 v = *reinterpret_cast<const uint4*>(stage + rl * EPI_ROW + sg * 16);
+          int8_t* dst = c.y + pixs[it] * c.yC + n;
           const int nvalid = min(16, c.N - n);
           if (nvalid == 16) {
-            uint4 v = make_uint4(packed[0], packed[1], packed[2], packed[3]);
             if (c.r != nullptr) {
-              uint4 rv = *reinterpret_cast<const uint4*>(c.r + pix * c.rC + n);
-              v.x = add_res4(v.x, rv.x, c.add_relu);
-              v.y = add_res4(v.y, rv.y, c.add_relu);
-              v.z = add_res4(v.z, rv.z, c.add_relu);
-              v.w = add_res4(v.w, rv.w, c.add_relu);
+              v.x = add_res4(v.x, resv[it].x, c.add_relu);
+              v.y = add_res4(v.y, resv[it].y, c.add_relu);
+              v.z = add_res4(v.z, resv[it].z, c.add_relu);
+              v.w = add_res4(v.w, resv[it].w, c.add_relu);
             }
             *reinterpret_cast<uint4*>(dst) = v;
           } else {
+            const unsigned char* vb = reinterpret_cast<const unsigned char*>(&v);
             for (int e = 0; e < nvalid; e++) {
-              int yv = (int)(signed char)((packed[e >> 2] >> (8 * (e & 3))) & 0xff);
+              int yv = (int)(signed char)vb[e];
               if (c.r != nullptr) {
-                int s = yv + (int)c.r[pix * c.rC + n + e];
-                s = max(-128, min(127, s));
-                if (c.add_relu) s = max(s, 0);
-                yv = s;
+                int sres = yv + (int)c.r[pixs[it] * c.rC + n + e];
+                sres = max(-128, min(127, sres));
+                if (c.add_relu) sres = max(sres, 0);
+                yv = sres;
               }
               dst[e] = (int8_t)yv;
             }
           }
         }
       }
-      // accumulator buffer drained: hand it back to the MMA warp
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar + 8 * buf);
-      tphase[buf] ^= 1;
-      buf ^= 1;
+    }
+    if (dbg && lane == 0) {
+      P.dbg[blockIdx.x * 8 + 5] = w_tfull;
+      P.dbg[blockIdx.x * 8 + 6] = clock64() - t_start;
     }
   }
 
@@ -433,7 +537,7 @@ void fill_geometry(MmaParams& P, const ConvParams& c, int planes8) {
   }
   P.b_bytes = P.BN * P.BK;
   const int stage_bytes = MMA_M * P.BK + planes8 * P.b_bytes;
-  int st = (200 * 1024) / stage_bytes;
+  int st = (184 * 1024) / stage_bytes;
   P.stages = st > MAX_STAGES ? MAX_STAGES : (st < 2 ? 2 : st);
   // instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): c_format S32 (2) at bit 4,
   // a/b format signed int8 (1) at bits 7 / 10, K-major A and B, N>>3 at bit 17, M>>4 at bit 24,
@@ -450,7 +554,11 @@ int mma_pick_bk(int Cp) { return pick_bk(Cp); }
 
 bool mma_layer_supported(const tf2b_layer_desc& L, int in_pitch, int planes8) {
   if (L.ipool) return false;
-  if (L.stride != 1) return false;            // strided taps stay on the shift kernel for now
+  if (L.stride < 1 || L.stride > 8) return false;   // TMA traversal stride limit
+  {
+    int tw = L.OW < MMA_M ? L.OW : MMA_M;
+    if ((tw - 1) * L.stride + 1 > 256) return false;  // TMA box limit
+  }
   if (planes8 < 1 || planes8 > kMaxPlanes) return false;
   if (in_pitch % 16 != 0) return false;
   if (L.OW > 256 || L.k > 7) return false;
@@ -480,8 +588,12 @@ int mma_build_tmaps(void* host_tmaps, const ConvParams& c, const int8_t* wgt8, i
   } else {
     cuuint64_t dims[4] = {(cuuint64_t)c.Cp, (cuuint64_t)c.IW, (cuuint64_t)c.IH, (cuuint64_t)c.B};
     cuuint64_t strides[3] = {(cuuint64_t)c.xC, (cuuint64_t)c.xC * c.IW, (cuuint64_t)c.xC * c.IW * c.IH};
-    cuuint32_t box[4] = {(cuuint32_t)P.BK, (cuuint32_t)P.tw, (cuuint32_t)P.th, (cuuint32_t)P.tn};
-    cuuint32_t es[4] = {1, 1, 1, 1};
+    // a strided convolution reads every stride-th pixel: the box spans (t-1)*stride+1 source
+    // elements and the traversal stride keeps ceil(box/stride) = t of them
+    const cuuint32_t st = (cuuint32_t)c.stride;
+    cuuint32_t box[4] = {(cuuint32_t)P.BK, (cuuint32_t)((P.tw - 1) * st + 1), (cuuint32_t)((P.th - 1) * st + 1),
+                         (cuuint32_t)P.tn};
+    cuuint32_t es[4] = {1, st, st, 1};
     r = enc(&tp->a, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, (void*)c.x, dims, strides, box, es,
             CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   }
@@ -519,14 +631,38 @@ cudaError_t launch_conv_mma(const ConvParams& c, const int8_t* /*wgt8*/, int pla
   const int stage_bytes = MMA_M * P.BK + planes8 * P.b_bytes;
   const size_t smem = (size_t)P.stages * stage_bytes + 1024;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
+    cudaError_t e = cudaFuncSetAttribute(conv_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 186 * 1024);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
   const int num_tiles = P.m_tiles * P.n_tiles;
   const int grid = num_tiles < num_sms ? num_tiles : num_sms;
   const TmapPair* tp = reinterpret_cast<const TmapPair*>(tmaps);
+  P.dbg = nullptr;
+  static const bool debug = getenv("TF2B_MMA_DEBUG") != nullptr;
+  static long long* dbg_dev = nullptr;
+  if (debug) {
+    if (!dbg_dev) cudaMalloc(&dbg_dev, sizeof(long long) * 8 * 148);
+    cudaMemsetAsync(dbg_dev, 0, sizeof(long long) * 8 * 148, stream);
+    P.dbg = dbg_dev;
+  }
   conv_mma_kernel<<<grid, NUM_THREADS, smem, stream>>>(P, *tp);
+  if (debug) {
+    long long h[8 * 148];
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(h, dbg_dev, sizeof h, cudaMemcpyDeviceToHost);
+    double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int b = 0; b < grid; b++)
+      for (int i = 0; i < 8; i++) a[i] += (double)h[b * 8 + i] / grid;
+    const double tiles_per_cta = (double)num_tiles / grid;
+    fprintf(stderr,
+            "[mma dbg] C%d N%d k%d s%d OH%d mode%d BK%d BN%d P%d stages%d tiles/cta %.1f kiters %d | per tile clk: "
+            "producer total %.0f (wait empty %.0f) | mma total %.0f (wait full %.0f, wait tmem-empty %.0f) | "
+            "epi total %.0f (wait tmem-full %.0f)\n",
+            c.Cp, c.N, c.k, c.stride, c.OH, P.mode, P.BK, P.BN, P.planes, P.stages, tiles_per_cta,
+            P.taps * P.kchunks, a[1] / tiles_per_cta, a[0] / tiles_per_cta, a[4] / tiles_per_cta, a[2] / tiles_per_cta,
+            a[3] / tiles_per_cta, a[6] / tiles_per_cta, a[5] / tiles_per_cta);
+  }
   return cudaGetLastError();
 }
 
