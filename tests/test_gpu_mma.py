@@ -52,6 +52,11 @@ def test_mma_first_layer_quirk():
         x = H.random_input(rng, *chw, nonneg=False, B=3)
         x[0, :, :2, :] = -128
         model = H.random_model(net, rng, x)
+        # sprinkle low absolute shifts (like the code-0 taps of the transformed first layer) among
+        # the high ones: exercises the unscaled "low" plane of the tensor-core path
+        codes, params = model[0]
+        m = (rng.random(codes.shape) < 0.1) & ((codes & 0x40) == 0)
+        codes[m] = (codes[m] & 0x80) | rng.integers(0, 4, size=int(m.sum())).astype(np.uint8)
         nw = NetWork(net, 0)
         nw.InitFromCodes(model, None, max_images=3, variant=capi.VARIANT_MMA)
         assert nw.layer_kernels() == ["mma"], nw.layer_kernels()

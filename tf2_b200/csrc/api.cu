@@ -55,14 +55,16 @@ struct LayerState {
   // --- mma kernel (int8 planes) ---
   int Npad_m = 0, Kp_m = 0, planes_m = 0;
   int plane_shift_m[tf2b::kMaxPlanes] = {0, 0, 0, 0};
+  int low_plane_m = -1;  // index of the plane that holds absolute shifts 0..6 (not scaled by 2^nshift), or -1
   std::vector<int8_t> h_w8;
+  std::vector<uint8_t> h_nshift_m;  // per-channel base shift of the tensor-core planes
   bool mma_ok = false;
   // --- per-channel params (padded to max(Npad_s, Npad_m)) ---
   int Npar = 0;
   std::vector<int32_t> h_bias, h_alpha, h_beta;
   std::vector<uint8_t> h_nshift;
   // device views inside the arena
-  size_t off_w16 = 0, off_w8 = 0, off_bias = 0, off_alpha = 0, off_beta = 0, off_nshift = 0;
+  size_t off_w16 = 0, off_w8 = 0, off_bias = 0, off_alpha = 0, off_beta = 0, off_nshift = 0, off_nshift_m = 0;
   int kernel = 0;  // 0 none (ipool), 1 shift, 2 mma
   std::vector<unsigned char> h_tmaps;  // CUtensorMap blobs for the mma path (host copy)
   size_t off_tmaps = 0;
@@ -70,8 +72,8 @@ struct LayerState {
 
 struct BlobLayerMeta {  // fixed-size, trivially copyable: travels inside the weight blob
   int32_t loaded, Cp, Cp_m, Npad_s, Kp_s, planes_s, plane_shift_s[4], plane_neg_s[4];
-  int32_t Npad_m, Kp_m, planes_m, plane_shift_m[4], mma_ok, Npar;
-  int64_t off_w16, off_w8, off_bias, off_alpha, off_beta, off_nshift;
+  int32_t Npad_m, Kp_m, planes_m, plane_shift_m[4], mma_ok, Npar, low_plane_m, nshift_m_len;
+  int64_t off_w16, off_w8, off_bias, off_alpha, off_beta, off_nshift, off_nshift_m;
 };
 
 struct tf2b_net {
@@ -196,24 +198,59 @@ static int prepare_layer(tf2b_net* net, LayerState& S, const uint8_t* codes,
   S.Cp_m = S.Cp;
   if (!quirk || d.in_tensor == 0) {
     const int lv = 7;
-    const int np = max_rel / lv + 1;
+    // Two decompositions: (a) every code relative to the channel's smallest shift; (b) codes with an
+    // absolute shift <= 6 (e.g. the code-0 taps LoadModel leaves in the transformed first layer,
+    // model_loader.cpp:247) go to a "low" plane that is added unscaled, the rest relative to the
+    // smallest shift above 6.  Take whichever needs fewer planes.
+    std::vector<uint8_t> base_hi(N, 0);
+    int max_rel_hi = 0;
+    bool any_low = false;
+    for (int n = 0; n < N; n++) {
+      int mn = 99, mx = -1;
+      const uint8_t* cn = codes + (size_t)n * C * k * k;
+      for (int i = 0; i < C * k * k; i++) {
+        if (cn[i] & 0x40) continue;
+        int sft = cn[i] & 0x1f;
+        if (sft < lv) { any_low = true; continue; }
+        mn = std::min(mn, sft);
+        mx = std::max(mx, sft);
+      }
+      if (mx < 0) { mn = 0; mx = 0; }
+      base_hi[n] = (uint8_t)mn;
+      max_rel_hi = std::max(max_rel_hi, mx - mn);
+    }
+    const int np_std = max_rel / lv + 1;
+    const int np_alt = (max_rel_hi / lv + 1) + (any_low ? 1 : 0);
+    const bool use_low = any_low && np_alt < np_std;
+    const int np = use_low ? np_alt : np_std;
+    const std::vector<uint8_t>& bm = use_low ? base_hi : base;
     const int in_pitch = net->tpitch[d.in_tensor];
     const bool dual = quirk;
     if (dual) S.Cp_m = 2 * S.Cp;
     if ((!dual || S.Cp == net->t0_neg_off) && np <= tf2b::kMaxPlanes && tf2b::mma_layer_supported(d, in_pitch, np)) {
       S.planes_m = np;
+      S.low_plane_m = use_low ? np - 1 : -1;
       S.Npad_m = round_up(N, tf2b::mma_bn());
       const int Cpm = round_up(S.Cp_m, tf2b::mma_pick_bk(S.Cp_m));
       S.Kp_m = k * k * Cpm;
       S.h_w8.assign((size_t)np * S.Npad_m * S.Kp_m, 0);
       for (int p = 0; p < np; p++) S.plane_shift_m[p] = lv * p;
+      if (use_low) S.plane_shift_m[np - 1] = 0;
       for (int n = 0; n < N; n++)
         for (int c = 0; c < C; c++)
           for (int t = 0; t < k * k; t++) {
             uint8_t cd = codes[((size_t)n * C + c) * k * k + t];
             if (cd & 0x40) continue;
-            int rel = (cd & 0x1f) - base[n];
-            int p = rel / lv, e = rel - p * lv;
+            const int sft = cd & 0x1f;
+            int p, e;
+            if (use_low && sft < lv) {
+              p = np - 1;
+              e = sft;
+            } else {
+              int rel = sft - bm[n];
+              p = rel / lv;
+              e = rel - p * lv;
+            }
             int v = 1 << e;
             int cc = c;
             if (cd & 0x80) {
@@ -221,6 +258,8 @@ static int prepare_layer(tf2b_net* net, LayerState& S, const uint8_t* codes,
             }
             S.h_w8[((size_t)p * S.Npad_m + n) * S.Kp_m + (size_t)t * Cpm + cc] = (int8_t)v;
           }
+      S.h_nshift_m.assign(round_up(std::max(round_up(N, tf2b::conv_shift_bn()), S.Npad_m), 16), 0);
+      for (int n = 0; n < N; n++) S.h_nshift_m[n] = bm[n];
       S.mma_ok = true;
     }
   }
@@ -409,6 +448,7 @@ static size_t layout_arena(tf2b_net* net) {
     S.off_alpha = off; off = align256(off + (size_t)S.Npar * 4);
     S.off_beta = off; off = align256(off + (size_t)S.Npar * 4);
     S.off_nshift = off; off = align256(off + S.h_nshift.size());
+    S.off_nshift_m = off; off = align256(off + S.h_nshift_m.size());
   }
   return off;
 }
@@ -448,6 +488,7 @@ int tf2b_finalize(tf2b_net* net, int max_images) {
     CUDA_TRY(net, up(S.off_alpha, S.h_alpha.data(), (size_t)S.Npar * 4));
     CUDA_TRY(net, up(S.off_beta, S.h_beta.data(), (size_t)S.Npar * 4));
     CUDA_TRY(net, up(S.off_nshift, S.h_nshift.data(), S.h_nshift.size()));
+    CUDA_TRY(net, up(S.off_nshift_m, S.h_nshift_m.data(), S.h_nshift_m.size()));
   }
   int rc = alloc_runtime(net);
   if (rc != TF2B_OK) return rc;
@@ -468,7 +509,8 @@ static ConvParams conv_params(tf2b_net* net, const LayerState& S, int B, int8_t*
   p.bias = reinterpret_cast<const int32_t*>(net->arena + S.off_bias);
   p.alpha = reinterpret_cast<const int32_t*>(net->arena + S.off_alpha);
   p.beta = reinterpret_cast<const int32_t*>(net->arena + S.off_beta);
-  p.nshift = net->arena + S.off_nshift;
+  p.nshift = net->arena + (mma ? S.off_nshift_m : S.off_nshift);
+  p.low_plane = mma ? S.low_plane_m : -1;
   p.acc_dump = nullptr;
   p.B = B; p.IH = ti.H; p.IW = ti.W; p.Cp = mma ? S.Cp_m : S.Cp; p.xC = net->tpitch[d.in_tensor];
   p.OH = d.OH; p.OW = d.OW; p.N = d.N; p.yC = dstC; p.rC = resC;
@@ -744,7 +786,8 @@ int tf2b_export_weight_blob(tf2b_net* net, void* dev_dst, void* stream) {
       m.plane_shift_s[i] = S.plane_shift_s[i]; m.plane_neg_s[i] = S.plane_neg_s[i]; m.plane_shift_m[i] = S.plane_shift_m[i];
     }
     m.off_w16 = S.off_w16; m.off_w8 = S.off_w8; m.off_bias = S.off_bias; m.off_alpha = S.off_alpha;
-    m.off_beta = S.off_beta; m.off_nshift = S.off_nshift;
+    m.off_beta = S.off_beta; m.off_nshift = S.off_nshift; m.off_nshift_m = S.off_nshift_m;
+    m.low_plane_m = S.low_plane_m; m.nshift_m_len = (int32_t)S.h_nshift_m.size();
     memcpy(hdr.data() + 16 + l * sizeof m, &m, sizeof m);
   }
   cudaStream_t st = (cudaStream_t)stream;
@@ -793,6 +836,8 @@ int tf2b_import_weight_blob(tf2b_net* net, const void* dev_src, void* stream) {
     CUDA_TRY(net, pull(S.h_alpha, (size_t)S.Npar, m.off_alpha));
     CUDA_TRY(net, pull(S.h_beta, (size_t)S.Npar, m.off_beta));
     CUDA_TRY(net, pull(S.h_nshift, (size_t)round_up(S.Npar, 16), m.off_nshift));
+    CUDA_TRY(net, pull(S.h_nshift_m, (size_t)m.nshift_m_len, m.off_nshift_m));
+    S.low_plane_m = m.low_plane_m;
   }
   return TF2B_OK;
 }

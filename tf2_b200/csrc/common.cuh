@@ -29,6 +29,7 @@ struct ConvParams {
   int planes;             // number of weight planes
   int plane_shift[kMaxPlanes];  // plane p contributes (sum_p << plane_shift[p])
   int plane_neg[kMaxPlanes];    // 1: plane multiplies the int8-negated activations (pe.cl:32-34)
+  int low_plane;                // tensor-core path: plane added without the per-channel 2^nshift, or -1
 };
 
 // pe.cl:185-203 — requantisation of one accumulator (int64 product, arithmetic shifts, clamp).

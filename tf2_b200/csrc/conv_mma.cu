@@ -202,19 +202,38 @@ __device__ __forceinline__ TileCoord decode_tile(const MmaParams& P, int tile) {
   return t;
 }
 
+// saturating pack of four int32 into int8x4 (y0 in byte 0): cvt.pack.sat clamps to [-128,127]
+__device__ __forceinline__ unsigned pack_sat4(int y0, int y1, int y2, int y3) {
+  unsigned hi, r;
+  asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(y3), "r"(y2), "r"(0));
+  asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(y1), "r"(y0), "r"(hi));
+  return r;
+}
+
+// pe.cl:185-203 without the final clamp (done by the saturating pack); lo folds relu.cl:54
+__device__ __forceinline__ int requant_lo(int32_t acc, int32_t alpha, int32_t beta, int lo) {
+  long long t = (long long)acc * (long long)alpha;
+  int a = (int)(t >> 20);
+  int s = (int)((unsigned)a + (unsigned)beta);
+  int y = ((s >> 14) + 1) >> 1;
+  return max(lo, y);
+}
+
+template <int BN, int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ TmapPair maps) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // carve: [stages][A | B planes] (1024-aligned), then barriers
   const unsigned smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int a_stage = MMA_M * P.BK;
-  const int b_plane = P.BN * P.BK;
+  const int b_plane = BN * P.BK;
   const int stage_bytes = a_stage + P.planes * b_plane;
 
   __shared__ __align__(8) unsigned long long bars[2 * MAX_STAGES + 4];
   __shared__ unsigned tmem_base_slot;
   __shared__ __align__(16) unsigned char epi_stage[NUM_EPI_WARPS][32 * EPI_ROW];  // int8 staging tiles
   __shared__ __align__(16) int epi_params[NUM_EPI_WARPS][4 * 32];                 // bias/alpha/beta/2^nshift
+  __shared__ unsigned row_lut[MMA_M];   // box mode: row -> (wl | hl<<8 | nl<<16 | inbox<<24)
   const unsigned full_bar = smem_u32(&bars[0]);                  // [stages]
   const unsigned empty_bar = smem_u32(&bars[MAX_STAGES]);        // [stages]
   const unsigned tfull_bar = smem_u32(&bars[2 * MAX_STAGES]);    // [2]
@@ -239,110 +258,123 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(smem_u32(&tmem_base_slot), TMEM_COLS);
+  if (MODE == 1 && threadIdx.x >= 64 && threadIdx.x < 64 + MMA_M) {
+    const int row = threadIdx.x - 64;
+    const int wl = row % P.tw;
+    const int r = row / P.tw;
+    const int hl = r % P.th;
+    const int nl = r / P.th;
+    row_lut[row] = (unsigned)wl | ((unsigned)hl << 8) | ((unsigned)nl << 16) | ((nl < P.tn ? 1u : 0u) << 24);
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const unsigned tmem_base = tmem_base_slot;
-  const int acc_cols = P.planes * P.BN;  // TMEM columns of one accumulator buffer
+  const int acc_cols = P.planes * BN;  // TMEM columns of one accumulator buffer
 
   if (warp == 0) {
     // ===================================================== TMA producer (whole warp, one elected lane issues)
-    {
-      int stage = 0;
-      unsigned phase = 0;
-      const bool dbg = P.dbg != nullptr;
-      long long w_empty = 0, t_start = clock64();
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile(P, tile);
-        for (int tap = 0; tap < P.taps; tap++) {
-          const int fh = tap / P.c.k, fw = tap - fh * P.c.k;
-          for (int kc = 0; kc < P.kchunks; kc++) {
-            mbar_wait_timed(empty_bar + 8 * stage, phase ^ 1, w_empty, dbg);
-            const unsigned fb = full_bar + 8 * stage;
-            const unsigned sa = smem_base + stage * stage_bytes;
-            if (elect_one()) {
-              mbar_expect_tx(fb, (unsigned)(P.a_bytes + P.planes * P.b_bytes));
-              if (P.mode == 0) {
-                tma_load_2d(sa, &maps.a, fb, kc * P.BK, t.m0);
-              } else {
-                tma_load_4d(sa, &maps.a, fb, kc * P.BK, t.ow0 * P.c.stride - P.c.pad + fw,
-                            t.oh0 * P.c.stride - P.c.pad + fh, t.b0);
-              }
-              for (int pl = 0; pl < P.planes; pl++)
-                tma_load_2d(sa + a_stage + pl * b_plane, &maps.b, fb, tap * P.Cpm + kc * P.BK, pl * P.Npad + t.n0);
-            }
-            __syncwarp();
-            if (++stage == P.stages) { stage = 0; phase ^= 1; }
-          }
-        }
-      }
-      if (dbg && lane == 0) {
-        P.dbg[blockIdx.x * 8 + 0] = w_empty;
-        P.dbg[blockIdx.x * 8 + 1] = clock64() - t_start;
-      }
-    }
-  } else if (warp == 1) {
-    // ===================================================== MMA issuer (whole warp, one elected lane issues)
-    {
-      int stage = 0;
-      unsigned phase = 0;
-      int buf = 0;
-      unsigned tphase[2] = {0, 0};
-      const bool dbg = P.dbg != nullptr;
-      long long w_full = 0, w_tempty = 0, t_start = clock64();
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait_timed(tempty_bar + 8 * buf, tphase[buf] ^ 1, w_tempty, dbg);   // epilogue has drained this accumulator
-        tc_fence_after();
-        const unsigned d_tmem = tmem_base + buf * acc_cols;
-        for (int it = 0; it < kiters; it++) {
-          mbar_wait_timed(full_bar + 8 * stage, phase, w_full, dbg);
-          tc_fence_after();
+    int stage = 0;
+    unsigned phase = 0;
+    const bool dbg = P.dbg != nullptr;
+    long long w_empty = 0, t_start = clock64();
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(P, tile);
+      for (int tap = 0; tap < P.taps; tap++) {
+        const int fh = tap / P.c.k, fw = tap - fh * P.c.k;
+        for (int kc = 0; kc < P.kchunks; kc++) {
+          mbar_wait_timed(empty_bar + 8 * stage, phase ^ 1, w_empty, dbg);
+          const unsigned fb = full_bar + 8 * stage;
           const unsigned sa = smem_base + stage * stage_bytes;
-          const unsigned long long da = make_smem_desc(sa, P.sbo16, P.layout_type);
           if (elect_one()) {
-            for (int pl = 0; pl < P.planes; pl++) {
-              const unsigned long long db = make_smem_desc(sa + a_stage + pl * b_plane, P.sbo16, P.layout_type);
-              for (int k4 = 0; k4 < P.BK / 32; k4++) {
-                // advance both descriptors by 32 bytes of K inside the swizzled row
-                umma_i8(d_tmem + pl * P.BN, da + (unsigned long long)(2 * k4), db + (unsigned long long)(2 * k4),
-                        P.idesc, (it > 0 || k4 > 0) ? 1u : 0u);
-              }
+            mbar_expect_tx(fb, (unsigned)(P.a_bytes + P.planes * P.b_bytes));
+            if (MODE == 0) {
+              tma_load_2d(sa, &maps.a, fb, kc * P.BK, t.m0);
+            } else {
+              tma_load_4d(sa, &maps.a, fb, kc * P.BK, t.ow0 * P.c.stride - P.c.pad + fw,
+                          t.oh0 * P.c.stride - P.c.pad + fh, t.b0);
             }
-            umma_commit(empty_bar + 8 * stage);             // frees the smem stage when the MMAs retire
-            if (it == kiters - 1) umma_commit(tfull_bar + 8 * buf);   // accumulators complete -> epilogue
+            for (int pl = 0; pl < P.planes; pl++)
+              tma_load_2d(sa + a_stage + pl * b_plane, &maps.b, fb, tap * P.Cpm + kc * P.BK, pl * P.Npad + t.n0);
           }
           __syncwarp();
           if (++stage == P.stages) { stage = 0; phase ^= 1; }
         }
-        tphase[buf] ^= 1;
-        buf ^= 1;
       }
-      if (dbg && lane == 0) {
-        P.dbg[blockIdx.x * 8 + 2] = w_full;
-        P.dbg[blockIdx.x * 8 + 3] = w_tempty;
-        P.dbg[blockIdx.x * 8 + 4] = clock64() - t_start;
+    }
+    if (dbg && lane == 0) {
+      P.dbg[blockIdx.x * 8 + 0] = w_empty;
+      P.dbg[blockIdx.x * 8 + 1] = clock64() - t_start;
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer (whole warp, one elected lane issues)
+    int stage = 0;
+    unsigned phase = 0;
+    int buf = 0;
+    unsigned tphase[2] = {0, 0};
+    const bool dbg = P.dbg != nullptr;
+    long long w_full = 0, w_tempty = 0, t_start = clock64();
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait_timed(tempty_bar + 8 * buf, tphase[buf] ^ 1, w_tempty, dbg);   // epilogue has drained this accumulator
+      tc_fence_after();
+      const unsigned d_tmem = tmem_base + buf * acc_cols;
+      for (int it = 0; it < kiters; it++) {
+        mbar_wait_timed(full_bar + 8 * stage, phase, w_full, dbg);
+        tc_fence_after();
+        const unsigned sa = smem_base + stage * stage_bytes;
+        const unsigned long long da = make_smem_desc(sa, P.sbo16, P.layout_type);
+        if (elect_one()) {
+          for (int pl = 0; pl < P.planes; pl++) {
+            const unsigned long long db = make_smem_desc(sa + a_stage + pl * b_plane, P.sbo16, P.layout_type);
+            for (int k4 = 0; k4 < P.BK / 32; k4++) {
+              // advance both descriptors by 32 bytes of K inside the swizzled row
+              umma_i8(d_tmem + pl * BN, da + (unsigned long long)(2 * k4), db + (unsigned long long)(2 * k4),
+                      P.idesc, (it > 0 || k4 > 0) ? 1u : 0u);
+            }
+          }
+          umma_commit(empty_bar + 8 * stage);             // frees the smem stage when the MMAs retire
+          if (it == kiters - 1) umma_commit(tfull_bar + 8 * buf);   // accumulators complete -> epilogue
+        }
+        __syncwarp();
+        if (++stage == P.stages) { stage = 0; phase ^= 1; }
       }
+      tphase[buf] ^= 1;
+      buf ^= 1;
+    }
+    if (dbg && lane == 0) {
+      P.dbg[blockIdx.x * 8 + 2] = w_full;
+      P.dbg[blockIdx.x * 8 + 3] = w_tempty;
+      P.dbg[blockIdx.x * 8 + 4] = clock64() - t_start;
     }
   } else {
     // ===================================================== epilogue warps
-    // Warp (quarter q, half h) owns rows 32q..32q+31 (its TMEM lane quarter) x W = BN/2 columns.
+    // Warp (quarter q, slice s) owns rows 32q..32q+31 (its TMEM lane quarter) x W = BN/4 columns.
     // Per tile: (1) before the accumulators are ready, fetch its per-channel params into its private
     // smem slice and prefetch its residual operand with the coalesced mapping; (2) tcgen05.ld ->
     // recombine planes -> requantise -> 16-byte st.shared into a private [32][W] staging tile;
     // (3) re-read the staging tile with lanes along the channel dimension so every global access
     // covers whole 32-byte sectors: residual add, 16-byte stores.  No cross-warp synchronisation.
-    const int ew = warp - 2;            // 0..15
-    const int quarter = warp & 3;       // TMEM lane quarter this warp may access
-    const int slice = ew >> 2;          // which quarter of the BN columns
+    constexpr int W = BN / 4;             // 16 or 32 columns per warp
+    constexpr int SEGS = W / 16;          // 16-byte segments per row (1 or 2) = iterations per tile
+    constexpr int ROWS_PER_IT = 32 / SEGS;
+    const int ew = warp - 2;              // 0..15
+    const int quarter = warp & 3;         // TMEM lane quarter this warp may access
+    const int slice = ew >> 2;            // which quarter of the BN columns
     const ConvParams& c = P.c;
     const int M = c.B * c.OH * c.OW;
-    const int W = P.BN / 4;             // 16 or 32 columns per warp
-    const int segs = W / 16;            // 16-byte segments per row (1 or 2)
-    const int rows_per_it = 32 / segs;  // rows covered by one warp-wide 16-byte access
-    const int nit = segs;               // iterations that cover the 32 x W tile
     const int lo_clamp = c.relu ? 0 : -128;   // relu.cl:54 folded into the clamp of pe.cl:194
     unsigned char* stage = epi_stage[ew];
-    int* prm = epi_params[ew];          // [4][32]: bias, alpha, beta, 2^nshift
+    int* prm = epi_params[ew];            // [4][32]: bias, alpha, beta, 2^nshift
+    // coalesced mapping (constant per thread): iteration it -> row rl[it], 16-byte segment sg
+    const int sg = lane % SEGS;
+    int rl[SEGS];
+    unsigned lut[SEGS];
+#pragma unroll
+    for (int it = 0; it < SEGS; it++) {
+      rl[it] = it * ROWS_PER_IT + lane / SEGS;
+      lut[it] = MODE == 1 ? row_lut[quarter * 32 + rl[it]] : 0u;
+    }
+    const bool has_res = c.r != nullptr;
     int buf = 0;
     unsigned tphase[2] = {0, 0};
     const bool dbg = P.dbg != nullptr && warp == 2;
@@ -350,64 +382,61 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(P, tile);
       const int ncol0 = t.n0 + slice * W;         // first output channel of this warp
+      const int n = ncol0 + sg * 16;              // first channel of this lane's 16-byte segment
       // ---- (1a) params of this warp's W channels -> smem (padded arrays: always in bounds)
       __syncwarp();
       if (lane < W) {
-        const int n = ncol0 + lane;
-        prm[lane] = __ldg(c.bias + n);
-        prm[32 + lane] = __ldg(c.alpha + n);
-        prm[64 + lane] = __ldg(c.beta + n);
-        prm[96 + lane] = 1 << (int)__ldg(c.nshift + n);   // (x << s) == x * 2^s  (mod 2^32)
+        const int nn = ncol0 + lane;
+        prm[lane] = __ldg(c.bias + nn);
+        prm[32 + lane] = __ldg(c.alpha + nn);
+        prm[64 + lane] = __ldg(c.beta + nn);
+        prm[96 + lane] = 1 << (int)__ldg(c.nshift + nn);   // (x << s) == x * 2^s  (mod 2^32)
       }
-      // ---- (1b) coalesced mapping: iteration it, lane -> (row, seg); pixel + residual prefetch
-      long long pixs[2];
-      uint4 resv[2];
+      // ---- (1b) output pixel of each of this lane's rows + residual prefetch
+      long long off[SEGS];
+      uint4 resv[SEGS];
 #pragma unroll
-      for (int it = 0; it < 2; it++) {
-        pixs[it] = -1;
-        resv[it] = make_uint4(0, 0, 0, 0);
-        if (it < nit) {
-          const int rl = it * rows_per_it + lane / segs;   // row inside the warp's 32 rows
-          const int row = quarter * 32 + rl;
-          bool valid;
-          long long pix;
-          if (P.mode == 0) {
-            int m = t.m0 + row;
-            valid = m < M;
-            pix = m;
-          } else {
-            int wl = row % P.tw;
-            int r = row / P.tw;
-            int hl = r % P.th;
-            int nl = r / P.th;
-            int ow = t.ow0 + wl, oh = t.oh0 + hl, b = t.b0 + nl;
-            valid = (nl < P.tn) && (ow < c.OW) && (oh < c.OH) && (b < c.B);
-            pix = ((long long)b * c.OH + oh) * c.OW + ow;
-          }
-          const int n = ncol0 + (lane % segs) * 16;
-          if (valid && n < c.N) {
-            pixs[it] = pix;
-            if (c.r != nullptr && n + 16 <= c.N)
-              resv[it] = __ldg(reinterpret_cast<const uint4*>(c.r + pix * c.rC + n));
-          }
+      for (int it = 0; it < SEGS; it++) {
+        bool valid;
+        long long pix;
+        if (MODE == 0) {
+          const int m = t.m0 + quarter * 32 + rl[it];
+          valid = m < M;
+          pix = m;
+        } else {
+          const int ow = t.ow0 + (int)(lut[it] & 0xff), oh = t.oh0 + (int)((lut[it] >> 8) & 0xff);
+          const int b = t.b0 + (int)((lut[it] >> 16) & 0xff);
+          valid = (lut[it] >> 24) && (ow < c.OW) && (oh < c.OH) && (b < c.B);
+          pix = ((long long)b * c.OH + oh) * c.OW + ow;
         }
+        off[it] = (valid && n < c.N) ? pix : -1;
+        resv[it] = make_uint4(0, 0, 0, 0);
+        if (has_res && off[it] >= 0 && n + 16 <= c.N)
+          resv[it] = __ldg(reinterpret_cast<const uint4*>(c.r + pix * c.rC + n));
       }
       __syncwarp();
       // ---- (2) accumulators -> int8 staging tile
       mbar_wait_timed(tfull_bar + 8 * buf, tphase[buf], w_tfull, dbg);
       tc_fence_after();
       const unsigned t_row = tmem_base + ((unsigned)(quarter * 32) << 16) + buf * acc_cols + slice * W;
-      for (int cc = 0; cc < W; cc += 16) {
-        unsigned tot[16];
-        tmem_ld16(t_row + cc, tot);
-        tmem_ld_wait();
-        for (int pl = 1; pl < P.planes; pl++) {
-          unsigned v[16];
-          tmem_ld16(t_row + pl * P.BN + cc, v);
-          tmem_ld_wait();
-          const unsigned mulp = 1u << P.plane8_shift[pl];
 #pragma unroll
-          for (int j = 0; j < 16; j++) tot[j] += v[j] * mulp;
+      for (int cc = 0; cc < W; cc += 16) {
+        unsigned tot[16], low[16];
+        tmem_ld16(t_row + cc, tot);
+        if (P.c.low_plane >= 0) tmem_ld16(t_row + P.c.low_plane * BN + cc, low);
+        tmem_ld_wait();
+        if (P.c.low_plane < 0) {
+#pragma unroll
+          for (int j = 0; j < 16; j++) low[j] = 0;
+        }
+        for (int pl = 1; pl < P.planes; pl++) {
+          if (pl == P.c.low_plane) continue;
+          unsigned v[16];
+          tmem_ld16(t_row + pl * BN + cc, v);
+          tmem_ld_wait();
+          const unsigned mulq = 1u << P.plane8_shift[pl];
+#pragma unroll
+          for (int j = 0; j < 16; j++) tot[j] += v[j] * mulq;
         }
         unsigned packed[4];
 #pragma unroll
@@ -416,12 +445,11 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
           const int4 pa = *reinterpret_cast<const int4*>(prm + 32 + cc + 4 * j4);
           const int4 pe = *reinterpret_cast<const int4*>(prm + 64 + cc + 4 * j4);
           const int4 pm = *reinterpret_cast<const int4*>(prm + 96 + cc + 4 * j4);
-          const int y0 = requant_clamped((int)(tot[4 * j4 + 0] * (unsigned)pm.x + (unsigned)pb.x), pa.x, pe.x, lo_clamp);
-          const int y1 = requant_clamped((int)(tot[4 * j4 + 1] * (unsigned)pm.y + (unsigned)pb.y), pa.y, pe.y, lo_clamp);
-          const int y2 = requant_clamped((int)(tot[4 * j4 + 2] * (unsigned)pm.z + (unsigned)pb.z), pa.z, pe.z, lo_clamp);
-          const int y3 = requant_clamped((int)(tot[4 * j4 + 3] * (unsigned)pm.w + (unsigned)pb.w), pa.w, pe.w, lo_clamp);
-          // byte 0 of each value -> one packed word
-          packed[j4] = __byte_perm(__byte_perm(y0, y1, 0x0040), __byte_perm(y2, y3, 0x0040), 0x5410);
+          const int y0 = requant_lo((int)(tot[4 * j4 + 0] * (unsigned)pm.x + (unsigned)pb.x + low[4 * j4 + 0]), pa.x, pe.x, lo_clamp);
+          const int y1 = requant_lo((int)(tot[4 * j4 + 1] * (unsigned)pm.y + (unsigned)pb.y + low[4 * j4 + 1]), pa.y, pe.y, lo_clamp);
+          const int y2 = requant_lo((int)(tot[4 * j4 + 2] * (unsigned)pm.z + (unsigned)pb.z + low[4 * j4 + 2]), pa.z, pe.z, lo_clamp);
+          const int y3 = requant_lo((int)(tot[4 * j4 + 3] * (unsigned)pm.w + (unsigned)pb.w + low[4 * j4 + 3]), pa.w, pe.w, lo_clamp);
+          packed[j4] = pack_sat4(y0, y1, y2, y3);
         }
         *reinterpret_cast<uint4*>(stage + lane * EPI_ROW + cc) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
       }
@@ -433,16 +461,13 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
       buf ^= 1;
       // ---- (3) coalesced residual add + store
 #pragma unroll
-      for (int it = 0; it < 2; it++) {
-        if (it < nit && pixs[it] >= 0) {
-          const int rl = it * rows_per_it + lane / segs;
-          const int sg = lane % segs;
-          const int n = ncol0 + sg * 16;
-          uint4 v = *reinterpret_cast<const uint4*>(stage + rl * EPI_ROW + sg * 16);
-          int8_t* dst = c.y + pixs[it] * c.yC + n;
-          const int nvalid = min(16, c.N - n);
-          if (nvalid == 16) {
-            if (c.r != nullptr) {
+      for (int it = 0; it < SEGS; it++) {
+        if (off[it] >= 0) {
+          uint4 v = *reinterpret_cast<const uint4*>(stage + rl[it] * EPI_ROW + sg * 16);
+          int8_t* dst = c.y + off[it] * c.yC + n;
+          const int nvalid = c.N - n;
+          if (nvalid >= 16) {
+            if (has_res) {
               v.x = add_res4(v.x, resv[it].x, c.add_relu);
               v.y = add_res4(v.y, resv[it].y, c.add_relu);
               v.z = add_res4(v.z, resv[it].z, c.add_relu);
@@ -450,11 +475,10 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
             }
             *reinterpret_cast<uint4*>(dst) = v;
           } else {
-            const unsigned char* vb = reinterpret_cast<const unsigned char*>(&v);
             for (int e = 0; e < nvalid; e++) {
-              int yv = (int)(signed char)vb[e];
-              if (c.r != nullptr) {
-                int sres = yv + (int)c.r[pixs[it] * c.rC + n + e];
+              int yv = (int)(signed char)((reinterpret_cast<const unsigned*>(&v)[e >> 2] >> (8 * (e & 3))) & 0xff);
+              if (has_res) {
+                int sres = yv + (int)c.r[off[it] * c.rC + n + e];
                 sres = max(-128, min(127, sres));
                 if (c.add_relu) sres = max(sres, 0);
                 yv = sres;
@@ -631,7 +655,11 @@ cudaError_t launch_conv_mma(const ConvParams& c, const int8_t* /*wgt8*/, int pla
   const int stage_bytes = MMA_M * P.BK + planes8 * P.b_bytes;
   const size_t smem = (size_t)P.stages * stage_bytes + 1024;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 186 * 1024);
+    const int lim = 186 * 1024;
+    cudaError_t e = cudaFuncSetAttribute(conv_mma_kernel<128, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_mma_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_mma_kernel<64, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_mma_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
@@ -646,7 +674,13 @@ cudaError_t launch_conv_mma(const ConvParams& c, const int8_t* /*wgt8*/, int pla
     cudaMemsetAsync(dbg_dev, 0, sizeof(long long) * 8 * 148, stream);
     P.dbg = dbg_dev;
   }
-  conv_mma_kernel<<<grid, NUM_THREADS, smem, stream>>>(P, *tp);
+  if (P.BN == 128) {
+    if (P.mode == 0) conv_mma_kernel<128, 0><<<grid, NUM_THREADS, smem, stream>>>(P, *tp);
+    else conv_mma_kernel<128, 1><<<grid, NUM_THREADS, smem, stream>>>(P, *tp);
+  } else {
+    if (P.mode == 0) conv_mma_kernel<64, 0><<<grid, NUM_THREADS, smem, stream>>>(P, *tp);
+    else conv_mma_kernel<64, 1><<<grid, NUM_THREADS, smem, stream>>>(P, *tp);
+  }
   if (debug) {
     long long h[8 * 148];
     cudaStreamSynchronize(stream);
