@@ -37,6 +37,12 @@ CASES = [
     ("s2_1x1_c256_56to28", (256, 56, 56), [dict(N=512, k=1, stride=2, relu=0)], 2, {}),
     ("s2_1x1_c1024_14to7", (1024, 14, 14), [dict(N=2048, k=1, stride=2, relu=0)], 3, {}),
     ("s2_3x3_odd_15to8", (64, 15, 15), [dict(N=64, k=3, pad=1, stride=2)], 3, {}),
+    # single-plane layers take the 256-wide N tile (two epilogue passes per warp)
+    ("bn256_flat_c256_n512", (256, 14, 14), [dict(N=512, k=1)], 3, dict(per_c_offset=0)),
+    ("bn256_box_c128_n256", (128, 14, 14), [dict(N=256, k=3, pad=1)], 3, dict(per_c_offset=0)),
+    ("bn256_n384_ragged", (64, 10, 10), [dict(N=384, k=1, relu=0)], 2, dict(per_c_offset=0)),
+    ("bn256_residual", (512, 7, 7), [dict(N=128, k=1), dict(N=512, k=1, relu=0, add=-1, add_relu=1)], 3, dict(per_c_offset=0)),
+    ("bn256_fc_n1000", (512, 1, 1), [dict(N=1000, k=1, relu=0, bias_en=1, bn_en=0)], 5, dict(per_c_offset=0)),
 ]
 
 

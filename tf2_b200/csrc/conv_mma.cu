@@ -37,6 +37,19 @@ constexpr int MAX_STAGES = 8;
 constexpr int TMEM_COLS = 512;
 constexpr int EPI_ROW = 48;   // bytes per staging row: 32 data + 16 pad (conflict-free 16-byte accesses)
 
+// x / d for 0 <= x, d < 2^20:  (x * ceil(2^40/d)) >> 40   (exact in that range)
+struct FastDiv {
+  unsigned long long mul;
+  int d;
+};
+__host__ __device__ __forceinline__ FastDiv make_fastdiv(int d) {
+  FastDiv f;
+  f.d = d < 1 ? 1 : d;
+  f.mul = ((1ull << 40) + (unsigned long long)f.d - 1) / (unsigned long long)f.d;
+  return f;
+}
+__device__ __forceinline__ int fdiv(int x, const FastDiv& f) { return (int)(((unsigned long long)(unsigned)x * f.mul) >> 40); }
+
 struct MmaParams {
   ConvParams c;
   int mode;                 // 0 = flat (1x1, stride 1, pad 0), 1 = box (one TMA box per filter tap)
@@ -54,6 +67,7 @@ struct MmaParams {
   unsigned sbo16;           // stride byte offset >> 4 of the smem descriptors
   unsigned layout_type;     // UMMA smem layout type (2 = SWIZZLE_128B, 4 = SWIZZLE_64B)
   long long* dbg;           // optional per-CTA cycle counters [grid][8] (TF2B_MMA_DEBUG), else nullptr
+  FastDiv d_ntiles, d_tiles_w, d_tiles_h;
 };
 
 struct TmapPair {
@@ -185,16 +199,16 @@ struct TileCoord {
 
 __device__ __forceinline__ TileCoord decode_tile(const MmaParams& P, int tile) {
   TileCoord t;
-  int nt = tile % P.n_tiles;
-  int mt = tile / P.n_tiles;
+  const int mt = fdiv(tile, P.d_ntiles);
+  const int nt = tile - mt * P.n_tiles;
   t.n0 = nt * P.BN;
   t.m0 = mt * MMA_M;
   t.b0 = t.oh0 = t.ow0 = 0;
   if (P.mode == 1) {
-    int wt = mt % P.tiles_w;
-    int r = mt / P.tiles_w;
-    int ht = r % P.tiles_h;
-    int bt = r / P.tiles_h;
+    const int r = fdiv(mt, P.d_tiles_w);
+    const int wt = mt - r * P.tiles_w;
+    const int bt = fdiv(r, P.d_tiles_h);
+    const int ht = r - bt * P.tiles_h;
     t.ow0 = wt * P.tw;
     t.oh0 = ht * P.th;
     t.b0 = bt * P.tn;
@@ -232,7 +246,7 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
   __shared__ __align__(8) unsigned long long bars[2 * MAX_STAGES + 4];
   __shared__ unsigned tmem_base_slot;
   __shared__ __align__(16) unsigned char epi_stage[NUM_EPI_WARPS][32 * EPI_ROW];  // int8 staging tiles
-  __shared__ __align__(16) int epi_params[NUM_EPI_WARPS][4 * 32];                 // bias/alpha/beta/2^nshift
+  __shared__ __align__(16) int epi_params[NUM_EPI_WARPS][4 * 64];                 // bias/alpha/beta/2^nshift
   __shared__ unsigned row_lut[MMA_M];   // box mode: row -> (wl | hl<<8 | nl<<16 | inbox<<24)
   const unsigned full_bar = smem_u32(&bars[0]);                  // [stages]
   const unsigned empty_bar = smem_u32(&bars[MAX_STAGES]);        // [stages]
@@ -354,8 +368,10 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
     // recombine planes -> requantise -> 16-byte st.shared into a private [32][W] staging tile;
     // (3) re-read the staging tile with lanes along the channel dimension so every global access
     // covers whole 32-byte sectors: residual add, 16-byte stores.  No cross-warp synchronisation.
-    constexpr int W = BN / 4;             // 16 or 32 columns per warp
-    constexpr int SEGS = W / 16;          // 16-byte segments per row (1 or 2) = iterations per tile
+    constexpr int WT = BN / 4;            // columns per warp: 16, 32 or 64
+    constexpr int W = WT > 32 ? 32 : WT;  // columns per pass (staging tile width)
+    constexpr int PASSES = WT / W;        // 1, or 2 for BN = 256
+    constexpr int SEGS = W / 16;          // 16-byte segments per row (1 or 2) = iterations per pass
     constexpr int ROWS_PER_IT = 32 / SEGS;
     const int ew = warp - 2;              // 0..15
     const int quarter = warp & 3;         // TMEM lane quarter this warp may access
@@ -364,7 +380,7 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
     const int M = c.B * c.OH * c.OW;
     const int lo_clamp = c.relu ? 0 : -128;   // relu.cl:54 folded into the clamp of pe.cl:194
     unsigned char* stage = epi_stage[ew];
-    int* prm = epi_params[ew];            // [4][32]: bias, alpha, beta, 2^nshift
+    int* prm = epi_params[ew];            // [4][64]: bias, alpha, beta, 2^nshift
     // coalesced mapping (constant per thread): iteration it -> row rl[it], 16-byte segment sg
     const int sg = lane % SEGS;
     int rl[SEGS];
@@ -375,26 +391,47 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
       lut[it] = MODE == 1 ? row_lut[quarter * 32 + rl[it]] : 0u;
     }
     const bool has_res = c.r != nullptr;
+    const int hi_clamp = 127;
+    const int res_lo = c.add_relu ? 0 : -128;   // feature_writer.cl:126 folded into the final clamp
+    const int my_row = quarter * 32 + lane;     // accumulator row (TMEM lane) of this thread
+    const unsigned my_lut = MODE == 1 ? row_lut[my_row] : 0u;
     int buf = 0;
     unsigned tphase[2] = {0, 0};
+    int cached_ncol0 = -1;
     const bool dbg = P.dbg != nullptr && warp == 2;
     long long w_tfull = 0, t_start = clock64();
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(P, tile);
-      const int ncol0 = t.n0 + slice * W;         // first output channel of this warp
-      const int n = ncol0 + sg * 16;              // first channel of this lane's 16-byte segment
-      // ---- (1a) params of this warp's W channels -> smem (padded arrays: always in bounds)
+      const int ncolw = t.n0 + slice * WT;        // first output channel of this warp
+      // ---- (1a) params of this warp's WT channels -> smem, only when the channel slice changes
       __syncwarp();
-      if (lane < W) {
-        const int nn = ncol0 + lane;
-        prm[lane] = __ldg(c.bias + nn);
-        prm[32 + lane] = __ldg(c.alpha + nn);
-        prm[64 + lane] = __ldg(c.beta + nn);
-        prm[96 + lane] = 1 << (int)__ldg(c.nshift + nn);   // (x << s) == x * 2^s  (mod 2^32)
+      if (ncolw != cached_ncol0) {
+        cached_ncol0 = ncolw;
+        for (int i = lane; i < WT; i += 32) {
+          const int nn = ncolw + i;
+          prm[i] = __ldg(c.bias + nn);
+          prm[64 + i] = __ldg(c.alpha + nn);
+          prm[128 + i] = __ldg(c.beta + nn);
+          prm[192 + i] = 1 << (int)__ldg(c.nshift + nn);   // (x << s) == x * 2^s  (mod 2^32)
+        }
       }
-      // ---- (1b) output pixel of each of this lane's rows + residual prefetch
-      long long off[SEGS];
-      uint4 resv[SEGS];
+      // ---- (1b) this thread's accumulator row -> pixel (for the residual), and the pixels of its
+      //           (row, segment) pairs in the coalesced store mapping
+      bool rvalid = false;
+      long long rpix = 0;
+      if (has_res) {
+        if (MODE == 0) {
+          const int m = t.m0 + my_row;
+          rvalid = m < M;
+          rpix = m;
+        } else {
+          const int ow = t.ow0 + (int)(my_lut & 0xff), oh = t.oh0 + (int)((my_lut >> 8) & 0xff);
+          const int b = t.b0 + (int)((my_lut >> 16) & 0xff);
+          rvalid = (my_lut >> 24) && (ow < c.OW) && (oh < c.OH) && (b < c.B);
+          rpix = ((long long)b * c.OH + oh) * c.OW + ow;
+        }
+      }
+      long long opix[SEGS];
 #pragma unroll
       for (int it = 0; it < SEGS; it++) {
         bool valid;
@@ -409,85 +446,112 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
           valid = (lut[it] >> 24) && (ow < c.OW) && (oh < c.OH) && (b < c.B);
           pix = ((long long)b * c.OH + oh) * c.OW + ow;
         }
-        off[it] = (valid && n < c.N) ? pix : -1;
-        resv[it] = make_uint4(0, 0, 0, 0);
-        if (has_res && off[it] >= 0 && n + 16 <= c.N)
-          resv[it] = __ldg(reinterpret_cast<const uint4*>(c.r + pix * c.rC + n));
+        opix[it] = valid ? pix : -1;
       }
-      __syncwarp();
-      // ---- (2) accumulators -> int8 staging tile
-      mbar_wait_timed(tfull_bar + 8 * buf, tphase[buf], w_tfull, dbg);
-      tc_fence_after();
-      const unsigned t_row = tmem_base + ((unsigned)(quarter * 32) << 16) + buf * acc_cols + slice * W;
+      // residual of this thread's own row for the first pass (whole 32-byte sectors)
+      uint4 resq[SEGS];
+      auto load_residual = [&](int ncolp) {
 #pragma unroll
-      for (int cc = 0; cc < W; cc += 16) {
-        unsigned tot[16], low[16];
-        tmem_ld16(t_row + cc, tot);
-        if (P.c.low_plane >= 0) tmem_ld16(t_row + P.c.low_plane * BN + cc, low);
-        tmem_ld_wait();
-        if (P.c.low_plane < 0) {
+        for (int q = 0; q < SEGS; q++) resq[q] = make_uint4(0, 0, 0, 0);
+        if (has_res && rvalid) {
+          const int8_t* rp = c.r + rpix * c.rC + ncolp;
 #pragma unroll
-          for (int j = 0; j < 16; j++) low[j] = 0;
-        }
-        for (int pl = 1; pl < P.planes; pl++) {
-          if (pl == P.c.low_plane) continue;
-          unsigned v[16];
-          tmem_ld16(t_row + pl * BN + cc, v);
-          tmem_ld_wait();
-          const unsigned mulq = 1u << P.plane8_shift[pl];
-#pragma unroll
-          for (int j = 0; j < 16; j++) tot[j] += v[j] * mulq;
-        }
-        unsigned packed[4];
-#pragma unroll
-        for (int j4 = 0; j4 < 4; j4++) {
-          const int4 pb = *reinterpret_cast<const int4*>(prm + cc + 4 * j4);
-          const int4 pa = *reinterpret_cast<const int4*>(prm + 32 + cc + 4 * j4);
-          const int4 pe = *reinterpret_cast<const int4*>(prm + 64 + cc + 4 * j4);
-          const int4 pm = *reinterpret_cast<const int4*>(prm + 96 + cc + 4 * j4);
-          const int y0 = requant_lo((int)(tot[4 * j4 + 0] * (unsigned)pm.x + (unsigned)pb.x + low[4 * j4 + 0]), pa.x, pe.x, lo_clamp);
-          const int y1 = requant_lo((int)(tot[4 * j4 + 1] * (unsigned)pm.y + (unsigned)pb.y + low[4 * j4 + 1]), pa.y, pe.y, lo_clamp);
-          const int y2 = requant_lo((int)(tot[4 * j4 + 2] * (unsigned)pm.z + (unsigned)pb.z + low[4 * j4 + 2]), pa.z, pe.z, lo_clamp);
-          const int y3 = requant_lo((int)(tot[4 * j4 + 3] * (unsigned)pm.w + (unsigned)pb.w + low[4 * j4 + 3]), pa.w, pe.w, lo_clamp);
-          packed[j4] = pack_sat4(y0, y1, y2, y3);
-        }
-        *reinterpret_cast<uint4*>(stage + lane * EPI_ROW + cc) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-      }
-      // accumulator buffer drained: hand it back to the MMA warp as early as possible
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar + 8 * buf);
-      tphase[buf] ^= 1;
-      buf ^= 1;
-      // ---- (3) coalesced residual add + store
-#pragma unroll
-      for (int it = 0; it < SEGS; it++) {
-        if (off[it] >= 0) {
-          uint4 v = *reinterpret_cast<const uint4*>(stage + rl[it] * EPI_ROW + sg * 16);
-          int8_t* dst = c.y + off[it] * c.yC + n;
-          const int nvalid = c.N - n;
-          if (nvalid >= 16) {
-            if (has_res) {
-              v.x = add_res4(v.x, resv[it].x, c.add_relu);
-              v.y = add_res4(v.y, resv[it].y, c.add_relu);
-              v.z = add_res4(v.z, resv[it].z, c.add_relu);
-              v.w = add_res4(v.w, resv[it].w, c.add_relu);
-            }
-            *reinterpret_cast<uint4*>(dst) = v;
-          } else {
-            for (int e = 0; e < nvalid; e++) {
-              int yv = (int)(signed char)((reinterpret_cast<const unsigned*>(&v)[e >> 2] >> (8 * (e & 3))) & 0xff);
-              if (has_res) {
-                int sres = yv + (int)c.r[off[it] * c.rC + n + e];
-                sres = max(-128, min(127, sres));
-                if (c.add_relu) sres = max(sres, 0);
-                yv = sres;
-              }
-              dst[e] = (int8_t)yv;
+          for (int q = 0; q < SEGS; q++) {
+            const int nq = ncolp + 16 * q;
+            if (nq + 16 <= c.N) {
+              resq[q] = __ldg(reinterpret_cast<const uint4*>(rp + 16 * q));
+            } else if (nq < c.N) {   // ragged channel tail: byte loads
+              unsigned w4[4] = {0, 0, 0, 0};
+              for (int e = 0; e < c.N - nq; e++) w4[e >> 2] |= (unsigned)(unsigned char)rp[16 * q + e] << (8 * (e & 3));
+              resq[q] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
             }
           }
         }
+      };
+      load_residual(ncolw);
+      __syncwarp();
+      // ---- (2) accumulators -> requantise (+ residual) -> int8 staging tile -> (3) coalesced store
+      mbar_wait_timed(tfull_bar + 8 * buf, tphase[buf], w_tfull, dbg);
+      tc_fence_after();
+#pragma unroll
+      for (int pass = 0; pass < PASSES; pass++) {
+        const int ncolp = ncolw + pass * W;         // first channel of this pass
+        const int n = ncolp + sg * 16;              // first channel of this lane's 16-byte segment
+        const unsigned t_row = tmem_base + ((unsigned)(quarter * 32) << 16) + buf * acc_cols + slice * WT + pass * W;
+#pragma unroll
+        for (int cc = 0; cc < W; cc += 16) {
+          unsigned tot[16], low[16];
+          tmem_ld16(t_row + cc, tot);
+          if (P.c.low_plane >= 0) tmem_ld16(t_row + P.c.low_plane * BN + cc, low);
+          tmem_ld_wait();
+          if (P.c.low_plane < 0) {
+#pragma unroll
+            for (int j = 0; j < 16; j++) low[j] = 0;
+          }
+          for (int pl = 1; pl < P.planes; pl++) {
+            if (pl == P.c.low_plane) continue;
+            unsigned v[16];
+            tmem_ld16(t_row + pl * BN + cc, v);
+            tmem_ld_wait();
+            const unsigned mulq = 1u << P.plane8_shift[pl];
+#pragma unroll
+            for (int j = 0; j < 16; j++) tot[j] += v[j] * mulq;
+          }
+          const uint4 rq = resq[cc / 16];
+          const unsigned rw[4] = {rq.x, rq.y, rq.z, rq.w};
+          unsigned packed[4];
+          const int pc = pass * W + cc;
+#pragma unroll
+          for (int j4 = 0; j4 < 4; j4++) {
+            const int4 pb = *reinterpret_cast<const int4*>(prm + pc + 4 * j4);
+            const int4 pa = *reinterpret_cast<const int4*>(prm + 64 + pc + 4 * j4);
+            const int4 pe = *reinterpret_cast<const int4*>(prm + 128 + pc + 4 * j4);
+            const int4 pm = *reinterpret_cast<const int4*>(prm + 192 + pc + 4 * j4);
+            int y0 = requant_lo((int)(tot[4 * j4 + 0] * (unsigned)pm.x + (unsigned)pb.x + low[4 * j4 + 0]), pa.x, pe.x, lo_clamp);
+            int y1 = requant_lo((int)(tot[4 * j4 + 1] * (unsigned)pm.y + (unsigned)pb.y + low[4 * j4 + 1]), pa.y, pe.y, lo_clamp);
+            int y2 = requant_lo((int)(tot[4 * j4 + 2] * (unsigned)pm.z + (unsigned)pb.z + low[4 * j4 + 2]), pa.z, pe.z, lo_clamp);
+            int y3 = requant_lo((int)(tot[4 * j4 + 3] * (unsigned)pm.w + (unsigned)pb.w + low[4 * j4 + 3]), pa.w, pe.w, lo_clamp);
+            if (has_res) {
+              // feature_writer.cl:124-127: the PE output is already an int8 (clamped) value; add the
+              // residual byte, clamp again (saturating pack), optional ReLU
+              const unsigned r4 = rw[j4];
+              y0 = max(res_lo, min(y0, hi_clamp) + ((int)(r4 << 24) >> 24));
+              y1 = max(res_lo, min(y1, hi_clamp) + ((int)(r4 << 16) >> 24));
+              y2 = max(res_lo, min(y2, hi_clamp) + ((int)(r4 << 8) >> 24));
+              y3 = max(res_lo, min(y3, hi_clamp) + ((int)r4 >> 24));
+            }
+            packed[j4] = pack_sat4(y0, y1, y2, y3);
+          }
+          *reinterpret_cast<uint4*>(stage + lane * EPI_ROW + cc) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+        }
+        if (pass == PASSES - 1) {
+          // accumulator buffer drained: hand it back to the MMA warp as early as possible
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar + 8 * buf);
+        } else {
+          __syncwarp();
+          load_residual(ncolp + W);   // prefetch the next pass's residual
+        }
+        // coalesced store of the finished int8 tile
+#pragma unroll
+        for (int it = 0; it < SEGS; it++) {
+          if (opix[it] >= 0 && n < c.N) {
+            const uint4 v = *reinterpret_cast<const uint4*>(stage + rl[it] * EPI_ROW + sg * 16);
+            int8_t* dst = c.y + opix[it] * c.yC + n;
+            const int nvalid = c.N - n;
+            if (nvalid >= 16) {
+              *reinterpret_cast<uint4*>(dst) = v;
+            } else {
+              const unsigned vw[4] = {v.x, v.y, v.z, v.w};
+              for (int e = 0; e < nvalid; e++) dst[e] = (int8_t)((vw[e >> 2] >> (8 * (e & 3))) & 0xff);
+            }
+          }
+        }
+        if (pass != PASSES - 1) __syncwarp();   // staging tile is reused by the next pass
       }
+      tphase[buf] ^= 1;
+      buf ^= 1;
     }
     if (dbg && lane == 0) {
       P.dbg[blockIdx.x * 8 + 5] = w_tfull;
@@ -524,6 +588,15 @@ EncodeTiledFn get_encode_fn(std::string* err) {
 
 int pick_bk(int Cp) { return (Cp % 128 == 0) ? 128 : 64; }
 
+// N tile: 256 for single-plane layers (one A tile feeds twice the MMA work; TMEM 2 x 256 columns),
+// 128 up to two planes, else 64 (TMEM: 2 buffers x planes x BN <= 512 columns)
+int pick_bn(int planes8, int N) {
+  static const bool allow256 = getenv("TF2B_MMA_BN256") == nullptr || atoi(getenv("TF2B_MMA_BN256")) != 0;
+  if (planes8 == 1 && N >= 256 && allow256) return 256;
+  if (planes8 <= 2 && N >= 128) return 128;
+  return 64;
+}
+
 // geometry shared by the support test, the tensor-map builder and the launcher
 void fill_geometry(MmaParams& P, const ConvParams& c, int planes8) {
   P.c = c;
@@ -532,7 +605,7 @@ void fill_geometry(MmaParams& P, const ConvParams& c, int planes8) {
   P.Cpm = (c.Cp + P.BK - 1) / P.BK * P.BK;
   P.kchunks = P.Cpm / P.BK;
   P.taps = c.k * c.k;
-  P.BN = (planes8 <= 2 && c.N >= 128) ? 128 : 64;
+  P.BN = pick_bn(planes8, c.N);
   P.Npad = c.Npad;
   P.n_tiles = (c.N + P.BN - 1) / P.BN;
   P.mode = (c.k == 1 && c.stride == 1 && c.pad == 0) ? 0 : 1;
@@ -561,7 +634,7 @@ void fill_geometry(MmaParams& P, const ConvParams& c, int planes8) {
   }
   P.b_bytes = P.BN * P.BK;
   const int stage_bytes = MMA_M * P.BK + planes8 * P.b_bytes;
-  int st = (184 * 1024) / stage_bytes;
+  int st = (176 * 1024) / stage_bytes;
   P.stages = st > MAX_STAGES ? MAX_STAGES : (st < 2 ? 2 : st);
   // instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): c_format S32 (2) at bit 4,
   // a/b format signed int8 (1) at bits 7 / 10, K-major A and B, N>>3 at bit 17, M>>4 at bit 24,
@@ -569,11 +642,14 @@ void fill_geometry(MmaParams& P, const ConvParams& c, int planes8) {
   P.idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(P.BN >> 3) << 17) | ((unsigned)(MMA_M >> 4) << 24);
   P.layout_type = (P.BK == 128) ? 2u : 4u;
   P.sbo16 = (unsigned)(8 * P.BK) >> 4;
+  P.d_ntiles = make_fastdiv(P.n_tiles);
+  P.d_tiles_w = make_fastdiv(P.tiles_w);
+  P.d_tiles_h = make_fastdiv(P.tiles_h);
 }
 
 }  // namespace
 
-int mma_bn() { return 128; }   // weight planes are padded to a multiple of this many rows
+int mma_bn() { return 256; }   // weight planes / params are padded to a multiple of this many rows
 int mma_pick_bk(int Cp) { return pick_bk(Cp); }
 
 bool mma_layer_supported(const tf2b_layer_desc& L, int in_pitch, int planes8) {
@@ -587,7 +663,7 @@ bool mma_layer_supported(const tf2b_layer_desc& L, int in_pitch, int planes8) {
   if (in_pitch % 16 != 0) return false;
   if (L.OW > 256 || L.k > 7) return false;
   // TMEM: two accumulator buffers of planes*BN columns
-  int BN = (planes8 <= 2 && L.N >= 128) ? 128 : 64;
+  int BN = pick_bn(planes8, L.N);
   if (2 * planes8 * BN > TMEM_COLS) return false;
   return true;
 }
@@ -655,9 +731,11 @@ cudaError_t launch_conv_mma(const ConvParams& c, const int8_t* /*wgt8*/, int pla
   const int stage_bytes = MMA_M * P.BK + planes8 * P.b_bytes;
   const size_t smem = (size_t)P.stages * stage_bytes + 1024;
   if (!attr_set) {
-    const int lim = 186 * 1024;
+    const int lim = 178 * 1024;
     cudaError_t e = cudaFuncSetAttribute(conv_mma_kernel<128, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_mma_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_mma_kernel<256, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_mma_kernel<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_mma_kernel<64, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_mma_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
     if (e != cudaSuccess) return e;
@@ -674,7 +752,10 @@ cudaError_t launch_conv_mma(const ConvParams& c, const int8_t* /*wgt8*/, int pla
     cudaMemsetAsync(dbg_dev, 0, sizeof(long long) * 8 * 148, stream);
     P.dbg = dbg_dev;
   }
-  if (P.BN == 128) {
+  if (P.BN == 256) {
+    if (P.mode == 0) conv_mma_kernel<256, 0><<<grid, NUM_THREADS, smem, stream>>>(P, *tp);
+    else conv_mma_kernel<256, 1><<<grid, NUM_THREADS, smem, stream>>>(P, *tp);
+  } else if (P.BN == 128) {
     if (P.mode == 0) conv_mma_kernel<128, 0><<<grid, NUM_THREADS, smem, stream>>>(P, *tp);
     else conv_mma_kernel<128, 1><<<grid, NUM_THREADS, smem, stream>>>(P, *tp);
   } else {
