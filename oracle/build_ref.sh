@@ -19,3 +19,8 @@ for net in RESNET50 GOOGLENET RESNET50_PRUNED; do
       -o "$out/libtf2ref_host_${lower}.so"
 done
 echo "built: $(ls "$out")"
+# the reference PE kernel (device/src/pe.cl) compiled as C behind the FIFO shim of ref_device/pe_harness.c
+dev="$ref/Runtime_Engine/cnn/device/src"
+/usr/bin/gcc -x c -std=gnu11 -O1 -fPIC -shared -w -DRESNET50 -I"$dev" -I"$host/inc" \
+    "$here/ref_device/pe_harness.c" -o "$out/libtf2ref_pe.so"
+echo "built: libtf2ref_pe.so"

@@ -6,14 +6,23 @@
  * legs may call it, and only as the checker / the timed CPU baseline.
  *
  * It is a plain-C restatement of the reference algorithm; every function cites the reference
- * file:line it follows (paths relative to the reference repo root).  Parity pinning: the reference
- * ships no integer golden vectors for this path (its Verify() is a float tolerance check and the
- * weights are not in the repo), so the restatement is pinned against the reference's OWN sources
- * compiled here (oracle/build_ref.sh -> oracle/_ref/): the host loaders (Get_real, filter_trans,
- * feature_trans, LoadModel, Quantization) compiled unmodified, and the OpenCL device kernels
- * (pe.cl, relu.cl, pool.cl, pool_tail.cl, feature_writer.cl, full_size_pool.cl, ...) compiled as C
- * behind a FIFO shim and run as a single-layer network.  Vectors produced that way are committed
- * under tests/golden/ with the generating script.
+ * file:line it follows (paths relative to the reference repo root).
+ *
+ * Parity pinning.  The reference ships no integer golden vectors for this path (its Verify() is a
+ * float tolerance check and the weights are not in the repository), so the restatement is pinned
+ * against the reference's OWN sources compiled here by oracle/build_ref.sh into oracle/_ref/:
+ *   - host loaders (model_loader.cpp, quantization.cpp, input_loader.cpp) compiled unmodified:
+ *     Get_real, filter_trans, feature_trans, LoadModel, Quantization — equal bit for bit on
+ *     ResNet50 / GoogLeNet / pruned ResNet50 (tests/test_formats.py, tests/golden/loader_golden.json);
+ *   - the PE kernel device/src/pe.cl compiled as C behind a FIFO shim (oracle/ref_device/
+ *     pe_harness.c): MUL exhaustively (65 536 cases) and PeFunction's MAC, bias seed, int32
+ *     wrap-around, requantisation and clamp for 1x1 and 3x3 mode reductions of up to 128 steps —
+ *     committed as tests/golden/pe_golden.npz (tests/test_pe_golden.py).
+ * NOT re-executed against compiled device code in this repository (restated from the cited source
+ * lines; SURVEY.md 8c reports a one-off probe that did): the pooling / stride-2 sub-sampling of
+ * pool.cl + pool_tail.cl, the residual add of feature_writer.cl, the global average of
+ * full_size_pool.cl and the convolution geometry of sequencer.cl / retriever.cl.  For those steps
+ * parity is "restated, unpinned".
  *
  * Layouts follow the reference host side: features [C][H][W] int8, codes [N][C][FH][FW] uint8.
  */
