@@ -94,3 +94,29 @@ def test_errors_do_not_exit():
     with pytest.raises(Tf2bError):
         Runner(nw).run_host(np.zeros((2, 16, 8, 8), np.int8))  # more images than max_images
     nw.CleanUp()
+
+
+def test_weight_blob_roundtrip():
+    """The init-time broadcast payload: export from a loaded engine, import into a fresh one built
+    from the same tables (no model file), identical results on both kernel families."""
+    import torch
+    from tf2_b200.network import NetWork, Runner
+    rng = np.random.default_rng(21)
+    net = nets.chain((64, 14, 14), [dict(N=256, k=1, relu=0), dict(N=64, k=1, src=-1), dict(N=64, k=3, pad=1),
+                                    dict(N=256, k=1, relu=0, add=0, add_relu=1)])
+    x = H.random_input(rng, 64, 14, 14, nonneg=False, B=2)
+    model = H.random_model(net, rng, x)
+    a = NetWork(net, 0)
+    a.InitFromCodes(model, None, max_images=2)
+    blob = torch.empty(a.weight_blob_bytes(), dtype=torch.uint8, device="cuda")
+    a.export_weight_blob(blob.data_ptr())
+    ya = Runner(a).run_device(torch.from_numpy(x).cuda()).cpu().numpy()
+    for variant in (capi.VARIANT_AUTO, capi.VARIANT_SHIFT):
+        b = NetWork(net, 0)
+        b.InitFromBlob(blob.data_ptr(), max_images=2, variant=variant)
+        yb = Runner(b).run_device(torch.from_numpy(x).cuda()).cpu().numpy()
+        assert np.array_equal(ya, yb)
+        if variant == capi.VARIANT_AUTO:
+            assert b.layer_kernels() == a.layer_kernels()
+        b.CleanUp()
+    a.CleanUp()

@@ -21,6 +21,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <string>
 
 #include "../../include/tf2b200.h"
@@ -285,6 +286,12 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
   tc_fence_after();
   const unsigned tmem_base = tmem_base_slot;
   const int acc_cols = P.planes * BN;  // TMEM columns of one accumulator buffer
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor
+  // prefetch, row LUT) overlaps the tail of the previous layer's kernel; from here on this grid
+  // reads what that kernel wrote, so wait for it to complete and flush.  The next layer's grid may
+  // be scheduled as soon as SMs free up (it blocks at its own wait).
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp == 0) {
     // ===================================================== TMA producer (whole warp, one elected lane issues)
@@ -752,15 +759,28 @@ cudaError_t launch_conv_mma(const ConvParams& c, const int8_t* /*wgt8*/, int pla
     cudaMemsetAsync(dbg_dev, 0, sizeof(long long) * 8 * 148, stream);
     P.dbg = dbg_dev;
   }
-  if (P.BN == 256) {
-    if (P.mode == 0) conv_mma_kernel<256, 0><<<grid, NUM_THREADS, smem, stream>>>(P, *tp);
-    else conv_mma_kernel<256, 1><<<grid, NUM_THREADS, smem, stream>>>(P, *tp);
-  } else if (P.BN == 128) {
-    if (P.mode == 0) conv_mma_kernel<128, 0><<<grid, NUM_THREADS, smem, stream>>>(P, *tp);
-    else conv_mma_kernel<128, 1><<<grid, NUM_THREADS, smem, stream>>>(P, *tp);
-  } else {
-    if (P.mode == 0) conv_mma_kernel<64, 0><<<grid, NUM_THREADS, smem, stream>>>(P, *tp);
-    else conv_mma_kernel<64, 1><<<grid, NUM_THREADS, smem, stream>>>(P, *tp);
+  {
+    static const bool use_pdl = getenv("TF2B_MMA_PDL") == nullptr || atoi(getenv("TF2B_MMA_PDL")) != 0;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = use_pdl ? 1 : 0;
+    cudaError_t le;
+    if (P.BN == 256) {
+      le = P.mode == 0 ? cudaLaunchKernelEx(&cfg, conv_mma_kernel<256, 0>, P, *tp) : cudaLaunchKernelEx(&cfg, conv_mma_kernel<256, 1>, P, *tp);
+    } else if (P.BN == 128) {
+      le = P.mode == 0 ? cudaLaunchKernelEx(&cfg, conv_mma_kernel<128, 0>, P, *tp) : cudaLaunchKernelEx(&cfg, conv_mma_kernel<128, 1>, P, *tp);
+    } else {
+      le = P.mode == 0 ? cudaLaunchKernelEx(&cfg, conv_mma_kernel<64, 0>, P, *tp) : cudaLaunchKernelEx(&cfg, conv_mma_kernel<64, 1>, P, *tp);
+    }
+    if (le != cudaSuccess) return le;
   }
   if (debug) {
     long long h[8 * 148];
