@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -56,6 +57,7 @@ struct LayerState {
   int Npad_m = 0, Kp_m = 0, planes_m = 0;
   int plane_shift_m[tf2b::kMaxPlanes] = {0, 0, 0, 0};
   int low_plane_m = -1;  // index of the plane that holds absolute shifts 0..6 (not scaled by 2^nshift), or -1
+  int fast_requant = 0;  // range analysis: no int32 intermediate of pe.cl:191-194 can wrap for this layer
   std::vector<int8_t> h_w8;
   std::vector<uint8_t> h_nshift_m;  // per-channel base shift of the tensor-core planes
   bool mma_ok = false;
@@ -72,7 +74,7 @@ struct LayerState {
 
 struct BlobLayerMeta {  // fixed-size, trivially copyable: travels inside the weight blob
   int32_t loaded, Cp, Cp_m, Npad_s, Kp_s, planes_s, plane_shift_s[4], plane_neg_s[4];
-  int32_t Npad_m, Kp_m, planes_m, plane_shift_m[4], mma_ok, Npar, low_plane_m, nshift_m_len;
+  int32_t Npad_m, Kp_m, planes_m, plane_shift_m[4], mma_ok, Npar, low_plane_m, nshift_m_len, fast_requant;
   int64_t off_w16, off_w8, off_bias, off_alpha, off_beta, off_nshift, off_nshift_m;
 };
 
@@ -262,6 +264,20 @@ static int prepare_layer(tf2b_net* net, LayerState& S, const uint8_t* codes,
       for (int n = 0; n < N; n++) S.h_nshift_m[n] = bm[n];
       S.mma_ok = true;
     }
+  }
+  // Range analysis for the fused requantisation of the tensor-core epilogue.  |acc| <= |bias| +
+  // 128 * sum_k 2^shift_k (capped at 2^31: a wrapped accumulator is still an int32), a = acc*alpha >> 20,
+  // s = a + beta, then (s >> 14 + 1) >> 1.  If |a| + |beta| + 2^14 < 2^31 for every channel nothing wraps and
+  // ((a + beta) >> 14 + 1) >> 1 == (acc*alpha + ((beta + 2^14) << 20)) >> 35 exactly.
+  S.fast_requant = 1;
+  for (int n = 0; n < N && S.fast_requant; n++) {
+    long double sum = fabsl((long double)params[n].bias);
+    const uint8_t* cn = codes + (size_t)n * C * k * k;
+    for (int i = 0; i < C * k * k; i++)
+      if (!(cn[i] & 0x40)) sum += 128.0L * (long double)(1ull << (cn[i] & 0x1f));
+    if (sum > 2147483648.0L) sum = 2147483648.0L;
+    const long double amax = sum * fabsl((long double)params[n].alpha) / 1048576.0L + 1.0L;
+    if (amax + fabsl((long double)params[n].beta) + 16384.0L + 2.0L >= 2147483647.0L) S.fast_requant = 0;
   }
   S.Npar = std::max(S.Npad_s, S.Npad_m);
   S.h_bias.assign(S.Npar, 0);
@@ -511,6 +527,7 @@ static ConvParams conv_params(tf2b_net* net, const LayerState& S, int B, int8_t*
   p.beta = reinterpret_cast<const int32_t*>(net->arena + S.off_beta);
   p.nshift = net->arena + (mma ? S.off_nshift_m : S.off_nshift);
   p.low_plane = mma ? S.low_plane_m : -1;
+  p.fast_requant = mma ? S.fast_requant : 0;
   p.acc_dump = nullptr;
   p.B = B; p.IH = ti.H; p.IW = ti.W; p.Cp = mma ? S.Cp_m : S.Cp; p.xC = net->tpitch[d.in_tensor];
   p.OH = d.OH; p.OW = d.OW; p.N = d.N; p.yC = dstC; p.rC = resC;
@@ -787,7 +804,7 @@ int tf2b_export_weight_blob(tf2b_net* net, void* dev_dst, void* stream) {
     }
     m.off_w16 = S.off_w16; m.off_w8 = S.off_w8; m.off_bias = S.off_bias; m.off_alpha = S.off_alpha;
     m.off_beta = S.off_beta; m.off_nshift = S.off_nshift; m.off_nshift_m = S.off_nshift_m;
-    m.low_plane_m = S.low_plane_m; m.nshift_m_len = (int32_t)S.h_nshift_m.size();
+    m.low_plane_m = S.low_plane_m; m.nshift_m_len = (int32_t)S.h_nshift_m.size(); m.fast_requant = S.fast_requant;
     memcpy(hdr.data() + 16 + l * sizeof m, &m, sizeof m);
   }
   cudaStream_t st = (cudaStream_t)stream;
@@ -838,6 +855,7 @@ int tf2b_import_weight_blob(tf2b_net* net, const void* dev_src, void* stream) {
     CUDA_TRY(net, pull(S.h_nshift, (size_t)round_up(S.Npar, 16), m.off_nshift));
     CUDA_TRY(net, pull(S.h_nshift_m, (size_t)m.nshift_m_len, m.off_nshift_m));
     S.low_plane_m = m.low_plane_m;
+    S.fast_requant = m.fast_requant;
   }
   return TF2B_OK;
 }

@@ -30,6 +30,8 @@ struct ConvParams {
   int plane_shift[kMaxPlanes];  // plane p contributes (sum_p << plane_shift[p])
   int plane_neg[kMaxPlanes];    // 1: plane multiplies the int8-negated activations (pe.cl:32-34)
   int low_plane;                // tensor-core path: plane added without the per-channel 2^nshift, or -1
+  int fast_requant;             // load-time range analysis proved that no int32 intermediate of the
+                                // requantisation can wrap: the fused 64-bit form is exact
 };
 
 // pe.cl:185-203 — requantisation of one accumulator (int64 product, arithmetic shifts, clamp).

@@ -37,6 +37,8 @@ constexpr int NUM_THREADS = 32 * (2 + NUM_EPI_WARPS);
 constexpr int MAX_STAGES = 8;
 constexpr int TMEM_COLS = 512;
 constexpr int EPI_ROW = 48;   // bytes per staging row: 32 data + 16 pad (conflict-free 16-byte accesses)
+constexpr int EPI_WARP_BYTES = 32 * EPI_ROW + 6 * 64 * 4;   // staging tile + params of one epilogue warp
+constexpr int EPI_BYTES = NUM_EPI_WARPS * EPI_WARP_BYTES;
 
 // x / d for 0 <= x, d < 2^20:  (x * ceil(2^40/d)) >> 40   (exact in that range)
 struct FastDiv {
@@ -234,7 +236,10 @@ __device__ __forceinline__ int requant_lo(int32_t acc, int32_t alpha, int32_t be
   return max(lo, y);
 }
 
-template <int BN, int MODE>
+// EPI < 0: exact requantisation, every option decided at run time.  EPI >= 0: fused 64-bit
+// requantisation (range-analysed layers) specialised on bit0 = second scaled plane, bit1 = low plane,
+// bit2 = residual operand.
+template <int BN, int MODE, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ TmapPair maps) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -246,8 +251,6 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
 
   __shared__ __align__(8) unsigned long long bars[2 * MAX_STAGES + 4];
   __shared__ unsigned tmem_base_slot;
-  __shared__ __align__(16) unsigned char epi_stage[NUM_EPI_WARPS][32 * EPI_ROW];  // int8 staging tiles
-  __shared__ __align__(16) int epi_params[NUM_EPI_WARPS][4 * 64];                 // bias/alpha/beta/2^nshift
   __shared__ unsigned row_lut[MMA_M];   // box mode: row -> (wl | hl<<8 | nl<<16 | inbox<<24)
   const unsigned full_bar = smem_u32(&bars[0]);                  // [stages]
   const unsigned empty_bar = smem_u32(&bars[MAX_STAGES]);        // [stages]
@@ -375,6 +378,10 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
     // recombine planes -> requantise -> 16-byte st.shared into a private [32][W] staging tile;
     // (3) re-read the staging tile with lanes along the channel dimension so every global access
     // covers whole 32-byte sectors: residual add, 16-byte stores.  No cross-warp synchronisation.
+    constexpr bool FAST = EPI >= 0;
+    constexpr bool CT_TWO = FAST && (EPI & 1);
+    constexpr bool CT_LOW = FAST && (EPI & 2);
+    constexpr bool CT_RES = FAST && (EPI & 4);
     constexpr int WT = BN / 4;            // columns per warp: 16, 32 or 64
     constexpr int W = WT > 32 ? 32 : WT;  // columns per pass (staging tile width)
     constexpr int PASSES = WT / W;        // 1, or 2 for BN = 256
@@ -386,8 +393,10 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
     const ConvParams& c = P.c;
     const int M = c.B * c.OH * c.OW;
     const int lo_clamp = c.relu ? 0 : -128;   // relu.cl:54 folded into the clamp of pe.cl:194
-    unsigned char* stage = epi_stage[ew];
-    int* prm = epi_params[ew];            // [4][64]: bias, alpha, beta, 2^nshift
+    // epilogue scratch lives behind the pipeline stages in dynamic shared memory
+    unsigned char* epi_base = smem_raw + (smem_base - smem_u32(smem_raw)) + P.stages * stage_bytes;
+    unsigned char* stage = epi_base + ew * EPI_WARP_BYTES;                         // int8 staging tile [32][EPI_ROW]
+    int* prm = reinterpret_cast<int*>(stage + 32 * EPI_ROW);                       // [6][64] per-channel params
     // coalesced mapping (constant per thread): iteration it -> row rl[it], 16-byte segment sg
     const int sg = lane % SEGS;
     int rl[SEGS];
@@ -397,7 +406,7 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
       rl[it] = it * ROWS_PER_IT + lane / SEGS;
       lut[it] = MODE == 1 ? row_lut[quarter * 32 + rl[it]] : 0u;
     }
-    const bool has_res = c.r != nullptr;
+    const bool has_res = FAST ? CT_RES : (c.r != nullptr);
     const int hi_clamp = 127;
     const int res_lo = c.add_relu ? 0 : -128;   // feature_writer.cl:126 folded into the final clamp
     const int my_row = quarter * 32 + lane;     // accumulator row (TMEM lane) of this thread
@@ -407,6 +416,37 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
     int cached_ncol0 = -1;
     const bool dbg = P.dbg != nullptr && warp == 2;
     long long w_tfull = 0, t_start = clock64();
+    // residual operand of this thread's accumulator row: pixel of a tile, and a 16-byte-segment loader
+    auto res_pixel = [&](const TileCoord& tc, bool& valid, long long& pix) {
+      if (MODE == 0) {
+        const int m = tc.m0 + my_row;
+        valid = m < M;
+        pix = m;
+      } else {
+        const int ow = tc.ow0 + (int)(my_lut & 0xff), oh = tc.oh0 + (int)((my_lut >> 8) & 0xff);
+        const int b = tc.b0 + (int)((my_lut >> 16) & 0xff);
+        valid = (my_lut >> 24) && (ow < c.OW) && (oh < c.OH) && (b < c.B);
+        pix = ((long long)b * c.OH + oh) * c.OW + ow;
+      }
+    };
+    auto load_res = [&](bool valid, long long pix, int ncolp, uint4 (&dst)[SEGS]) {
+#pragma unroll
+      for (int q = 0; q < SEGS; q++) dst[q] = make_uint4(0, 0, 0, 0);
+      if (has_res && valid) {
+        const int8_t* rp = c.r + pix * c.rC + ncolp;
+#pragma unroll
+        for (int q = 0; q < SEGS; q++) {
+          const int nq = ncolp + 16 * q;
+          if (nq + 16 <= c.N) {
+            dst[q] = __ldg(reinterpret_cast<const uint4*>(rp + 16 * q));
+          } else if (nq < c.N) {   // ragged channel tail: byte loads
+            unsigned w4[4] = {0, 0, 0, 0};
+            for (int e = 0; e < c.N - nq; e++) w4[e >> 2] |= (unsigned)(unsigned char)rp[16 * q + e] << (8 * (e & 3));
+            dst[q] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+          }
+        }
+      }
+    };
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(P, tile);
       const int ncolw = t.n0 + slice * WT;        // first output channel of this warp
@@ -416,28 +456,28 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
         cached_ncol0 = ncolw;
         for (int i = lane; i < WT; i += 32) {
           const int nn = ncolw + i;
+          const int be = __ldg(c.beta + nn);
+          const int nsh = (int)__ldg(c.nshift + nn);
           prm[i] = __ldg(c.bias + nn);
           prm[64 + i] = __ldg(c.alpha + nn);
-          prm[128 + i] = __ldg(c.beta + nn);
-          prm[192 + i] = 1 << (int)__ldg(c.nshift + nn);   // (x << s) == x * 2^s  (mod 2^32)
+          if (FAST) {
+            // ((a + beta) >> 14 + 1) >> 1 == (acc*alpha + ((beta + 2^14) << 20)) >> 35 when nothing
+            // wraps (checked per layer at load time, api.cu range analysis)
+            const long long b64 = ((long long)be + 16384ll) << 20;
+            prm[128 + i] = (int)(unsigned)(b64 & 0xffffffffll);
+            prm[192 + i] = (int)(b64 >> 32);
+          } else {
+            prm[128 + i] = be;
+          }
+          prm[256 + i] = 1 << nsh;                                   // (x << s) == x * 2^s  (mod 2^32)
+          prm[320 + i] = (nsh + 7 < 32) ? (1 << (nsh + 7)) : 0;      // second plane: x * 2^(s+7)
         }
       }
       // ---- (1b) this thread's accumulator row -> pixel (for the residual), and the pixels of its
       //           (row, segment) pairs in the coalesced store mapping
       bool rvalid = false;
       long long rpix = 0;
-      if (has_res) {
-        if (MODE == 0) {
-          const int m = t.m0 + my_row;
-          rvalid = m < M;
-          rpix = m;
-        } else {
-          const int ow = t.ow0 + (int)(my_lut & 0xff), oh = t.oh0 + (int)((my_lut >> 8) & 0xff);
-          const int b = t.b0 + (int)((my_lut >> 16) & 0xff);
-          rvalid = (my_lut >> 24) && (ow < c.OW) && (oh < c.OH) && (b < c.B);
-          rpix = ((long long)b * c.OH + oh) * c.OW + ow;
-        }
-      }
+      if (has_res) res_pixel(t, rvalid, rpix);
       long long opix[SEGS];
 #pragma unroll
       for (int it = 0; it < SEGS; it++) {
@@ -455,27 +495,10 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
         }
         opix[it] = valid ? pix : -1;
       }
-      // residual of this thread's own row for the first pass (whole 32-byte sectors)
+      // residual of this thread's own row for the first pass (whole 32-byte sectors), requested
+      // before the accumulators are waited for
       uint4 resq[SEGS];
-      auto load_residual = [&](int ncolp) {
-#pragma unroll
-        for (int q = 0; q < SEGS; q++) resq[q] = make_uint4(0, 0, 0, 0);
-        if (has_res && rvalid) {
-          const int8_t* rp = c.r + rpix * c.rC + ncolp;
-#pragma unroll
-          for (int q = 0; q < SEGS; q++) {
-            const int nq = ncolp + 16 * q;
-            if (nq + 16 <= c.N) {
-              resq[q] = __ldg(reinterpret_cast<const uint4*>(rp + 16 * q));
-            } else if (nq < c.N) {   // ragged channel tail: byte loads
-              unsigned w4[4] = {0, 0, 0, 0};
-              for (int e = 0; e < c.N - nq; e++) w4[e >> 2] |= (unsigned)(unsigned char)rp[16 * q + e] << (8 * (e & 3));
-              resq[q] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
-            }
-          }
-        }
-      };
-      load_residual(ncolw);
+      load_res(rvalid, rpix, ncolw, resq);
       __syncwarp();
       // ---- (2) accumulators -> requantise (+ residual) -> int8 staging tile -> (3) coalesced store
       mbar_wait_timed(tfull_bar + 8 * buf, tphase[buf], w_tfull, dbg);
@@ -487,22 +510,31 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
         const unsigned t_row = tmem_base + ((unsigned)(quarter * 32) << 16) + buf * acc_cols + slice * WT + pass * W;
 #pragma unroll
         for (int cc = 0; cc < W; cc += 16) {
-          unsigned tot[16], low[16];
+          unsigned tot[16], low[16], tot1[16];
+          const bool two = CT_TWO;                                          // a second scaled plane
+          const bool has_low = FAST ? CT_LOW : (P.c.low_plane >= 0);
           tmem_ld16(t_row + cc, tot);
-          if (P.c.low_plane >= 0) tmem_ld16(t_row + P.c.low_plane * BN + cc, low);
+          if (has_low) tmem_ld16(t_row + P.c.low_plane * BN + cc, low);
+          if (two) tmem_ld16(t_row + BN + cc, tot1);
           tmem_ld_wait();
-          if (P.c.low_plane < 0) {
+          if (!has_low) {
 #pragma unroll
             for (int j = 0; j < 16; j++) low[j] = 0;
           }
-          for (int pl = 1; pl < P.planes; pl++) {
-            if (pl == P.c.low_plane) continue;
-            unsigned v[16];
-            tmem_ld16(t_row + pl * BN + cc, v);
-            tmem_ld_wait();
-            const unsigned mulq = 1u << P.plane8_shift[pl];
+          if (!two) {
 #pragma unroll
-            for (int j = 0; j < 16; j++) tot[j] += v[j] * mulq;
+            for (int j = 0; j < 16; j++) tot1[j] = 0;
+          }
+          if (!FAST) {
+            for (int pl = 1; pl < P.planes; pl++) {
+              if (pl == P.c.low_plane) continue;
+              unsigned v[16];
+              tmem_ld16(t_row + pl * BN + cc, v);
+              tmem_ld_wait();
+              const unsigned mulq = 1u << P.plane8_shift[pl];
+#pragma unroll
+              for (int j = 0; j < 16; j++) tot[j] += v[j] * mulq;
+            }
           }
           const uint4 rq = resq[cc / 16];
           const unsigned rw[4] = {rq.x, rq.y, rq.z, rq.w};
@@ -513,21 +545,45 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
             const int4 pb = *reinterpret_cast<const int4*>(prm + pc + 4 * j4);
             const int4 pa = *reinterpret_cast<const int4*>(prm + 64 + pc + 4 * j4);
             const int4 pe = *reinterpret_cast<const int4*>(prm + 128 + pc + 4 * j4);
-            const int4 pm = *reinterpret_cast<const int4*>(prm + 192 + pc + 4 * j4);
-            int y0 = requant_lo((int)(tot[4 * j4 + 0] * (unsigned)pm.x + (unsigned)pb.x + low[4 * j4 + 0]), pa.x, pe.x, lo_clamp);
-            int y1 = requant_lo((int)(tot[4 * j4 + 1] * (unsigned)pm.y + (unsigned)pb.y + low[4 * j4 + 1]), pa.y, pe.y, lo_clamp);
-            int y2 = requant_lo((int)(tot[4 * j4 + 2] * (unsigned)pm.z + (unsigned)pb.z + low[4 * j4 + 2]), pa.z, pe.z, lo_clamp);
-            int y3 = requant_lo((int)(tot[4 * j4 + 3] * (unsigned)pm.w + (unsigned)pb.w + low[4 * j4 + 3]), pa.w, pe.w, lo_clamp);
+            const int4 pm = *reinterpret_cast<const int4*>(prm + 256 + pc + 4 * j4);
+            const int bb[4] = {pb.x, pb.y, pb.z, pb.w}, aa[4] = {pa.x, pa.y, pa.z, pa.w};
+            const int ee[4] = {pe.x, pe.y, pe.z, pe.w}, mm[4] = {pm.x, pm.y, pm.z, pm.w};
+            int yy[4];
+            if (FAST) {
+              const int4 ph = *reinterpret_cast<const int4*>(prm + 192 + pc + 4 * j4);
+              const int hh[4] = {ph.x, ph.y, ph.z, ph.w};
+              int m1[4] = {0, 0, 0, 0};
+              if (two) {
+                const int4 pq = *reinterpret_cast<const int4*>(prm + 320 + pc + 4 * j4);
+                m1[0] = pq.x; m1[1] = pq.y; m1[2] = pq.z; m1[3] = pq.w;
+              }
+#pragma unroll
+              for (int u = 0; u < 4; u++) {
+                const int j = 4 * j4 + u;
+                unsigned a32 = tot[j] * (unsigned)mm[u] + (unsigned)bb[u];
+                if (two) a32 = tot1[j] * (unsigned)m1[u] + a32;
+                if (has_low) a32 += low[j];
+                const long long b64 = ((long long)hh[u] << 32) | (unsigned)ee[u];
+                const long long t = (long long)(int)a32 * (long long)aa[u] + b64;   // IMAD.WIDE with 64-bit addend
+                yy[u] = max(lo_clamp, (int)(t >> 35));
+              }
+            } else {
+#pragma unroll
+              for (int u = 0; u < 4; u++) {
+                const int j = 4 * j4 + u;
+                yy[u] = requant_lo((int)(tot[j] * (unsigned)mm[u] + (unsigned)bb[u] + low[j]), aa[u], ee[u], lo_clamp);
+              }
+            }
             if (has_res) {
               // feature_writer.cl:124-127: the PE output is already an int8 (clamped) value; add the
               // residual byte, clamp again (saturating pack), optional ReLU
               const unsigned r4 = rw[j4];
-              y0 = max(res_lo, min(y0, hi_clamp) + ((int)(r4 << 24) >> 24));
-              y1 = max(res_lo, min(y1, hi_clamp) + ((int)(r4 << 16) >> 24));
-              y2 = max(res_lo, min(y2, hi_clamp) + ((int)(r4 << 8) >> 24));
-              y3 = max(res_lo, min(y3, hi_clamp) + ((int)r4 >> 24));
+              yy[0] = max(res_lo, min(yy[0], hi_clamp) + ((int)(r4 << 24) >> 24));
+              yy[1] = max(res_lo, min(yy[1], hi_clamp) + ((int)(r4 << 16) >> 24));
+              yy[2] = max(res_lo, min(yy[2], hi_clamp) + ((int)(r4 << 8) >> 24));
+              yy[3] = max(res_lo, min(yy[3], hi_clamp) + ((int)r4 >> 24));
             }
-            packed[j4] = pack_sat4(y0, y1, y2, y3);
+            packed[j4] = pack_sat4(yy[0], yy[1], yy[2], yy[3]);
           }
           *reinterpret_cast<uint4*>(stage + lane * EPI_ROW + cc) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
         }
@@ -538,7 +594,7 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
           if (lane == 0) mbar_arrive(tempty_bar + 8 * buf);
         } else {
           __syncwarp();
-          load_residual(ncolp + W);   // prefetch the next pass's residual
+          load_res(rvalid, rpix, ncolp + W, resq);   // prefetch the next pass's residual
         }
         // coalesced store of the finished int8 tile
 #pragma unroll
@@ -641,7 +697,7 @@ void fill_geometry(MmaParams& P, const ConvParams& c, int planes8) {
   }
   P.b_bytes = P.BN * P.BK;
   const int stage_bytes = MMA_M * P.BK + planes8 * P.b_bytes;
-  int st = (176 * 1024) / stage_bytes;
+  int st = (224 * 1024 - EPI_BYTES) / stage_bytes;
   P.stages = st > MAX_STAGES ? MAX_STAGES : (st < 2 ? 2 : st);
   // instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): c_format S32 (2) at bit 4,
   // a/b format signed int8 (1) at bits 7 / 10, K-major A and B, N>>3 at bit 17, M>>4 at bit 24,
@@ -736,18 +792,31 @@ cudaError_t launch_conv_mma(const ConvParams& c, const int8_t* /*wgt8*/, int pla
   fill_geometry(P, c, planes8);
   for (int i = 0; i < kMaxPlanes; i++) P.plane8_shift[i] = plane8_shift[i];
   const int stage_bytes = MMA_M * P.BK + planes8 * P.b_bytes;
-  const size_t smem = (size_t)P.stages * stage_bytes + 1024;
+  const size_t smem = (size_t)P.stages * stage_bytes + EPI_BYTES + 1024;
+  using KernelFn = void (*)(MmaParams, TmapPair);
+#define TF2B_EPI_ROW(BN_, MODE_)                                                                              \
+  {conv_mma_kernel<BN_, MODE_, -1>, conv_mma_kernel<BN_, MODE_, 0>, conv_mma_kernel<BN_, MODE_, 1>,            \
+   conv_mma_kernel<BN_, MODE_, 2>,  conv_mma_kernel<BN_, MODE_, 3>, conv_mma_kernel<BN_, MODE_, 4>,            \
+   conv_mma_kernel<BN_, MODE_, 5>,  conv_mma_kernel<BN_, MODE_, 6>, conv_mma_kernel<BN_, MODE_, 7>}
+  static const KernelFn table[3][2][9] = {{TF2B_EPI_ROW(64, 0), TF2B_EPI_ROW(64, 1)},
+                                          {TF2B_EPI_ROW(128, 0), TF2B_EPI_ROW(128, 1)},
+                                          {TF2B_EPI_ROW(256, 0), TF2B_EPI_ROW(256, 1)}};
+#undef TF2B_EPI_ROW
   if (!attr_set) {
-    const int lim = 178 * 1024;
-    cudaError_t e = cudaFuncSetAttribute(conv_mma_kernel<128, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_mma_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_mma_kernel<256, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_mma_kernel<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_mma_kernel<64, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_mma_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
-    if (e != cudaSuccess) return e;
+    const int lim = 226 * 1024;
+    for (int a = 0; a < 3; a++)
+      for (int b = 0; b < 2; b++)
+        for (int f = 0; f < 9; f++) {
+          cudaError_t e = cudaFuncSetAttribute(table[a][b][f], cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+          if (e != cudaSuccess) return e;
+        }
     attr_set = true;
   }
+  // the fast requantisation needs at most two scaled planes (+ the optional low plane)
+  const int scaled_planes = planes8 - (c.low_plane >= 0 ? 1 : 0);
+  const bool fast = c.fast_requant != 0 && scaled_planes <= 2 && (c.low_plane < 0 || c.low_plane == planes8 - 1);
+  const int epi = fast ? (1 + ((scaled_planes == 2 ? 1 : 0) | (c.low_plane >= 0 ? 2 : 0) | (c.r != nullptr ? 4 : 0))) : 0;
+  const KernelFn kfn = table[P.BN == 256 ? 2 : (P.BN == 128 ? 1 : 0)][P.mode][epi];
   const int num_tiles = P.m_tiles * P.n_tiles;
   const int grid = num_tiles < num_sms ? num_tiles : num_sms;
   const TmapPair* tp = reinterpret_cast<const TmapPair*>(tmaps);
@@ -772,14 +841,7 @@ cudaError_t launch_conv_mma(const ConvParams& c, const int8_t* /*wgt8*/, int pla
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = use_pdl ? 1 : 0;
-    cudaError_t le;
-    if (P.BN == 256) {
-      le = P.mode == 0 ? cudaLaunchKernelEx(&cfg, conv_mma_kernel<256, 0>, P, *tp) : cudaLaunchKernelEx(&cfg, conv_mma_kernel<256, 1>, P, *tp);
-    } else if (P.BN == 128) {
-      le = P.mode == 0 ? cudaLaunchKernelEx(&cfg, conv_mma_kernel<128, 0>, P, *tp) : cudaLaunchKernelEx(&cfg, conv_mma_kernel<128, 1>, P, *tp);
-    } else {
-      le = P.mode == 0 ? cudaLaunchKernelEx(&cfg, conv_mma_kernel<64, 0>, P, *tp) : cudaLaunchKernelEx(&cfg, conv_mma_kernel<64, 1>, P, *tp);
-    }
+    cudaError_t le = cudaLaunchKernelEx(&cfg, kfn, P, *tp);
     if (le != cudaSuccess) return le;
   }
   if (debug) {
