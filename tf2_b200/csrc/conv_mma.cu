@@ -71,6 +71,7 @@ struct MmaParams {
   unsigned layout_type;     // UMMA smem layout type (2 = SWIZZLE_128B, 4 = SWIZZLE_64B)
   long long* dbg;           // optional per-CTA cycle counters [grid][8] (TF2B_MMA_DEBUG), else nullptr
   FastDiv d_ntiles, d_tiles_w, d_tiles_h;
+  int direct256;            // output/residual rows are 32-byte aligned: row-per-lane 32-byte accesses
 };
 
 struct TmapPair {
@@ -217,6 +218,18 @@ __device__ __forceinline__ TileCoord decode_tile(const MmaParams& P, int tile) {
     t.b0 = bt * P.tn;
   }
   return t;
+}
+
+// 32-byte global accesses (LDG/STG.E.ENL2.256): one whole sector per lane and instruction
+__device__ __forceinline__ void ldg256(const void* p, uint4& lo, uint4& hi) {
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w)
+               : "l"(p));
+}
+__device__ __forceinline__ void stg256(void* p, const uint4& lo, const uint4& hi) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w),
+               "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w)
+               : "memory");
 }
 
 // saturating pack of four int32 into int8x4 (y0 in byte 0): cvt.pack.sat clamps to [-128,127]
@@ -434,6 +447,10 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
       for (int q = 0; q < SEGS; q++) dst[q] = make_uint4(0, 0, 0, 0);
       if (has_res && valid) {
         const int8_t* rp = c.r + pix * c.rC + ncolp;
+        if (SEGS == 2 && P.direct256 && ncolp + 32 <= c.N) {
+          ldg256(rp, dst[0], dst[SEGS - 1]);
+          return;
+        }
 #pragma unroll
         for (int q = 0; q < SEGS; q++) {
           const int nq = ncolp + 16 * q;
@@ -477,7 +494,9 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
       //           (row, segment) pairs in the coalesced store mapping
       bool rvalid = false;
       long long rpix = 0;
-      if (has_res) res_pixel(t, rvalid, rpix);
+      res_pixel(t, rvalid, rpix);
+      const bool dvalid = rvalid;
+      const long long dpix = rpix;
       long long opix[SEGS];
 #pragma unroll
       for (int it = 0; it < SEGS; it++) {
@@ -503,6 +522,8 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
       // ---- (2) accumulators -> requantise (+ residual) -> int8 staging tile -> (3) coalesced store
       mbar_wait_timed(tfull_bar + 8 * buf, tphase[buf], w_tfull, dbg);
       tc_fence_after();
+      const bool direct = (SEGS == 2) && P.direct256 != 0;
+      uint4 out_lo = make_uint4(0, 0, 0, 0), out_hi = make_uint4(0, 0, 0, 0);
 #pragma unroll
       for (int pass = 0; pass < PASSES; pass++) {
         const int ncolp = ncolw + pass * W;         // first channel of this pass
@@ -585,7 +606,12 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
             }
             packed[j4] = pack_sat4(yy[0], yy[1], yy[2], yy[3]);
           }
-          *reinterpret_cast<uint4*>(stage + lane * EPI_ROW + cc) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+          if (direct) {
+            if (cc == 0) out_lo = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+            else out_hi = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+          } else {
+            *reinterpret_cast<uint4*>(stage + lane * EPI_ROW + cc) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+          }
         }
         if (pass == PASSES - 1) {
           // accumulator buffer drained: hand it back to the MMA warp as early as possible
@@ -593,8 +619,19 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
           __syncwarp();
           if (lane == 0) mbar_arrive(tempty_bar + 8 * buf);
         } else {
-          __syncwarp();
+          if (!direct) __syncwarp();
           load_res(rvalid, rpix, ncolp + W, resq);   // prefetch the next pass's residual
+        }
+        if (direct) {
+          // this lane's own row: 32 contiguous bytes = one sector
+          if (dvalid && ncolp + 32 <= c.N) {
+            stg256(c.y + dpix * c.yC + ncolp, out_lo, out_hi);
+          } else if (dvalid && ncolp < c.N) {
+            const unsigned vw[8] = {out_lo.x, out_lo.y, out_lo.z, out_lo.w, out_hi.x, out_hi.y, out_hi.z, out_hi.w};
+            int8_t* dst = c.y + dpix * c.yC + ncolp;
+            for (int e = 0; e < c.N - ncolp && e < 32; e++) dst[e] = (int8_t)((vw[e >> 2] >> (8 * (e & 3))) & 0xff);
+          }
+          continue;
         }
         // coalesced store of the finished int8 tile
 #pragma unroll
@@ -708,6 +745,12 @@ void fill_geometry(MmaParams& P, const ConvParams& c, int planes8) {
   P.d_ntiles = make_fastdiv(P.n_tiles);
   P.d_tiles_w = make_fastdiv(P.tiles_w);
   P.d_tiles_h = make_fastdiv(P.tiles_h);
+  P.direct256 = (c.yC % 32 == 0) && (((unsigned long long)c.y) % 32 == 0) &&
+                (c.r == nullptr || ((c.rC % 32 == 0) && (((unsigned long long)c.r) % 32 == 0)));
+  {
+    static const bool allow = getenv("TF2B_MMA_DIRECT") == nullptr || atoi(getenv("TF2B_MMA_DIRECT")) != 0;
+    if (!allow) P.direct256 = 0;
+  }
 }
 
 }  // namespace
