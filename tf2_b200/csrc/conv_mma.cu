@@ -72,6 +72,8 @@ struct MmaParams {
   long long* dbg;           // optional per-CTA cycle counters [grid][8] (TF2B_MMA_DEBUG), else nullptr
   FastDiv d_ntiles, d_tiles_w, d_tiles_h;
   int direct256;            // output/residual rows are 32-byte aligned: row-per-lane 32-byte accesses
+  int b_resident;           // the CTA's weight slab (all taps/chunks/planes of its n-tile) stays in smem
+  int res_bytes;            // bytes of that slab
 };
 
 struct TmapPair {
@@ -256,19 +258,21 @@ template <int BN, int MODE, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ TmapPair maps) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  // carve: [stages][A | B planes] (1024-aligned), then barriers
-  const unsigned smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  // carve: [resident weight slab] [stages][A | B planes] (1024-aligned) [epilogue scratch]
+  const unsigned smem_res = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const unsigned smem_base = smem_res + (unsigned)P.res_bytes;
   const int a_stage = MMA_M * P.BK;
   const int b_plane = BN * P.BK;
-  const int stage_bytes = a_stage + P.planes * b_plane;
+  const int stage_bytes = a_stage + (P.b_resident ? 0 : P.planes * b_plane);
 
-  __shared__ __align__(8) unsigned long long bars[2 * MAX_STAGES + 4];
+  __shared__ __align__(8) unsigned long long bars[2 * MAX_STAGES + 5];
   __shared__ unsigned tmem_base_slot;
   __shared__ unsigned row_lut[MMA_M];   // box mode: row -> (wl | hl<<8 | nl<<16 | inbox<<24)
   const unsigned full_bar = smem_u32(&bars[0]);                  // [stages]
   const unsigned empty_bar = smem_u32(&bars[MAX_STAGES]);        // [stages]
   const unsigned tfull_bar = smem_u32(&bars[2 * MAX_STAGES]);    // [2]
   const unsigned tempty_bar = smem_u32(&bars[2 * MAX_STAGES + 2]);  // [2]
+  const unsigned bres_bar = smem_u32(&bars[2 * MAX_STAGES + 4]);    // resident weight slab landed
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -286,6 +290,7 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
       mbar_init(tfull_bar + 8 * b, 1);
       mbar_init(tempty_bar + 8 * b, NUM_EPI_WARPS);
     }
+    mbar_init(bres_bar, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(smem_u32(&tmem_base_slot), TMEM_COLS);
@@ -315,6 +320,20 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
     unsigned phase = 0;
     const bool dbg = P.dbg != nullptr;
     long long w_empty = 0, t_start = clock64();
+    if (P.b_resident && (int)blockIdx.x < num_tiles) {
+      // weight-stationary: every tile of this CTA has the same n-tile (grid is a multiple of
+      // n_tiles), so its whole weight slab is fetched once
+      const int n0 = decode_tile(P, blockIdx.x).n0;
+      if (elect_one()) {
+        mbar_expect_tx(bres_bar, (unsigned)P.res_bytes);
+        for (int tap = 0; tap < P.taps; tap++)
+          for (int kc = 0; kc < P.kchunks; kc++)
+            for (int pl = 0; pl < P.planes; pl++)
+              tma_load_2d(smem_res + ((tap * P.kchunks + kc) * P.planes + pl) * b_plane, &maps.b, bres_bar,
+                          tap * P.Cpm + kc * P.BK, pl * P.Npad + n0);
+      }
+      __syncwarp();
+    }
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(P, tile);
       for (int tap = 0; tap < P.taps; tap++) {
@@ -324,15 +343,16 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
           const unsigned fb = full_bar + 8 * stage;
           const unsigned sa = smem_base + stage * stage_bytes;
           if (elect_one()) {
-            mbar_expect_tx(fb, (unsigned)(P.a_bytes + P.planes * P.b_bytes));
+            mbar_expect_tx(fb, (unsigned)(P.a_bytes + (P.b_resident ? 0 : P.planes * P.b_bytes)));
             if (MODE == 0) {
               tma_load_2d(sa, &maps.a, fb, kc * P.BK, t.m0);
             } else {
               tma_load_4d(sa, &maps.a, fb, kc * P.BK, t.ow0 * P.c.stride - P.c.pad + fw,
                           t.oh0 * P.c.stride - P.c.pad + fh, t.b0);
             }
-            for (int pl = 0; pl < P.planes; pl++)
-              tma_load_2d(sa + a_stage + pl * b_plane, &maps.b, fb, tap * P.Cpm + kc * P.BK, pl * P.Npad + t.n0);
+            if (!P.b_resident)
+              for (int pl = 0; pl < P.planes; pl++)
+                tma_load_2d(sa + a_stage + pl * b_plane, &maps.b, fb, tap * P.Cpm + kc * P.BK, pl * P.Npad + t.n0);
           }
           __syncwarp();
           if (++stage == P.stages) { stage = 0; phase ^= 1; }
@@ -351,6 +371,7 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
     unsigned tphase[2] = {0, 0};
     const bool dbg = P.dbg != nullptr;
     long long w_full = 0, w_tempty = 0, t_start = clock64();
+    if (P.b_resident && (int)blockIdx.x < num_tiles) mbar_wait(bres_bar, 0);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       mbar_wait_timed(tempty_bar + 8 * buf, tphase[buf] ^ 1, w_tempty, dbg);   // epilogue has drained this accumulator
       tc_fence_after();
@@ -362,7 +383,8 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
         const unsigned long long da = make_smem_desc(sa, P.sbo16, P.layout_type);
         if (elect_one()) {
           for (int pl = 0; pl < P.planes; pl++) {
-            const unsigned long long db = make_smem_desc(sa + a_stage + pl * b_plane, P.sbo16, P.layout_type);
+            const unsigned bsrc = P.b_resident ? smem_res + (it * P.planes + pl) * b_plane : sa + a_stage + pl * b_plane;
+            const unsigned long long db = make_smem_desc(bsrc, P.sbo16, P.layout_type);
             for (int k4 = 0; k4 < P.BK / 32; k4++) {
               // advance both descriptors by 32 bytes of K inside the swizzled row
               umma_i8(d_tmem + pl * BN, da + (unsigned long long)(2 * k4), db + (unsigned long long)(2 * k4),
@@ -733,8 +755,15 @@ void fill_geometry(MmaParams& P, const ConvParams& c, int planes8) {
     P.a_bytes = P.tw * P.th * P.tn * P.BK;
   }
   P.b_bytes = P.BN * P.BK;
-  const int stage_bytes = MMA_M * P.BK + planes8 * P.b_bytes;
-  int st = (224 * 1024 - EPI_BYTES) / stage_bytes;
+  // weight-stationary when the CTA's slab is small and the grid can be a multiple of n_tiles
+  {
+    static const bool allow = getenv("TF2B_MMA_BRES") == nullptr || atoi(getenv("TF2B_MMA_BRES")) != 0;
+    const long long slab = (long long)P.taps * P.kchunks * planes8 * P.b_bytes;
+    P.b_resident = allow && slab <= 96 * 1024 && P.taps * P.kchunks * planes8 <= 64 && P.n_tiles <= 16;
+    P.res_bytes = P.b_resident ? (int)slab : 0;
+  }
+  const int stage_bytes = MMA_M * P.BK + (P.b_resident ? 0 : planes8 * P.b_bytes);
+  int st = (224 * 1024 - EPI_BYTES - P.res_bytes) / stage_bytes;
   P.stages = st > MAX_STAGES ? MAX_STAGES : (st < 2 ? 2 : st);
   // instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): c_format S32 (2) at bit 4,
   // a/b format signed int8 (1) at bits 7 / 10, K-major A and B, N>>3 at bit 17, M>>4 at bit 24,
@@ -834,8 +863,8 @@ cudaError_t launch_conv_mma(const ConvParams& c, const int8_t* /*wgt8*/, int pla
   MmaParams P;
   fill_geometry(P, c, planes8);
   for (int i = 0; i < kMaxPlanes; i++) P.plane8_shift[i] = plane8_shift[i];
-  const int stage_bytes = MMA_M * P.BK + planes8 * P.b_bytes;
-  const size_t smem = (size_t)P.stages * stage_bytes + EPI_BYTES + 1024;
+  const int stage_bytes = MMA_M * P.BK + (P.b_resident ? 0 : planes8 * P.b_bytes);
+  const size_t smem = (size_t)P.res_bytes + (size_t)P.stages * stage_bytes + EPI_BYTES + 1024;
   using KernelFn = void (*)(MmaParams, TmapPair);
 #define TF2B_EPI_ROW(BN_, MODE_)                                                                              \
   {conv_mma_kernel<BN_, MODE_, -1>, conv_mma_kernel<BN_, MODE_, 0>, conv_mma_kernel<BN_, MODE_, 1>,            \
@@ -861,7 +890,12 @@ cudaError_t launch_conv_mma(const ConvParams& c, const int8_t* /*wgt8*/, int pla
   const int epi = fast ? (1 + ((scaled_planes == 2 ? 1 : 0) | (c.low_plane >= 0 ? 2 : 0) | (c.r != nullptr ? 4 : 0))) : 0;
   const KernelFn kfn = table[P.BN == 256 ? 2 : (P.BN == 128 ? 1 : 0)][P.mode][epi];
   const int num_tiles = P.m_tiles * P.n_tiles;
-  const int grid = num_tiles < num_sms ? num_tiles : num_sms;
+  int grid = num_tiles < num_sms ? num_tiles : num_sms;
+  if (P.b_resident) {
+    // every CTA must keep one n-tile: grid = multiple of n_tiles
+    grid = (grid / P.n_tiles) * P.n_tiles;
+    if (grid < P.n_tiles) grid = P.n_tiles;
+  }
   const TmapPair* tp = reinterpret_cast<const TmapPair*>(tmaps);
   P.dbg = nullptr;
   static const bool debug = getenv("TF2B_MMA_DEBUG") != nullptr;

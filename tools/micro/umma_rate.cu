@@ -19,7 +19,7 @@ __device__ __forceinline__ unsigned long long make_desc(unsigned saddr, unsigned
   return d;
 }
 template <int KIND>  // 0 = i8, 1 = f16 (bf16 inputs, K=16)
-__global__ void __launch_bounds__(128, 1) rate_kernel(int N, int iters, int nacc, long long* out) {
+__global__ void __launch_bounds__(128, 1) rate_kernel(int N, int iters, int nacc, long long* out, int sw64) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ __align__(8) unsigned long long bar;
   __shared__ unsigned tmem_slot;
@@ -44,13 +44,15 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int N, int iters, int nacc
   else idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(N >> 3) << 17) | (8u << 24);   // f32 acc, bf16 a/b
   if (warp == 0) {
     long long t0 = clock64();
-    const unsigned long long da = make_desc(base, 64, 2);
-    const unsigned long long db = make_desc(base + 16384, 64, 2);
+    // sw64: SWIZZLE_64B operands (64-byte rows, 8-row groups 512 B apart), else SWIZZLE_128B
+    const unsigned long long da = sw64 ? make_desc(base, 32, 4) : make_desc(base, 64, 2);
+    const unsigned long long db = sw64 ? make_desc(base + 16384, 32, 4) : make_desc(base + 16384, 64, 2);
+    const int kmask = sw64 ? 1 : 3;
     if (elect_one()) {
       for (int i = 0; i < iters; i++) {
         const unsigned d = tmem + (unsigned)((i % nacc) * N);
-        const unsigned long long ka = da + (unsigned long long)(2 * (i & 3));
-        const unsigned long long kb = db + (unsigned long long)(2 * (i & 3));
+        const unsigned long long ka = da + (unsigned long long)(2 * (i & kmask));
+        const unsigned long long kb = db + (unsigned long long)(2 * (i & kmask));
         if (KIND == 0)
           asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
                        ::"r"(d), "l"(ka), "l"(kb), "r"(idesc), "r"(i >= nacc ? 1u : 0u) : "memory");
@@ -83,15 +85,17 @@ int main() {
     for (int N : {64, 128, 256})
       for (int nacc : {1, 2}) {
         for (int grid : {1, 148}) {
-          if (kind == 0) rate_kernel<0><<<grid, 128, 80 * 1024>>>(N, iters, nacc, d);
-          else rate_kernel<1><<<grid, 128, 80 * 1024>>>(N, iters, nacc, d);
+         for (int sw64 : {0, 1}) {
+          if (kind == 0) rate_kernel<0><<<grid, 128, 80 * 1024>>>(N, iters, nacc, d, sw64);
+          else rate_kernel<1><<<grid, 128, 80 * 1024>>>(N, iters, nacc, d, sw64);
           cudaError_t e = cudaDeviceSynchronize();
           long long h[148];
           cudaMemcpy(h, d, grid * 8, cudaMemcpyDeviceToHost);
           double avg = 0;
           for (int i = 0; i < grid; i++) avg += (double)h[i] / grid;
-          printf("%s N=%3d nacc=%d grid=%3d : %.1f clk/MMA  (%s)\n", kind ? "bf16" : "i8  ", N, nacc, grid, avg / iters,
-                 cudaGetErrorString(e));
+          printf("%s N=%3d nacc=%d grid=%3d %s : %.1f clk/MMA  (%s)\n", kind ? "bf16" : "i8  ", N, nacc, grid,
+                 sw64 ? "SW64 " : "SW128", avg / iters, cudaGetErrorString(e));
+         }
         }
       }
   return 0;
