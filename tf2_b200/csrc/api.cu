@@ -37,6 +37,7 @@ int mma_build_tmaps(void* host_tmaps, const ConvParams& p, const int8_t* wgt8, i
                     std::string* err);
 int mma_bn();
 int mma_pick_bk(int Cp);
+bool mma_pair_mode(int k, int stride, int pad, int Cp, int xC, int OW);
 }  // namespace tf2b
 
 using tf2b::ConvParams;
@@ -233,8 +234,11 @@ static int prepare_layer(tf2b_net* net, LayerState& S, const uint8_t* codes,
       S.planes_m = np;
       S.low_plane_m = use_low ? np - 1 : -1;
       S.Npad_m = round_up(N, tf2b::mma_bn());
-      const int Cpm = round_up(S.Cp_m, tf2b::mma_pick_bk(S.Cp_m));
-      S.Kp_m = k * k * Cpm;
+      // pixel-pair rows (conv_mma.cu pair_mode): K = filter row x ceil(k/2) chunks of [tap 2j | tap 2j+1]
+      const bool pair = tf2b::mma_pair_mode(k, d.stride, d.pad, S.Cp_m, in_pitch, d.OW);
+      const int pair_chunks = (k + 1) / 2;
+      const int Cpm = pair ? pair_chunks * 128 : round_up(S.Cp_m, tf2b::mma_pick_bk(S.Cp_m));
+      S.Kp_m = pair ? k * Cpm : k * k * Cpm;
       S.h_w8.assign((size_t)np * S.Npad_m * S.Kp_m, 0);
       for (int p = 0; p < np; p++) S.plane_shift_m[p] = lv * p;
       if (use_low) S.plane_shift_m[np - 1] = 0;
@@ -258,7 +262,12 @@ static int prepare_layer(tf2b_net* net, LayerState& S, const uint8_t* codes,
             if (cd & 0x80) {
               if (dual) cc = S.Cp + c; else v = -v;
             }
-            S.h_w8[((size_t)p * S.Npad_m + n) * S.Kp_m + (size_t)t * Cpm + cc] = (int8_t)v;
+            size_t kidx = (size_t)t * Cpm + cc;
+            if (pair) {
+              const int fh = t / k, fw = t - fh * k;
+              kidx = (size_t)fh * Cpm + (size_t)(fw / 2) * 128 + (size_t)(fw & 1) * 64 + cc;
+            }
+            S.h_w8[((size_t)p * S.Npad_m + n) * S.Kp_m + kidx] = (int8_t)v;
           }
       S.h_nshift_m.assign(round_up(std::max(round_up(N, tf2b::conv_shift_bn()), S.Npad_m), 16), 0);
       for (int n = 0; n < N; n++) S.h_nshift_m[n] = bm[n];
