@@ -556,7 +556,8 @@ static int alloc_runtime(tf2b_net* net) {
   const int B = net->max_images;
   net->tbuf.assign(net->tensors.size(), nullptr);
   for (size_t t = 0; t < net->tensors.size(); t++) {
-    size_t bytes = (size_t)B * net->tensors[t].H * net->tensors[t].W * net->tpitch[t];
+    // + slack: the pixel-pair rows of the tensor-core path read one pixel past the last one
+    size_t bytes = (size_t)B * net->tensors[t].H * net->tensors[t].W * net->tpitch[t] + 256;
     CUDA_TRY(net, cudaMalloc(&net->tbuf[t], bytes));
     CUDA_TRY(net, cudaMemset(net->tbuf[t], 0, bytes));
   }

@@ -858,7 +858,9 @@ int mma_build_tmaps(void* host_tmaps, const ConvParams& c, const int8_t* wgt8, i
   CUresult r;
   if (P.pair) {
     // rows = pixels, 128 bytes (this pixel and the next) per row: overlapping rows, stride 64 bytes
-    cuuint64_t dims[2] = {128, (cuuint64_t)c.B * c.IH * c.IW - 1};
+    // the row of the very last pixel reaches 64 bytes past the tensor: buffers carry that much slack
+    // (api.cu alloc_runtime) and the weights of that slot are zero
+    cuuint64_t dims[2] = {128, (cuuint64_t)c.B * c.IH * c.IW};
     cuuint64_t strides[1] = {64};
     cuuint32_t box[2] = {128, (cuuint32_t)P.tw};
     cuuint32_t es[2] = {1, 1};
