@@ -74,6 +74,7 @@ struct MmaParams {
   int direct256;            // output/residual rows are 32-byte aligned: row-per-lane 32-byte accesses
   int pair;                 // "pixel pair" rows: 64-byte pixels, pad 0: one 128-byte TMA row = 2 adjacent
                             // pixels = 2 horizontal taps (taps = filter rows, kchunks = ceil(k/2))
+  int noepi;                // experiment switch: epilogue warps only hand the accumulators back (no math, no stores)
   int poll_lane0;           // experiment switch: one lane polls mbarriers (else all lanes)
   int roles_top;            // experiment switch: producer/MMA warps at the highest warp ids
   int b_resident;           // the CTA's weight slab (all taps/chunks/planes of its n-tile) stays in smem
@@ -564,6 +565,14 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
       // ---- (2) accumulators -> requantise (+ residual) -> int8 staging tile -> (3) coalesced store
       mbar_wait_timed(tfull_bar + 8 * buf, tphase[buf], w_tfull, dbg, P.poll_lane0);
       tc_fence_after();
+      if (P.noepi) {   // TF2B_MMA_NOEPI: measure the TMA/MMA pipeline alone
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar + 8 * buf);
+        tphase[buf] ^= 1;
+        buf ^= 1;
+        continue;
+      }
       const bool direct = (SEGS == 2) && P.direct256 != 0;
       uint4 out_lo = make_uint4(0, 0, 0, 0), out_hi = make_uint4(0, 0, 0, 0);
 #pragma unroll
@@ -815,6 +824,8 @@ void fill_geometry(MmaParams& P, const ConvParams& c, int planes8) {
     static const int top = getenv("TF2B_MMA_TOP") ? atoi(getenv("TF2B_MMA_TOP")) : 0;
     P.poll_lane0 = poll;
     P.roles_top = top;
+    static const int noepi = getenv("TF2B_MMA_NOEPI") ? atoi(getenv("TF2B_MMA_NOEPI")) : 0;
+    P.noepi = noepi;
   }
   P.direct256 = (c.yC % 32 == 0) && (((unsigned long long)c.y) % 32 == 0) &&
                 (c.r == nullptr || ((c.rC % 32 == 0) && (((unsigned long long)c.r) % 32 == 0)));
