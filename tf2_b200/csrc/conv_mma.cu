@@ -488,7 +488,7 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
     auto load_res = [&](bool valid, long long pix, int ncolp, uint4 (&dst)[SEGS]) {
 #pragma unroll
       for (int q = 0; q < SEGS; q++) dst[q] = make_uint4(0, 0, 0, 0);
-      if (has_res && valid) {
+      if (has_res && valid && !(P.noepi & 2)) {
         const int8_t* rp = c.r + pix * c.rC + ncolp;
         if (SEGS == 2 && P.direct256 && ncolp + 32 <= c.N) {
           ldg256(rp, dst[0], dst[SEGS - 1]);
@@ -565,7 +565,7 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
       // ---- (2) accumulators -> requantise (+ residual) -> int8 staging tile -> (3) coalesced store
       mbar_wait_timed(tfull_bar + 8 * buf, tphase[buf], w_tfull, dbg, P.poll_lane0);
       tc_fence_after();
-      if (P.noepi) {   // TF2B_MMA_NOEPI: measure the TMA/MMA pipeline alone
+      if (P.noepi & 1) {   // TF2B_MMA_NOEPI bit0: measure the TMA/MMA pipeline alone
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty_bar + 8 * buf);
@@ -676,7 +676,7 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
         if (direct) {
           // this lane's own row: 32 contiguous bytes = one sector
           if (dvalid && ncolp + 32 <= c.N) {
-            stg256(c.y + dpix * c.yC + ncolp, out_lo, out_hi);
+            if (!(P.noepi & 4)) stg256(c.y + dpix * c.yC + ncolp, out_lo, out_hi);
           } else if (dvalid && ncolp < c.N) {
             const unsigned vw[8] = {out_lo.x, out_lo.y, out_lo.z, out_lo.w, out_hi.x, out_hi.y, out_hi.z, out_hi.w};
             int8_t* dst = c.y + dpix * c.yC + ncolp;
