@@ -125,6 +125,15 @@ int tf2b_run_raw224(tf2b_net* net, const int8_t* raw_dev, int n_images, int8_t* 
  * runner.cpp:195 happen inside (synchronous; pinned buffers give async copies). */
 int tf2b_run_raw224_host(tf2b_net* net, const int8_t* raw_host, int n_images, int8_t* out_host,
                          int out_layout);
+/* Pipelined form of tf2b_run_raw224_host — the analogue of Runner::EnqueueKernels (runner.cpp:32)
+ * followed later by WaitForAllKernels (runner.cpp:183): returns as soon as the H2D copy, the run and
+ * the D2H copy of this batch are enqueued on `slot` (0 or 1); tf2b_wait(slot) blocks until out_host
+ * holds the result.  With two slots the copies of neighbouring batches overlap the computation.
+ * Host buffers should be pinned; they must stay valid until tf2b_wait returns. */
+int tf2b_submit_raw224_host(tf2b_net* net, const int8_t* raw_host, int n_images, int8_t* out_host,
+                            int out_layout, int slot);
+int tf2b_wait(tf2b_net* net, int slot);
+
 int tf2b_run_host(tf2b_net* net, const int8_t* in_host, int in_layout, int n_images,
                   int8_t* out_host, int out_layout);
 

@@ -120,3 +120,31 @@ def test_weight_blob_roundtrip():
             assert b.layer_kernels() == a.layer_kernels()
         b.CleanUp()
     a.CleanUp()
+
+
+def test_pipelined_host_api():
+    """tf2b_submit_raw224_host / tf2b_wait: same results as the synchronous call, slots reusable."""
+    import torch
+    from tf2_b200.network import NetWork, Runner
+    rng = np.random.default_rng(31)
+    net = nets.chain((27, 114, 114), [dict(N=64, k=3, pad=0, pool=1, pool_stride=2, pool_pad=1, PH=56, PW=56),
+                                      dict(N=32, k=1, gap=0)])
+    B = 3
+    raws = [rng.integers(-128, 128, size=(B, 3, 224, 224), dtype=np.int8) for _ in range(5)]
+    from tf2_b200 import formats
+    t0 = formats.feature_trans(raws[0]).reshape(B, 27, 114, 114)
+    model = H.random_model(net, rng, t0)
+    nw = NetWork(net, 0)
+    nw.InitFromCodes(model, None, max_images=B)
+    r = Runner(nw)
+    ref = [r.run_host(x, raw224=True).copy() for x in raws]
+    pins = [torch.from_numpy(x).pin_memory() for x in raws]
+    outs = [torch.empty(ref[0].shape, dtype=torch.int8).pin_memory() for _ in raws]
+    for i in range(len(raws)):
+        r.submit_host(pins[i], outs[i], i % 2)
+        if i >= 1:
+            r.wait((i - 1) % 2)
+    r.wait((len(raws) - 1) % 2)
+    for i in range(len(raws)):
+        assert np.array_equal(outs[i].numpy(), ref[i]), f"batch {i}"
+    nw.CleanUp()

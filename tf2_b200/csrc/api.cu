@@ -100,6 +100,12 @@ struct tf2b_net {
   int8_t* io_out = nullptr;
   size_t io_in_bytes = 0, io_out_bytes = 0;
   cudaStream_t own_stream = nullptr;
+  // pipelined host entry point (tf2b_submit_raw224_host / tf2b_wait): two slots, three streams
+  int8_t* slot_in[2] = {nullptr, nullptr};
+  int8_t* slot_out[2] = {nullptr, nullptr};
+  cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+  cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
+  bool slot_used[2] = {false, false};
   int last_launches = 0;
   int last_images = 0;
   bool profile = false;
@@ -743,6 +749,55 @@ int tf2b_run_raw224_host(tf2b_net* net, const int8_t* raw_host, int n_images, in
   return TF2B_OK;
 }
 
+// Pipelined form of tf2b_run_raw224_host: the reference's host also only *enqueues* its finite
+// kernels (Runner::EnqueueKernels, runner.cpp:32) and waits later (WaitForAllKernels).  Two slots:
+// while batch i computes, the H2D copy of batch i+1 and the D2H copy of batch i-1 run on their own
+// copy engines.  tf2b_wait(slot) returns when that slot's result is in out_host.
+int tf2b_submit_raw224_host(tf2b_net* net, const int8_t* raw_host, int n_images, int8_t* out_host, int out_layout,
+                            int slot) {
+  int rc = check_run(net, n_images);
+  if (rc) return rc;
+  if (!raw_host || !out_host || slot < 0 || slot > 1) return fail(net, TF2B_ERR_ARG, "bad pointer or slot");
+  CUDA_TRY(net, cudaSetDevice(net->device));
+  if (!net->s_h2d) {
+    CUDA_TRY(net, cudaStreamCreateWithFlags(&net->s_h2d, cudaStreamNonBlocking));
+    CUDA_TRY(net, cudaStreamCreateWithFlags(&net->s_d2h, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+      CUDA_TRY(net, cudaMalloc(&net->slot_in[i], net->io_in_bytes));
+      CUDA_TRY(net, cudaMalloc(&net->slot_out[i], net->io_out_bytes));
+      CUDA_TRY(net, cudaEventCreateWithFlags(&net->ev_h2d[i], cudaEventDisableTiming));
+      CUDA_TRY(net, cudaEventCreateWithFlags(&net->ev_comp[i], cudaEventDisableTiming));
+      CUDA_TRY(net, cudaEventCreateWithFlags(&net->ev_d2h[i], cudaEventDisableTiming));
+    }
+  }
+  const tf2b_tensor_desc& tr = net->tensors[net->result_tensor];
+  cudaStream_t sc = net->own_stream;
+  // the slot's input staging buffer is free once the previous batch that used it has been consumed
+  if (net->slot_used[slot]) CUDA_TRY(net, cudaStreamWaitEvent(net->s_h2d, net->ev_comp[slot], 0));
+  CUDA_TRY(net, cudaMemcpyAsync(net->slot_in[slot], raw_host, (size_t)n_images * 3 * 224 * 224, cudaMemcpyHostToDevice,
+                                net->s_h2d));
+  CUDA_TRY(net, cudaEventRecord(net->ev_h2d[slot], net->s_h2d));
+  CUDA_TRY(net, cudaStreamWaitEvent(sc, net->ev_h2d[slot], 0));
+  if (net->slot_used[slot]) CUDA_TRY(net, cudaStreamWaitEvent(sc, net->ev_d2h[slot], 0));  // slot_out still being read back
+  rc = tf2b_run_raw224(net, net->slot_in[slot], n_images, net->slot_out[slot], out_layout, sc);
+  if (rc) return rc;
+  CUDA_TRY(net, cudaEventRecord(net->ev_comp[slot], sc));
+  CUDA_TRY(net, cudaStreamWaitEvent(net->s_d2h, net->ev_comp[slot], 0));
+  CUDA_TRY(net, cudaMemcpyAsync(out_host, net->slot_out[slot], (size_t)n_images * tr.C * tr.H * tr.W,
+                                cudaMemcpyDeviceToHost, net->s_d2h));
+  CUDA_TRY(net, cudaEventRecord(net->ev_d2h[slot], net->s_d2h));
+  net->slot_used[slot] = true;
+  return TF2B_OK;
+}
+
+int tf2b_wait(tf2b_net* net, int slot) {
+  if (!net || slot < 0 || slot > 1) return TF2B_ERR_ARG;
+  if (!net->slot_used[slot]) return TF2B_OK;
+  CUDA_TRY(net, cudaSetDevice(net->device));
+  CUDA_TRY(net, cudaEventSynchronize(net->ev_d2h[slot]));
+  return TF2B_OK;
+}
+
 int tf2b_run_host(tf2b_net* net, const int8_t* in_host, int in_layout, int n_images, int8_t* out_host,
                   int out_layout) {
   int rc = check_run(net, n_images);
@@ -913,6 +968,15 @@ void tf2b_destroy(tf2b_net* net) {
   if (net->io_in) cudaFree(net->io_in);
   if (net->io_out) cudaFree(net->io_out);
   if (net->own_stream) cudaStreamDestroy(net->own_stream);
+  for (int i = 0; i < 2; i++) {
+    if (net->slot_in[i]) cudaFree(net->slot_in[i]);
+    if (net->slot_out[i]) cudaFree(net->slot_out[i]);
+    if (net->ev_h2d[i]) cudaEventDestroy(net->ev_h2d[i]);
+    if (net->ev_comp[i]) cudaEventDestroy(net->ev_comp[i]);
+    if (net->ev_d2h[i]) cudaEventDestroy(net->ev_d2h[i]);
+  }
+  if (net->s_h2d) cudaStreamDestroy(net->s_h2d);
+  if (net->s_d2h) cudaStreamDestroy(net->s_d2h);
   for (auto e : net->ev) cudaEventDestroy(e);
   delete net;
 }

@@ -198,6 +198,16 @@ class Runner:
         self.network._check(rc)
         return out_host
 
+    # -- pipelined host path: EnqueueKernels now, WaitForAllKernels later (runner.cpp:32,183) ------
+    def submit_host(self, x_host, out_host, slot: int, out_layout: int = capi.LAYOUT_CHW):
+        """Enqueue H2D + run + D2H of one raw int8 batch on `slot` (0/1); pinned buffers."""
+        xp, B = _host_ptr(x_host)
+        op, _ = _host_ptr(out_host)
+        self.network._check(self._lib.tf2b_submit_raw224_host(self.network.handle, xp, B, op, out_layout, slot))
+
+    def wait(self, slot: int):
+        self.network._check(self._lib.tf2b_wait(self.network.handle, slot))
+
     # -- Runner::Run (runner.cpp:54-196) ------------------------------------------------------
     def Run(self, images_f32: np.ndarray) -> np.ndarray:
         """Float images [B][3][224][224] (mean-subtracted, as the reference's .bin files) ->
