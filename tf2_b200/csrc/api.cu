@@ -591,7 +591,9 @@ static int alloc_runtime(tf2b_net* net) {
     bool to_scratch = d.pool || d.gap;
     int8_t* dst = to_scratch ? net->scratch0 : net->tbuf[d.out_tensor] + d.out_ch0;
     int dstC = to_scratch ? round_up(d.N, 16) : net->tpitch[d.out_tensor];
-    ConvParams p = conv_params(net, S, B, dst, dstC, nullptr, 0, true);
+    const int8_t* res = (d.add_tensor >= 0 && !d.pool) ? net->tbuf[d.add_tensor] : nullptr;
+    const int resC = (d.add_tensor >= 0 && !d.pool) ? net->tpitch[d.add_tensor] : 0;
+    ConvParams p = conv_params(net, S, B, dst, dstC, res, resC, true);
     S.h_tmaps.assign(tf2b::mma_tmap_bytes(), 0);
     std::string err;
     int rc = tf2b::mma_build_tmaps(S.h_tmaps.data(), p,

@@ -77,6 +77,8 @@ struct MmaParams {
   int noepi;                // experiment switch: epilogue warps only hand the accumulators back (no math, no stores)
   int poll_lane0;           // experiment switch: one lane polls mbarriers (else all lanes)
   int roles_top;            // experiment switch: producer/MMA warps at the highest warp ids
+  int res_tma;              // residual tiles arrive through TMA into a smem ring (flat layers, BN >= 128)
+  int res_bufs;             // ring depth (1 or 2)
   int b_resident;           // the CTA's weight slab (all taps/chunks/planes of its n-tile) stays in smem
   int res_bytes;            // bytes of that slab
 };
@@ -84,6 +86,7 @@ struct MmaParams {
 struct TmapPair {
   CUtensorMap a;
   CUtensorMap b;
+  CUtensorMap r;   // residual operand (flat layers): [pixels][channels], 128 x 128-byte boxes
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -278,8 +281,10 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
   const int a_stage = MMA_M * P.BK;
   const int b_plane = BN * P.BK;
   const int stage_bytes = a_stage + (P.b_resident ? 0 : P.planes * b_plane);
+  const int res_tile = BN * 128;   // one residual tile: 128 rows x BN bytes as BN/128 SWIZZLE_128B sub-tiles
+  const unsigned smem_rres = smem_base + (unsigned)(P.stages * stage_bytes + EPI_BYTES);   // residual ring
 
-  __shared__ __align__(8) unsigned long long bars[2 * MAX_STAGES + 5];
+  __shared__ __align__(8) unsigned long long bars[2 * MAX_STAGES + 9];
   __shared__ unsigned tmem_base_slot;
   __shared__ unsigned row_lut[MMA_M];   // box mode: row -> (wl | hl<<8 | nl<<16 | inbox<<24)
   const unsigned full_bar = smem_u32(&bars[0]);                  // [stages]
@@ -287,6 +292,8 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
   const unsigned tfull_bar = smem_u32(&bars[2 * MAX_STAGES]);    // [2]
   const unsigned tempty_bar = smem_u32(&bars[2 * MAX_STAGES + 2]);  // [2]
   const unsigned bres_bar = smem_u32(&bars[2 * MAX_STAGES + 4]);    // resident weight slab landed
+  const unsigned rfull_bar = smem_u32(&bars[2 * MAX_STAGES + 5]);   // [2] residual tile landed
+  const unsigned rempty_bar = smem_u32(&bars[2 * MAX_STAGES + 7]);  // [2] residual tile consumed
 
   // Warp roles.  The SM's issue arbiter favours higher warp ids, so the two single-issuer warps that
   // feed the tensor pipe sit at the top and are never starved by the ALU-heavy epilogue warps:
@@ -309,6 +316,10 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
       mbar_init(tempty_bar + 8 * b, NUM_EPI_WARPS);
     }
     mbar_init(bres_bar, 1);
+    for (int b = 0; b < 2; b++) {
+      mbar_init(rfull_bar + 8 * b, 1);
+      mbar_init(rempty_bar + 8 * b, NUM_EPI_WARPS);
+    }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(smem_u32(&tmem_base_slot), TMEM_COLS);
@@ -352,8 +363,21 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
       }
       __syncwarp();
     }
+    int rb = 0;
+    unsigned rphase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(P, tile);
+      if (MODE == 0 && P.res_tma) {
+        // residual operand of this tile: full 128-byte lines, no L1, latency hidden by the run-ahead
+        mbar_wait_warp(rempty_bar + 8 * rb, rphase ^ 1, P.poll_lane0);
+        if (elect_one()) {
+          mbar_expect_tx(rfull_bar + 8 * rb, (unsigned)res_tile);
+          for (int j = 0; j < BN / 128; j++)
+            tma_load_2d(smem_rres + rb * res_tile + j * (128 * 128), &maps.r, rfull_bar + 8 * rb, t.n0 + j * 128, t.m0);
+        }
+        __syncwarp();
+        if (++rb == P.res_bufs) { rb = 0; rphase ^= 1; }
+      }
       for (int tap = 0; tap < P.taps; tap++) {
         const int fh = P.pair ? tap : tap / P.c.k, fw = P.pair ? 0 : tap - fh * P.c.k;
         for (int kc = 0; kc < P.kchunks; kc++) {
@@ -485,6 +509,19 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
         pix = ((long long)b * c.OH + oh) * c.OW + ow;
       }
     };
+    int rb = 0;
+    unsigned rphase = 0;
+    const bool res_tma = (MODE == 0) && (BN >= 128) && P.res_tma != 0;
+    // residual bytes of this thread's row, columns [col, col + 16*SEGS) of the CTA tile, from the smem ring
+    auto lds_res = [&](int col, uint4 (&dst)[SEGS]) {
+      const unsigned rbase = smem_rres + rb * res_tile + (col >> 7) * (128 * 128) + my_row * 128;
+#pragma unroll
+      for (int q = 0; q < SEGS; q++) {
+        const int chunk = ((col & 127) >> 4) + q;
+        const unsigned a = rbase + (unsigned)(((chunk ^ (my_row & 7)) & 7) << 4);
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(dst[q].x), "=r"(dst[q].y), "=r"(dst[q].z), "=r"(dst[q].w) : "r"(a));
+      }
+    };
     auto load_res = [&](bool valid, long long pix, int ncolp, uint4 (&dst)[SEGS]) {
 #pragma unroll
       for (int q = 0; q < SEGS; q++) dst[q] = make_uint4(0, 0, 0, 0);
@@ -560,12 +597,18 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
       // residual of this thread's own row for the first pass (whole 32-byte sectors), requested
       // before the accumulators are waited for
       uint4 resq[SEGS];
-      load_res(rvalid, rpix, ncolw, resq);
+      if (!res_tma) load_res(rvalid, rpix, ncolw, resq);
       __syncwarp();
       // ---- (2) accumulators -> requantise (+ residual) -> int8 staging tile -> (3) coalesced store
       mbar_wait_timed(tfull_bar + 8 * buf, tphase[buf], w_tfull, dbg, P.poll_lane0);
       tc_fence_after();
       if (P.noepi & 1) {   // TF2B_MMA_NOEPI bit0: measure the TMA/MMA pipeline alone
+        if (has_res && (MODE == 0) && (BN >= 128) && P.res_tma) {
+          mbar_wait_warp(rfull_bar + 8 * rb, rphase, P.poll_lane0);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(rempty_bar + 8 * rb);
+          if (++rb == P.res_bufs) { rb = 0; rphase ^= 1; }
+        }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty_bar + 8 * buf);
@@ -575,6 +618,10 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
       }
       const bool direct = (SEGS == 2) && P.direct256 != 0;
       uint4 out_lo = make_uint4(0, 0, 0, 0), out_hi = make_uint4(0, 0, 0, 0);
+      if (has_res && res_tma) {
+        mbar_wait_warp(rfull_bar + 8 * rb, rphase, P.poll_lane0);
+        lds_res(slice * WT, resq);
+      }
 #pragma unroll
       for (int pass = 0; pass < PASSES; pass++) {
         const int ncolp = ncolw + pass * W;         // first channel of this pass
@@ -671,7 +718,8 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
           if (lane == 0) mbar_arrive(tempty_bar + 8 * buf);
         } else {
           if (!direct) __syncwarp();
-          load_res(rvalid, rpix, ncolp + W, resq);   // prefetch the next pass's residual
+          if (has_res && res_tma) lds_res(slice * WT + (pass + 1) * W, resq);
+          else load_res(rvalid, rpix, ncolp + W, resq);   // prefetch the next pass's residual
         }
         if (direct) {
           // this lane's own row: 32 contiguous bytes = one sector
@@ -700,6 +748,11 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
           }
         }
         if (pass != PASSES - 1) __syncwarp();   // staging tile is reused by the next pass
+      }
+      if (has_res && res_tma) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(rempty_bar + 8 * rb);
+        if (++rb == P.res_bufs) { rb = 0; rphase ^= 1; }
       }
       tphase[buf] ^= 1;
       buf ^= 1;
@@ -808,7 +861,19 @@ void fill_geometry(MmaParams& P, const ConvParams& c, int planes8) {
     P.res_bytes = P.b_resident ? (int)slab : 0;
   }
   const int stage_bytes = MMA_M * P.BK + (P.b_resident ? 0 : planes8 * P.b_bytes);
-  int st = (224 * 1024 - EPI_BYTES - P.res_bytes) / stage_bytes;
+  {
+    static const bool allow = getenv("TF2B_MMA_RESTMA") == nullptr || atoi(getenv("TF2B_MMA_RESTMA")) != 0;
+    P.res_tma = allow && c.r != nullptr && P.mode == 0 && P.BN >= 128 && (c.rC % 16 == 0);
+    P.res_bufs = 2;
+    if (P.res_tma) {
+      // keep at least three pipeline stages; drop to a single residual buffer, then give up
+      auto stages_with = [&](int bufs) { return (224 * 1024 - EPI_BYTES - P.res_bytes - bufs * P.BN * 128) / stage_bytes; };
+      if (stages_with(2) < 3) P.res_bufs = 1;
+      if (stages_with(P.res_bufs) < 2) P.res_tma = 0;
+    }
+  }
+  const int rres_bytes = P.res_tma ? P.res_bufs * P.BN * 128 : 0;
+  int st = (224 * 1024 - EPI_BYTES - P.res_bytes - rres_bytes) / stage_bytes;
   P.stages = st > MAX_STAGES ? MAX_STAGES : (st < 2 ? 2 : st);
   // instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): c_format S32 (2) at bit 4,
   // a/b format signed int8 (1) at bits 7 / 10, K-major A and B, N>>3 at bit 17, M>>4 at bit 24,
@@ -912,6 +977,19 @@ int mma_build_tmaps(void* host_tmaps, const ConvParams& c, const int8_t* wgt8, i
     if (err) *err = "cuTensorMapEncodeTiled(B) failed with CUresult " + std::to_string((int)r);
     return -1;
   }
+  memset(&tp->r, 0, sizeof tp->r);
+  if (P.res_tma) {
+    cuuint64_t dims[2] = {(cuuint64_t)c.N, (cuuint64_t)c.B * c.OH * c.OW};
+    cuuint64_t strides[1] = {(cuuint64_t)c.rC};
+    cuuint32_t box[2] = {128, (cuuint32_t)MMA_M};
+    cuuint32_t es[2] = {1, 1};
+    r = enc(&tp->r, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)c.r, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      if (err) *err = "cuTensorMapEncodeTiled(R) failed with CUresult " + std::to_string((int)r);
+      return -1;
+    }
+  }
   return 0;
 }
 
@@ -928,7 +1006,8 @@ cudaError_t launch_conv_mma(const ConvParams& c, const int8_t* /*wgt8*/, int pla
   fill_geometry(P, c, planes8);
   for (int i = 0; i < kMaxPlanes; i++) P.plane8_shift[i] = plane8_shift[i];
   const int stage_bytes = MMA_M * P.BK + (P.b_resident ? 0 : planes8 * P.b_bytes);
-  const size_t smem = (size_t)P.res_bytes + (size_t)P.stages * stage_bytes + EPI_BYTES + 1024;
+  const size_t smem = (size_t)P.res_bytes + (size_t)P.stages * stage_bytes + EPI_BYTES +
+                      (P.res_tma ? (size_t)P.res_bufs * P.BN * 128 : 0) + 1024;
   using KernelFn = void (*)(MmaParams, TmapPair);
 #define TF2B_EPI_ROW(BN_, MODE_)                                                                              \
   {conv_mma_kernel<BN_, MODE_, -1>, conv_mma_kernel<BN_, MODE_, 0>, conv_mma_kernel<BN_, MODE_, 1>,            \
