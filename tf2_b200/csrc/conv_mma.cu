@@ -77,6 +77,7 @@ struct MmaParams {
   int noepi;                // experiment switch: epilogue warps only hand the accumulators back (no math, no stores)
   int poll_lane0;           // experiment switch: one lane polls mbarriers (else all lanes)
   int roles_top;            // experiment switch: producer/MMA warps at the highest warp ids
+  int l2_prefetch;          // tiles ahead whose activation boxes are prefetched into L2 (0 = off)
   int res_tma;              // residual tiles arrive through TMA into a smem ring (flat layers, BN >= 128)
   int res_bufs;             // ring depth (1 or 2)
   int b_resident;           // the CTA's weight slab (all taps/chunks/planes of its n-tile) stays in smem
@@ -153,6 +154,15 @@ __device__ __forceinline__ void tma_load_4d(unsigned smem, const CUtensorMap* ma
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
       ::"r"(smem), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
+}
+// L2 prefetch of a tile (no smem, no barrier): hides the DRAM latency of streamed activations
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global [%0, {%1, %2, %3, %4}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2),
+               "r"(c3)
+               : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -367,6 +377,29 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
     unsigned rphase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(P, tile);
+      if (P.l2_prefetch > 0) {
+        // activations are streamed from HBM once; with only a few stages in flight the ~2 us DRAM
+        // latency is not covered, so the boxes of a later tile of this CTA are pulled into L2 now
+        const int ptile = tile + P.l2_prefetch * (int)gridDim.x;
+        if (ptile < num_tiles && elect_one()) {
+          const TileCoord pt = decode_tile(P, ptile);
+          if (MODE == 0) {
+            for (int kc = 0; kc < P.kchunks; kc++) tma_prefetch_2d(&maps.a, kc * P.BK, pt.m0);
+          } else if (P.pair) {
+            for (int fh = 0; fh < P.taps; fh++)
+              tma_prefetch_2d(&maps.a, 0, ((pt.b0 * P.c.IH + pt.oh0 + fh) * P.c.IW + pt.ow0));
+          } else {
+            // the centre column of taps covers every input row/column the tile reads (side taps only
+            // add one pixel that belongs to the neighbouring tile or to the zero padding)
+            const int fwc = P.c.k / 2;
+            for (int fh = 0; fh < P.c.k; fh++)
+              for (int kc = 0; kc < P.kchunks; kc++)
+                tma_prefetch_4d(&maps.a, kc * P.BK, pt.ow0 * P.c.stride - P.c.pad + fwc,
+                                pt.oh0 * P.c.stride - P.c.pad + fh, pt.b0);
+          }
+        }
+        __syncwarp();
+      }
       if (MODE == 0 && P.res_tma) {
         // residual operand of this tile: full 128-byte lines, no L1, latency hidden by the run-ahead
         mbar_wait_warp(rempty_bar + 8 * rb, rphase ^ 1, P.poll_lane0);
@@ -868,8 +901,7 @@ void fill_geometry(MmaParams& P, const ConvParams& c, int planes8) {
     if (P.res_tma) {
       // keep at least three pipeline stages; drop to a single residual buffer, then give up
       auto stages_with = [&](int bufs) { return (224 * 1024 - EPI_BYTES - P.res_bytes - bufs * P.BN * 128) / stage_bytes; };
-      if (stages_with(2) < 3) P.res_bufs = 1;
-      if (stages_with(P.res_bufs) < 2) P.res_tma = 0;
+      if (stages_with(2) < 3) P.res_tma = 0;   // a single buffer would serialise the producer
     }
   }
   const int rres_bytes = P.res_tma ? P.res_bufs * P.BN * 128 : 0;
@@ -891,6 +923,8 @@ void fill_geometry(MmaParams& P, const ConvParams& c, int planes8) {
     P.roles_top = top;
     static const int noepi = getenv("TF2B_MMA_NOEPI") ? atoi(getenv("TF2B_MMA_NOEPI")) : 0;
     P.noepi = noepi;
+    static const int l2pf = getenv("TF2B_MMA_L2PF") ? atoi(getenv("TF2B_MMA_L2PF")) : 2;
+    P.l2_prefetch = l2pf;
   }
   P.direct256 = (c.yC % 32 == 0) && (((unsigned long long)c.y) % 32 == 0) &&
                 (c.r == nullptr || ((c.rC % 32 == 0) && (((unsigned long long)c.r) % 32 == 0)));
