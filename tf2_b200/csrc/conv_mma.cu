@@ -907,6 +907,10 @@ void fill_geometry(MmaParams& P, const ConvParams& c, int planes8) {
   const int rres_bytes = P.res_tma ? P.res_bufs * P.BN * 128 : 0;
   int st = (224 * 1024 - EPI_BYTES - P.res_bytes - rres_bytes) / stage_bytes;
   P.stages = st > MAX_STAGES ? MAX_STAGES : (st < 2 ? 2 : st);
+  {
+    static const int cap = getenv("TF2B_MMA_STAGES") ? atoi(getenv("TF2B_MMA_STAGES")) : 0;   // experiment switch
+    if (cap >= 1 && P.stages > cap) P.stages = cap;
+  }
   // instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): c_format S32 (2) at bit 4,
   // a/b format signed int8 (1) at bits 7 / 10, K-major A and B, N>>3 at bit 17, M>>4 at bit 24,
   // saturate (bit 3) off
@@ -923,7 +927,7 @@ void fill_geometry(MmaParams& P, const ConvParams& c, int planes8) {
     P.roles_top = top;
     static const int noepi = getenv("TF2B_MMA_NOEPI") ? atoi(getenv("TF2B_MMA_NOEPI")) : 0;
     P.noepi = noepi;
-    static const int l2pf = getenv("TF2B_MMA_L2PF") ? atoi(getenv("TF2B_MMA_L2PF")) : 2;
+    static const int l2pf = getenv("TF2B_MMA_L2PF") ? atoi(getenv("TF2B_MMA_L2PF")) : 0;
     P.l2_prefetch = l2pf;
   }
   P.direct256 = (c.yC % 32 == 0) && (((unsigned long long)c.y) % 32 == 0) &&
