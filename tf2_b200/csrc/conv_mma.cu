@@ -448,7 +448,7 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
     int buf = 0;
     unsigned tphase[2] = {0, 0};
     const bool dbg = P.dbg != nullptr;
-    long long w_full = 0, w_tempty = 0, t_start = clock64();
+    long long w_full = 0, w_tempty = 0, t_issue = 0, t_start = clock64();
     if (P.b_resident && (int)blockIdx.x < num_tiles) mbar_wait_warp(bres_bar, 0, P.poll_lane0);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       mbar_wait_timed(tempty_bar + 8 * buf, tphase[buf] ^ 1, w_tempty, dbg, P.poll_lane0);   // epilogue has drained this accumulator
@@ -459,6 +459,8 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
         tc_fence_after();
         const unsigned sa = smem_base + stage * stage_bytes;
         const unsigned long long da = make_smem_desc(sa, P.sbo16, P.layout_type);
+        long long ti0 = 0;
+        if (dbg) ti0 = clock64();
         if (elect_one()) {
           for (int pl = 0; pl < P.planes; pl++) {
             const unsigned bsrc = P.b_resident ? smem_res + (it * P.planes + pl) * b_plane : sa + a_stage + pl * b_plane;
@@ -473,6 +475,7 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
           if (it == kiters - 1) umma_commit(tfull_bar + 8 * buf);   // accumulators complete -> epilogue
         }
         __syncwarp();
+        if (dbg) t_issue += clock64() - ti0;
         if (++stage == P.stages) { stage = 0; phase ^= 1; }
       }
       tphase[buf] ^= 1;
@@ -482,6 +485,7 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
       P.dbg[blockIdx.x * 8 + 2] = w_full;
       P.dbg[blockIdx.x * 8 + 3] = w_tempty;
       P.dbg[blockIdx.x * 8 + 4] = clock64() - t_start;
+      P.dbg[blockIdx.x * 8 + 7] = t_issue;
     }
   } else {
     // ===================================================== epilogue warps
@@ -1112,11 +1116,11 @@ cudaError_t launch_conv_mma(const ConvParams& c, const int8_t* /*wgt8*/, int pla
     const double tiles_per_cta = (double)num_tiles / grid;
     fprintf(stderr,
             "[mma dbg] C%d N%d k%d s%d OH%d mode%d BK%d BN%d P%d stages%d tiles/cta %.1f kiters %d | per tile clk: "
-            "producer total %.0f (wait empty %.0f) | mma total %.0f (wait full %.0f, wait tmem-empty %.0f) | "
+            "producer total %.0f (wait empty %.0f) | mma total %.0f (wait full %.0f, wait tmem-empty %.0f, issue %.0f) | "
             "epi total %.0f (wait tmem-full %.0f)\n",
             c.Cp, c.N, c.k, c.stride, c.OH, P.mode, P.BK, P.BN, P.planes, P.stages, tiles_per_cta,
             P.taps * P.kchunks, a[1] / tiles_per_cta, a[0] / tiles_per_cta, a[4] / tiles_per_cta, a[2] / tiles_per_cta,
-            a[3] / tiles_per_cta, a[6] / tiles_per_cta, a[5] / tiles_per_cta);
+            a[3] / tiles_per_cta, a[7] / tiles_per_cta, a[6] / tiles_per_cta, a[5] / tiles_per_cta);
   }
   return cudaGetLastError();
 }
