@@ -20,23 +20,22 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                  : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
 }
-__device__ __forceinline__ unsigned long long make_desc(unsigned saddr) {
+__device__ __forceinline__ unsigned long long make_desc(unsigned saddr, int BK) {
   unsigned long long d = 0;
   d |= (unsigned long long)((saddr >> 4) & 0x3FFF);
   d |= (unsigned long long)1 << 16;
-  d |= (unsigned long long)64 << 32;
+  d |= (unsigned long long)(BK == 128 ? 64 : 32) << 32;
   d |= (unsigned long long)1 << 46;
-  d |= (unsigned long long)2 << 61;
+  d |= (unsigned long long)(BK == 128 ? 2 : 4) << 61;
   return d;
 }
 __global__ void __launch_bounds__(64, 1) mainloop(const __grid_constant__ Maps maps, int BN, int stages, int kiters,
-                                                  int stream_rows, int krange, long long* out) {
+                                                  int stream_rows, int krange, long long* out, int BK, int planes) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ __align__(8) unsigned long long bars[2 * 8 + 1];
   __shared__ unsigned tmem_slot;
   const unsigned base = (smem_u32(smem) + 1023u) & ~1023u;
-  const int BK = 128;
-  const int stage_bytes = 128 * BK + BN * BK;
+  const int stage_bytes = 128 * BK + planes * BN * BK;
   const unsigned full = smem_u32(&bars[0]), empty = smem_u32(&bars[8]), done = smem_u32(&bars[16]);
   const int warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
@@ -69,8 +68,9 @@ __global__ void __launch_bounds__(64, 1) mainloop(const __grid_constant__ Maps m
         const int row = stream_rows ? (int)(blockIdx.x * 128 + (it / krange) % 4 * 148 * 128) : 0;
         asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                      ::"r"(sa), "l"(&maps.a), "r"(fb), "r"(k0), "r"(row) : "memory");
-        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-                     ::"r"(sa + 128 * BK), "l"(&maps.b), "r"(fb), "r"(k0), "r"(0) : "memory");
+        for (int pl = 0; pl < planes; pl++)
+          asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                       ::"r"(sa + 128 * BK + pl * BN * BK), "l"(&maps.b), "r"(fb), "r"(k0), "r"(0) : "memory");
       }
       __syncwarp();
       if (++stage == stages) { stage = 0; phase ^= 1; }
@@ -81,11 +81,14 @@ __global__ void __launch_bounds__(64, 1) mainloop(const __grid_constant__ Maps m
       mbar_wait(full + 8 * stage, phase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const unsigned sa = base + stage * stage_bytes;
-      const unsigned long long da = make_desc(sa), db = make_desc(sa + 128 * BK);
+      const unsigned long long da = make_desc(sa, BK);
       if (elect_one()) {
-        for (int k4 = 0; k4 < 4; k4++)
-          asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
-                       ::"r"(tmem), "l"(da + 2ull * k4), "l"(db + 2ull * k4), "r"(idesc), "r"((it | k4) ? 1u : 0u) : "memory");
+        for (int pl = 0; pl < planes; pl++) {
+          const unsigned long long db = make_desc(sa + 128 * BK + pl * BN * BK, BK);
+          for (int k4 = 0; k4 < BK / 32; k4++)
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+                         ::"r"(tmem + pl * BN), "l"(da + 2ull * k4), "l"(db + 2ull * k4), "r"(idesc), "r"((it | k4) ? 1u : 0u) : "memory");
+        }
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(empty + 8 * stage) : "memory");
         if (it == kiters - 1)
           asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(done) : "memory");
@@ -112,29 +115,35 @@ int main() {
   cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fnp, cudaEnableDefault, &q);
   EncodeFn enc = (EncodeFn)fnp;
   cudaFuncSetAttribute(mainloop, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-  for (int BN : {64, 128, 256}) {
+  struct Cfg { int BN, BK, planes; };
+  const Cfg cfgs[] = {{64, 64, 2}, {64, 128, 2}, {64, 128, 1}, {128, 128, 2}, {128, 128, 1}, {256, 128, 1}, {128, 64, 2}};
+  for (const Cfg& cf : cfgs) {
+    const int BN = cf.BN, BK = cf.BK, planes = cf.planes;
     Maps m;
     cuuint64_t da[2] = {K, MA}, sa[1] = {K}, db[2] = {K, MB};
-    cuuint32_t ba[2] = {128, 128}, bb[2] = {128, (cuuint32_t)BN}, es[2] = {1, 1};
-    enc(&m.a, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, A, da, sa, ba, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+    cuuint32_t ba[2] = {(cuuint32_t)BK, 128}, bb[2] = {(cuuint32_t)BK, (cuuint32_t)BN}, es[2] = {1, 1};
+    const CUtensorMapSwizzle sw = BK == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    enc(&m.a, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, A, da, sa, ba, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    enc(&m.b, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, B, db, sa, bb, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+    enc(&m.b, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, B, db, sa, bb, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    for (int stages : {2, 4, 6}) {
-      const int stage_bytes = 128 * 128 + BN * 128;
+    for (int stages : {3, 6}) {
+      const int stage_bytes = 128 * BK + planes * BN * BK;
       if (stages * stage_bytes > 200 * 1024) continue;
       for (int stream_rows : {0, 1})
-        for (int grid : {1, 148}) {
+        for (int grid : {148}) {
           const int kiters = 2048;
           for (int rep = 0; rep < 2; rep++) {
-            mainloop<<<grid, 64, stages * stage_bytes + 1024>>>(m, BN, stages, kiters, stream_rows, 32, d);
+            mainloop<<<grid, 64, stages * stage_bytes + 1024>>>(m, BN, stages, kiters, stream_rows, 4096 / BK, d, BK, planes);
             cudaDeviceSynchronize();
           }
           cudaError_t e = cudaGetLastError();
           long long h[148]; cudaMemcpy(h, d, grid * 8, cudaMemcpyDeviceToHost);
           double avg = 0; for (int i = 0; i < grid; i++) avg += (double)h[i] / grid;
-          printf("BN=%3d stages=%d %s grid=%3d : %.1f clk/MMA  stage %d KB  (%s)\n", BN, stages,
-                 stream_rows ? "stream" : "same  ", grid, avg / (kiters * 4.0), stage_bytes / 1024, cudaGetErrorString(e));
+          const int mmas = planes * BK / 32;
+          printf("BN=%3d BK=%3d P=%d stages=%d %s grid=%3d : %.0f clk/k-iter (%d MMAs: %.1f clk/MMA) stage %d KB (%s)\n", BN, BK,
+                 planes, stages, stream_rows ? "stream" : "same  ", grid, avg / kiters, mmas, avg / kiters / mmas,
+                 stage_bytes / 1024, cudaGetErrorString(e));
         }
     }
   }
