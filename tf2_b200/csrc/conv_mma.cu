@@ -462,14 +462,21 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
         long long ti0 = 0;
         if (dbg) ti0 = clock64();
         if (elect_one()) {
-          for (int pl = 0; pl < P.planes; pl++) {
-            const unsigned bsrc = P.b_resident ? smem_res + (it * P.planes + pl) * b_plane : sa + a_stage + pl * b_plane;
-            const unsigned long long db = make_smem_desc(bsrc, P.sbo16, P.layout_type);
-            for (int k4 = 0; k4 < P.BK / 32; k4++) {
-              // advance both descriptors by 32 bytes of K inside the swizzled row
-              umma_i8(d_tmem + pl * BN, da + (unsigned long long)(2 * k4), db + (unsigned long long)(2 * k4),
-                      P.idesc, (it > 0 || k4 > 0) ? 1u : 0u);
-            }
+          // The planes of one k-chunk lie back to back in shared memory and in TMEM, so ONE instruction
+          // of N = planes*BN (<= 256) covers them all: an N <= 128 instruction occupies the tensor pipe
+          // as long as an N = 128 one, and fewer, wider instructions leave no issue bubble.
+          const unsigned bsrc = P.b_resident ? smem_res + it * P.planes * b_plane : sa + a_stage;
+          const unsigned long long db = make_smem_desc(bsrc, P.sbo16, P.layout_type);
+          const unsigned acc0 = it > 0 ? 1u : 0u;
+          // advance both descriptors by 32 bytes of K inside the swizzled row
+          if (P.BK == 128) {
+            umma_i8(d_tmem, da, db, P.idesc, acc0);
+            umma_i8(d_tmem, da + 2ull, db + 2ull, P.idesc, 1u);
+            umma_i8(d_tmem, da + 4ull, db + 4ull, P.idesc, 1u);
+            umma_i8(d_tmem, da + 6ull, db + 6ull, P.idesc, 1u);
+          } else {
+            umma_i8(d_tmem, da, db, P.idesc, acc0);
+            umma_i8(d_tmem, da + 2ull, db + 2ull, P.idesc, 1u);
           }
           umma_commit(empty_bar + 8 * stage);             // frees the smem stage when the MMAs retire
           if (it == kiters - 1) umma_commit(tfull_bar + 8 * buf);   // accumulators complete -> epilogue
@@ -918,7 +925,7 @@ void fill_geometry(MmaParams& P, const ConvParams& c, int planes8) {
   // instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): c_format S32 (2) at bit 4,
   // a/b format signed int8 (1) at bits 7 / 10, K-major A and B, N>>3 at bit 17, M>>4 at bit 24,
   // saturate (bit 3) off
-  P.idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(P.BN >> 3) << 17) | ((unsigned)(MMA_M >> 4) << 24);
+  P.idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((unsigned)((P.BN * P.planes) >> 3) << 17) | ((unsigned)(MMA_M >> 4) << 24);
   P.layout_type = (P.BK == 128) ? 2u : 4u;
   P.sbo16 = (unsigned)(8 * P.BK) >> 4;
   P.d_ntiles = make_fastdiv(P.n_tiles);
