@@ -5,75 +5,9 @@
  * bias seed, int32 wrap-around accumulation, requantisation and clamp of PeFunction) for arbitrary
  * reduction lengths.  Built by oracle/build_ref.sh into oracle/_ref/libtf2ref_pe.so.
  *
- * OpenCL-isms are mapped by a small shim: `channel` objects become statics and
- * read/write_channel_altera become operations on unbounded FIFOs keyed by the channel's address;
- * reading an empty FIFO leaves the kernel through longjmp (the kernel has consumed all its input).
+ * OpenCL-isms are mapped by fifo_shim.h (channels -> unbounded FIFOs).
  */
-#include <setjmp.h>
-#include <stdbool.h>
-#include <stdio.h>
-#include <stdlib.h>
-#include <string.h>
-
-typedef unsigned char uchar;
-typedef unsigned short ushort;
-typedef unsigned int uint;
-
-#define OPENCL
-#define DISABLE_INFINITE_LOOPS
-#define DISABLE_AUTORUN_KERNELS
-#define constant static const
-#define kernel
-#define global
-#define restrict __restrict__
-#define channel static
-static inline int max(int a, int b) { return a > b ? a : b; }
-
-typedef struct {
-  const void* key;
-  unsigned char* buf;
-  size_t head, tail, cap;
-} fifo_t;
-static fifo_t g_fifos[256];
-static int g_nfifos = 0;
-static jmp_buf g_exit;
-
-static fifo_t* fifo_of(const void* key) {
-  for (int i = 0; i < g_nfifos; i++)
-    if (g_fifos[i].key == key) return &g_fifos[i];
-  fifo_t* f = &g_fifos[g_nfifos++];
-  f->key = key;
-  f->buf = NULL;
-  f->head = f->tail = f->cap = 0;
-  return f;
-}
-static void fifo_push(const void* key, const void* v, size_t n) {
-  fifo_t* f = fifo_of(key);
-  if (f->tail + n > f->cap) {
-    f->cap = f->cap ? f->cap * 2 : (1u << 20);
-    while (f->tail + n > f->cap) f->cap *= 2;
-    f->buf = (unsigned char*)realloc(f->buf, f->cap);
-  }
-  memcpy(f->buf + f->tail, v, n);
-  f->tail += n;
-}
-static void fifo_pop(const void* key, void* v, size_t n) {
-  fifo_t* f = fifo_of(key);
-  if (f->head + n > f->tail) longjmp(g_exit, 1);
-  memcpy(v, f->buf + f->head, n);
-  f->head += n;
-}
-static size_t fifo_count(const void* key, size_t n) {
-  fifo_t* f = fifo_of(key);
-  return (f->tail - f->head) / n;
-}
-static void fifo_reset_all(void) {
-  for (int i = 0; i < g_nfifos; i++) g_fifos[i].head = g_fifos[i].tail = 0;
-}
-
-#define read_channel_altera(c) ({ __typeof__(c) v__; fifo_pop(&(c), &v__, sizeof v__); v__; })
-#define write_channel_altera(c, v) do { __typeof__(c) t__ = (v); fifo_push(&(c), &t__, sizeof t__); } while (0)
-#define read_channel_nb_altera(c, valid) ({ __typeof__(c) v__; memset(&v__, 0, sizeof v__); *(valid) = false; v__; })
+#include "fifo_shim.h"
 
 /* the reference source, unmodified */
 #include "pe.cl"
