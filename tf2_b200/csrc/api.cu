@@ -37,7 +37,7 @@ int mma_build_tmaps(void* host_tmaps, const ConvParams& p, const int8_t* wgt8, i
                     std::string* err);
 int mma_bn();
 int mma_pick_bk(int Cp);
-bool mma_pair_mode(int k, int stride, int pad, int Cp, int xC, int OW);
+bool mma_pair_mode(int k, int stride, int pad, int Cp, int xC, int OW, int OH, int N, int planes8);
 }  // namespace tf2b
 
 using tf2b::ConvParams;
@@ -241,7 +241,7 @@ static int prepare_layer(tf2b_net* net, LayerState& S, const uint8_t* codes,
       S.low_plane_m = use_low ? np - 1 : -1;
       S.Npad_m = round_up(N, tf2b::mma_bn());
       // pixel-pair rows (conv_mma.cu pair_mode): K = filter row x ceil(k/2) chunks of [tap 2j | tap 2j+1]
-      const bool pair = tf2b::mma_pair_mode(k, d.stride, d.pad, S.Cp_m, in_pitch, d.OW);
+      const bool pair = tf2b::mma_pair_mode(k, d.stride, d.pad, S.Cp_m, in_pitch, d.OW, d.OH, N, np);
       const int pair_chunks = (k + 1) / 2;
       const int Cpm = pair ? pair_chunks * 128 : round_up(S.Cp_m, tf2b::mma_pick_bk(S.Cp_m));
       S.Kp_m = pair ? k * Cpm : k * k * Cpm;
@@ -293,6 +293,22 @@ static int prepare_layer(tf2b_net* net, LayerState& S, const uint8_t* codes,
     if (sum > 2147483648.0L) sum = 2147483648.0L;
     const long double amax = sum * fabsl((long double)params[n].alpha) / 1048576.0L + 1.0L;
     if (amax + fabsl((long double)params[n].beta) + 16384.0L + 2.0L >= 2147483647.0L) S.fast_requant = 0;
+  }
+  // Folded form of the tensor-core epilogue: acc = tot * 2^nshift + bias must hold in the integers (no
+  // wrap-around of the accumulator) and alpha << nshift must be an int32; then
+  // acc*alpha + ((beta + 2^14) << 20) = tot * (alpha << nshift) + [bias*alpha + ((beta + 2^14) << 20)].
+  if (S.fast_requant && S.mma_ok) {
+    bool fold = true;
+    for (int n = 0; n < N && fold; n++) {
+      long double sum = fabsl((long double)params[n].bias);
+      const uint8_t* cn = codes + (size_t)n * C * k * k;
+      for (int i = 0; i < C * k * k; i++)
+        if (!(cn[i] & 0x40)) sum += 128.0L * (long double)(1ull << (cn[i] & 0x1f));
+      if (sum >= 2147483647.0L) fold = false;
+      const long double a = fabsl((long double)params[n].alpha) * (long double)(1ull << S.h_nshift_m[n]);
+      if (a >= 2147483647.0L) fold = false;
+    }
+    if (fold) S.fast_requant = 2;
   }
   S.Npar = std::max(S.Npad_s, S.Npad_m);
   S.h_bias.assign(S.Npar, 0);

@@ -19,6 +19,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -82,6 +83,12 @@ struct MmaParams {
   int res_bufs;             // ring depth (1 or 2)
   int b_resident;           // the CTA's weight slab (all taps/chunks/planes of its n-tile) stays in smem
   int res_bytes;            // bytes of that slab
+  int halo;                 // halo mode (box tiles, stride 1, resident weights): ONE TMA box per tile and
+                            // channel chunk holds the (th + k - 1) x Wp input pixels of the tile in raster
+                            // order; every filter tap is a row-shifted view of it (UMMA descriptor start
+                            // address + (fh * Wp + fw) * BK: the swizzle is a function of the address bits)
+  int Wp;                   // halo mode: row width of the position space = tw + k - 1
+  int a_stage_bytes;        // bytes reserved per pipeline stage for the activation tile
 };
 
 struct TmapPair {
@@ -269,18 +276,49 @@ __device__ __forceinline__ unsigned pack_sat4(int y0, int y1, int y2, int y3) {
   return r;
 }
 
-// pe.cl:185-203 without the final clamp (done by the saturating pack); lo folds relu.cl:54
-__device__ __forceinline__ int requant_lo(int32_t acc, int32_t alpha, int32_t beta, int lo) {
+// pe.cl:185-203 without the final clamp (done by the saturating pack)
+__device__ __forceinline__ int requant_raw(int32_t acc, int32_t alpha, int32_t beta) {
   long long t = (long long)acc * (long long)alpha;
   int a = (int)(t >> 20);
   int s = (int)((unsigned)a + (unsigned)beta);
-  int y = ((s >> 14) + 1) >> 1;
-  return max(lo, y);
+  return ((s >> 14) + 1) >> 1;
+}
+
+// relu.cl:54 on four packed int8: PRMT replicates each byte's sign bit into a byte mask
+__device__ __forceinline__ unsigned relu_s8x4(unsigned v) {
+  unsigned m;
+  asm("prmt.b32 %0, %1, %1, 0xba98;" : "=r"(m) : "r"(v));
+  return v & ~m;
+}
+
+// feature_writer.cl:124-127 on four packed int8: y + r in int16 lanes (VIADD.16x2), clamp to int8
+// (with ReLU: VIMNMX.S16x2.RELU clamps to [0,127] in one instruction), repack
+template <bool RELU>
+__device__ __forceinline__ unsigned add_res_s8x4(unsigned y4, unsigned r4) {
+  unsigned ylo, yhi, rlo, rhi, slo, shi, out;
+  asm("prmt.b32 %0, %1, %1, 0x9180;" : "=r"(ylo) : "r"(y4));   // bytes 0,1 sign-extended to s16x2
+  asm("prmt.b32 %0, %1, %1, 0xb3a2;" : "=r"(yhi) : "r"(y4));   // bytes 2,3
+  asm("prmt.b32 %0, %1, %1, 0x9180;" : "=r"(rlo) : "r"(r4));
+  asm("prmt.b32 %0, %1, %1, 0xb3a2;" : "=r"(rhi) : "r"(r4));
+  asm("add.s16x2 %0, %1, %2;" : "=r"(slo) : "r"(ylo), "r"(rlo));
+  asm("add.s16x2 %0, %1, %2;" : "=r"(shi) : "r"(yhi), "r"(rhi));
+  if (RELU) {
+    asm("min.relu.s16x2 %0, %1, %2;" : "=r"(slo) : "r"(slo), "r"(0x007f007fu));
+    asm("min.relu.s16x2 %0, %1, %2;" : "=r"(shi) : "r"(shi), "r"(0x007f007fu));
+  } else {
+    asm("min.s16x2 %0, %1, %2;" : "=r"(slo) : "r"(slo), "r"(0x007f007fu));
+    asm("min.s16x2 %0, %1, %2;" : "=r"(shi) : "r"(shi), "r"(0x007f007fu));
+    asm("max.s16x2 %0, %1, %2;" : "=r"(slo) : "r"(slo), "r"(0xff80ff80u));
+    asm("max.s16x2 %0, %1, %2;" : "=r"(shi) : "r"(shi), "r"(0xff80ff80u));
+  }
+  asm("prmt.b32 %0, %1, %2, 0x6420;" : "=r"(out) : "r"(slo), "r"(shi));
+  return out;
 }
 
 // EPI < 0: exact requantisation, every option decided at run time.  EPI >= 0: fused 64-bit
 // requantisation (range-analysed layers) specialised on bit0 = second scaled plane, bit1 = low plane,
-// bit2 = residual operand.
+// bit2 = residual operand, bit3 = folded form: y = (tot * (alpha << nshift) + (bias*alpha +
+// ((beta + 2^14) << 20))) >> 35 with tot = plane0 + (plane1 << 7) — one IMAD.HI per output.
 template <int BN, int MODE, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ TmapPair maps) {
@@ -288,7 +326,7 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
   // carve: [resident weight slab] [stages][A | B planes] (1024-aligned) [epilogue scratch]
   const unsigned smem_res = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const unsigned smem_base = smem_res + (unsigned)P.res_bytes;
-  const int a_stage = MMA_M * P.BK;
+  const int a_stage = P.a_stage_bytes;
   const int b_plane = BN * P.BK;
   const int stage_bytes = a_stage + (P.b_resident ? 0 : P.planes * b_plane);
   const int res_tile = BN * 128;   // one residual tile: 128 rows x BN bytes as BN/128 SWIZZLE_128B sub-tiles
@@ -312,7 +350,7 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
   const int warp = P.roles_top ? (hw_warp < NUM_EPI_WARPS ? hw_warp + 2 : hw_warp - NUM_EPI_WARPS) : hw_warp;
   const int lane = threadIdx.x & 31;
   const int num_tiles = P.m_tiles * P.n_tiles;
-  const int kiters = P.taps * P.kchunks;
+  const int kiters = P.halo ? P.kchunks : P.taps * P.kchunks;   // pipeline stages consumed per tile
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&maps.a);
@@ -335,11 +373,12 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
   if (warp == 1) tmem_alloc(smem_u32(&tmem_base_slot), TMEM_COLS);
   if (MODE == 1 && threadIdx.x >= 64 && threadIdx.x < 64 + MMA_M) {
     const int row = threadIdx.x - 64;
-    const int wl = row % P.tw;
-    const int r = row / P.tw;
+    const int roww = P.halo ? P.Wp : P.tw;   // halo mode: accumulator rows walk the padded raster
+    const int wl = row % roww;
+    const int r = row / roww;
     const int hl = r % P.th;
     const int nl = r / P.th;
-    row_lut[row] = (unsigned)wl | ((unsigned)hl << 8) | ((unsigned)nl << 16) | ((nl < P.tn ? 1u : 0u) << 24);
+    row_lut[row] = (unsigned)wl | ((unsigned)hl << 8) | ((unsigned)nl << 16) | (((nl < P.tn && wl < P.tw) ? 1u : 0u) << 24);
   }
   tc_fence_before();
   __syncthreads();
@@ -411,6 +450,19 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
         __syncwarp();
         if (++rb == P.res_bufs) { rb = 0; rphase ^= 1; }
       }
+      if (P.halo) {
+        for (int kc = 0; kc < P.kchunks; kc++) {
+          mbar_wait_timed(empty_bar + 8 * stage, phase ^ 1, w_empty, dbg, P.poll_lane0);
+          const unsigned fb = full_bar + 8 * stage;
+          if (elect_one()) {
+            mbar_expect_tx(fb, (unsigned)P.a_bytes);
+            tma_load_4d(smem_base + stage * stage_bytes, &maps.a, fb, kc * P.BK, t.ow0 - P.c.pad, t.oh0 - P.c.pad, t.b0);
+          }
+          __syncwarp();
+          if (++stage == P.stages) { stage = 0; phase ^= 1; }
+        }
+        continue;
+      }
       for (int tap = 0; tap < P.taps; tap++) {
         const int fh = P.pair ? tap : tap / P.c.k, fw = P.pair ? 0 : tap - fh * P.c.k;
         for (int kc = 0; kc < P.kchunks; kc++) {
@@ -461,7 +513,26 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
         const unsigned long long da = make_smem_desc(sa, P.sbo16, P.layout_type);
         long long ti0 = 0;
         if (dbg) ti0 = clock64();
-        if (elect_one()) {
+        if (P.halo) {
+          if (elect_one()) {
+            // all taps of this channel chunk read the same halo tile through row-shifted descriptors
+            for (int tap = 0; tap < P.taps; tap++) {
+              const int fh = tap / P.c.k, fw = tap - fh * P.c.k;
+              const unsigned long long dat = make_smem_desc(sa + (unsigned)((fh * P.Wp + fw) * P.BK), P.sbo16, P.layout_type);
+              const unsigned long long db =
+                  make_smem_desc(smem_res + ((tap * P.kchunks + it) * P.planes) * b_plane, P.sbo16, P.layout_type);
+              const unsigned acc0 = (it > 0 || tap > 0) ? 1u : 0u;
+              umma_i8(d_tmem, dat, db, P.idesc, acc0);
+              umma_i8(d_tmem, dat + 2ull, db + 2ull, P.idesc, 1u);
+              if (P.BK == 128) {
+                umma_i8(d_tmem, dat + 4ull, db + 4ull, P.idesc, 1u);
+                umma_i8(d_tmem, dat + 6ull, db + 6ull, P.idesc, 1u);
+              }
+            }
+            umma_commit(empty_bar + 8 * stage);
+            if (it == kiters - 1) umma_commit(tfull_bar + 8 * buf);
+          }
+        } else if (elect_one()) {
           // The planes of one k-chunk lie back to back in shared memory and in TMEM, so ONE instruction
           // of N = planes*BN (<= 256) covers them all: an N <= 128 instruction occupies the tensor pipe
           // as long as an N = 128 one, and fewer, wider instructions leave no issue bubble.
@@ -506,6 +577,7 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
     constexpr bool CT_TWO = FAST && (EPI & 1);
     constexpr bool CT_LOW = FAST && (EPI & 2);
     constexpr bool CT_RES = FAST && (EPI & 4);
+    constexpr bool FOLD = FAST && (EPI & 8);
     constexpr int WT = BN / 4;            // columns per warp: 16, 32 or 64
     constexpr int W = WT > 32 ? 32 : WT;  // columns per pass (staging tile width)
     constexpr int PASSES = WT / W;        // 1, or 2 for BN = 256
@@ -516,7 +588,8 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
     const int slice = ew >> 2;            // which quarter of the BN columns
     const ConvParams& c = P.c;
     const int M = c.B * c.OH * c.OW;
-    const int lo_clamp = c.relu ? 0 : -128;   // relu.cl:54 folded into the clamp of pe.cl:194
+    const bool conv_relu = c.relu != 0;       // relu.cl:54, applied to the packed int8 values
+    const bool add_relu = c.add_relu != 0;    // feature_writer.cl:126
     // epilogue scratch lives behind the pipeline stages in dynamic shared memory
     unsigned char* epi_base = smem_raw + (smem_base - smem_u32(smem_raw)) + P.stages * stage_bytes;
     unsigned char* stage = epi_base + ew * EPI_WARP_BYTES;                         // int8 staging tile [32][EPI_ROW]
@@ -531,8 +604,6 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
       lut[it] = MODE == 1 ? row_lut[quarter * 32 + rl[it]] : 0u;
     }
     const bool has_res = FAST ? CT_RES : (c.r != nullptr);
-    const int hi_clamp = 127;
-    const int res_lo = c.add_relu ? 0 : -128;   // feature_writer.cl:126 folded into the final clamp
     const int my_row = quarter * 32 + lane;     // accumulator row (TMEM lane) of this thread
     const unsigned my_lut = MODE == 1 ? row_lut[my_row] : 0u;
     int buf = 0;
@@ -599,19 +670,28 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
           const int nn = ncolw + i;
           const int be = __ldg(c.beta + nn);
           const int nsh = (int)__ldg(c.nshift + nn);
-          prm[i] = __ldg(c.bias + nn);
-          prm[64 + i] = __ldg(c.alpha + nn);
-          if (FAST) {
-            // ((a + beta) >> 14 + 1) >> 1 == (acc*alpha + ((beta + 2^14) << 20)) >> 35 when nothing
-            // wraps (checked per layer at load time, api.cu range analysis)
-            const long long b64 = ((long long)be + 16384ll) << 20;
-            prm[128 + i] = (int)(unsigned)(b64 & 0xffffffffll);
-            prm[192 + i] = (int)(b64 >> 32);
+          const int bi = __ldg(c.bias + nn);
+          const int al = __ldg(c.alpha + nn);
+          if (FOLD) {
+            // acc = tot * 2^nsh + bias without wrap-around (api.cu range analysis), so
+            // acc*alpha + ((beta + 2^14) << 20) = tot * (alpha << nsh) + [bias*alpha + ((beta + 2^14) << 20)]
+            prm[i] = (int)((unsigned)al << nsh);
+            reinterpret_cast<long long*>(prm + 128)[i] = (long long)bi * (long long)al + (((long long)be + 16384ll) << 20);
           } else {
-            prm[128 + i] = be;
+            prm[i] = bi;
+            prm[64 + i] = al;
+            if (FAST) {
+              // ((a + beta) >> 14 + 1) >> 1 == (acc*alpha + ((beta + 2^14) << 20)) >> 35 when nothing
+              // wraps (checked per layer at load time, api.cu range analysis)
+              const long long b64 = ((long long)be + 16384ll) << 20;
+              prm[128 + i] = (int)(unsigned)(b64 & 0xffffffffll);
+              prm[192 + i] = (int)(b64 >> 32);
+            } else {
+              prm[128 + i] = be;
+            }
+            prm[256 + i] = 1 << nsh;                                   // (x << s) == x * 2^s  (mod 2^32)
+            prm[320 + i] = (nsh + 7 < 32) ? (1 << (nsh + 7)) : 0;      // second plane: x * 2^(s+7)
           }
-          prm[256 + i] = 1 << nsh;                                   // (x << s) == x * 2^s  (mod 2^32)
-          prm[320 + i] = (nsh + 7 < 32) ? (1 << (nsh + 7)) : 0;      // second plane: x * 2^(s+7)
         }
       }
       // ---- (1b) this thread's accumulator row -> pixel (for the residual), and the pixels of its
@@ -705,48 +785,58 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
           const int pc = pass * W + cc;
 #pragma unroll
           for (int j4 = 0; j4 < 4; j4++) {
-            const int4 pb = *reinterpret_cast<const int4*>(prm + pc + 4 * j4);
-            const int4 pa = *reinterpret_cast<const int4*>(prm + 64 + pc + 4 * j4);
-            const int4 pe = *reinterpret_cast<const int4*>(prm + 128 + pc + 4 * j4);
-            const int4 pm = *reinterpret_cast<const int4*>(prm + 256 + pc + 4 * j4);
-            const int bb[4] = {pb.x, pb.y, pb.z, pb.w}, aa[4] = {pa.x, pa.y, pa.z, pa.w};
-            const int ee[4] = {pe.x, pe.y, pe.z, pe.w}, mm[4] = {pm.x, pm.y, pm.z, pm.w};
             int yy[4];
-            if (FAST) {
-              const int4 ph = *reinterpret_cast<const int4*>(prm + 192 + pc + 4 * j4);
-              const int hh[4] = {ph.x, ph.y, ph.z, ph.w};
-              int m1[4] = {0, 0, 0, 0};
-              if (two) {
-                const int4 pq = *reinterpret_cast<const int4*>(prm + 320 + pc + 4 * j4);
-                m1[0] = pq.x; m1[1] = pq.y; m1[2] = pq.z; m1[3] = pq.w;
-              }
+            if (FOLD) {
+              const int4 pa = *reinterpret_cast<const int4*>(prm + pc + 4 * j4);
+              const longlong2 pb0 = *reinterpret_cast<const longlong2*>(prm + 128 + 2 * (pc + 4 * j4));
+              const longlong2 pb1 = *reinterpret_cast<const longlong2*>(prm + 128 + 2 * (pc + 4 * j4) + 4);
+              const int aa[4] = {pa.x, pa.y, pa.z, pa.w};
+              const long long bq[4] = {pb0.x, pb0.y, pb1.x, pb1.y};
 #pragma unroll
               for (int u = 0; u < 4; u++) {
                 const int j = 4 * j4 + u;
-                unsigned a32 = tot[j] * (unsigned)mm[u] + (unsigned)bb[u];
-                if (two) a32 = tot1[j] * (unsigned)m1[u] + a32;
-                if (has_low) a32 += low[j];
-                const long long b64 = ((long long)hh[u] << 32) | (unsigned)ee[u];
-                const long long t = (long long)(int)a32 * (long long)aa[u] + b64;   // IMAD.WIDE with 64-bit addend
-                yy[u] = max(lo_clamp, (int)(t >> 35));
+                const int tt = two ? (int)(tot1[j] * 128u + tot[j]) : (int)tot[j];
+                const long long t = (long long)tt * (long long)aa[u] + bq[u];   // IMAD.HI with the 64-bit addend
+                yy[u] = (int)(t >> 35);
               }
             } else {
+              const int4 pb = *reinterpret_cast<const int4*>(prm + pc + 4 * j4);
+              const int4 pa = *reinterpret_cast<const int4*>(prm + 64 + pc + 4 * j4);
+              const int4 pe = *reinterpret_cast<const int4*>(prm + 128 + pc + 4 * j4);
+              const int4 pm = *reinterpret_cast<const int4*>(prm + 256 + pc + 4 * j4);
+              const int bb[4] = {pb.x, pb.y, pb.z, pb.w}, aa[4] = {pa.x, pa.y, pa.z, pa.w};
+              const int ee[4] = {pe.x, pe.y, pe.z, pe.w}, mm[4] = {pm.x, pm.y, pm.z, pm.w};
+              if (FAST) {
+                const int4 ph = *reinterpret_cast<const int4*>(prm + 192 + pc + 4 * j4);
+                const int hh[4] = {ph.x, ph.y, ph.z, ph.w};
+                int m1[4] = {0, 0, 0, 0};
+                if (two) {
+                  const int4 pq = *reinterpret_cast<const int4*>(prm + 320 + pc + 4 * j4);
+                  m1[0] = pq.x; m1[1] = pq.y; m1[2] = pq.z; m1[3] = pq.w;
+                }
 #pragma unroll
-              for (int u = 0; u < 4; u++) {
-                const int j = 4 * j4 + u;
-                yy[u] = requant_lo((int)(tot[j] * (unsigned)mm[u] + (unsigned)bb[u] + low[j]), aa[u], ee[u], lo_clamp);
+                for (int u = 0; u < 4; u++) {
+                  const int j = 4 * j4 + u;
+                  unsigned a32 = tot[j] * (unsigned)mm[u] + (unsigned)bb[u];
+                  if (two) a32 = tot1[j] * (unsigned)m1[u] + a32;
+                  if (has_low) a32 += low[j];
+                  const long long b64 = ((long long)hh[u] << 32) | (unsigned)ee[u];
+                  const long long t = (long long)(int)a32 * (long long)aa[u] + b64;   // IMAD.WIDE with 64-bit addend
+                  yy[u] = (int)(t >> 35);
+                }
+              } else {
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                  const int j = 4 * j4 + u;
+                  yy[u] = requant_raw((int)(tot[j] * (unsigned)mm[u] + (unsigned)bb[u] + low[j]), aa[u], ee[u]);
+                }
               }
             }
-            if (has_res) {
-              // feature_writer.cl:124-127: the PE output is already an int8 (clamped) value; add the
-              // residual byte, clamp again (saturating pack), optional ReLU
-              const unsigned r4 = rw[j4];
-              yy[0] = max(res_lo, min(yy[0], hi_clamp) + ((int)(r4 << 24) >> 24));
-              yy[1] = max(res_lo, min(yy[1], hi_clamp) + ((int)(r4 << 16) >> 24));
-              yy[2] = max(res_lo, min(yy[2], hi_clamp) + ((int)(r4 << 8) >> 24));
-              yy[3] = max(res_lo, min(yy[3], hi_clamp) + ((int)r4 >> 24));
-            }
-            packed[j4] = pack_sat4(yy[0], yy[1], yy[2], yy[3]);
+            // pe.cl:194 clamp = saturating pack; relu.cl:54 and feature_writer.cl:124-127 on packed bytes
+            unsigned y4 = pack_sat4(yy[0], yy[1], yy[2], yy[3]);
+            if (conv_relu) y4 = relu_s8x4(y4);
+            if (has_res) y4 = add_relu ? add_res_s8x4<true>(y4, rw[j4]) : add_res_s8x4<false>(y4, rw[j4]);
+            packed[j4] = y4;
           }
           if (direct) {
             if (cc == 0) out_lo = make_uint4(packed[0], packed[1], packed[2], packed[3]);
@@ -839,6 +929,26 @@ int pick_bk(int Cp) { return (Cp % 128 == 0) ? 128 : 64; }
 // "Pixel pair" rows: a tensor whose pixel is exactly 64 bytes (e.g. tensor 0: 27 channels + negated
 // copy) read by an unpadded stride-1 convolution.  Two horizontally adjacent pixels are 128 contiguous
 // bytes, so one SWIZZLE_128B row carries two taps; TMA cost is per row, so this halves it.
+int pick_bn(int planes8, int N);
+
+// Halo mode: k x k, stride 1, the whole weight slab of an n-tile resident in shared memory and a
+// position-space row (OW + k - 1) that fits the 128 accumulator rows.  One TMA box per tile instead
+// of one per filter tap; measured: the 64-channel layers were bound by the number of TMA boxes/rows.
+bool halo_mode(int k, int stride, int Cp, int OW, int OH, int N, int planes8) {
+  static const bool allow = getenv("TF2B_MMA_HALO") == nullptr || atoi(getenv("TF2B_MMA_HALO")) != 0;
+  if (!allow || k < 2 || stride != 1 || OW + k - 1 > MMA_M) return false;
+  const int BK = pick_bk(Cp), BN = pick_bn(planes8, N);
+  const int kchunks = (Cp + BK - 1) / BK, n_tiles = (N + BN - 1) / BN;
+  const long long slab = (long long)k * k * kchunks * planes8 * BN * BK;
+  if (slab > 112 * 1024 || n_tiles > 16) return false;
+  const int Wp = OW + k - 1;
+  int th = MMA_M / Wp;
+  if (th > OH) th = OH;
+  const int rows = std::max(Wp * (th + k - 1), MMA_M + (k - 1) * (Wp + 1));
+  const long long stage = ((long long)rows * BK + 1023) / 1024 * 1024;
+  return slab + 2 * stage + EPI_BYTES + 2048 <= 226 * 1024;
+}
+
 bool pair_mode(int k, int stride, int pad, int Cp, int xC, int OW) {
   static const bool allow = getenv("TF2B_MMA_PAIR") == nullptr || atoi(getenv("TF2B_MMA_PAIR")) != 0;
   return allow && k >= 2 && stride == 1 && pad == 0 && Cp == 64 && xC == 64 && OW <= MMA_M;
@@ -857,7 +967,9 @@ int pick_bn(int planes8, int N) {
 void fill_geometry(MmaParams& P, const ConvParams& c, int planes8) {
   P.c = c;
   P.planes = planes8;
-  P.pair = pair_mode(c.k, c.stride, c.pad, c.Cp, c.xC, c.OW) ? 1 : 0;
+  P.halo = halo_mode(c.k, c.stride, c.Cp, c.OW, c.OH, c.N, planes8) ? 1 : 0;
+  P.Wp = c.OW + c.k - 1;
+  P.pair = (!P.halo && pair_mode(c.k, c.stride, c.pad, c.Cp, c.xC, c.OW)) ? 1 : 0;
   if (P.pair) {
     P.BK = 128;
     P.kchunks = (c.k + 1) / 2;
@@ -881,12 +993,12 @@ void fill_geometry(MmaParams& P, const ConvParams& c, int planes8) {
     P.a_bytes = MMA_M * P.BK;
   } else {
     P.tw = c.OW < MMA_M ? c.OW : MMA_M;
-    P.th = P.pair ? 1 : MMA_M / P.tw;
+    P.th = P.pair ? 1 : MMA_M / (P.halo ? P.Wp : P.tw);
     if (P.th > c.OH) P.th = c.OH;
     // balance rows over the tiles of one image (14 rows -> 7+7 rather than 9+5)
     int th_tiles = (c.OH + P.th - 1) / P.th;
     P.th = (c.OH + th_tiles - 1) / th_tiles;
-    P.tn = (P.th == c.OH && !P.pair) ? (MMA_M / (P.tw * P.th)) : 1;
+    P.tn = (P.th == c.OH && !P.pair && !P.halo) ? (MMA_M / (P.tw * P.th)) : 1;
     if (P.tn < 1) P.tn = 1;
     // NB: tn must not depend on the batch size of a particular run (the tensor map is built once for
     // max_images); images past the batch end are zero-filled / masked rows
@@ -894,17 +1006,23 @@ void fill_geometry(MmaParams& P, const ConvParams& c, int planes8) {
     P.tiles_h = (c.OH + P.th - 1) / P.th;
     P.tiles_b = (c.B + P.tn - 1) / P.tn;
     P.m_tiles = P.tiles_w * P.tiles_h * P.tiles_b;
-    P.a_bytes = P.tw * P.th * P.tn * P.BK;
+    P.a_bytes = P.halo ? P.Wp * (P.th + c.k - 1) * P.BK : P.tw * P.th * P.tn * P.BK;
+  }
+  P.a_stage_bytes = MMA_M * P.BK;
+  if (P.halo) {
+    // the shifted views of the last tap read (k-1)*(Wp+1) rows past the 128th (junk rows only)
+    const int rows = std::max(P.Wp * (P.th + c.k - 1), MMA_M + (c.k - 1) * (P.Wp + 1));
+    P.a_stage_bytes = (rows * P.BK + 1023) / 1024 * 1024;
   }
   P.b_bytes = P.BN * P.BK;
   // weight-stationary when the CTA's slab is small and the grid can be a multiple of n_tiles
   {
     static const bool allow = getenv("TF2B_MMA_BRES") == nullptr || atoi(getenv("TF2B_MMA_BRES")) != 0;
     const long long slab = (long long)P.taps * P.kchunks * planes8 * P.b_bytes;
-    P.b_resident = allow && slab <= 96 * 1024 && P.taps * P.kchunks * planes8 <= 64 && P.n_tiles <= 16;
+    P.b_resident = P.halo || (allow && slab <= 96 * 1024 && P.taps * P.kchunks * planes8 <= 64 && P.n_tiles <= 16);
     P.res_bytes = P.b_resident ? (int)slab : 0;
   }
-  const int stage_bytes = MMA_M * P.BK + (P.b_resident ? 0 : planes8 * P.b_bytes);
+  const int stage_bytes = P.a_stage_bytes + (P.b_resident ? 0 : planes8 * P.b_bytes);
   {
     static const bool allow = getenv("TF2B_MMA_RESTMA") == nullptr || atoi(getenv("TF2B_MMA_RESTMA")) != 0;
     P.res_tma = allow && c.r != nullptr && P.mode == 0 && P.BN >= 128 && (c.rC % 16 == 0);
@@ -953,7 +1071,9 @@ void fill_geometry(MmaParams& P, const ConvParams& c, int planes8) {
 
 int mma_bn() { return 256; }   // weight planes / params are padded to a multiple of this many rows
 int mma_pick_bk(int Cp) { return pick_bk(Cp); }
-bool mma_pair_mode(int k, int stride, int pad, int Cp, int xC, int OW) { return pair_mode(k, stride, pad, Cp, xC, OW); }
+bool mma_pair_mode(int k, int stride, int pad, int Cp, int xC, int OW, int OH, int N, int planes8) {
+  return !halo_mode(k, stride, Cp, OW, OH, N, planes8) && pair_mode(k, stride, pad, Cp, xC, OW);
+}
 
 bool mma_layer_supported(const tf2b_layer_desc& L, int in_pitch, int planes8) {
   if (L.ipool) return false;
@@ -1006,6 +1126,10 @@ int mma_build_tmaps(void* host_tmaps, const ConvParams& c, const int8_t* wgt8, i
     const cuuint32_t st = (cuuint32_t)c.stride;
     cuuint32_t box[4] = {(cuuint32_t)P.BK, (cuuint32_t)((P.tw - 1) * st + 1), (cuuint32_t)((P.th - 1) * st + 1),
                          (cuuint32_t)P.tn};
+    if (P.halo) {   // the whole input window of the tile: Wp x (th + k - 1) pixels (stride 1)
+      box[1] = (cuuint32_t)P.Wp;
+      box[2] = (cuuint32_t)(P.th + c.k - 1);
+    }
     cuuint32_t es[4] = {1, st, st, 1};
     r = enc(&tp->a, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, (void*)c.x, dims, strides, box, es,
             CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1054,23 +1178,26 @@ cudaError_t launch_conv_mma(const ConvParams& c, const int8_t* /*wgt8*/, int pla
   MmaParams P;
   fill_geometry(P, c, planes8);
   for (int i = 0; i < kMaxPlanes; i++) P.plane8_shift[i] = plane8_shift[i];
-  const int stage_bytes = MMA_M * P.BK + (P.b_resident ? 0 : planes8 * P.b_bytes);
+  const int stage_bytes = P.a_stage_bytes + (P.b_resident ? 0 : planes8 * P.b_bytes);
   const size_t smem = (size_t)P.res_bytes + (size_t)P.stages * stage_bytes + EPI_BYTES +
                       (P.res_tma ? (size_t)P.res_bufs * P.BN * 128 : 0) + 1024;
   using KernelFn = void (*)(MmaParams, TmapPair);
 #define TF2B_EPI_ROW(BN_, MODE_)                                                                              \
   {conv_mma_kernel<BN_, MODE_, -1>, conv_mma_kernel<BN_, MODE_, 0>, conv_mma_kernel<BN_, MODE_, 1>,            \
    conv_mma_kernel<BN_, MODE_, 2>,  conv_mma_kernel<BN_, MODE_, 3>, conv_mma_kernel<BN_, MODE_, 4>,            \
-   conv_mma_kernel<BN_, MODE_, 5>,  conv_mma_kernel<BN_, MODE_, 6>, conv_mma_kernel<BN_, MODE_, 7>}
-  static const KernelFn table[3][2][9] = {{TF2B_EPI_ROW(64, 0), TF2B_EPI_ROW(64, 1)},
-                                          {TF2B_EPI_ROW(128, 0), TF2B_EPI_ROW(128, 1)},
-                                          {TF2B_EPI_ROW(256, 0), TF2B_EPI_ROW(256, 1)}};
+   conv_mma_kernel<BN_, MODE_, 5>,  conv_mma_kernel<BN_, MODE_, 6>, conv_mma_kernel<BN_, MODE_, 7>,            \
+   conv_mma_kernel<BN_, MODE_, 8>,  conv_mma_kernel<BN_, MODE_, 9>, nullptr, nullptr,                          \
+   conv_mma_kernel<BN_, MODE_, 12>, conv_mma_kernel<BN_, MODE_, 13>, nullptr, nullptr}
+  static const KernelFn table[3][2][17] = {{TF2B_EPI_ROW(64, 0), TF2B_EPI_ROW(64, 1)},
+                                           {TF2B_EPI_ROW(128, 0), TF2B_EPI_ROW(128, 1)},
+                                           {TF2B_EPI_ROW(256, 0), TF2B_EPI_ROW(256, 1)}};
 #undef TF2B_EPI_ROW
   if (!attr_set) {
     const int lim = 226 * 1024;
     for (int a = 0; a < 3; a++)
       for (int b = 0; b < 2; b++)
-        for (int f = 0; f < 9; f++) {
+        for (int f = 0; f < 17; f++) {
+          if (!table[a][b][f]) continue;
           cudaError_t e = cudaFuncSetAttribute(table[a][b][f], cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
           if (e != cudaSuccess) return e;
         }
@@ -1079,7 +1206,13 @@ cudaError_t launch_conv_mma(const ConvParams& c, const int8_t* /*wgt8*/, int pla
   // the fast requantisation needs at most two scaled planes (+ the optional low plane)
   const int scaled_planes = planes8 - (c.low_plane >= 0 ? 1 : 0);
   const bool fast = c.fast_requant != 0 && scaled_planes <= 2 && (c.low_plane < 0 || c.low_plane == planes8 - 1);
-  const int epi = fast ? (1 + ((scaled_planes == 2 ? 1 : 0) | (c.low_plane >= 0 ? 2 : 0) | (c.r != nullptr ? 4 : 0))) : 0;
+  // folded form (one IMAD.HI per output): additionally needs alpha << nshift in int32 and an accumulator
+  // that cannot wrap (fast_requant == 2, api.cu), and no unscaled low plane
+  static const bool allow_fold = getenv("TF2B_MMA_FOLD") == nullptr || atoi(getenv("TF2B_MMA_FOLD")) != 0;
+  const bool fold = fast && allow_fold && c.fast_requant >= 2 && c.low_plane < 0;
+  const int epi = fast ? (1 + ((scaled_planes == 2 ? 1 : 0) | (c.low_plane >= 0 ? 2 : 0) | (c.r != nullptr ? 4 : 0) |
+                               (fold ? 8 : 0)))
+                       : 0;
   const KernelFn kfn = table[P.BN == 256 ? 2 : (P.BN == 128 ? 1 : 0)][P.mode][epi];
   const int num_tiles = P.m_tiles * P.n_tiles;
   int grid = num_tiles < num_sms ? num_tiles : num_sms;
