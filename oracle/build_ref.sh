@@ -24,3 +24,11 @@ dev="$ref/Runtime_Engine/cnn/device/src"
 /usr/bin/gcc -x c -std=gnu11 -O1 -fPIC -shared -w -DRESNET50 -I"$dev" -I"$host/inc" \
     "$here/ref_device/pe_harness.c" -o "$out/libtf2ref_pe.so"
 echo "built: libtf2ref_pe.so"
+# the reference's post-PE kernels (relu / pool / pool_tail / feature_writer / full_size_pool) compiled as
+# C with each network's own tables (ref_device/post_harness.c)
+for net in RESNET50 GOOGLENET RESNET50_PRUNED; do
+  lower=$(echo "$net" | tr 'A-Z' 'a-z')
+  /usr/bin/gcc -x c -std=gnu11 -O1 -fPIC -shared -w -D"$net" -I"$dev" -I"$host/inc" -I"$here/ref_device" \
+      "$here/ref_device/post_harness.c" -o "$out/libtf2ref_post_${lower}.so"
+done
+echo "built: libtf2ref_post_{resnet50,googlenet,resnet50_pruned}.so"

@@ -147,3 +147,101 @@ def ref_host_lib(net_name: str):
     L.ref_load_model.argtypes = [C.c_char_p, vp, vp, vp]
     L.ref_load_input_image.argtypes = [C.c_char_p, vp, vp]
     return L
+
+
+# ---- compiled reference post-PE kernels (oracle/_ref/libtf2ref_post_<net>.so) --------------------
+POST_TABLES = ["N", "OH1", "OW1", "stride", "k", "relu", "pool", "pool_s2", "pool_pad", "PH", "PW", "add",
+               "add_relu", "gap", "ipool", "n_start", "n_end", "ddr_wen", "ddr_wbase", "ddr_rbase", "cache_wen",
+               "cache_wbase", "nvec", "pwvec"]
+
+
+class RefPost:
+    """relu.cl -> pool.cl -> pool_tail.cl -> feature_writer.cl -> full_size_pool.cl of the reference,
+    compiled as C with the network's own tables (oracle/ref_device/post_harness.c)."""
+
+    def __init__(self, net_name: str):
+        p = os.path.join(_HERE, "_ref", f"libtf2ref_post_{net_name}.so")
+        if not os.path.exists(p):
+            raise FileNotFoundError(p)
+        L = C.CDLL(p)
+        L.post_output_offset.restype = C.c_longlong
+        L.post_ddr_bytes.restype = C.c_longlong
+        L.post_const.restype = C.c_longlong
+        L.post_run.argtypes = [C.c_int] + [C.c_void_p] * 4 + [C.c_longlong, C.c_void_p, C.c_void_p, C.c_longlong,
+                                                              C.c_void_p, C.c_void_p]
+        self.L = L
+        self.n_layers = L.post_num_layers()
+        self.tab = [{k: L.post_table(i, l) for i, k in enumerate(POST_TABLES)} for l in range(self.n_layers)]
+        self.consts = [L.post_const(i) for i in range(4)]
+        self.item_bytes = L.post_item_bytes()
+        self.item_off = L.post_item_data_offset()
+
+    def pe_shape(self, l):
+        """shape of the PE-output map of layer l: channels, rows (stride applied), columns (stride 1)"""
+        t = self.tab[l]
+        return (t["n_end"] - t["n_start"], -(-t["OH1"] // t["stride"]), t["OW1"])
+
+    def _run(self, maps, n_feed):
+        offs = np.zeros(self.n_layers, np.int64)
+        chunks, o = [], 0
+        for l in range(self.n_layers):
+            m = np.ascontiguousarray(maps[l], dtype=np.int8).reshape(-1)
+            offs[l] = o
+            chunks.append(m)
+            o += m.size
+        y = np.concatenate(chunks)
+        ddr = np.zeros(self.L.post_ddr_bytes(), np.int8)
+        cap = 200000
+        cache = np.zeros(cap * self.item_bytes, np.uint8)
+        gap = np.zeros(4096 * self.item_bytes, np.uint8)
+        nc, ng = C.c_longlong(0), C.c_longlong(0)
+        counts = np.zeros(4, np.int64)
+        rc = self.L.post_run(n_feed, y.ctypes.data, offs.ctypes.data, ddr.ctypes.data, cache.ctypes.data, cap,
+                             C.byref(nc), gap.ctypes.data, 4096, C.byref(ng), counts.ctypes.data)
+        if rc != 0:
+            raise RuntimeError(f"post_run failed: {rc}")
+        ci = cache[: nc.value * self.item_bytes].reshape(nc.value, self.item_bytes)
+        gi = gap[: ng.value * self.item_bytes].reshape(ng.value, self.item_bytes)
+        return ddr, ci, gi, counts
+
+    def _tiles_to_map(self, tiles, nch, PH, PW):
+        """[nvec][PH][pwvec][8][16] tiles (w_inc, n_inc) -> [nch][PH][PW]"""
+        nvec, _, pwvec = tiles.shape[:3]
+        t = tiles[:, :, :, :7, :]                                  # w_inc 0..6 used (W_VECTOR = 7)
+        t = t.transpose(0, 4, 1, 2, 3).reshape(nvec * 16, PH, pwvec * 7)
+        return np.ascontiguousarray(t[:nch, :, :PW])
+
+    def run(self, maps):
+        """maps[l]: int8 [nch][H][W1] PE outputs of layer l.  Returns (outs, counts): outs[l] is the
+        int8 [nch][PH][PW] map the reference produced for layer l ([nch] for global-average layers)."""
+        ddr, ci, gi, counts = self._run(maps, self.n_layers)
+        data = ci[:, self.item_off:self.item_off + 128].view(np.int8).reshape(-1, 8, 16)
+        gdata = gi[:, self.item_off:self.item_off + 128].view(np.int8).reshape(-1, 8, 16)
+        outs = [None] * self.n_layers
+        pos = gpos = 0
+        for l, t in enumerate(self.tab):
+            nch = t["n_end"] - t["n_start"]
+            PH, PW, nvec, pwvec = t["PH"], t["PW"], t["nvec"], t["pwvec"]
+            cnt = nvec * PH * pwvec
+            if t["gap"]:
+                g = gdata[gpos:gpos + nvec]
+                gpos += nvec
+                outs[l] = np.ascontiguousarray(g[:, 0, :].reshape(-1)[:nch])
+            elif t["cache_wen"]:
+                tiles = data[pos:pos + cnt].reshape(nvec, PH, pwvec, 8, 16)
+                pos += cnt
+                outs[l] = self._tiles_to_map(tiles, nch, PH, PW)
+        assert pos == data.shape[0] and gpos == gdata.shape[0], "unconsumed reference items"
+        # layers that only go to feature_ddr: read the DDR image right after that layer ran
+        oo = self.L.post_output_offset()
+        for l, t in enumerate(self.tab):
+            if outs[l] is not None:
+                continue
+            last = l == self.n_layers - 1
+            d = ddr if last else self._run(maps, l + 1)[0]
+            nch, PH, PW, nvec = t["n_end"] - t["n_start"], t["PH"], t["PW"], t["nvec"]
+            pwv = -(-PW // 7)
+            base = (t["ddr_wbase"] + (t["n_start"] // 16) * PH * pwv) * 128 + (oo if last else 0)
+            tiles = d[base: base + nvec * PH * pwv * 128].reshape(nvec, PH, pwv, 8, 16)
+            outs[l] = self._tiles_to_map(tiles, nch, PH, PW)
+        return outs, counts

@@ -74,17 +74,20 @@ int post_table(int which, int l) {
  * N_VECTOR, oh, ow by OW_VECTOR (3x3 mode) or W_VECTOR (1x1 mode); an item exists where
  * kNStart+n < kNEnd, oh < H, ow < W), then runs relu -> pool -> pool_tail -> feature_writer ->
  * full_size_pool to completion for ONE frame.
+ *   n_feed_layers : only layers [0, n_feed_layers) are fed; the kernels stop when their input runs
+ *                   dry, so feature_ddr then shows the state right after that layer (the DDR pages
+ *                   are ping-pong buffers that later layers overwrite)
  *   y, y_off : concatenated per-layer maps [N][H][W1] and their byte offsets
  *   ddr      : feature_ddr image (caller-zeroed, post_ddr_bytes() long)
  *   cache_items / n_cache : raw PoolTailOutput items feature_writer sent to the retriever
  *   gap_items / n_gap     : raw PoolTailOutput items full_size_pool emitted
  * returns 0, or a negative code when an item count disagrees with the reference's cycle constants */
-int post_run(const signed char* y, const long long* y_off, signed char* ddr, unsigned char* cache_items,
+int post_run(int n_feed_layers, const signed char* y, const long long* y_off, signed char* ddr, unsigned char* cache_items,
              long long cache_cap, long long* n_cache, unsigned char* gap_items, long long gap_cap,
              long long* n_gap, long long* counts /* [4]: relu in, pool out, fw in, fw out */) {
   fifo_reset_all();
   long long n_relu_in = 0;
-  for (int l = 0; l < NUM_CONVOLUTIONS; l++) {
+  for (int l = 0; l < NUM_CONVOLUTIONS && l < n_feed_layers; l++) {
     const int N = kNEndWithOffset[l], OH = kOhEndWithOffset[l], OW = kOwEndWithOffset[l];
     const int H = CEIL(kOutputHeight[l], kConvStride[l]), W = kOutputWidth[l];
     const int FH = kFilterSize[l];
