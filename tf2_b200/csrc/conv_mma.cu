@@ -36,6 +36,7 @@ constexpr int MMA_M = 128;
 constexpr int NUM_EPI_WARPS = 16;
 constexpr int NUM_THREADS = 32 * (2 + NUM_EPI_WARPS);
 constexpr int MAX_STAGES = 8;
+constexpr int MAX_RBUFS = 6;   // residual tile ring (flat layers with a TMA-fed residual operand)
 constexpr int TMEM_COLS = 512;
 constexpr int EPI_ROW = 48;   // bytes per staging row: 32 data + 16 pad (conflict-free 16-byte accesses)
 constexpr int EPI_WARP_BYTES = 32 * EPI_ROW + 6 * 64 * 4;   // staging tile + params of one epilogue warp
@@ -80,7 +81,7 @@ struct MmaParams {
   int roles_top;            // experiment switch: producer/MMA warps at the highest warp ids
   int l2_prefetch;          // tiles ahead whose activation boxes are prefetched into L2 (0 = off)
   int res_tma;              // residual tiles arrive through TMA into a smem ring (flat layers, BN >= 128)
-  int res_bufs;             // ring depth (1 or 2)
+  int res_bufs;             // ring depth (2..MAX_RBUFS)
   int b_resident;           // the CTA's weight slab (all taps/chunks/planes of its n-tile) stays in smem
   int res_bytes;            // bytes of that slab
   int halo;                 // halo mode (box tiles, stride 1, resident weights): ONE TMA box per tile and
@@ -332,7 +333,7 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
   const int res_tile = BN * 128;   // one residual tile: 128 rows x BN bytes as BN/128 SWIZZLE_128B sub-tiles
   const unsigned smem_rres = smem_base + (unsigned)(P.stages * stage_bytes + EPI_BYTES);   // residual ring
 
-  __shared__ __align__(8) unsigned long long bars[2 * MAX_STAGES + 9];
+  __shared__ __align__(8) unsigned long long bars[2 * MAX_STAGES + 5 + 2 * MAX_RBUFS];
   __shared__ unsigned tmem_base_slot;
   __shared__ unsigned row_lut[MMA_M];   // box mode: row -> (wl | hl<<8 | nl<<16 | inbox<<24)
   const unsigned full_bar = smem_u32(&bars[0]);                  // [stages]
@@ -340,8 +341,8 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
   const unsigned tfull_bar = smem_u32(&bars[2 * MAX_STAGES]);    // [2]
   const unsigned tempty_bar = smem_u32(&bars[2 * MAX_STAGES + 2]);  // [2]
   const unsigned bres_bar = smem_u32(&bars[2 * MAX_STAGES + 4]);    // resident weight slab landed
-  const unsigned rfull_bar = smem_u32(&bars[2 * MAX_STAGES + 5]);   // [2] residual tile landed
-  const unsigned rempty_bar = smem_u32(&bars[2 * MAX_STAGES + 7]);  // [2] residual tile consumed
+  const unsigned rfull_bar = smem_u32(&bars[2 * MAX_STAGES + 5]);                // [MAX_RBUFS] residual tile landed
+  const unsigned rempty_bar = smem_u32(&bars[2 * MAX_STAGES + 5 + MAX_RBUFS]);   // [MAX_RBUFS] residual tile consumed
 
   // Warp roles.  The SM's issue arbiter favours higher warp ids, so the two single-issuer warps that
   // feed the tensor pipe sit at the top and are never starved by the ALU-heavy epilogue warps:
@@ -364,7 +365,7 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
       mbar_init(tempty_bar + 8 * b, NUM_EPI_WARPS);
     }
     mbar_init(bres_bar, 1);
-    for (int b = 0; b < 2; b++) {
+    for (int b = 0; b < MAX_RBUFS; b++) {
       mbar_init(rfull_bar + 8 * b, 1);
       mbar_init(rempty_bar + 8 * b, NUM_EPI_WARPS);
     }
@@ -424,6 +425,8 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
           const TileCoord pt = decode_tile(P, ptile);
           if (MODE == 0) {
             for (int kc = 0; kc < P.kchunks; kc++) tma_prefetch_2d(&maps.a, kc * P.BK, pt.m0);
+            if (P.res_tma)
+              for (int j = 0; j < BN / 128; j++) tma_prefetch_2d(&maps.r, pt.n0 + j * 128, pt.m0);
           } else if (P.pair) {
             for (int fh = 0; fh < P.taps; fh++)
               tma_prefetch_2d(&maps.a, 0, ((pt.b0 * P.c.IH + pt.oh0 + fh) * P.c.IW + pt.ow0));
@@ -515,19 +518,30 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
         if (dbg) ti0 = clock64();
         if (P.halo) {
           if (elect_one()) {
-            // all taps of this channel chunk read the same halo tile through row-shifted descriptors
-            for (int tap = 0; tap < P.taps; tap++) {
-              const int fh = tap / P.c.k, fw = tap - fh * P.c.k;
-              const unsigned long long dat = make_smem_desc(sa + (unsigned)((fh * P.Wp + fw) * P.BK), P.sbo16, P.layout_type);
-              const unsigned long long db =
-                  make_smem_desc(smem_res + ((tap * P.kchunks + it) * P.planes) * b_plane, P.sbo16, P.layout_type);
-              const unsigned acc0 = (it > 0 || tap > 0) ? 1u : 0u;
-              umma_i8(d_tmem, dat, db, P.idesc, acc0);
-              umma_i8(d_tmem, dat + 2ull, db + 2ull, P.idesc, 1u);
-              if (P.BK == 128) {
-                umma_i8(d_tmem, dat + 4ull, db + 4ull, P.idesc, 1u);
-                umma_i8(d_tmem, dat + 6ull, db + 6ull, P.idesc, 1u);
+            // all taps of this channel chunk read the same halo tile through row-shifted descriptors.
+            // Only the 14-bit start-address field differs between taps, so the descriptors advance by
+            // plain additions (no per-tap division / descriptor rebuild on this single-thread path).
+            const unsigned long long a_px16 = (unsigned long long)(P.BK >> 4);
+            const unsigned long long a_row16 = (unsigned long long)((P.Wp * P.BK) >> 4);
+            const unsigned long long b_tap16 = (unsigned long long)((P.kchunks * P.planes * b_plane) >> 4);
+            unsigned long long da_row = da;
+            unsigned long long db = make_smem_desc(smem_res + it * P.planes * b_plane, P.sbo16, P.layout_type);
+            unsigned acc0 = it > 0 ? 1u : 0u;
+            const int kk = P.c.k;
+            for (int fh = 0; fh < kk; fh++) {
+              unsigned long long dat = da_row;
+              for (int fw = 0; fw < kk; fw++) {
+                umma_i8(d_tmem, dat, db, P.idesc, acc0);
+                umma_i8(d_tmem, dat + 2ull, db + 2ull, P.idesc, 1u);
+                if (P.BK == 128) {
+                  umma_i8(d_tmem, dat + 4ull, db + 4ull, P.idesc, 1u);
+                  umma_i8(d_tmem, dat + 6ull, db + 6ull, P.idesc, 1u);
+                }
+                acc0 = 1u;
+                dat += a_px16;
+                db += b_tap16;
               }
+              da_row += a_row16;
             }
             umma_commit(empty_bar + 8 * stage);
             if (it == kiters - 1) umma_commit(tfull_bar + 8 * buf);
@@ -1028,9 +1042,20 @@ void fill_geometry(MmaParams& P, const ConvParams& c, int planes8) {
     P.res_tma = allow && c.r != nullptr && P.mode == 0 && P.BN >= 128 && (c.rC % 16 == 0);
     P.res_bufs = 2;
     if (P.res_tma) {
-      // keep at least three pipeline stages; drop to a single residual buffer, then give up
-      auto stages_with = [&](int bufs) { return (224 * 1024 - EPI_BYTES - P.res_bytes - bufs * P.BN * 128) / stage_bytes; };
-      if (stages_with(2) < 3) P.res_tma = 0;   // a single buffer would serialise the producer
+      // The residual operand streams from HBM once; what hides its latency is the number of tiles in
+      // flight (measured: with two buffers the producer idles on the ring).  Split shared memory into
+      // whole tiles in flight: (activation stages of one tile + one residual tile) each.
+      static const int cap = getenv("TF2B_MMA_RBUFS") ? atoi(getenv("TF2B_MMA_RBUFS")) : 2;   // measured: deeper rings do not help
+      const int budget = 224 * 1024 - EPI_BYTES - P.res_bytes;
+      const int per_tile = P.kchunks * stage_bytes + P.BN * 128;
+      int t = budget / per_tile;
+      if (t > MAX_RBUFS) t = MAX_RBUFS;
+      if (t > cap) t = cap;
+      if (t < 2) t = 2;
+      P.res_bufs = t;
+      auto stages_with = [&](int bufs) { return (budget - bufs * P.BN * 128) / stage_bytes; };
+      if (stages_with(P.res_bufs) < 3) P.res_bufs = 2;
+      if (stages_with(P.res_bufs) < 3) P.res_tma = 0;   // a single buffer would serialise the producer
     }
   }
   const int rres_bytes = P.res_tma ? P.res_bufs * P.BN * 128 : 0;
