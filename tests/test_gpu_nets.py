@@ -1,0 +1,47 @@
+"""GPU parity for the other shipped networks — GoogLeNet (BASELINE configs[4]: 1x1 inception branches,
+5x5 convs, concat offsets, ipool pseudo layers, ceil-mode pools) and channel-pruned ResNet50 (ragged
+channel counts) — whole network vs the CPU oracle, every tensor of image 0."""
+import os
+
+import numpy as np
+import pytest
+
+from tests import helpers as H
+from tests.conftest import GOLDEN
+from tf2_b200 import capi, formats, nets, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _model(name):
+    net = nets.load(name)
+    q = formats.parse_q_file(net, os.path.join(GOLDEN, f"{name}_Q"))
+    blob = synth.synth_float_blob(net, seed=5, q=q)
+    return net, q, formats.load_float_blob(net, blob, q)
+
+
+@pytest.mark.parametrize("name,variant", [("googlenet", capi.VARIANT_AUTO), ("googlenet", capi.VARIANT_SHIFT),
+                                          ("resnet50_pruned", capi.VARIANT_AUTO)],
+                         ids=["googlenet-auto", "googlenet-shift", "resnet50_pruned-auto"])
+def test_network_matches_oracle(name, variant):
+    import torch
+    from oracle import oracle as O
+    from tf2_b200.network import NetWork, Runner
+    net, q, model = _model(name)
+    B = 3
+    imgs = synth.synth_images(B, seed=17)
+    raw, t0 = formats.prepare_input(net, imgs, q)
+    nw = NetWork(net, 0)
+    nw.InitFromCodes(model, q, max_images=B, variant=variant)
+    r = Runner(nw)
+    got = r.run_device(torch.from_numpy(raw).cuda(), raw224=True).cpu().numpy()
+    exp = O.run_network(net, model, t0)
+    assert got.shape == exp.shape
+    assert np.array_equal(got, exp), f"{name}: result differs in {(got != exp).sum()} of {exp.size}"
+    tens, accs = H.oracle_tensors(net, model, t0[0])
+    for t in range(1, len(net.tensors)):
+        g = r.read_tensor(t, B).cpu().numpy()[0]
+        assert np.array_equal(g, tens[t]), f"{name}: tensor {t} ({net.tensors[t].name}) differs in {(g != tens[t]).sum()}"
+    kinds = set(nw.layer_kernels())
+    assert ("mma" in kinds) == (variant != capi.VARIANT_SHIFT)
+    nw.CleanUp()

@@ -39,7 +39,8 @@ constexpr int MAX_STAGES = 8;
 constexpr int MAX_RBUFS = 6;   // residual tile ring (flat layers with a TMA-fed residual operand)
 constexpr int TMEM_COLS = 512;
 constexpr int EPI_ROW = 48;   // bytes per staging row: 32 data + 16 pad (conflict-free 16-byte accesses)
-constexpr int EPI_WARP_BYTES = 32 * EPI_ROW + 6 * 64 * 4;   // staging tile + params of one epilogue warp
+constexpr int PSTR = 64;      // per-channel parameter arrays of one epilogue warp: [6][PSTR] int32
+constexpr int EPI_WARP_BYTES = 32 * EPI_ROW + 6 * PSTR * 4;   // staging tile + params of one epilogue warp
 constexpr int EPI_BYTES = NUM_EPI_WARPS * EPI_WARP_BYTES;
 
 // x / d for 0 <= x, d < 2^20:  (x * ceil(2^40/d)) >> 40   (exact in that range)
@@ -90,6 +91,8 @@ struct MmaParams {
                             // address + (fh * Wp + fw) * BK: the swizzle is a function of the address bits)
   int Wp;                   // halo mode: row width of the position space = tw + k - 1
   int a_stage_bytes;        // bytes reserved per pipeline stage for the activation tile
+  int egroups;              // epilogue warp groups (1: all 16 warps share every tile; 2: 8 warps per tile,
+                            // the groups take alternate tiles = alternate TMEM buffers)
 };
 
 struct TmapPair {
@@ -319,7 +322,8 @@ __device__ __forceinline__ unsigned add_res_s8x4(unsigned y4, unsigned r4) {
 // EPI < 0: exact requantisation, every option decided at run time.  EPI >= 0: fused 64-bit
 // requantisation (range-analysed layers) specialised on bit0 = second scaled plane, bit1 = low plane,
 // bit2 = residual operand, bit3 = folded form: y = (tot * (alpha << nshift) + (bias*alpha +
-// ((beta + 2^14) << 20))) >> 35 with tot = plane0 + (plane1 << 7) — one IMAD.HI per output.
+// ((beta + 2^14) << 20))) >> 35 with tot = plane0 + (plane1 << 7) — one IMAD.HI per output; bit4 = two
+// epilogue groups of 8 warps that take alternate tiles (one tile's serial latency no longer paces the CTA).
 template <int BN, int MODE, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ TmapPair maps) {
@@ -362,12 +366,12 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
     }
     for (int b = 0; b < 2; b++) {
       mbar_init(tfull_bar + 8 * b, 1);
-      mbar_init(tempty_bar + 8 * b, NUM_EPI_WARPS);
+      mbar_init(tempty_bar + 8 * b, NUM_EPI_WARPS / P.egroups);
     }
     mbar_init(bres_bar, 1);
     for (int b = 0; b < MAX_RBUFS; b++) {
       mbar_init(rfull_bar + 8 * b, 1);
-      mbar_init(rempty_bar + 8 * b, NUM_EPI_WARPS);
+      mbar_init(rempty_bar + 8 * b, NUM_EPI_WARPS / P.egroups);
     }
     fence_barrier_init();
   }
@@ -500,13 +504,13 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
     // ===================================================== MMA issuer (whole warp, one elected lane issues)
     int stage = 0;
     unsigned phase = 0;
-    int buf = 0;
-    unsigned tphase[2] = {0, 0};
     const bool dbg = P.dbg != nullptr;
     long long w_full = 0, w_tempty = 0, t_issue = 0, t_start = clock64();
     if (P.b_resident && (int)blockIdx.x < num_tiles) mbar_wait_warp(bres_bar, 0, P.poll_lane0);
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      mbar_wait_timed(tempty_bar + 8 * buf, tphase[buf] ^ 1, w_tempty, dbg, P.poll_lane0);   // epilogue has drained this accumulator
+    int li = 0;   // CTA-local tile index: TMEM buffer li & 1, its phase (li >> 1) & 1
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, li++) {
+      const int buf = li & 1;
+      mbar_wait_timed(tempty_bar + 8 * buf, ((unsigned)(li >> 1) & 1u) ^ 1u, w_tempty, dbg, P.poll_lane0);   // epilogue has drained this accumulator
       tc_fence_after();
       const unsigned d_tmem = tmem_base + buf * acc_cols;
       for (int it = 0; it < kiters; it++) {
@@ -570,8 +574,6 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
         if (dbg) t_issue += clock64() - ti0;
         if (++stage == P.stages) { stage = 0; phase ^= 1; }
       }
-      tphase[buf] ^= 1;
-      buf ^= 1;
     }
     if (dbg && lane == 0) {
       P.dbg[blockIdx.x * 8 + 2] = w_full;
@@ -592,14 +594,17 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
     constexpr bool CT_LOW = FAST && (EPI & 2);
     constexpr bool CT_RES = FAST && (EPI & 4);
     constexpr bool FOLD = FAST && (EPI & 8);
-    constexpr int WT = BN / 4;            // columns per warp: 16, 32 or 64
+    constexpr int G = 1;                  // epilogue groups; group g owns the tiles with local index % G == g
+    constexpr int SLICES = 4 / G;         // column slices of a tile (one warp per lane quarter and slice)
+    constexpr int WT = BN / SLICES;       // columns per warp: 16..128
     constexpr int W = WT > 32 ? 32 : WT;  // columns per pass (staging tile width)
-    constexpr int PASSES = WT / W;        // 1, or 2 for BN = 256
+    constexpr int PASSES = WT / W;        // 1, 2 or 4
     constexpr int SEGS = W / 16;          // 16-byte segments per row (1 or 2) = iterations per pass
     constexpr int ROWS_PER_IT = 32 / SEGS;
     const int ew = warp - 2;              // 0..15 == hardware warp id
     const int quarter = hw_warp & 3;      // TMEM lane quarter this warp may access (hardware warp id % 4)
-    const int slice = ew >> 2;            // which quarter of the BN columns
+    const int slice = (ew >> 2) & (SLICES - 1);   // which part of the BN columns
+    const int group = G == 2 ? (ew >> 3) : 0;
     const ConvParams& c = P.c;
     const int M = c.B * c.OH * c.OW;
     const bool conv_relu = c.relu != 0;       // relu.cl:54, applied to the packed int8 values
@@ -607,7 +612,7 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
     // epilogue scratch lives behind the pipeline stages in dynamic shared memory
     unsigned char* epi_base = smem_raw + (smem_base - smem_u32(smem_raw)) + P.stages * stage_bytes;
     unsigned char* stage = epi_base + ew * EPI_WARP_BYTES;                         // int8 staging tile [32][EPI_ROW]
-    int* prm = reinterpret_cast<int*>(stage + 32 * EPI_ROW);                       // [6][64] per-channel params
+    int* prm = reinterpret_cast<int*>(stage + 32 * EPI_ROW);                       // [6][PSTR] per-channel params
     // coalesced mapping (constant per thread): iteration it -> row rl[it], 16-byte segment sg
     const int sg = lane % SEGS;
     int rl[SEGS];
@@ -620,8 +625,6 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
     const bool has_res = FAST ? CT_RES : (c.r != nullptr);
     const int my_row = quarter * 32 + lane;     // accumulator row (TMEM lane) of this thread
     const unsigned my_lut = MODE == 1 ? row_lut[my_row] : 0u;
-    int buf = 0;
-    unsigned tphase[2] = {0, 0};
     int cached_ncol0 = -1;
     const bool dbg = P.dbg != nullptr && warp == 2;   // first epilogue warp
     long long w_tfull = 0, t_start = clock64();
@@ -638,8 +641,10 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
         pix = ((long long)b * c.OH + oh) * c.OW + ow;
       }
     };
-    int rb = 0;
-    unsigned rphase = 0;
+    int rb = 0;            // residual ring slot / phase and TMEM buffer / phase of the current tile,
+    unsigned rphase = 0;   // all derived from the CTA-local tile index li
+    int buf = 0;
+    unsigned tph = 0;
     const bool res_tma = (MODE == 0) && (BN >= 128) && P.res_tma != 0;
     // residual bytes of this thread's row, columns [col, col + 16*SEGS) of the CTA tile, from the smem ring
     auto lds_res = [&](int col, uint4 (&dst)[SEGS]) {
@@ -673,7 +678,15 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
         }
       }
     };
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    int li = group;   // CTA-local tile index
+    for (int tile = blockIdx.x + group * gridDim.x; tile < num_tiles; tile += G * gridDim.x, li += G) {
+      buf = li & 1;
+      tph = (unsigned)(li >> 1) & 1u;
+      if (MODE == 0 && P.res_tma) {
+        const int q = li / P.res_bufs;
+        rb = li - q * P.res_bufs;
+        rphase = (unsigned)q & 1u;
+      }
       const TileCoord t = decode_tile(P, tile);
       const int ncolw = t.n0 + slice * WT;        // first output channel of this warp
       // ---- (1a) params of this warp's WT channels -> smem, only when the channel slice changes
@@ -690,21 +703,21 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
             // acc = tot * 2^nsh + bias without wrap-around (api.cu range analysis), so
             // acc*alpha + ((beta + 2^14) << 20) = tot * (alpha << nsh) + [bias*alpha + ((beta + 2^14) << 20)]
             prm[i] = (int)((unsigned)al << nsh);
-            reinterpret_cast<long long*>(prm + 128)[i] = (long long)bi * (long long)al + (((long long)be + 16384ll) << 20);
+            reinterpret_cast<long long*>(prm + PSTR)[i] = (long long)bi * (long long)al + (((long long)be + 16384ll) << 20);
           } else {
             prm[i] = bi;
-            prm[64 + i] = al;
+            prm[PSTR + i] = al;
             if (FAST) {
               // ((a + beta) >> 14 + 1) >> 1 == (acc*alpha + ((beta + 2^14) << 20)) >> 35 when nothing
               // wraps (checked per layer at load time, api.cu range analysis)
               const long long b64 = ((long long)be + 16384ll) << 20;
-              prm[128 + i] = (int)(unsigned)(b64 & 0xffffffffll);
-              prm[192 + i] = (int)(b64 >> 32);
+              prm[2 * PSTR + i] = (int)(unsigned)(b64 & 0xffffffffll);
+              prm[3 * PSTR + i] = (int)(b64 >> 32);
             } else {
-              prm[128 + i] = be;
+              prm[2 * PSTR + i] = be;
             }
-            prm[256 + i] = 1 << nsh;                                   // (x << s) == x * 2^s  (mod 2^32)
-            prm[320 + i] = (nsh + 7 < 32) ? (1 << (nsh + 7)) : 0;      // second plane: x * 2^(s+7)
+            prm[4 * PSTR + i] = 1 << nsh;                                   // (x << s) == x * 2^s  (mod 2^32)
+            prm[5 * PSTR + i] = (nsh + 7 < 32) ? (1 << (nsh + 7)) : 0;      // second plane: x * 2^(s+7)
           }
         }
       }
@@ -738,20 +751,17 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
       if (!res_tma) load_res(rvalid, rpix, ncolw, resq);
       __syncwarp();
       // ---- (2) accumulators -> requantise (+ residual) -> int8 staging tile -> (3) coalesced store
-      mbar_wait_timed(tfull_bar + 8 * buf, tphase[buf], w_tfull, dbg, P.poll_lane0);
+      mbar_wait_timed(tfull_bar + 8 * buf, tph, w_tfull, dbg, P.poll_lane0);
       tc_fence_after();
       if (P.noepi & 1) {   // TF2B_MMA_NOEPI bit0: measure the TMA/MMA pipeline alone
         if (has_res && (MODE == 0) && (BN >= 128) && P.res_tma) {
           mbar_wait_warp(rfull_bar + 8 * rb, rphase, P.poll_lane0);
           __syncwarp();
           if (lane == 0) mbar_arrive(rempty_bar + 8 * rb);
-          if (++rb == P.res_bufs) { rb = 0; rphase ^= 1; }
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty_bar + 8 * buf);
-        tphase[buf] ^= 1;
-        buf ^= 1;
         continue;
       }
       const bool direct = (SEGS == 2) && P.direct256 != 0;
@@ -802,8 +812,8 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
             int yy[4];
             if (FOLD) {
               const int4 pa = *reinterpret_cast<const int4*>(prm + pc + 4 * j4);
-              const longlong2 pb0 = *reinterpret_cast<const longlong2*>(prm + 128 + 2 * (pc + 4 * j4));
-              const longlong2 pb1 = *reinterpret_cast<const longlong2*>(prm + 128 + 2 * (pc + 4 * j4) + 4);
+              const longlong2 pb0 = *reinterpret_cast<const longlong2*>(prm + PSTR + 2 * (pc + 4 * j4));
+              const longlong2 pb1 = *reinterpret_cast<const longlong2*>(prm + PSTR + 2 * (pc + 4 * j4) + 4);
               const int aa[4] = {pa.x, pa.y, pa.z, pa.w};
               const long long bq[4] = {pb0.x, pb0.y, pb1.x, pb1.y};
 #pragma unroll
@@ -815,17 +825,17 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
               }
             } else {
               const int4 pb = *reinterpret_cast<const int4*>(prm + pc + 4 * j4);
-              const int4 pa = *reinterpret_cast<const int4*>(prm + 64 + pc + 4 * j4);
-              const int4 pe = *reinterpret_cast<const int4*>(prm + 128 + pc + 4 * j4);
-              const int4 pm = *reinterpret_cast<const int4*>(prm + 256 + pc + 4 * j4);
+              const int4 pa = *reinterpret_cast<const int4*>(prm + PSTR + pc + 4 * j4);
+              const int4 pe = *reinterpret_cast<const int4*>(prm + 2 * PSTR + pc + 4 * j4);
+              const int4 pm = *reinterpret_cast<const int4*>(prm + 4 * PSTR + pc + 4 * j4);
               const int bb[4] = {pb.x, pb.y, pb.z, pb.w}, aa[4] = {pa.x, pa.y, pa.z, pa.w};
               const int ee[4] = {pe.x, pe.y, pe.z, pe.w}, mm[4] = {pm.x, pm.y, pm.z, pm.w};
               if (FAST) {
-                const int4 ph = *reinterpret_cast<const int4*>(prm + 192 + pc + 4 * j4);
+                const int4 ph = *reinterpret_cast<const int4*>(prm + 3 * PSTR + pc + 4 * j4);
                 const int hh[4] = {ph.x, ph.y, ph.z, ph.w};
                 int m1[4] = {0, 0, 0, 0};
                 if (two) {
-                  const int4 pq = *reinterpret_cast<const int4*>(prm + 320 + pc + 4 * j4);
+                  const int4 pq = *reinterpret_cast<const int4*>(prm + 5 * PSTR + pc + 4 * j4);
                   m1[0] = pq.x; m1[1] = pq.y; m1[2] = pq.z; m1[3] = pq.w;
                 }
 #pragma unroll
@@ -900,10 +910,7 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
       if (has_res && res_tma) {
         __syncwarp();
         if (lane == 0) mbar_arrive(rempty_bar + 8 * rb);
-        if (++rb == P.res_bufs) { rb = 0; rphase ^= 1; }
       }
-      tphase[buf] ^= 1;
-      buf ^= 1;
     }
     if (dbg && lane == 0) {
       P.dbg[blockIdx.x * 8 + 5] = w_tfull;
@@ -1213,15 +1220,16 @@ cudaError_t launch_conv_mma(const ConvParams& c, const int8_t* /*wgt8*/, int pla
    conv_mma_kernel<BN_, MODE_, 5>,  conv_mma_kernel<BN_, MODE_, 6>, conv_mma_kernel<BN_, MODE_, 7>,            \
    conv_mma_kernel<BN_, MODE_, 8>,  conv_mma_kernel<BN_, MODE_, 9>, nullptr, nullptr,                          \
    conv_mma_kernel<BN_, MODE_, 12>, conv_mma_kernel<BN_, MODE_, 13>, nullptr, nullptr}
-  static const KernelFn table[3][2][17] = {{TF2B_EPI_ROW(64, 0), TF2B_EPI_ROW(64, 1)},
-                                           {TF2B_EPI_ROW(128, 0), TF2B_EPI_ROW(128, 1)},
-                                           {TF2B_EPI_ROW(256, 0), TF2B_EPI_ROW(256, 1)}};
+  constexpr int kEpiVariants = 17;   // index = EPI + 1
+  static const KernelFn table[3][2][kEpiVariants] = {{TF2B_EPI_ROW(64, 0), TF2B_EPI_ROW(64, 1)},
+                                                     {TF2B_EPI_ROW(128, 0), TF2B_EPI_ROW(128, 1)},
+                                                     {TF2B_EPI_ROW(256, 0), TF2B_EPI_ROW(256, 1)}};
 #undef TF2B_EPI_ROW
   if (!attr_set) {
     const int lim = 226 * 1024;
     for (int a = 0; a < 3; a++)
       for (int b = 0; b < 2; b++)
-        for (int f = 0; f < 17; f++) {
+        for (int f = 0; f < kEpiVariants; f++) {
           if (!table[a][b][f]) continue;
           cudaError_t e = cudaFuncSetAttribute(table[a][b][f], cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
           if (e != cudaSuccess) return e;
@@ -1238,7 +1246,11 @@ cudaError_t launch_conv_mma(const ConvParams& c, const int8_t* /*wgt8*/, int pla
   const int epi = fast ? (1 + ((scaled_planes == 2 ? 1 : 0) | (c.low_plane >= 0 ? 2 : 0) | (c.r != nullptr ? 4 : 0) |
                                (fold ? 8 : 0)))
                        : 0;
-  const KernelFn kfn = table[P.BN == 256 ? 2 : (P.BN == 128 ? 1 : 0)][P.mode][epi];
+  // (a variant with two epilogue groups of 8 warps taking alternate tiles was measured: no gain on the
+  // epilogue-bound layers, slower with a residual operand — the epilogue is throughput bound, L1TEX ~72 %)
+  const int epi_idx = epi;
+  P.egroups = 1;
+  const KernelFn kfn = table[P.BN == 256 ? 2 : (P.BN == 128 ? 1 : 0)][P.mode][epi_idx];
   const int num_tiles = P.m_tiles * P.n_tiles;
   int grid = num_tiles < num_sms ? num_tiles : num_sms;
   if (P.b_resident) {

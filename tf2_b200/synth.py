@@ -67,6 +67,16 @@ def synth_float_blob(net: NetDesc, seed: int = 0, zero_frac: float = 0.2,
         # He-style scale -> largest magnitude level 2^max_exp, 7 levels below it
         std = np.sqrt(2.0 / fan_in)
         max_exp = int(np.clip(np.round(np.log2(std * 2.5)), -8, 0))
+        if q is not None and not ld.bn_en:
+            # no BatchNorm to rescale (GoogLeNet, fc layers): pick the layer's largest weight level so
+            # that the conv output itself has about target_rms LSBs of 2^-Q_out
+            Cq = net.input_c if ld.first_layer_7x7 else C
+            Qin = -q[ld.q_in_row, :Cq].astype(np.float64)
+            Qout = -q[ld.q_out_row, :N].astype(np.float64)
+            x_rms = (50.0 if ld.q_in_row == 0 else target_rms / np.sqrt(2.0)) * np.mean(np.exp2(-Qin))
+            rel2 = float(np.sum(lvl_p * np.exp2(-2.0 * np.arange(7))))
+            want = target_rms * np.mean(np.exp2(-Qout)) / (np.sqrt(fan_in * (1.0 - zero_frac) * rel2) * x_rms)
+            max_exp = int(np.clip(np.round(np.log2(want)), -8, 0))
         lv = rng.choice(7, size=(N, C, H, W), p=lvl_p)
         mag = np.exp2((max_exp - lv).astype(np.float32))
         sign = rng.choice(np.array([-1.0, 1.0], dtype=np.float32), size=(N, C, H, W))
