@@ -158,6 +158,11 @@ int tf2b_get_profile(tf2b_net* net, float* conv_ms, float* layer_ms, int n_layer
 int tf2b_last_launches(tf2b_net* net);
 /* Name of the convolution kernel the plan uses for a layer ("shift", "mma", "none"). */
 const char* tf2b_layer_kernel(tf2b_net* net, int layer);
+/* Launch plan of `layer` for a batch of n_images (0 = max_images): "shift", "pool", or for the
+ * tensor-core kernel e.g. "mma BN128 BK128 planes2 box fold ctapair stages5" (tile sizes, operand
+ * staging mode — flat / box / halo / pixelpair —, resident weights, folded requantisation, CTA-pair
+ * MMA).  Introspection for tests and profiles; the string lives until the next call for that layer. */
+const char* tf2b_layer_mode(tf2b_net* net, int layer, int n_images);
 
 const char* tf2b_last_error(tf2b_net* net);
 const char* tf2b_version(void);

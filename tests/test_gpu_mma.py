@@ -115,3 +115,57 @@ def test_mma_parity(name, chw, specs, B, ckw):
         out1 = r.run_device(torch.from_numpy(x[:1].copy()).cuda()).cpu().numpy()
         assert np.array_equal(out1[0], out[0])
     nw.CleanUp()
+
+
+# ---- staging / MMA modes: make sure each one is actually selected and is bit-exact -----------------
+# name, input CHW, spec, batch, random_codes kwargs, substring the launch plan must contain
+MODE_CASES = [
+    # CTA pairs (tcgen05.mma.cta_group::2): streamed weights, 256-wide MMA; odd and even m-tile counts
+    ("pair_flat_p1_c512_n256", (512, 14, 14), dict(N=256, k=1), 5, dict(per_c_offset=0), "ctapair"),
+    ("pair_flat_p2_c512_n128", (512, 28, 28), dict(N=128, k=1), 1, dict(per_c_offset=4, per_n_offset=5), "ctapair"),
+    ("pair_flat_odd_tiles", (1024, 9, 9), dict(N=256, k=1), 7, dict(per_c_offset=0), "ctapair"),   # 567 pixels: 5 m-tiles
+    ("pair_box_p1_c256_14", (256, 14, 14), dict(N=256, k=3, pad=1), 9, dict(per_c_offset=0), "box"),
+    ("pair_box_p2_c128_28", (128, 28, 28), dict(N=128, k=3, pad=1), 3, dict(shift_lo=1, per_c_offset=4, per_n_offset=0), "box"),
+    ("pair_box_s2_c256", (256, 28, 28), dict(N=256, k=3, pad=1, stride=2), 5, dict(per_c_offset=0), "box"),
+    ("pair_box_residual", (256, 14, 14), dict(N=256, k=3, pad=1, relu=0, add=0, add_relu=1), 6, dict(per_c_offset=0), "ctapair"),
+    # halo tiles: one TMA box per tile, taps as row-shifted descriptor views
+    ("halo_3x3_c64_56", (64, 56, 56), dict(N=64, k=3, pad=1), 2, {}, "halo"),
+    ("halo_3x3_c64_56_p1", (64, 56, 56), dict(N=64, k=3, pad=1), 2, dict(per_c_offset=0), "halo"),
+    ("halo_5x5_c16_28", (16, 28, 28), dict(N=32, k=5, pad=2), 3, dict(per_c_offset=0), "halo"),
+    ("halo_3x3_nopad_c32_30", (32, 30, 30), dict(N=64, k=3, pad=0), 2, {}, "halo"),
+    ("halo_3x3_c192_9_three_chunks", (192, 9, 9), dict(N=64, k=3, pad=1), 4, dict(per_c_offset=0), "halo"),
+    ("halo_ragged_rows_c32_13", (32, 13, 13), dict(N=32, k=3, pad=1), 3, {}, "halo"),
+]
+
+
+@pytest.mark.parametrize("name,chw,spec,B,ckw,want", MODE_CASES, ids=[c[0] for c in MODE_CASES])
+def test_mma_modes(name, chw, spec, B, ckw, want):
+    import torch
+    from tf2_b200.network import NetWork, Runner
+    rng = np.random.default_rng(zlib.crc32(name.encode()))
+    net = nets.chain(chw, [dict(N=chw[0], k=1, relu=1), dict(spec)], name)
+    x = H.random_input(rng, *chw, nonneg=True, B=B)
+    old = H.random_codes
+    try:
+        if ckw:
+            H.random_codes = lambda rng_, N, C, k, **kw: old(rng_, N, C, k, **ckw)
+        model = H.random_model(net, rng, x)
+    finally:
+        H.random_codes = old
+    nw = NetWork(net, 0)
+    nw.InitFromCodes(model, None, max_images=B, variant=capi.VARIANT_MMA)
+    plan = nw.layer_modes(B)[1]
+    assert want in plan, f"{name}: expected '{want}' in the launch plan, got '{plan}'"
+    if name.startswith("pair"):
+        assert "ctapair" in plan and "fold" in plan, plan
+    r = Runner(nw)
+    out = r.run_device(torch.from_numpy(x).cuda()).cpu().numpy()
+    for b in range(B):
+        tens, _ = H.oracle_tensors(net, model, x[b])
+        bad = out[b] != tens[net.result_tensor()]
+        assert not bad.any(), f"{name} [{plan}]: image {b} differs in {bad.sum()} of {bad.size} (first {np.argwhere(bad)[:4].tolist()})"
+    # fewer images than max_images: other tile counts (pairs with a missing partner, ragged last tile)
+    for nb in {1, max(1, B - 1)}:
+        o = r.run_device(torch.from_numpy(x[:nb].copy()).cuda()).cpu().numpy()
+        assert np.array_equal(o, out[:nb]), f"{name}: sub-batch of {nb} differs"
+    nw.CleanUp()

@@ -35,7 +35,7 @@ SYMBOLS = [
     "tf2b_create", "tf2b_load_layer", "tf2b_load_layer_packed4", "tf2b_finalize", "tf2b_set_variant",
     "tf2b_weight_blob_bytes", "tf2b_export_weight_blob", "tf2b_import_weight_blob", "tf2b_run",
     "tf2b_run_raw224", "tf2b_run_raw224_host", "tf2b_submit_raw224_host", "tf2b_wait", "tf2b_run_host", "tf2b_set_result", "tf2b_read_tensor",
-    "tf2b_dump_acc", "tf2b_set_profile", "tf2b_get_profile", "tf2b_last_launches", "tf2b_layer_kernel", "tf2b_last_error", "tf2b_version",
+    "tf2b_dump_acc", "tf2b_set_profile", "tf2b_get_profile", "tf2b_last_launches", "tf2b_layer_kernel", "tf2b_layer_mode", "tf2b_last_error", "tf2b_version",
     "tf2b_destroy",
 ]
 
@@ -80,6 +80,8 @@ def load() -> C.CDLL:
     lib.tf2b_last_launches.argtypes = [vp]
     lib.tf2b_layer_kernel.argtypes = [vp, i32]
     lib.tf2b_layer_kernel.restype = C.c_char_p
+    lib.tf2b_layer_mode.argtypes = [vp, i32, i32]
+    lib.tf2b_layer_mode.restype = C.c_char_p
     lib.tf2b_last_error.argtypes = [vp]
     lib.tf2b_last_error.restype = C.c_char_p
     lib.tf2b_version.restype = C.c_char_p

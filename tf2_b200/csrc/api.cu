@@ -33,6 +33,7 @@ bool mma_layer_supported(const tf2b_layer_desc& L, int in_pitch, int planes8);
 cudaError_t launch_conv_mma(const ConvParams& p, const int8_t* wgt8, int planes8,
                             const int* plane8_shift, void* tmaps, cudaStream_t stream);
 size_t mma_tmap_bytes();
+std::string mma_describe(const ConvParams& p, int planes8);
 int mma_build_tmaps(void* host_tmaps, const ConvParams& p, const int8_t* wgt8, int planes8,
                     std::string* err);
 int mma_bn();
@@ -70,6 +71,7 @@ struct LayerState {
   size_t off_w16 = 0, off_w8 = 0, off_bias = 0, off_alpha = 0, off_beta = 0, off_nshift = 0, off_nshift_m = 0;
   int kernel = 0;  // 0 none (ipool), 1 shift, 2 mma
   std::vector<unsigned char> h_tmaps;  // CUtensorMap blobs for the mma path (host copy)
+  std::string mode_desc;               // tf2b_layer_mode() text
   size_t off_tmaps = 0;
 };
 
@@ -974,6 +976,22 @@ const char* tf2b_layer_kernel(tf2b_net* net, int layer) {
   const LayerState& S = net->layers[layer];
   if (S.d.ipool) return "none";
   return (S.kernel == 2 && S.mma_ok) ? "mma" : "shift";
+}
+
+const char* tf2b_layer_mode(tf2b_net* net, int layer, int n_images) {
+  if (!net || !net->finalized || layer < 0 || layer >= (int)net->layers.size()) return "none";
+  LayerState& S = net->layers[layer];
+  if (S.d.ipool) return "pool";
+  if (!(S.kernel == 2 && S.mma_ok)) return "shift";
+  const tf2b_layer_desc& d = S.d;
+  const bool to_scratch = d.pool || d.gap;
+  int8_t* dst = to_scratch ? net->scratch0 : net->tbuf[d.out_tensor] + d.out_ch0;
+  const int dstC = to_scratch ? round_up(d.N, 16) : net->tpitch[d.out_tensor];
+  const int8_t* res = (d.add_tensor >= 0 && !d.pool) ? net->tbuf[d.add_tensor] : nullptr;
+  const int resC = (d.add_tensor >= 0 && !d.pool) ? net->tpitch[d.add_tensor] : 0;
+  ConvParams p = conv_params(net, S, n_images > 0 ? n_images : net->max_images, dst, dstC, res, resC, true);
+  S.mode_desc = tf2b::mma_describe(p, S.planes_m);
+  return S.mode_desc.c_str();
 }
 
 void tf2b_destroy(tf2b_net* net) {

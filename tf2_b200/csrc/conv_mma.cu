@@ -91,6 +91,9 @@ struct MmaParams {
                             // address + (fh * Wp + fw) * BK: the swizzle is a function of the address bits)
   int Wp;                   // halo mode: row width of the position space = tw + k - 1
   int a_stage_bytes;        // bytes reserved per pipeline stage for the activation tile
+  int cg2;                  // CTA-pair mode: clusters of two CTAs, tcgen05.mma.cta_group::2 (M = 256 over two
+                            // SMs, each CTA stages its own 128 activation rows and HALF of the weight tile)
+  int b_stage_bytes;        // bytes of weights one CTA stages per k-iteration
   int egroups;              // epilogue warp groups (1: all 16 warps share every tile; 2: 8 warps per tile,
                             // the groups take alternate tiles = alternate TMEM buffers)
 };
@@ -208,6 +211,67 @@ __device__ __forceinline__ void tmem_ld16(unsigned taddr, unsigned (&v)[16]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---- CTA-pair (cta_group::2) forms.  Shared-memory window addresses carry the CTA rank of the pair in
+// bit 24 (cute/arch/copy_sm100_tma.hpp Sm100MmaPeerBitMask): clearing it names the leader's copy.
+constexpr unsigned kPeerBitMask = 0xFEFFFFFFu;
+__device__ __forceinline__ unsigned cluster_ctarank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the leader CTA's copy of a barrier (from either CTA of the pair)
+__device__ __forceinline__ void mbar_arrive_leader(unsigned bar) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, 0;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(bar)
+      : "memory");
+}
+// TMA loads issued by either CTA of the pair into its OWN shared memory, completing on the LEADER's barrier
+__device__ __forceinline__ void tma_load_2d_cg2(unsigned smem, const CUtensorMap* map, unsigned bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem), "l"(map), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_cg2(unsigned smem, const CUtensorMap* map, unsigned bar, int c0, int c1,
+                                                int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem), "l"(map), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_cg2(unsigned smem_dst, unsigned ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_cg2(unsigned taddr, unsigned ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// completion of all prior MMAs of the pair -> the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void umma_commit_cg2(unsigned bar) {
+  asm volatile(
+      "{\n\t.reg .b16 m;\n\tmov.b16 m, 3;\n\t"
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n\t}"
+      ::"r"(bar)
+      : "memory");
+}
+// D[tmem of both CTAs] (+)= A[smem of both] * B[smem halves of both], M = 256
+__device__ __forceinline__ void umma_i8_cg2(unsigned tmem_d, unsigned long long desc_a, unsigned long long desc_b,
+                                            unsigned idesc, unsigned accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 // One elected lane of a converged warp (the form CUTLASS uses: keeps the surrounding code
 // warp-uniform so descriptors live in uniform registers and UTCIMMA/UTMALDG issue back to back).
 __device__ __forceinline__ bool elect_one() {
@@ -324,7 +388,7 @@ __device__ __forceinline__ unsigned add_res_s8x4(unsigned y4, unsigned r4) {
 // bit2 = residual operand, bit3 = folded form: y = (tot * (alpha << nshift) + (bias*alpha +
 // ((beta + 2^14) << 20))) >> 35 with tot = plane0 + (plane1 << 7) — one IMAD.HI per output; bit4 = two
 // epilogue groups of 8 warps that take alternate tiles (one tile's serial latency no longer paces the CTA).
-template <int BN, int MODE, int EPI>
+template <int BN, int MODE, int EPI, bool CG2 = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ TmapPair maps) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -333,7 +397,12 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
   const unsigned smem_base = smem_res + (unsigned)P.res_bytes;
   const int a_stage = P.a_stage_bytes;
   const int b_plane = BN * P.BK;
-  const int stage_bytes = a_stage + (P.b_resident ? 0 : P.planes * b_plane);
+  const int stage_bytes = a_stage + (P.b_resident ? 0 : P.b_stage_bytes);
+  // CG2 is a template parameter: a kernel that contains cta_group::2 instructions can only be launched
+  // as a cluster of CTA pairs
+  constexpr bool cg2 = CG2;
+  unsigned cta_rank = 0u;
+  if constexpr (CG2) cta_rank = cluster_ctarank();
   const int res_tile = BN * 128;   // one residual tile: 128 rows x BN bytes as BN/128 SWIZZLE_128B sub-tiles
   const unsigned smem_rres = smem_base + (unsigned)(P.stages * stage_bytes + EPI_BYTES);   // residual ring
 
@@ -361,12 +430,12 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
     tma_prefetch_desc(&maps.a);
     tma_prefetch_desc(&maps.b);
     for (int s = 0; s < P.stages; s++) {
-      mbar_init(full_bar + 8 * s, 1);
+      mbar_init(full_bar + 8 * s, cg2 ? 2 : 1);   // pair mode: the producers of both CTAs arrive on the leader's
       mbar_init(empty_bar + 8 * s, 1);
     }
     for (int b = 0; b < 2; b++) {
       mbar_init(tfull_bar + 8 * b, 1);
-      mbar_init(tempty_bar + 8 * b, NUM_EPI_WARPS / P.egroups);
+      mbar_init(tempty_bar + 8 * b, (cg2 ? 2 : 1) * NUM_EPI_WARPS / P.egroups);   // pair: both CTAs' epilogues
     }
     mbar_init(bres_bar, 1);
     for (int b = 0; b < MAX_RBUFS; b++) {
@@ -375,7 +444,10 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(smem_u32(&tmem_base_slot), TMEM_COLS);
+  if (warp == 1) {
+    if constexpr (cg2) tmem_alloc_cg2(smem_u32(&tmem_base_slot), TMEM_COLS);
+    else tmem_alloc(smem_u32(&tmem_base_slot), TMEM_COLS);
+  }
   if (MODE == 1 && threadIdx.x >= 64 && threadIdx.x < 64 + MMA_M) {
     const int row = threadIdx.x - 64;
     const int roww = P.halo ? P.Wp : P.tw;   // halo mode: accumulator rows walk the padded raster
@@ -387,9 +459,20 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (cg2) cluster_sync_all();   // the peer's barriers must be initialised before anything signals them
   tc_fence_after();
   const unsigned tmem_base = tmem_base_slot;
   const int acc_cols = P.planes * BN;  // TMEM columns of one accumulator buffer
+  // Work items of this CTA: tiles blockIdx.x, +gridDim.x, ...  Pair mode: work item q = (pair of adjacent
+  // m-tiles, n-tile); the pair blockIdx.x/2 walks q, rank r of the pair owns m-tile 2*mp + r.
+  const int q_first = cg2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int q_step = cg2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int q_count = cg2 ? ((P.m_tiles + 1) >> 1) * P.n_tiles : num_tiles;
+  auto tile_of = [&](int q) -> int {
+    if (!cg2) return q;
+    const int mp = fdiv(q, P.d_ntiles);
+    return (2 * mp + (int)cta_rank) * P.n_tiles + (q - mp * P.n_tiles);
+  };
   // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor
   // prefetch, row LUT) overlaps the tail of the previous layer's kernel; from here on this grid
   // reads what that kernel wrote, so wait for it to complete and flush.  The next layer's grid may
@@ -419,9 +502,10 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
     }
     int rb = 0;
     unsigned rphase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int q = q_first; q < q_count; q += q_step) {
+      const int tile = tile_of(q);
       const TileCoord t = decode_tile(P, tile);
-      if (P.l2_prefetch > 0) {
+      if (P.l2_prefetch > 0 && !cg2) {
         // activations are streamed from HBM once; with only a few stages in flight the ~2 us DRAM
         // latency is not covered, so the boxes of a later tile of this CTA are pulled into L2 now
         const int ptile = tile + P.l2_prefetch * (int)gridDim.x;
@@ -476,7 +560,23 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
           mbar_wait_timed(empty_bar + 8 * stage, phase ^ 1, w_empty, dbg, P.poll_lane0);
           const unsigned fb = full_bar + 8 * stage;
           const unsigned sa = smem_base + stage * stage_bytes;
-          if (elect_one()) {
+          if constexpr (cg2) {
+            // Pair mode: both producers signal the LEADER's full barrier (its MMA warp drives both SMs).
+            // This CTA stages its own 128 activation rows and its half of the weight tile: plane
+            // `rank` of a two-plane layer, or rows rank*128.. of a 256-wide single plane.
+            if (elect_one()) {
+              if (cta_rank == 0) mbar_expect_tx(fb, 2u * (unsigned)(P.a_bytes + P.b_stage_bytes));
+              else mbar_arrive_leader(fb);
+              if (MODE == 0) {
+                tma_load_2d_cg2(sa, &maps.a, fb, kc * P.BK, t.m0);
+              } else {
+                tma_load_4d_cg2(sa, &maps.a, fb, kc * P.BK, t.ow0 * P.c.stride - P.c.pad + fw,
+                                t.oh0 * P.c.stride - P.c.pad + fh, t.b0);
+              }
+              const int brow = P.planes == 2 ? (int)cta_rank * P.Npad + t.n0 : t.n0 + (int)cta_rank * (BN / 2);
+              tma_load_2d_cg2(sa + a_stage, &maps.r, fb, tap * P.Cpm + kc * P.BK, brow);
+            }
+          } else if (elect_one()) {
             mbar_expect_tx(fb, (unsigned)(P.a_bytes + (P.b_resident ? 0 : P.planes * P.b_bytes)));
             if (MODE == 0) {
               tma_load_2d(sa, &maps.a, fb, kc * P.BK, t.m0);
@@ -508,7 +608,7 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
     long long w_full = 0, w_tempty = 0, t_issue = 0, t_start = clock64();
     if (P.b_resident && (int)blockIdx.x < num_tiles) mbar_wait_warp(bres_bar, 0, P.poll_lane0);
     int li = 0;   // CTA-local tile index: TMEM buffer li & 1, its phase (li >> 1) & 1
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, li++) {
+    for (int q = q_first; q < q_count && (!cg2 || cta_rank == 0); q += q_step, li++) {   // pair mode: the leader issues
       const int buf = li & 1;
       mbar_wait_timed(tempty_bar + 8 * buf, ((unsigned)(li >> 1) & 1u) ^ 1u, w_tempty, dbg, P.poll_lane0);   // epilogue has drained this accumulator
       tc_fence_after();
@@ -558,7 +658,17 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
           const unsigned long long db = make_smem_desc(bsrc, P.sbo16, P.layout_type);
           const unsigned acc0 = it > 0 ? 1u : 0u;
           // advance both descriptors by 32 bytes of K inside the swizzled row
-          if (P.BK == 128) {
+          if constexpr (cg2) {
+            // one M = 256 instruction spans both SMs: A = the two CTAs' activation tiles, B = their halves
+            umma_i8_cg2(d_tmem, da, db, P.idesc, acc0);
+            umma_i8_cg2(d_tmem, da + 2ull, db + 2ull, P.idesc, 1u);
+            if (P.BK == 128) {
+              umma_i8_cg2(d_tmem, da + 4ull, db + 4ull, P.idesc, 1u);
+              umma_i8_cg2(d_tmem, da + 6ull, db + 6ull, P.idesc, 1u);
+            }
+            umma_commit_cg2(empty_bar + 8 * stage);
+            if (it == kiters - 1) umma_commit_cg2(tfull_bar + 8 * buf);
+          } else if (P.BK == 128) {
             umma_i8(d_tmem, da, db, P.idesc, acc0);
             umma_i8(d_tmem, da + 2ull, db + 2ull, P.idesc, 1u);
             umma_i8(d_tmem, da + 4ull, db + 4ull, P.idesc, 1u);
@@ -567,8 +677,10 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
             umma_i8(d_tmem, da, db, P.idesc, acc0);
             umma_i8(d_tmem, da + 2ull, db + 2ull, P.idesc, 1u);
           }
-          umma_commit(empty_bar + 8 * stage);             // frees the smem stage when the MMAs retire
-          if (it == kiters - 1) umma_commit(tfull_bar + 8 * buf);   // accumulators complete -> epilogue
+          if (!cg2) {
+            umma_commit(empty_bar + 8 * stage);             // frees the smem stage when the MMAs retire
+            if (it == kiters - 1) umma_commit(tfull_bar + 8 * buf);   // accumulators complete -> epilogue
+          }
         }
         __syncwarp();
         if (dbg) t_issue += clock64() - ti0;
@@ -679,7 +791,8 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
       }
     };
     int li = group;   // CTA-local tile index
-    for (int tile = blockIdx.x + group * gridDim.x; tile < num_tiles; tile += G * gridDim.x, li += G) {
+    for (int q = q_first + group * q_step; q < q_count; q += G * q_step, li += G) {
+      const int tile = tile_of(q);
       buf = li & 1;
       tph = (unsigned)(li >> 1) & 1u;
       if (MODE == 0 && P.res_tma) {
@@ -761,7 +874,10 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar + 8 * buf);
+        if (lane == 0) {
+            if constexpr (cg2) mbar_arrive_leader(tempty_bar + 8 * buf);   // the leader's MMA warp waits for both CTAs
+            else mbar_arrive(tempty_bar + 8 * buf);
+          }
         continue;
       }
       const bool direct = (SEGS == 2) && P.direct256 != 0;
@@ -873,7 +989,10 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
           // accumulator buffer drained: hand it back to the MMA warp as early as possible
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(tempty_bar + 8 * buf);
+          if (lane == 0) {
+            if constexpr (cg2) mbar_arrive_leader(tempty_bar + 8 * buf);   // the leader's MMA warp waits for both CTAs
+            else mbar_arrive(tempty_bar + 8 * buf);
+          }
         } else {
           if (!direct) __syncwarp();
           if (has_res && res_tma) lds_res(slice * WT + (pass + 1) * W, resq);
@@ -920,9 +1039,11 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (cg2) cluster_sync_all();   // neither CTA may leave while its peer can still signal its barriers / read its smem
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if constexpr (cg2) tmem_dealloc_cg2(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -985,6 +1106,13 @@ int pick_bn(int planes8, int N) {
 }
 
 // geometry shared by the support test, the tensor-map builder and the launcher
+// the folded requantisation (one IMAD.HI per output) applies: range analysis passed, <= 2 scaled planes,
+// no unscaled low plane
+bool fold_applies(const ConvParams& c, int planes8) {
+  static const bool allow_fold = getenv("TF2B_MMA_FOLD") == nullptr || atoi(getenv("TF2B_MMA_FOLD")) != 0;
+  return allow_fold && c.fast_requant >= 2 && c.low_plane < 0 && planes8 <= 2;
+}
+
 void fill_geometry(MmaParams& P, const ConvParams& c, int planes8) {
   P.c = c;
   P.planes = planes8;
@@ -1066,7 +1194,20 @@ void fill_geometry(MmaParams& P, const ConvParams& c, int planes8) {
     }
   }
   const int rres_bytes = P.res_tma ? P.res_bufs * P.BN * 128 : 0;
-  int st = (224 * 1024 - EPI_BYTES - P.res_bytes - rres_bytes) / stage_bytes;
+  // CTA-pair mode for streaming-weight layers whose MMA is 256 wide: one SM ingests ~64 B/clk, an
+  // M128 x N256 x K32 step needs 12 KB per 128 clk (96 B/clk); the pair's M256 x N256 step needs 8 KB per SM.
+  P.b_stage_bytes = planes8 * P.b_bytes;
+  P.cg2 = 0;
+  {
+    static const bool allow = getenv("TF2B_MMA_CG2") == nullptr || atoi(getenv("TF2B_MMA_CG2")) != 0;
+    if (allow && !P.halo && !P.pair && !P.b_resident && !P.res_tma && planes8 * P.BN == 256 && planes8 <= 2 &&
+        P.m_tiles >= 4 && P.BK == 128 && fold_applies(c, planes8)) {
+      P.cg2 = 1;
+      P.b_stage_bytes = 128 * P.BK;   // half of the 256 weight rows
+    }
+  }
+  const int stage_bytes_final = P.a_stage_bytes + (P.b_resident ? 0 : P.b_stage_bytes);
+  int st = (224 * 1024 - EPI_BYTES - P.res_bytes - rres_bytes) / stage_bytes_final;
   P.stages = st > MAX_STAGES ? MAX_STAGES : (st < 2 ? 2 : st);
   {
     static const int cap = getenv("TF2B_MMA_STAGES") ? atoi(getenv("TF2B_MMA_STAGES")) : 0;   // experiment switch
@@ -1075,7 +1216,8 @@ void fill_geometry(MmaParams& P, const ConvParams& c, int planes8) {
   // instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): c_format S32 (2) at bit 4,
   // a/b format signed int8 (1) at bits 7 / 10, K-major A and B, N>>3 at bit 17, M>>4 at bit 24,
   // saturate (bit 3) off
-  P.idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((unsigned)((P.BN * P.planes) >> 3) << 17) | ((unsigned)(MMA_M >> 4) << 24);
+  P.idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((unsigned)((P.BN * P.planes) >> 3) << 17) |
+            ((unsigned)((P.cg2 ? 2 * MMA_M : MMA_M) >> 4) << 24);
   P.layout_type = (P.BK == 128) ? 2u : 4u;
   P.sbo16 = (unsigned)(8 * P.BK) >> 4;
   P.d_ntiles = make_fastdiv(P.n_tiles);
@@ -1124,6 +1266,17 @@ bool mma_layer_supported(const tf2b_layer_desc& L, int in_pitch, int planes8) {
 }
 
 size_t mma_tmap_bytes() { return sizeof(TmapPair); }
+
+// human-readable launch plan of a tensor-core layer (introspection for tests / profiles)
+std::string mma_describe(const ConvParams& c, int planes8) {
+  MmaParams P;
+  fill_geometry(P, c, planes8);
+  char b[192];
+  snprintf(b, sizeof b, "mma BN%d BK%d planes%d %s%s%s%s%s stages%d", P.BN, P.BK, planes8,
+           P.mode == 0 ? "flat" : (P.halo ? "halo" : (P.pair ? "pixelpair" : "box")), P.b_resident ? " wres" : "",
+           P.res_tma ? " restma" : "", fold_applies(c, planes8) ? " fold" : "", P.cg2 ? " ctapair" : "", P.stages);
+  return std::string(b);
+}
 
 int mma_build_tmaps(void* host_tmaps, const ConvParams& c, const int8_t* wgt8, int planes8, std::string* err) {
   EncodeTiledFn enc = get_encode_fn(err);
@@ -1183,6 +1336,18 @@ int mma_build_tmaps(void* host_tmaps, const ConvParams& c, const int8_t* wgt8, i
     return -1;
   }
   memset(&tp->r, 0, sizeof tp->r);
+  if (P.cg2) {
+    cuuint64_t dims[2] = {(cuuint64_t)c.Kp, (cuuint64_t)planes8 * c.Npad};
+    cuuint64_t strides[1] = {(cuuint64_t)c.Kp};
+    cuuint32_t box[2] = {(cuuint32_t)P.BK, 128};
+    cuuint32_t es[2] = {1, 1};
+    r = enc(&tp->r, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)wgt8, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      if (err) *err = "cuTensorMapEncodeTiled(B half) failed with CUresult " + std::to_string((int)r);
+      return -1;
+    }
+  }
   if (P.res_tma) {
     cuuint64_t dims[2] = {(cuuint64_t)c.N, (cuuint64_t)c.B * c.OH * c.OW};
     cuuint64_t strides[1] = {(cuuint64_t)c.rC};
@@ -1210,7 +1375,7 @@ cudaError_t launch_conv_mma(const ConvParams& c, const int8_t* /*wgt8*/, int pla
   MmaParams P;
   fill_geometry(P, c, planes8);
   for (int i = 0; i < kMaxPlanes; i++) P.plane8_shift[i] = plane8_shift[i];
-  const int stage_bytes = P.a_stage_bytes + (P.b_resident ? 0 : planes8 * P.b_bytes);
+  const int stage_bytes = P.a_stage_bytes + (P.b_resident ? 0 : P.b_stage_bytes);
   const size_t smem = (size_t)P.res_bytes + (size_t)P.stages * stage_bytes + EPI_BYTES +
                       (P.res_tma ? (size_t)P.res_bufs * P.BN * 128 : 0) + 1024;
   using KernelFn = void (*)(MmaParams, TmapPair);
@@ -1241,8 +1406,7 @@ cudaError_t launch_conv_mma(const ConvParams& c, const int8_t* /*wgt8*/, int pla
   const bool fast = c.fast_requant != 0 && scaled_planes <= 2 && (c.low_plane < 0 || c.low_plane == planes8 - 1);
   // folded form (one IMAD.HI per output): additionally needs alpha << nshift in int32 and an accumulator
   // that cannot wrap (fast_requant == 2, api.cu), and no unscaled low plane
-  static const bool allow_fold = getenv("TF2B_MMA_FOLD") == nullptr || atoi(getenv("TF2B_MMA_FOLD")) != 0;
-  const bool fold = fast && allow_fold && c.fast_requant >= 2 && c.low_plane < 0;
+  const bool fold = fast && fold_applies(c, planes8);
   const int epi = fast ? (1 + ((scaled_planes == 2 ? 1 : 0) | (c.low_plane >= 0 ? 2 : 0) | (c.r != nullptr ? 4 : 0) |
                                (fold ? 8 : 0)))
                        : 0;
@@ -1250,13 +1414,38 @@ cudaError_t launch_conv_mma(const ConvParams& c, const int8_t* /*wgt8*/, int pla
   // epilogue-bound layers, slower with a residual operand — the epilogue is throughput bound, L1TEX ~72 %)
   const int epi_idx = epi;
   P.egroups = 1;
-  const KernelFn kfn = table[P.BN == 256 ? 2 : (P.BN == 128 ? 1 : 0)][P.mode][epi_idx];
+  KernelFn kfn = table[P.BN == 256 ? 2 : (P.BN == 128 ? 1 : 0)][P.mode][epi_idx];
+  // CTA-pair kernels exist for the folded epilogues of 256-wide MMAs: BN = 256 single plane, BN = 128 two planes
+  static const KernelFn pair_table[2][2][2] = {
+      {{conv_mma_kernel<128, 0, 9, true>, conv_mma_kernel<128, 0, 13, true>},
+       {conv_mma_kernel<128, 1, 9, true>, conv_mma_kernel<128, 1, 13, true>}},
+      {{conv_mma_kernel<256, 0, 8, true>, conv_mma_kernel<256, 0, 12, true>},
+       {conv_mma_kernel<256, 1, 8, true>, conv_mma_kernel<256, 1, 12, true>}}};
+  static bool pair_attr_set = false;
+  if (!pair_attr_set) {
+    for (int a = 0; a < 2; a++)
+      for (int b = 0; b < 2; b++)
+        for (int f = 0; f < 2; f++) {
+          cudaError_t e = cudaFuncSetAttribute(pair_table[a][b][f], cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+          if (e != cudaSuccess) return e;
+        }
+    pair_attr_set = true;
+  }
+  if (P.cg2) {
+    if (!fold) return cudaErrorInvalidValue;   // fill_geometry() only picks pair mode for folded epilogues
+    kfn = pair_table[P.BN == 256 ? 1 : 0][P.mode][c.r != nullptr ? 1 : 0];
+  }
   const int num_tiles = P.m_tiles * P.n_tiles;
   int grid = num_tiles < num_sms ? num_tiles : num_sms;
   if (P.b_resident) {
     // every CTA must keep one n-tile: grid = multiple of n_tiles
     grid = (grid / P.n_tiles) * P.n_tiles;
     if (grid < P.n_tiles) grid = P.n_tiles;
+  }
+  if (P.cg2) {
+    // pairs of CTAs (one cluster per TPC pair); work items = pairs of m-tiles x n-tiles
+    const int items = ((P.m_tiles + 1) / 2) * P.n_tiles;
+    grid = 2 * std::min(items, num_sms / 2);
   }
   const TmapPair* tp = reinterpret_cast<const TmapPair*>(tmaps);
   P.dbg = nullptr;
@@ -1275,11 +1464,22 @@ cudaError_t launch_conv_mma(const ConvParams& c, const int8_t* /*wgt8*/, int pla
     cfg.blockDim = dim3(NUM_THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (use_pdl) {
+      attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[na].val.programmaticStreamSerializationAllowed = 1;
+      na++;
+    }
+    if (P.cg2) {
+      attr[na].id = cudaLaunchAttributeClusterDimension;
+      attr[na].val.clusterDim.x = 2;
+      attr[na].val.clusterDim.y = 1;
+      attr[na].val.clusterDim.z = 1;
+      na++;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = use_pdl ? 1 : 0;
+    cfg.numAttrs = na;
     cudaError_t le = cudaLaunchKernelEx(&cfg, kfn, P, *tp);
     if (le != cudaSuccess) return le;
   }

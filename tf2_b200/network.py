@@ -111,6 +111,10 @@ class NetWork:
     def layer_kernels(self) -> List[str]:
         return [self._lib.tf2b_layer_kernel(self._h, l).decode() for l in range(self.net.num_layers)]
 
+    def layer_modes(self, n_images: int = 0) -> List[str]:
+        """Launch plan of every layer (tile sizes, staging mode, CTA-pair MMA ...) for `n_images`."""
+        return [self._lib.tf2b_layer_mode(self._h, l, n_images).decode() for l in range(self.net.num_layers)]
+
     def weight_blob_bytes(self) -> int:
         n = self._lib.tf2b_weight_blob_bytes(self._h)
         if n < 0:
