@@ -308,11 +308,25 @@ def main():
     dom_s = fam_time[dom] * 1e-3
     int8_peak = 2.0 * peaks["bf16_tflops_sustained"]   # INT8 tcgen05 rate = 2x bf16 on sm_100a
     achieved = dom_ops / dom_s / 1e12
-    roofline = {"bound": "tensor", "kernel": f"conv_{dom}", "achieved": achieved, "peak": int8_peak, "unit": "TOP/s",
+    # DRAM bytes per launch of the dominant kernel from the committed ncu capture of this command
+    # (profiles/r01_ncu_traffic.json, written by tools/ncu_traffic.py); null when absent
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            tj = json.load(f)
+        if tj.get("kernel") == f"conv_{dom}" and tj.get("batch") == B:
+            traffic = tj.get("dram_bytes_per_launch")
+    modes = nw.layer_modes(B)
+    roofline = {"bound": "tensor", "kernel": f"conv_{dom}", "achieved": achieved, "peak": int8_peak, "unit": "TFLOP/s",
+                "ops_kind": "int8 x int8 -> int32 multiply-accumulate counted as 2 ops (true convolution, conv1 as 7x7x3)",
                 "frac": achieved / int8_peak,
                 "peak_source": f"2 x {peaks['src']} sustained bf16 cuBLAS TF/s (INT8 MMA issues at twice the bf16 rate)",
-                "launches_per_step": len(dom_layers), "share_of_step": dom_s / (float(layer_ms.sum()) * 1e-3),
-                "traffic": None,
+                "launches_per_step": len(dom_layers), "launch_avg_us": 1e6 * dom_s / max(1, len(dom_layers)),
+                "algorithmic_ops_per_launch": dom_ops / max(1, len(dom_layers)),
+                "share_of_step": dom_s / (float(layer_ms.sum()) * 1e-3),
+                "traffic": traffic,
+                "staging_modes": {k: sum(1 for m in modes if k in m) for k in ("flat", "box", "halo", "ctapair", "fold", "wres")},
                 "hbm_view": {"algorithmic_bytes_per_image": algorithmic_bytes_per_image(net),
                              "achieved_gbs": algorithmic_bytes_per_image(net) * B / (float(layer_ms.sum()) * 1e-3) / 1e9,
                              "peak_gbs": peaks["hbm_gbs"]}}
