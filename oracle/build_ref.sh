@@ -32,3 +32,10 @@ for net in RESNET50 GOOGLENET RESNET50_PRUNED; do
       "$here/ref_device/post_harness.c" -o "$out/libtf2ref_post_${lower}.so"
 done
 echo "built: libtf2ref_post_{resnet50,googlenet,resnet50_pruned}.so"
+# the reference's whole device pipeline (cnn.cl) for layer 0 of each network (ref_device/full_harness.c)
+for net in RESNET50 GOOGLENET RESNET50_PRUNED; do
+  lower=$(echo "$net" | tr 'A-Z' 'a-z')
+  /usr/bin/gcc -x c -std=gnu11 -O1 -fPIC -shared -w -D"$net" -I"$dev" -I"$host/inc" -I"$here/ref_device" \
+      "$here/ref_device/full_harness.c" -o "$out/libtf2ref_full_${lower}.so"
+done
+echo "built: libtf2ref_full_{resnet50,googlenet,resnet50_pruned}.so"

@@ -245,3 +245,51 @@ class RefPost:
             tiles = d[base: base + nvec * PH * pwv * 128].reshape(nvec, PH, pwv, 8, 16)
             outs[l] = self._tiles_to_map(tiles, nch, PH, PW)
         return outs, counts
+
+
+# ---- compiled reference device pipeline for layer 0 (oracle/_ref/libtf2ref_full_<net>.so) -------
+def ref_full_layer0(net_name: str, x: np.ndarray, codes: np.ndarray, params: np.ndarray):
+    """Runs the reference's own input_reader -> filter_reader -> sequencer -> retriever -> 16 PEs ->
+    relu -> pool -> pool_tail -> feature_writer (cnn.cl compiled as C, oracle/ref_device/
+    full_harness.c) for layer 0, from device buffers laid out by the reference's InputConvert /
+    FilterConvert.  x int8 [C0][H0][W0], codes uint8 [N][C0][k][k], params int32 [N][3].
+    Returns (int8 [N][PH][PW], item counts, the reference's cycle constants)."""
+    Lh = ref_host_lib(net_name)
+    p = os.path.join(_HERE, "_ref", f"libtf2ref_full_{net_name}.so")
+    if Lh is None or not os.path.exists(p):
+        raise FileNotFoundError(p)
+    Lf = C.CDLL(p)
+    Lf.full_const.restype = C.c_longlong
+    Lh.ref_input_device_size.restype = C.c_longlong
+    Lh.ref_filter_device_size.restype = C.c_longlong
+    consts = [Lf.full_const(i) for i in range(5)]
+    isz, fsz, mb = Lh.ref_input_device_size(), Lh.ref_filter_device_size(), Lh.ref_max_bias_size()
+    nl = Lh.ref_num_layer()
+    inp_f = np.zeros(isz, np.float32)
+    xr = np.ascontiguousarray(x, dtype=np.float32)
+    Lh.ref_input_convert.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    Lh.ref_input_convert(xr.ctypes.data, inp_f.ctypes.data, 1)
+    inp = inp_f.astype(np.int8)
+    fraw = np.full(fsz, 64, np.uint8)
+    fraw[:codes.size] = np.ascontiguousarray(codes, dtype=np.uint8).reshape(-1)
+    freal = np.full(fsz, 64, np.uint8)
+    scratch = np.zeros(fsz, np.uint8)
+    Lh.ref_filter_convert.argtypes = [C.c_void_p] * 3
+    Lh.ref_filter_convert(scratch.ctypes.data, fraw.ctypes.data, freal.ctypes.data)
+    N = codes.shape[0]
+    bb = np.zeros((nl * mb, 3), np.int32)
+    bb[:N] = params
+    ddr = np.zeros(8 << 20, np.int8)
+    ib, io = Lf.full_item_bytes(), Lf.full_item_data_offset()
+    cap = 8000
+    cache = np.zeros(cap * ib, np.uint8)
+    nc = C.c_longlong(0)
+    counts = np.zeros(8, np.int64)
+    Lf.full_run_layer0.argtypes = [C.c_void_p] * 3 + [C.c_longlong] + [C.c_void_p] * 2 + [C.c_longlong, C.c_void_p, C.c_void_p]
+    rc = Lf.full_run_layer0(inp.ctypes.data, freal.ctypes.data, bb.ctypes.data, consts[0], ddr.ctypes.data,
+                            cache.ctypes.data, cap, C.byref(nc), counts.ctypes.data)
+    if rc != 0:
+        raise RuntimeError(f"full_run_layer0 failed: {rc}")
+    n = nc.value
+    data = cache[: n * ib].reshape(n, ib)[:, io:io + 128].view(np.int8)
+    return data, counts, consts

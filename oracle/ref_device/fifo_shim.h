@@ -47,8 +47,13 @@ static fifo_t* fifo_of(const void* key) {
   f->head = f->tail = f->cap = 0;
   return f;
 }
+/* optional cap on the number of items one channel accepts: the writer leaves through longjmp when it
+ * is reached (used to stop the sequencer after the first layer's schedule) */
+static const void* g_limit_key = NULL;
+static size_t g_limit_bytes = 0;
 static void fifo_push(const void* key, const void* v, size_t n) {
   fifo_t* f = fifo_of(key);
+  if (key == g_limit_key && f->tail + n > g_limit_bytes) longjmp(g_exit, 2);
   if (f->tail + n > f->cap) {
     f->cap = f->cap ? f->cap * 2 : (1u << 20);
     while (f->tail + n > f->cap) f->cap *= 2;

@@ -24,5 +24,11 @@ void ref_filter_trans(char* in49, char* out81) { filter_trans(in49, out81); }
 void ref_feature_trans(float* in, float* out) { feature_trans(in, out); }
 void ref_quantization(char* q, char* file_name) { Quantization(q, nullptr, file_name); }
 void ref_load_model(char* filename, char* filter_raw, BiasBnParam* bias_bn, char* q) { LoadModel(filename, filter_raw, bias_bn, q); }
+void ref_input_convert(float* input_raw, float* input, int num_images) { InputConvert(input_raw, input, num_images); }
+long long ref_input_device_size() {
+  return (long long)CEIL(kInputChannels[0], C_VECTOR) * kInputHeight[0] * CEIL(kInputWidth[0], W_VECTOR) * NEXT_POWER_OF_2(W_VECTOR * C_VECTOR);
+}
+long long ref_filter_device_size() { return (long long)NUM_CONVOLUTIONS * MAX_FILTER_SIZE * NEXT_POWER_OF_2(FW_VECTOR * C_VECTOR); }
+void ref_filter_convert(char* scratch, char* filter_raw, char* filter_real) { FilterConvert(scratch, filter_raw, filter_real); }
 void ref_load_input_image(char* image_name, float* input_raw, float* raw_images) { LoadInputImage(image_name, input_raw, raw_images, 0); }
 }

@@ -18,11 +18,18 @@
  *     pe_harness.c): MUL exhaustively (65 536 cases) and PeFunction's MAC, bias seed, int32
  *     wrap-around, requantisation and clamp for 1x1 and 3x3 mode reductions of up to 128 steps —
  *     committed as tests/golden/pe_golden.npz (tests/test_pe_golden.py).
+ *   - the post-PE kernels device/src/{relu,pool,pool_tail,feature_writer,full_size_pool}.cl compiled
+ *     as C with each network's own tables (oracle/ref_device/post_harness.c) and run over EVERY
+ *     layer of ResNet50, GoogLeNet and pruned ResNet50 on seeded random PE-output maps: ReLU, the
+ *     3x3 max pool with zero border and its alignment, the conv stride in W, the ipool pseudo layer,
+ *     the residual add through the DDR ping-pong, concat offsets and the 7x7 global average — equal
+ *     bit for bit (tests/test_post_golden.py live in the build container; SHA-256 of the reference
+ *     outputs committed as tests/golden/post_golden.json); the item counts the harness feeds equal
+ *     the reference's own cycle constants (CONV_TOTAL_WRITE_CACHE, POOL_TOTAL_CYCLE, ...).
  * NOT re-executed against compiled device code in this repository (restated from the cited source
- * lines; SURVEY.md 8c reports a one-off probe that did): the pooling / stride-2 sub-sampling of
- * pool.cl + pool_tail.cl, the residual add of feature_writer.cl, the global average of
- * full_size_pool.cl and the convolution geometry of sequencer.cl / retriever.cl.  For those steps
- * parity is "restated, unpinned".
+ * lines; SURVEY.md 8c reports a one-off probe that ran them for layer 0): the convolution geometry
+ * of sequencer.cl / retriever.cl (zero padding, h = oh*stride - pad + fh, tap order).  The PE
+ * arithmetic fed by that geometry and everything after it is pinned as listed above.
  *
  * Layouts follow the reference host side: features [C][H][W] int8, codes [N][C][FH][FW] uint8.
  */
