@@ -11,7 +11,7 @@ objs=()
 for f in conv_shift aux_kernels conv_mma api; do
   o="$out/$f.o"
   if [ ! -f "$o" ] || [ "$here/$f.cu" -nt "$o" ] || [ "$here/common.cuh" -nt "$o" ] || [ "$here/../../include/tf2b200.h" -nt "$o" ]; then
-    "$NVCC" "${FLAGS[@]}" ${PTXAS_V:+-Xptxas -v} -c "$here/$f.cu" -o "$o"
+    "$NVCC" "${FLAGS[@]}" ${PTXAS_V:+-Xptxas -v} ${TF2B_EXPERIMENTS:+-DTF2B_EXPERIMENTS=1} -c "$here/$f.cu" -o "$o"
   fi
   objs+=("$o")
 done

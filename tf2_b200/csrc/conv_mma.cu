@@ -32,6 +32,15 @@ namespace tf2b {
 
 namespace {
 
+// Experiment switches (TF2B_MMA_DEBUG role counters, TF2B_MMA_NOEPI, TF2B_MMA_POLL0, TF2B_MMA_TOP,
+// TF2B_MMA_L2PF) cost a few uniform branches per tile in the hot loops; they are compiled in only
+// with -DTF2B_EXPERIMENTS (TF2B_EXPERIMENTS=1 tf2_b200/csrc/build.sh).
+#ifdef TF2B_EXPERIMENTS
+constexpr bool kExp = true;
+#else
+constexpr bool kExp = false;
+#endif
+
 constexpr int MMA_M = 128;
 constexpr int NUM_EPI_WARPS = 16;
 constexpr int NUM_THREADS = 32 * (2 + NUM_EPI_WARPS);
@@ -421,7 +430,7 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
   // feed the tensor pipe sit at the top and are never starved by the ALU-heavy epilogue warps:
   //   hardware warps 0..15 -> epilogue (role ids 2..17), warp 16 -> TMA producer (role 0), warp 17 -> MMA (role 1)
   const int hw_warp = threadIdx.x >> 5;
-  const int warp = P.roles_top ? (hw_warp < NUM_EPI_WARPS ? hw_warp + 2 : hw_warp - NUM_EPI_WARPS) : hw_warp;
+  const int warp = (kExp && P.roles_top) ? (hw_warp < NUM_EPI_WARPS ? hw_warp + 2 : hw_warp - NUM_EPI_WARPS) : hw_warp;
   const int lane = threadIdx.x & 31;
   const int num_tiles = P.m_tiles * P.n_tiles;
   const int kiters = P.halo ? P.kchunks : P.taps * P.kchunks;   // pipeline stages consumed per tile
@@ -484,7 +493,7 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
     // ===================================================== TMA producer (whole warp, one elected lane issues)
     int stage = 0;
     unsigned phase = 0;
-    const bool dbg = P.dbg != nullptr;
+    const bool dbg = kExp && P.dbg != nullptr;
     long long w_empty = 0, t_start = clock64();
     if (P.b_resident && (int)blockIdx.x < num_tiles) {
       // weight-stationary: every tile of this CTA has the same n-tile (grid is a multiple of
@@ -505,7 +514,7 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
     for (int q = q_first; q < q_count; q += q_step) {
       const int tile = tile_of(q);
       const TileCoord t = decode_tile(P, tile);
-      if (P.l2_prefetch > 0 && !cg2) {
+      if (kExp && P.l2_prefetch > 0 && !cg2) {
         // activations are streamed from HBM once; with only a few stages in flight the ~2 us DRAM
         // latency is not covered, so the boxes of a later tile of this CTA are pulled into L2 now
         const int ptile = tile + P.l2_prefetch * (int)gridDim.x;
@@ -532,7 +541,7 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
       }
       if (MODE == 0 && P.res_tma) {
         // residual operand of this tile: full 128-byte lines, no L1, latency hidden by the run-ahead
-        mbar_wait_warp(rempty_bar + 8 * rb, rphase ^ 1, P.poll_lane0);
+        mbar_wait_warp(rempty_bar + 8 * rb, rphase ^ 1, (kExp ? P.poll_lane0 : 0));
         if (elect_one()) {
           mbar_expect_tx(rfull_bar + 8 * rb, (unsigned)res_tile);
           for (int j = 0; j < BN / 128; j++)
@@ -543,7 +552,7 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
       }
       if (P.halo) {
         for (int kc = 0; kc < P.kchunks; kc++) {
-          mbar_wait_timed(empty_bar + 8 * stage, phase ^ 1, w_empty, dbg, P.poll_lane0);
+          mbar_wait_timed(empty_bar + 8 * stage, phase ^ 1, w_empty, dbg, (kExp ? P.poll_lane0 : 0));
           const unsigned fb = full_bar + 8 * stage;
           if (elect_one()) {
             mbar_expect_tx(fb, (unsigned)P.a_bytes);
@@ -557,7 +566,7 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
       for (int tap = 0; tap < P.taps; tap++) {
         const int fh = P.pair ? tap : tap / P.c.k, fw = P.pair ? 0 : tap - fh * P.c.k;
         for (int kc = 0; kc < P.kchunks; kc++) {
-          mbar_wait_timed(empty_bar + 8 * stage, phase ^ 1, w_empty, dbg, P.poll_lane0);
+          mbar_wait_timed(empty_bar + 8 * stage, phase ^ 1, w_empty, dbg, (kExp ? P.poll_lane0 : 0));
           const unsigned fb = full_bar + 8 * stage;
           const unsigned sa = smem_base + stage * stage_bytes;
           if constexpr (cg2) {
@@ -604,17 +613,17 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
     // ===================================================== MMA issuer (whole warp, one elected lane issues)
     int stage = 0;
     unsigned phase = 0;
-    const bool dbg = P.dbg != nullptr;
+    const bool dbg = kExp && P.dbg != nullptr;
     long long w_full = 0, w_tempty = 0, t_issue = 0, t_start = clock64();
-    if (P.b_resident && (int)blockIdx.x < num_tiles) mbar_wait_warp(bres_bar, 0, P.poll_lane0);
+    if (P.b_resident && (int)blockIdx.x < num_tiles) mbar_wait_warp(bres_bar, 0, (kExp ? P.poll_lane0 : 0));
     int li = 0;   // CTA-local tile index: TMEM buffer li & 1, its phase (li >> 1) & 1
     for (int q = q_first; q < q_count && (!cg2 || cta_rank == 0); q += q_step, li++) {   // pair mode: the leader issues
       const int buf = li & 1;
-      mbar_wait_timed(tempty_bar + 8 * buf, ((unsigned)(li >> 1) & 1u) ^ 1u, w_tempty, dbg, P.poll_lane0);   // epilogue has drained this accumulator
+      mbar_wait_timed(tempty_bar + 8 * buf, ((unsigned)(li >> 1) & 1u) ^ 1u, w_tempty, dbg, (kExp ? P.poll_lane0 : 0));   // epilogue has drained this accumulator
       tc_fence_after();
       const unsigned d_tmem = tmem_base + buf * acc_cols;
       for (int it = 0; it < kiters; it++) {
-        mbar_wait_timed(full_bar + 8 * stage, phase, w_full, dbg, P.poll_lane0);
+        mbar_wait_timed(full_bar + 8 * stage, phase, w_full, dbg, (kExp ? P.poll_lane0 : 0));
         tc_fence_after();
         const unsigned sa = smem_base + stage * stage_bytes;
         const unsigned long long da = make_smem_desc(sa, P.sbo16, P.layout_type);
@@ -738,7 +747,7 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
     const int my_row = quarter * 32 + lane;     // accumulator row (TMEM lane) of this thread
     const unsigned my_lut = MODE == 1 ? row_lut[my_row] : 0u;
     int cached_ncol0 = -1;
-    const bool dbg = P.dbg != nullptr && warp == 2;   // first epilogue warp
+    const bool dbg = kExp && P.dbg != nullptr && warp == 2;   // first epilogue warp
     long long w_tfull = 0, t_start = clock64();
     // residual operand of this thread's accumulator row: pixel of a tile, and a 16-byte-segment loader
     auto res_pixel = [&](const TileCoord& tc, bool& valid, long long& pix) {
@@ -771,7 +780,7 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
     auto load_res = [&](bool valid, long long pix, int ncolp, uint4 (&dst)[SEGS]) {
 #pragma unroll
       for (int q = 0; q < SEGS; q++) dst[q] = make_uint4(0, 0, 0, 0);
-      if (has_res && valid && !(P.noepi & 2)) {
+      if (has_res && valid && !(kExp && (P.noepi & 2))) {
         const int8_t* rp = c.r + pix * c.rC + ncolp;
         if (SEGS == 2 && P.direct256 && ncolp + 32 <= c.N) {
           ldg256(rp, dst[0], dst[SEGS - 1]);
@@ -793,12 +802,20 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
     int li = group;   // CTA-local tile index
     for (int q = q_first + group * q_step; q < q_count; q += G * q_step, li += G) {
       const int tile = tile_of(q);
-      buf = li & 1;
-      tph = (unsigned)(li >> 1) & 1u;
-      if (MODE == 0 && P.res_tma) {
-        const int q = li / P.res_bufs;
-        rb = li - q * P.res_bufs;
-        rphase = (unsigned)q & 1u;
+      if (G == 1) {
+        if (li > 0) {   // next TMEM buffer / residual ring slot
+          buf ^= 1;
+          if (buf == 0) tph ^= 1u;
+          if (MODE == 0 && P.res_tma && ++rb == P.res_bufs) { rb = 0; rphase ^= 1u; }
+        }
+      } else {
+        buf = li & 1;
+        tph = (unsigned)(li >> 1) & 1u;
+        if (MODE == 0 && P.res_tma) {
+          const int qq = li / P.res_bufs;
+          rb = li - qq * P.res_bufs;
+          rphase = (unsigned)qq & 1u;
+        }
       }
       const TileCoord t = decode_tile(P, tile);
       const int ncolw = t.n0 + slice * WT;        // first output channel of this warp
@@ -841,9 +858,12 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
       res_pixel(t, rvalid, rpix);
       const bool dvalid = rvalid;
       const long long dpix = rpix;
+      const bool direct = (SEGS == 2) && P.direct256 != 0;
       long long opix[SEGS];
 #pragma unroll
       for (int it = 0; it < SEGS; it++) {
+        opix[it] = -1;
+        if (direct) continue;   // the direct path stores this thread's own row (dvalid / dpix)
         bool valid;
         long long pix;
         if (MODE == 0) {
@@ -864,11 +884,11 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
       if (!res_tma) load_res(rvalid, rpix, ncolw, resq);
       __syncwarp();
       // ---- (2) accumulators -> requantise (+ residual) -> int8 staging tile -> (3) coalesced store
-      mbar_wait_timed(tfull_bar + 8 * buf, tph, w_tfull, dbg, P.poll_lane0);
+      mbar_wait_timed(tfull_bar + 8 * buf, tph, w_tfull, dbg, (kExp ? P.poll_lane0 : 0));
       tc_fence_after();
-      if (P.noepi & 1) {   // TF2B_MMA_NOEPI bit0: measure the TMA/MMA pipeline alone
+      if (kExp && (P.noepi & 1)) {   // TF2B_MMA_NOEPI bit0: measure the TMA/MMA pipeline alone
         if (has_res && (MODE == 0) && (BN >= 128) && P.res_tma) {
-          mbar_wait_warp(rfull_bar + 8 * rb, rphase, P.poll_lane0);
+          mbar_wait_warp(rfull_bar + 8 * rb, rphase, (kExp ? P.poll_lane0 : 0));
           __syncwarp();
           if (lane == 0) mbar_arrive(rempty_bar + 8 * rb);
         }
@@ -880,10 +900,9 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
           }
         continue;
       }
-      const bool direct = (SEGS == 2) && P.direct256 != 0;
       uint4 out_lo = make_uint4(0, 0, 0, 0), out_hi = make_uint4(0, 0, 0, 0);
       if (has_res && res_tma) {
-        mbar_wait_warp(rfull_bar + 8 * rb, rphase, P.poll_lane0);
+        mbar_wait_warp(rfull_bar + 8 * rb, rphase, (kExp ? P.poll_lane0 : 0));
         lds_res(slice * WT, resq);
       }
 #pragma unroll
@@ -1001,7 +1020,7 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
         if (direct) {
           // this lane's own row: 32 contiguous bytes = one sector
           if (dvalid && ncolp + 32 <= c.N) {
-            if (!(P.noepi & 4)) stg256(c.y + dpix * c.yC + ncolp, out_lo, out_hi);
+            if (!(kExp && (P.noepi & 4))) stg256(c.y + dpix * c.yC + ncolp, out_lo, out_hi);
           } else if (dvalid && ncolp < c.N) {
             const unsigned vw[8] = {out_lo.x, out_lo.y, out_lo.z, out_lo.w, out_hi.x, out_hi.y, out_hi.z, out_hi.w};
             int8_t* dst = c.y + dpix * c.yC + ncolp;
