@@ -100,6 +100,7 @@ struct MmaParams {
                             // address + (fh * Wp + fw) * BK: the swizzle is a function of the address bits)
   int Wp;                   // halo mode: row width of the position space = tw + k - 1
   int a_stage_bytes;        // bytes reserved per pipeline stage for the activation tile
+  int idx32;                // output / residual tensors are smaller than 2 GiB: 32-bit byte offsets
   int cg2;                  // CTA-pair mode: clusters of two CTAs, tcgen05.mma.cta_group::2 (M = 256 over two
                             // SMs, each CTA stages its own 128 activation rows and HALF of the weight tile)
   int b_stage_bytes;        // bytes of weights one CTA stages per k-iteration
@@ -781,7 +782,7 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
 #pragma unroll
       for (int q = 0; q < SEGS; q++) dst[q] = make_uint4(0, 0, 0, 0);
       if (has_res && valid && !(kExp && (P.noepi & 2))) {
-        const int8_t* rp = c.r + pix * c.rC + ncolp;
+        const int8_t* rp = P.idx32 ? c.r + (unsigned)((int)pix * c.rC + ncolp) : c.r + pix * c.rC + ncolp;
         if (SEGS == 2 && P.direct256 && ncolp + 32 <= c.N) {
           ldg256(rp, dst[0], dst[SEGS - 1]);
           return;
@@ -799,6 +800,13 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
         }
       }
     };
+    // barrier addresses pinned in registers (otherwise the shared-window base is rebuilt from
+    // SR_CgaCtaId before every wait / arrive)
+    unsigned e_tfull, e_tempty;
+    asm volatile("mov.u32 %0, %1;" : "=r"(e_tfull) : "r"(tfull_bar));
+    asm volatile("mov.u32 %0, %1;" : "=r"(e_tempty) : "r"(tempty_bar));
+    int e_mt = 0, e_nt = 0;
+    const int step_mt = fdiv(G * q_step, P.d_ntiles), step_nt = G * q_step - step_mt * P.n_tiles;
     int li = group;   // CTA-local tile index
     for (int q = q_first + group * q_step; q < q_count; q += G * q_step, li += G) {
       const int tile = tile_of(q);
@@ -817,7 +825,26 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
           rphase = (unsigned)qq & 1u;
         }
       }
-      const TileCoord t = decode_tile(P, tile);
+      // (m-tile, n-tile) of this tile: advanced incrementally (tile += q_step per iteration), the
+      // 64-bit fast division of decode_tile() only for the box geometry
+      if (!cg2) {
+        if (li == group) {
+          e_mt = fdiv(tile, P.d_ntiles);
+          e_nt = tile - e_mt * P.n_tiles;
+        } else {
+          e_mt += step_mt;
+          e_nt += step_nt;
+          if (e_nt >= P.n_tiles) { e_nt -= P.n_tiles; e_mt++; }
+        }
+      }
+      TileCoord t;
+      if (MODE == 0 && !cg2) {
+        t.n0 = e_nt * BN;
+        t.m0 = e_mt * MMA_M;
+        t.b0 = t.oh0 = t.ow0 = 0;
+      } else {
+        t = decode_tile(P, tile);
+      }
       const int ncolw = t.n0 + slice * WT;        // first output channel of this warp
       // ---- (1a) params of this warp's WT channels -> smem, only when the channel slice changes
       __syncwarp();
@@ -884,7 +911,7 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
       if (!res_tma) load_res(rvalid, rpix, ncolw, resq);
       __syncwarp();
       // ---- (2) accumulators -> requantise (+ residual) -> int8 staging tile -> (3) coalesced store
-      mbar_wait_timed(tfull_bar + 8 * buf, tph, w_tfull, dbg, (kExp ? P.poll_lane0 : 0));
+      mbar_wait_timed(e_tfull + 8 * buf, tph, w_tfull, dbg, (kExp ? P.poll_lane0 : 0));
       tc_fence_after();
       if (kExp && (P.noepi & 1)) {   // TF2B_MMA_NOEPI bit0: measure the TMA/MMA pipeline alone
         if (has_res && (MODE == 0) && (BN >= 128) && P.res_tma) {
@@ -895,8 +922,8 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-            if constexpr (cg2) mbar_arrive_leader(tempty_bar + 8 * buf);   // the leader's MMA warp waits for both CTAs
-            else mbar_arrive(tempty_bar + 8 * buf);
+            if constexpr (cg2) mbar_arrive_leader(e_tempty + 8 * buf);   // the leader's MMA warp waits for both CTAs
+            else mbar_arrive(e_tempty + 8 * buf);
           }
         continue;
       }
@@ -1009,8 +1036,8 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
           tc_fence_before();
           __syncwarp();
           if (lane == 0) {
-            if constexpr (cg2) mbar_arrive_leader(tempty_bar + 8 * buf);   // the leader's MMA warp waits for both CTAs
-            else mbar_arrive(tempty_bar + 8 * buf);
+            if constexpr (cg2) mbar_arrive_leader(e_tempty + 8 * buf);   // the leader's MMA warp waits for both CTAs
+            else mbar_arrive(e_tempty + 8 * buf);
           }
         } else {
           if (!direct) __syncwarp();
@@ -1020,7 +1047,10 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
         if (direct) {
           // this lane's own row: 32 contiguous bytes = one sector
           if (dvalid && ncolp + 32 <= c.N) {
-            if (!(kExp && (P.noepi & 4))) stg256(c.y + dpix * c.yC + ncolp, out_lo, out_hi);
+            if (!(kExp && (P.noepi & 4))) {
+              if (P.idx32) stg256(c.y + (unsigned)((int)dpix * c.yC + ncolp), out_lo, out_hi);
+              else stg256(c.y + dpix * c.yC + ncolp, out_lo, out_hi);
+            }
           } else if (dvalid && ncolp < c.N) {
             const unsigned vw[8] = {out_lo.x, out_lo.y, out_lo.z, out_lo.w, out_hi.x, out_hi.y, out_hi.z, out_hi.w};
             int8_t* dst = c.y + dpix * c.yC + ncolp;
@@ -1252,6 +1282,7 @@ void fill_geometry(MmaParams& P, const ConvParams& c, int planes8) {
     static const int l2pf = getenv("TF2B_MMA_L2PF") ? atoi(getenv("TF2B_MMA_L2PF")) : 0;
     P.l2_prefetch = l2pf;
   }
+  P.idx32 = ((long long)c.B * c.OH * c.OW * c.yC < (1ll << 31)) && ((long long)c.B * c.OH * c.OW * (c.rC > 0 ? c.rC : 1) < (1ll << 31));
   P.direct256 = (c.yC % 32 == 0) && (((unsigned long long)c.y) % 32 == 0) &&
                 (c.r == nullptr || ((c.rC % 32 == 0) && (((unsigned long long)c.r) % 32 == 0)));
   {
