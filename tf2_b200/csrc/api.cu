@@ -310,7 +310,13 @@ static int prepare_layer(tf2b_net* net, LayerState& S, const uint8_t* codes,
       const long double a = fabsl((long double)params[n].alpha) * (long double)(1ull << S.h_nshift_m[n]);
       if (a >= 2147483647.0L) fold = false;
     }
-    if (fold) S.fast_requant = 2;
+    if (fold) {
+      S.fast_requant = 2;
+      // every base shift >= 3: the epilogue can drop the final shift (conv_mma.cu HI32)
+      bool hi = true;
+      for (int n = 0; n < N; n++) hi = hi && S.h_nshift_m[n] >= 3;
+      if (hi) S.fast_requant = 3;
+    }
   }
   S.Npar = std::max(S.Npad_s, S.Npad_m);
   S.h_bias.assign(S.Npar, 0);

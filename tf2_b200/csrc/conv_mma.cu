@@ -396,8 +396,8 @@ __device__ __forceinline__ unsigned add_res_s8x4(unsigned y4, unsigned r4) {
 // EPI < 0: exact requantisation, every option decided at run time.  EPI >= 0: fused 64-bit
 // requantisation (range-analysed layers) specialised on bit0 = second scaled plane, bit1 = low plane,
 // bit2 = residual operand, bit3 = folded form: y = (tot * (alpha << nshift) + (bias*alpha +
-// ((beta + 2^14) << 20))) >> 35 with tot = plane0 + (plane1 << 7) — one IMAD.HI per output; bit4 = two
-// epilogue groups of 8 warps that take alternate tiles (one tile's serial latency no longer paces the CTA).
+// ((beta + 2^14) << 20))) >> 35 with tot = plane0 + (plane1 << 7) — one IMAD.HI per output; bit4 (with
+// bit3) = every nshift >= 3, so alpha << (nshift-3) and the addend >> 3 make the high word the result.
 template <int BN, int MODE, int EPI, bool CG2 = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ TmapPair maps) {
@@ -716,6 +716,7 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
     constexpr bool CT_LOW = FAST && (EPI & 2);
     constexpr bool CT_RES = FAST && (EPI & 4);
     constexpr bool FOLD = FAST && (EPI & 8);
+    constexpr bool HI32 = FOLD && (EPI & 16);   // every channel has nshift >= 3: y = hi32(tot*(alpha<<(nshift-3)) + (B>>3))
     constexpr int G = 1;                  // epilogue groups; group g owns the tiles with local index % G == g
     constexpr int SLICES = 4 / G;         // column slices of a tile (one warp per lane quarter and slice)
     constexpr int WT = BN / SLICES;       // columns per warp: 16..128
@@ -859,8 +860,11 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
           if (FOLD) {
             // acc = tot * 2^nsh + bias without wrap-around (api.cu range analysis), so
             // acc*alpha + ((beta + 2^14) << 20) = tot * (alpha << nsh) + [bias*alpha + ((beta + 2^14) << 20)]
-            prm[i] = (int)((unsigned)al << nsh);
-            reinterpret_cast<long long*>(prm + PSTR)[i] = (long long)bi * (long long)al + (((long long)be + 16384ll) << 20);
+            // HI32: floor((8*X + B) / 2^35) = floor((X + floor(B/8)) / 2^32), so with alpha << (nsh-3) and
+            // B >> 3 the result is the high word itself and the shift by 3 disappears
+            const long long b64 = (long long)bi * (long long)al + (((long long)be + 16384ll) << 20);
+            prm[i] = HI32 ? (int)((unsigned)al << (nsh - 3)) : (int)((unsigned)al << nsh);
+            reinterpret_cast<long long*>(prm + PSTR)[i] = HI32 ? (b64 >> 3) : b64;
           } else {
             prm[i] = bi;
             prm[PSTR + i] = al;
@@ -983,7 +987,7 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
                 const int j = 4 * j4 + u;
                 const int tt = two ? (int)(tot1[j] * 128u + tot[j]) : (int)tot[j];
                 const long long t = (long long)tt * (long long)aa[u] + bq[u];   // IMAD.HI with the 64-bit addend
-                yy[u] = (int)(t >> 35);
+                yy[u] = HI32 ? (int)(t >> 32) : (int)(t >> 35);
               }
             } else {
               const int4 pb = *reinterpret_cast<const int4*>(prm + pc + 4 * j4);
@@ -1324,7 +1328,8 @@ std::string mma_describe(const ConvParams& c, int planes8) {
   char b[192];
   snprintf(b, sizeof b, "mma BN%d BK%d planes%d %s%s%s%s%s stages%d", P.BN, P.BK, planes8,
            P.mode == 0 ? "flat" : (P.halo ? "halo" : (P.pair ? "pixelpair" : "box")), P.b_resident ? " wres" : "",
-           P.res_tma ? " restma" : "", fold_applies(c, planes8) ? " fold" : "", P.cg2 ? " ctapair" : "", P.stages);
+           P.res_tma ? " restma" : "", fold_applies(c, planes8) ? (c.fast_requant >= 3 ? " fold hi32" : " fold") : "",
+           P.cg2 ? " ctapair" : "", P.stages);
   return std::string(b);
 }
 
@@ -1434,8 +1439,10 @@ cudaError_t launch_conv_mma(const ConvParams& c, const int8_t* /*wgt8*/, int pla
    conv_mma_kernel<BN_, MODE_, 2>,  conv_mma_kernel<BN_, MODE_, 3>, conv_mma_kernel<BN_, MODE_, 4>,            \
    conv_mma_kernel<BN_, MODE_, 5>,  conv_mma_kernel<BN_, MODE_, 6>, conv_mma_kernel<BN_, MODE_, 7>,            \
    conv_mma_kernel<BN_, MODE_, 8>,  conv_mma_kernel<BN_, MODE_, 9>, nullptr, nullptr,                          \
-   conv_mma_kernel<BN_, MODE_, 12>, conv_mma_kernel<BN_, MODE_, 13>, nullptr, nullptr}
-  constexpr int kEpiVariants = 17;   // index = EPI + 1
+   conv_mma_kernel<BN_, MODE_, 12>, conv_mma_kernel<BN_, MODE_, 13>, nullptr, nullptr,                         \
+   conv_mma_kernel<BN_, MODE_, 24>, conv_mma_kernel<BN_, MODE_, 25>, conv_mma_kernel<BN_, MODE_, 28>,          \
+   conv_mma_kernel<BN_, MODE_, 29>}
+  constexpr int kEpiVariants = 21;   // index = EPI + 1 for EPI <= 15; 17..20 = the hi32 forms of 8, 9, 12, 13
   static const KernelFn table[3][2][kEpiVariants] = {{TF2B_EPI_ROW(64, 0), TF2B_EPI_ROW(64, 1)},
                                                      {TF2B_EPI_ROW(128, 0), TF2B_EPI_ROW(128, 1)},
                                                      {TF2B_EPI_ROW(256, 0), TF2B_EPI_ROW(256, 1)}};
@@ -1462,28 +1469,39 @@ cudaError_t launch_conv_mma(const ConvParams& c, const int8_t* /*wgt8*/, int pla
                        : 0;
   // (a variant with two epilogue groups of 8 warps taking alternate tiles was measured: no gain on the
   // epilogue-bound layers, slower with a residual operand — the epilogue is throughput bound, L1TEX ~72 %)
-  const int epi_idx = epi;
+  static const bool allow_hi32 = getenv("TF2B_MMA_HI32") == nullptr || atoi(getenv("TF2B_MMA_HI32")) != 0;
+  const bool hi32 = fold && allow_hi32 && c.fast_requant >= 3;
+  int epi_idx = epi;
+  if (hi32) {
+    const int bits = epi - 1;   // 8, 9, 12 or 13
+    epi_idx = 17 + ((bits & 1) | ((bits & 4) >> 1));
+  }
   P.egroups = 1;
   KernelFn kfn = table[P.BN == 256 ? 2 : (P.BN == 128 ? 1 : 0)][P.mode][epi_idx];
   // CTA-pair kernels exist for the folded epilogues of 256-wide MMAs: BN = 256 single plane, BN = 128 two planes
-  static const KernelFn pair_table[2][2][2] = {
-      {{conv_mma_kernel<128, 0, 9, true>, conv_mma_kernel<128, 0, 13, true>},
-       {conv_mma_kernel<128, 1, 9, true>, conv_mma_kernel<128, 1, 13, true>}},
-      {{conv_mma_kernel<256, 0, 8, true>, conv_mma_kernel<256, 0, 12, true>},
-       {conv_mma_kernel<256, 1, 8, true>, conv_mma_kernel<256, 1, 12, true>}}};
+  static const KernelFn pair_table[2][2][2][2] = {
+      {{{conv_mma_kernel<128, 0, 9, true>, conv_mma_kernel<128, 0, 25, true>},
+        {conv_mma_kernel<128, 0, 13, true>, conv_mma_kernel<128, 0, 29, true>}},
+       {{conv_mma_kernel<128, 1, 9, true>, conv_mma_kernel<128, 1, 25, true>},
+        {conv_mma_kernel<128, 1, 13, true>, conv_mma_kernel<128, 1, 29, true>}}},
+      {{{conv_mma_kernel<256, 0, 8, true>, conv_mma_kernel<256, 0, 24, true>},
+        {conv_mma_kernel<256, 0, 12, true>, conv_mma_kernel<256, 0, 28, true>}},
+       {{conv_mma_kernel<256, 1, 8, true>, conv_mma_kernel<256, 1, 24, true>},
+        {conv_mma_kernel<256, 1, 12, true>, conv_mma_kernel<256, 1, 28, true>}}}};
   static bool pair_attr_set = false;
   if (!pair_attr_set) {
     for (int a = 0; a < 2; a++)
       for (int b = 0; b < 2; b++)
-        for (int f = 0; f < 2; f++) {
-          cudaError_t e = cudaFuncSetAttribute(pair_table[a][b][f], cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
-          if (e != cudaSuccess) return e;
-        }
+        for (int f = 0; f < 2; f++)
+          for (int h = 0; h < 2; h++) {
+            cudaError_t e = cudaFuncSetAttribute(pair_table[a][b][f][h], cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+            if (e != cudaSuccess) return e;
+          }
     pair_attr_set = true;
   }
   if (P.cg2) {
     if (!fold) return cudaErrorInvalidValue;   // fill_geometry() only picks pair mode for folded epilogues
-    kfn = pair_table[P.BN == 256 ? 1 : 0][P.mode][c.r != nullptr ? 1 : 0];
+    kfn = pair_table[P.BN == 256 ? 1 : 0][P.mode][c.r != nullptr ? 1 : 0][hi32 ? 1 : 0];
   }
   const int num_tiles = P.m_tiles * P.n_tiles;
   int grid = num_tiles < num_sms ? num_tiles : num_sms;
