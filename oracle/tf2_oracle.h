@@ -26,10 +26,16 @@
  *     bit for bit (tests/test_post_golden.py live in the build container; SHA-256 of the reference
  *     outputs committed as tests/golden/post_golden.json); the item counts the harness feeds equal
  *     the reference's own cycle constants (CONV_TOTAL_WRITE_CACHE, POOL_TOTAL_CYCLE, ...).
- * NOT re-executed against compiled device code in this repository (restated from the cited source
- * lines; SURVEY.md 8c reports a one-off probe that ran them for layer 0): the convolution geometry
- * of sequencer.cl / retriever.cl (zero padding, h = oh*stride - pad + fh, tap order).  The PE
- * arithmetic fed by that geometry and everything after it is pinned as listed above.
+ *   - the WHOLE device pipeline device/src/cnn.cl compiled as C (oracle/ref_device/full_harness.c:
+ *     input_reader -> filter_reader -> sequencer -> retriever -> 16 PEs -> relu -> pool -> pool_tail ->
+ *     feature_writer, fed from InputConvert / FilterConvert device buffers): layer 0 of the three
+ *     shipped networks (tests/test_full_layer0.py) and 20 one-layer networks generated from the
+ *     reference's googlenet.h (oracle/ref_device/one_layer.py: 1x1, padded 3x3, stride 2, 5x5, ragged
+ *     channel counts, 7..56-wide maps; tests/test_single_layer_ref.py) — the convolution geometry of
+ *     sequencer.cl / retriever.cl; 0 mismatches, item counts equal the reference's cycle model.
+ * NOT executed against compiled device code: the retriever's ipool feed (retriever.cl:285-302) and
+ * multi-layer feedback through the on-chip cache (retriever.cl:328-329 needs cycle-accurate
+ * co-scheduling) — layers are pinned one at a time, chaining is plain tensor hand-over.
  *
  * Layouts follow the reference host side: features [C][H][W] int8, codes [N][C][FH][FW] uint8.
  */
