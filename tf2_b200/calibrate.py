@@ -82,6 +82,8 @@ def float_forward(net: NetDesc, blob: bytes, images: np.ndarray):
     pos = 0
     x0 = torch.from_numpy(np.ascontiguousarray(images, dtype=np.float32))
     tens: Dict[int, "torch.Tensor"] = {}
+    if not any(ld.first_layer_7x7 for ld in net.layers):
+        tens[0] = x0     # plain stem: tensor 0 is the image itself (no 7x7 -> 3x3 input transform)
     pre: List[Optional[np.ndarray]] = []
     post: List[np.ndarray] = []
     for l, ld in enumerate(net.layers):

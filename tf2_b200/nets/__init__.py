@@ -103,3 +103,31 @@ def chain(input_chw, specs: List[dict], name: str = "chain") -> NetDesc:
     mo = max(max(t.C for t in tensors), 1)
     return NetDesc(name=name, tensors=tensors, layers=layers, max_out_channel=mo,
                    num_q_rows=len(layers) + 1, input_c=C0, input_h=H0, input_w=W0)
+
+
+def vgg16(width_div: int = 1, classes: int = 1000, name: Optional[str] = None) -> NetDesc:
+    """VGG16 in the runtime's vocabulary (BASELINE configs[3]; the reference ships no table for it):
+    thirteen 3x3/pad-1 convolutions with bias + ReLU on 224x224x3, a pool after each of the five
+    stages, fc6 as a 7x7 convolution on the 7x7 map, fc7/fc8 as 1x1 convolutions.  VGG's 2x2/stride-2
+    max pools do not exist in the reference (`pool.cl:194-199` pools 3x3 only), so the stages end in
+    the runtime's 3x3/stride-2 pool without padding (GoogLeNet's form: 224 -> 112 -> ... -> 7, zero
+    fill past the far edge).  The first layer is a plain 3-channel convolution: the 7x7 -> 3x3 input
+    transform of `input_loader.cpp:27-73` is specific to ResNet/GoogLeNet stems.  `width_div` scales
+    all channel counts down (tests)."""
+    w = lambda c: max(16, c // width_div)
+    specs: List[dict] = []
+    size = 224
+    for n, reps in ((64, 2), (128, 2), (256, 3), (512, 3), (512, 3)):
+        for r in range(reps):
+            s = dict(N=w(n), k=3, pad=1, bias_en=1, bn_en=0)
+            if r == reps - 1:
+                s.update(pool=1, pool_stride=2, pool_pad=0, PH=size // 2, PW=size // 2)
+                size //= 2
+            specs.append(s)
+    specs.append(dict(N=w(4096), k=7, pad=0, bias_en=1, bn_en=0))
+    specs.append(dict(N=w(4096), k=1, bias_en=1, bn_en=0))
+    specs.append(dict(N=classes, k=1, relu=0, bias_en=1, bn_en=0))
+    net = chain((3, 224, 224), specs, name or ("vgg16" if width_div == 1 else f"vgg16_div{width_div}"))
+    for ld in net.layers:                      # Q-table rows as quantization.cpp lays them out
+        ld.q_in_row = net.tensors[ld.in_tensor].q_row
+    return net
