@@ -9,13 +9,20 @@
 // < 2^31, so nothing saturates or wraps inside the tensor core) and the epilogue recombines
 // sum_p acc_p << 7p, adds the bias seed and requantises exactly like pe.cl:185-203.
 //
-// Structure (one persistent CTA per SM, warp specialised):
-//   warp 0      TMA producer: activation tile (flat [pixels x BK] for 1x1, or a (BK, tw, th, tn) box
-//               of the NHWC tensor per filter tap with hardware zero fill = the conv padding) and
-//               one weight tile per plane, SWIZZLE_128B/64B, into an mbarrier ring
-//   warp 1      MMA issuer: tcgen05.mma cta_group::1 kind::i8, M=128, N=BN, K=32 per instruction,
-//               accumulators double-buffered in TMEM; tcgen05.commit frees smem stages
-//   warps 2..9  epilogue: tcgen05.ld -> plane recombination -> requant/ReLU/residual -> 16-byte stores
+// Structure (one persistent CTA per SM, 18 warps, warp specialised):
+//   warp 0       TMA producer: the activation tile into an mbarrier ring, in one of the staging modes
+//                  flat      1x1/stride 1: the NHWC tensor as a [pixels x BK] matrix
+//                  box       one (BK, tw, th, tn) box per filter tap, hardware zero fill = the padding,
+//                            traversal stride = the convolution stride
+//                  halo      stride-1 kxk with resident weights: ONE box per tile (the input window in
+//                            raster order); the taps are row-shifted UMMA descriptor views of it
+//                  pixelpair 64-byte pixels, two horizontal taps per 128-byte row
+//                + one weight tile per plane (or the whole slab of the n-tile once: resident weights)
+//   warp 1       MMA issuer: tcgen05.mma kind::i8, M=128 (cta_group::1) or M=256 over a CTA pair
+//                (cta_group::2: each CTA stages its activation rows and half of the weight tile),
+//                N = planes*BN <= 256, K=32 per instruction, accumulators double-buffered in TMEM
+//   warps 2..17  epilogue: tcgen05.ld -> plane recombination -> requantisation (folded: one IMAD.HI per
+//                output) -> packed int8 ReLU / residual (s16x2 lanes) -> 32-byte row stores
 #include <cuda.h>
 #include <cuda_runtime.h>
 
