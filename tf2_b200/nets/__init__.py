@@ -131,3 +131,60 @@ def vgg16(width_div: int = 1, classes: int = 1000, name: Optional[str] = None) -
     for ld in net.layers:                      # Q-table rows as quantization.cpp lays them out
         ld.q_in_row = net.tensors[ld.in_tensor].q_row
     return net
+
+
+def squeezenet(classes: int = 1000, name: str = "squeezenet") -> NetDesc:
+    """SqueezeNet 1.1 in the runtime's vocabulary (BASELINE configs[0]; the reference only carries a
+    160x160 FaceNet variant as a PyTorch model, `TransForm_Kit/Quantization/models/SqueezeNet/
+    SqueezeNet.py:45-87`, and no table): conv1 3x3/stride 2 on 224x224x3, 3x3/stride-2 pools
+    (zero fill past the far edge), eight fire modules (1x1 squeeze, then 1x1 and 3x3 expand writing
+    one concat buffer), conv10 1x1 -> `classes` maps of 13x13.  The network ends there: the 13x13
+    global average that follows in the original is outside `full_size_pool.cl` (7x7 only,
+    constant 669)."""
+    specs: List[dict] = []
+    cat = [0]
+
+    def fire(src, squeeze, expand, pool_after=None):
+        """src: index of the producing spec, or a concat group id given as ('cat', gid)"""
+        specs.append(dict(N=squeeze, k=1, bias_en=1, bn_en=0, src=src))
+        sq = len(specs) - 1
+        gid = cat[0]
+        cat[0] += 1
+        e1 = dict(N=expand, k=1, bias_en=1, bn_en=0, src=sq, concat=(gid, 0, 2 * expand))
+        e3 = dict(N=expand, k=3, pad=1, bias_en=1, bn_en=0, src=sq, concat=(gid, expand, 2 * expand))
+        specs.extend([e1, e3])
+        return len(specs) - 1            # any member of the group names the concat tensor
+
+    specs.append(dict(N=64, k=3, stride=2, pad=0, bias_en=1, bn_en=0, pool=1, pool_stride=2, pool_pad=0, PH=55, PW=55))
+    last = 0
+    last = fire(last, 16, 64)
+    last = fire(last, 16, 64)
+    # the pools between fire modules act on a concat buffer: stand-alone 3x3/stride-2 pools do not exist
+    # in the reference (ipool is stride 1), so the stride-2 pool is fused into BOTH expand layers of the
+    # preceding module (max pooling commutes with channel concatenation)
+    for s in specs[-2:]:
+        s.update(pool=1, pool_stride=2, pool_pad=0, PH=27, PW=27)
+    last = fire(last, 32, 128)
+    last = fire(last, 32, 128)
+    for s in specs[-2:]:
+        s.update(pool=1, pool_stride=2, pool_pad=0, PH=13, PW=13)
+    last = fire(last, 48, 192)
+    last = fire(last, 48, 192)
+    last = fire(last, 64, 256)
+    last = fire(last, 64, 256)
+    specs.append(dict(N=classes, k=1, bias_en=1, bn_en=0, src=last))
+    net = chain((3, 224, 224), specs, name)
+    # Q rows: l + 1 per layer, one more per concat buffer (quantization.cpp:36-50)
+    nl = net.num_layers
+    tails, cats = [0] * nl, [0] * nl
+    for l, ld in enumerate(net.layers):
+        t = net.tensors[ld.out_tensor]
+        if t.name.startswith("concat"):
+            gid = int(t.name[len("concat"):])
+            tails[l], cats[l] = 1, gid
+            t.q_row = nl + 1 + gid
+    for ld in net.layers:
+        ld.q_in_row = net.tensors[ld.in_tensor].q_row
+    net.branch_tail, net.concat_layer = tails, cats
+    net.num_q_rows = nl + 1 + cat[0]
+    return net
