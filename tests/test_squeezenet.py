@@ -40,3 +40,32 @@ def test_squeezenet_single_image_through_the_cpu_path():
     top_ref = np.argsort(ref.mean(axis=(1, 2)))[-5:]
     top_int = np.argsort(deq.mean(axis=(1, 2)))[-20:]
     assert len(set(top_ref) & set(top_int)) >= 3
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.gpu
+def test_squeezenet_matches_oracle_on_gpu():
+    """every tensor of image 0 and the 13x13 class maps of both images, both kernel families"""
+    import torch
+    from oracle import oracle as O
+    from tests import helpers as H
+    from tf2_b200 import capi
+    from tf2_b200.network import NetWork, Runner
+    net = nets.squeezenet()
+    rng = np.random.default_rng(21)
+    B = 2
+    x = H.random_input(rng, 3, 224, 224, nonneg=False, B=B)
+    model = H.random_model(net, rng, x)
+    exp = O.run_network(net, model, x)
+    tens, _ = H.oracle_tensors(net, model, x[0])
+    for variant in (capi.VARIANT_AUTO, capi.VARIANT_SHIFT):
+        nw = NetWork(net, 0)
+        nw.InitFromCodes(model, None, max_images=B, variant=variant)
+        r = Runner(nw)
+        got = r.run_device(torch.from_numpy(x).cuda()).cpu().numpy()
+        assert np.array_equal(got, exp)
+        for t in range(1, len(net.tensors)):
+            assert np.array_equal(r.read_tensor(t, B).cpu().numpy()[0], tens[t]), f"tensor {t}"
+        nw.CleanUp()
