@@ -10,9 +10,8 @@ The tests compare every function here with the reference's own sources compiled 
 """
 from __future__ import annotations
 
-import io
 import struct
-from typing import List, Sequence, Tuple
+from typing import List, Tuple
 
 import numpy as np
 

@@ -14,7 +14,7 @@ Errors are raised as `Tf2bError` instead of the reference's print-and-exit (open
 from __future__ import annotations
 
 import ctypes as C
-from typing import List, Optional, Sequence
+from typing import List, Optional
 
 import numpy as np
 
