@@ -15,7 +15,7 @@ for net in RESNET50 GOOGLENET RESNET50_PRUNED; do
   g++ -std=c++11 -O1 -fPIC -shared -w -fopenmp -D"$net" -DPRINT_LEVEL_QUIET \
       -I"$here/stub" -I"$common" -I"$host/inc" \
       "$host/src/model_loader.cpp" "$host/src/quantization.cpp" "$host/src/input_loader.cpp" \
-      "$host/src/debug.cpp" "$here/ref_host_shim.cpp" \
+      "$host/src/debug.cpp" "$host/src/network_helper.cpp" "$here/ref_host_shim.cpp" \
       -o "$out/libtf2ref_host_${lower}.so"
 done
 echo "built: $(ls "$out")"

@@ -98,6 +98,7 @@ def build(cfg: Dict[str, int]) -> str:
                            "-I" + out, "-include", os.path.join(out, "prelude.h"),
                            os.path.join(host, "src", "model_loader.cpp"), os.path.join(host, "src", "quantization.cpp"),
                            os.path.join(host, "src", "input_loader.cpp"), os.path.join(host, "src", "debug.cpp"),
+                           os.path.join(host, "src", "network_helper.cpp"),
                            os.path.join(os.path.dirname(_HERE), "ref_host_shim.cpp"), "-o", os.path.join(out, "libhost.so")])
     subprocess.check_call(["/usr/bin/gcc", "-x", "c", "-std=gnu11", "-O1", "-fPIC", "-shared", "-w", "-DTF2_ONE_LAYER",
                            "-I" + dev, "-I" + os.path.join(host, "inc"), "-I" + _HERE, "-I" + out,

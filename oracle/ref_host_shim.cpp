@@ -3,6 +3,7 @@
 // points so ctypes can call the reference's own C++ functions.  Test infrastructure only.
 #include <cstdlib>
 #include "includes.h"
+#include "network_helper.h"
 
 namespace aocl_utils {
 void* alignedMalloc(size_t size) { void* p = nullptr; if (posix_memalign(&p, 64, size)) return nullptr; return p; }
@@ -30,5 +31,10 @@ long long ref_input_device_size() {
 }
 long long ref_filter_device_size() { return (long long)NUM_CONVOLUTIONS * MAX_FILTER_SIZE * NEXT_POWER_OF_2(FW_VECTOR * C_VECTOR); }
 void ref_filter_convert(char* scratch, char* filter_raw, char* filter_real) { FilterConvert(scratch, filter_raw, filter_real); }
+// network_helper.cpp:18-207 (both read the tiled feature_ddr image; Verify writes Lastconv<n>.dat in the cwd)
+void ref_evaluation(int n, char* q, char* output, int* top_labels) { Evaluation(n, q, (real*)output, top_labels); }
+void ref_verify(int n, char* file_name, char* q, char* output) { Verify(n, file_name, q, (real*)output); }
+long long ref_output_offset() { return (long long)OUTPUT_OFFSET; }
+long long ref_last_ddr_write_base() { return (long long)kDDRWriteBase[NUM_LAYER - 1] * NEXT_POWER_OF_2(W_VECTOR * NARROW_N_VECTOR); }
 void ref_load_input_image(char* image_name, float* input_raw, float* raw_images) { LoadInputImage(image_name, input_raw, raw_images, 0); }
 }

@@ -33,6 +33,9 @@
  *     reference's googlenet.h (oracle/ref_device/one_layer.py: 1x1, padded 3x3, stride 2, 5x5, ragged
  *     channel counts, 7..56-wide maps; tests/test_single_layer_ref.py) — the convolution geometry of
  *     sequencer.cl / retriever.cl; 0 mismatches, item counts equal the reference's cycle model.
+ *   - host result readers network_helper.cpp (Verify, Evaluation) compiled unmodified: the feature_ddr
+ *     tile addressing, the top-5 order including ties, and the relative-error figure
+ *     (tests/test_verify_eval.py, tests/golden/eval_golden.json).
  * NOT executed against compiled device code: the retriever's ipool feed (retriever.cl:285-302) and
  * multi-layer feedback through the on-chip cache (retriever.cl:328-329 needs cycle-accurate
  * co-scheduling) — layers are pinned one at a time, chaining is plain tensor hand-over.

@@ -343,3 +343,34 @@ def codes_from_nibbles(nib: np.ndarray, min_exp: int, q_in: np.ndarray, q_out: n
     w = nibbles_to_weights(nib, min_exp)
     expand = (INFLAT + q_in.astype(np.int32)[None, :] - q_out.astype(np.int32)[:, None]).astype(np.int8)
     return get_real(w, expand[:, :, None, None])
+
+
+# --------------------------------------------------------------------------------------------
+# Device (feature_ddr) layout of a feature map
+# --------------------------------------------------------------------------------------------
+W_VECTOR = 7          # archs.h:41 (FW_VECTOR + OW_VECTOR - 1)
+N_VECTOR = 16         # archs.h:26 / NARROW_N_VECTOR
+TILE = 128            # NEXT_POWER_OF_2(W_VECTOR * NARROW_N_VECTOR)
+
+
+def to_device_layout(fmap: np.ndarray) -> np.ndarray:
+    """[C][H][W] int8 -> the tile order feature_writer.cl:116-137 writes to feature_ddr and
+    network_helper.cpp:95-118 / 160-170 reads back: [C/16][H][ceil(W/7)][128 slots: (w % 7) * 16 + c % 16]
+    (slots 112..127 and the padding of ragged C / W are zero)."""
+    fmap = np.asarray(fmap, dtype=np.int8)
+    C_, H, W = fmap.shape
+    nv, wv = -(-C_ // N_VECTOR), -(-W // W_VECTOR)
+    pad = np.zeros((nv * N_VECTOR, H, wv * W_VECTOR), np.int8)
+    pad[:C_, :, :W] = fmap
+    t = pad.reshape(nv, N_VECTOR, H, wv, W_VECTOR).transpose(0, 2, 3, 4, 1)          # [nv][H][wv][7][16]
+    out = np.zeros((nv, H, wv, TILE), np.int8)
+    out[..., :W_VECTOR * N_VECTOR] = t.reshape(nv, H, wv, W_VECTOR * N_VECTOR)
+    return out.reshape(-1)
+
+
+def from_device_layout(buf: np.ndarray, C_: int, H: int, W: int) -> np.ndarray:
+    """Inverse of to_device_layout: the un-tiling Verify() does element by element."""
+    nv, wv = -(-C_ // N_VECTOR), -(-W // W_VECTOR)
+    t = np.asarray(buf, dtype=np.int8)[: nv * H * wv * TILE].reshape(nv, H, wv, TILE)[..., :W_VECTOR * N_VECTOR]
+    t = t.reshape(nv, H, wv, W_VECTOR, N_VECTOR).transpose(0, 4, 1, 2, 3).reshape(nv * N_VECTOR, H, wv * W_VECTOR)
+    return np.ascontiguousarray(t[:C_, :, :W])

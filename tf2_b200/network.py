@@ -273,9 +273,15 @@ def Verify(output_int8: np.ndarray, expect_f32: np.ndarray, q_row: np.ndarray) -
 
 
 def Evaluation(output_int8: np.ndarray, q_row: np.ndarray, top: int = 5):
-    """network_helper.cpp:143-207: dequantise, softmax, top-5 (label, probability)."""
-    v = output_int8.reshape(-1).astype(np.float64) * np.exp2(q_row[:output_int8.size].astype(np.float64))
-    e = np.exp(v - v.max())
-    p = e / e.sum()
-    idx = np.argsort(-p, kind="stable")[:top]
-    return [(int(i), float(p[i])) for i in idx]
+    """network_helper.cpp:143-207: dequantise (float32: feature = int8 / (1 << Q)), softmax, top-5 as
+    (label, probability).  Ties are ordered like the reference's five bubble passes with a strict
+    `>` (:187-193): among equal features the HIGHER label ranks first."""
+    x = output_int8.reshape(-1).astype(np.float32)
+    trans = np.exp2(-q_row[:x.size].astype(np.float64)).astype(np.float32)        # 1 << (-current_q)
+    feat = (x / trans).astype(np.float32)
+    sum_exp = np.float32(0)
+    with np.errstate(over="ignore"):                                               # features > 88: inf, like the float there
+        for v in np.exp(feat.astype(np.float64)):                                  # float sum_exp += exp(double)
+            sum_exp = np.float32(np.float64(sum_exp) + v)
+    order = np.lexsort((np.arange(x.size), feat))[::-1][:top]                      # feature desc, label desc
+    return [(int(i), float(np.exp(np.float64(feat[i])) / np.float64(sum_exp))) for i in order]
