@@ -39,3 +39,10 @@ for net in RESNET50 GOOGLENET RESNET50_PRUNED; do
       "$here/ref_device/full_harness.c" -o "$out/libtf2ref_full_${lower}.so"
 done
 echo "built: libtf2ref_full_{resnet50,googlenet,resnet50_pruned}.so"
+# the reference's whole device program over ALL layers, kernels as coroutines (ref_device/net_harness.c)
+for net in RESNET50 GOOGLENET RESNET50_PRUNED; do
+  lower=$(echo "$net" | tr 'A-Z' 'a-z')
+  /usr/bin/gcc -x c -std=gnu11 -O1 -fPIC -shared -w -D"$net" -I"$dev" -I"$host/inc" -I"$here/ref_device" \
+      "$here/ref_device/net_harness.c" -o "$out/libtf2ref_net_${lower}.so"
+done
+echo "built: libtf2ref_net_{resnet50,googlenet,resnet50_pruned}.so"

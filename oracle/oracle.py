@@ -293,3 +293,87 @@ def ref_full_layer0(net_name: str, x: np.ndarray, codes: np.ndarray, params: np.
     n = nc.value
     data = cache[: n * ib].reshape(n, ib)[:, io:io + 128].view(np.int8)
     return data, counts, consts
+
+
+# ---- compiled reference device program over ALL layers (oracle/_ref/libtf2ref_net_<net>.so) -------
+def ref_run_network(net_name: str, x: np.ndarray, model):
+    """Runs the reference's whole device program (cnn.cl compiled as C, kernels as coroutines:
+    oracle/ref_device/net_harness.c) for one image through every layer of a shipped network.
+    x int8 [C0][H0][W0] (tensor 0: the transformed, quantised image); model: per layer (codes uint8
+    [N][C][k][k], params int32 [N][3]) or (None, None) for ipool layers.
+    Returns (per_layer, final, stats): per_layer[l] = int8 [N][PH][PW] the feature writer sent to the
+    on-chip cache for layer l (after add / ReLU; [N][1][1] from full_size_pool for end-pool layers; None
+    when the layer writes no cache), final = the last layer's map read back from feature_ddr."""
+    Lh = ref_host_lib(net_name)
+    p = os.path.join(_HERE, "_ref", f"libtf2ref_net_{net_name}.so")
+    if Lh is None or not os.path.exists(p):
+        raise FileNotFoundError(p)
+    Ln = C.CDLL(p)
+    for fn in ("net_ddr_bytes", "net_output_offset", "net_layer_info"):
+        getattr(Ln, fn).restype = C.c_longlong
+    Lh.ref_input_device_size.restype = C.c_longlong
+    Lh.ref_filter_device_size.restype = C.c_longlong
+    nl = Ln.net_num_layer()
+    assert nl == len(model)
+    isz, fsz, mb, stride = Lh.ref_input_device_size(), Lh.ref_filter_device_size(), Lh.ref_max_bias_size(), Lh.ref_filter_layer_stride()
+    inp_f = np.zeros(isz, np.float32)
+    xr = np.ascontiguousarray(x, dtype=np.float32)
+    Lh.ref_input_convert.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    Lh.ref_input_convert(xr.ctypes.data, inp_f.ctypes.data, 1)
+    inp = inp_f.astype(np.int8)
+    fraw = np.full(fsz, 64, np.uint8)
+    bb = np.zeros((nl * mb + 16, 3), np.int32)
+    for l, (codes, params) in enumerate(model):
+        if codes is None:
+            continue
+        fraw[l * stride: l * stride + codes.size] = np.ascontiguousarray(codes, dtype=np.uint8).reshape(-1)
+        bb[l * mb: l * mb + params.shape[0]] = params
+    freal = np.full(fsz, 64, np.uint8)
+    scratch = np.zeros(fsz, np.uint8)
+    Lh.ref_filter_convert.argtypes = [C.c_void_p] * 3
+    Lh.ref_filter_convert(scratch.ctypes.data, fraw.ctypes.data, freal.ctypes.data)
+    ddr = np.zeros(Ln.net_ddr_bytes() + (1 << 20), np.int8)
+    info = lambda l, w: Ln.net_layer_info(l, w)
+    total = sum(info(l, 2) for l in range(nl)) + 4096
+    rb, do = Ln.net_tap_record_bytes(), Ln.net_tap_data_offset()
+    tap = np.zeros(total * rb, np.uint8)
+    ntap = C.c_longlong(0)
+    stats = np.zeros(64, np.int64)
+    Ln.net_run.argtypes = [C.c_void_p] * 5 + [C.c_longlong, C.c_void_p, C.c_void_p]
+    rc = Ln.net_run(inp.ctypes.data, freal.ctypes.data, bb.ctypes.data, ddr.ctypes.data, tap.ctypes.data, total,
+                    C.byref(ntap), stats.ctypes.data)
+    if rc != 0:
+        raise RuntimeError(f"net_run failed: {rc}")
+    rec = tap[: ntap.value * rb].reshape(ntap.value, rb)
+    which = rec[:, :4].copy().view(np.int32).reshape(-1)
+    tiles = [rec[which == w][:, do:do + 128].view(np.int8) for w in (0, 1)]
+    pos = [0, 0]
+    per_layer = []
+
+    def untile(t, nvec, ph, pwv, N, pw):
+        t = t.reshape(nvec, ph, pwv, 8, 16)[:, :, :, :7, :]
+        return np.ascontiguousarray(t.transpose(0, 4, 1, 2, 3).reshape(nvec * 16, ph, pwv * 7)[:N, :, :pw])
+
+    for l in range(nl):
+        nvec, ph, pwv, N, pw = info(l, 9), info(l, 10), info(l, 11), info(l, 12), info(l, 13)
+        if info(l, 1):                       # end pool: one tile per 16 channels from full_size_pool
+            t = tiles[1][pos[1]: pos[1] + nvec]
+            pos[1] += nvec
+            per_layer.append(untile(t, nvec, 1, 1, N, 1) if t.shape[0] == nvec else None)
+        elif info(l, 0):
+            n = nvec * ph * pwv
+            t = tiles[0][pos[0]: pos[0] + n]
+            pos[0] += n
+            per_layer.append(untile(t, nvec, ph, pwv, N, pw) if t.shape[0] == n else None)
+        else:
+            per_layer.append(None)
+    l = nl - 1
+    nvec, ph, pwv, N, pw = info(l, 9), info(l, 10), info(l, 11), info(l, 12), info(l, 13)
+    if info(l, 1):
+        ph = pw = pwv = 1
+    base = Ln.net_output_offset() + info(l, 4)
+    final = untile(ddr[base: base + nvec * ph * pwv * 128].copy(), nvec, ph, pwv, N, pw)
+    st = {"done": int(stats[0]), "parked": int(stats[1]), "parked_ids": [int(v) for v in stats[8:8 + int(stats[1])]],
+          "switches": int(stats[2]), "tap_dropped": int(stats[3]), "fifo_bytes_left": int(stats[4]),
+          "tap_used": pos, "tap_counts": [int(t.shape[0]) for t in tiles], "ddr": ddr}
+    return per_layer, final, st

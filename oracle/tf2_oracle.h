@@ -36,9 +36,11 @@
  *   - host result readers network_helper.cpp (Verify, Evaluation) compiled unmodified: the feature_ddr
  *     tile addressing, the top-5 order including ties, and the relative-error figure
  *     (tests/test_verify_eval.py, tests/golden/eval_golden.json).
- * NOT executed against compiled device code: the retriever's ipool feed (retriever.cl:285-302) and
- * multi-layer feedback through the on-chip cache (retriever.cl:328-329 needs cycle-accurate
- * co-scheduling) — layers are pinned one at a time, chaining is plain tensor hand-over.
+ *   - WHOLE NETWORKS through the complete device program: cnn.cl as C with all 25 kernels running
+ *     concurrently as coroutines (oracle/ref_device/net_harness.c) — every layer of ResNet50, GoogLeNet
+ *     and pruned ResNet50 chained through the on-chip feature cache (the retriever's non-blocking reads,
+ *     retriever.cl:328-329), the ipool feed (retriever.cl:285-302), the DDR residual ping-pong and concat
+ *     offsets; 0 mismatches on every layer (tests/test_whole_net_ref.py, tests/golden/whole_net_golden.json).
  *
  * Layouts follow the reference host side: features [C][H][W] int8, codes [N][C][FH][FW] uint8.
  */

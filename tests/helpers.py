@@ -99,3 +99,50 @@ def oracle_tensors(net: NetDesc, model, x0):
             tens[ld.out_tensor] = np.zeros((to.C, to.H, to.W), np.int8)
         tens[ld.out_tensor][ld.out_ch0:ld.out_ch0 + ld.N] = y.reshape(ld.N, to.H, to.W)
     return tens, accs
+
+
+# ---- the synthetic whole-network cases shared by the GPU parity tests and the compiled-reference pin ----
+SYNTH_CASES = {"resnet50": (3, 11), "googlenet": (5, 17), "resnet50_pruned": (5, 17)}      # (blob seed, image seed)
+
+
+def synth_case(name):
+    """(net, q, model, t0 of image 0) exactly as tests/test_gpu_resnet50.py / test_gpu_nets.py build them."""
+    import os
+    from tf2_b200 import formats, synth
+    golden = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    blob_seed, img_seed = SYNTH_CASES[name]
+    net = nets.load(name)
+    q = formats.parse_q_file(net, os.path.join(golden, f"{name}_Q"))
+    model = formats.load_float_blob(net, synth.synth_float_blob(net, seed=blob_seed, q=q), q)
+    _, t0 = formats.prepare_input(net, synth.synth_images(1, seed=img_seed), q)
+    return net, q, model, t0[0]
+
+
+def layer_output_hashes(net: NetDesc, tens):
+    """SHA-256 of every layer's slice of its output tensor (int8 [N][H][W]) — the form in which
+    tests/golden/whole_net_golden.json records what the reference's device program produced."""
+    import hashlib
+    out = []
+    for ld in net.layers:
+        a = np.ascontiguousarray(np.asarray(tens[ld.out_tensor])[ld.out_ch0:ld.out_ch0 + ld.N], dtype=np.int8)
+        out.append(hashlib.sha256(a.tobytes()).hexdigest())
+    return out
+
+
+def assert_reference_hashes(case, net: NetDesc, tens):
+    """`tens` (tensor id -> int8 [C][H][W] of image 0, from the oracle or read back from the GPU) against
+    what the reference's own device program produced for this case (tests/golden/whole_net_golden.json)."""
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "whole_net_golden.json")) as f:
+        g = json.load(f)[case]
+    got = layer_output_hashes(net, tens)
+    assert len(got) == len(g["layers"])
+    checked = 0
+    for l, (a, b) in enumerate(zip(got, g["layers"])):
+        if b is not None:                            # layers that only write feature_ddr are checked by their consumers
+            assert a == b, f"{case}: layer {l} differs from the reference device program"
+            checked += 1
+    assert checked >= len(got) - 5
+    assert got[-1] == g["final"], f"{case}: final map differs from the reference device program"
+    return g

@@ -39,9 +39,12 @@ def test_network_matches_oracle(name, variant):
     assert got.shape == exp.shape
     assert np.array_equal(got, exp), f"{name}: result differs in {(got != exp).sum()} of {exp.size}"
     tens, accs = H.oracle_tensors(net, model, t0[0])
+    dev = {}
     for t in range(1, len(net.tensors)):
-        g = r.read_tensor(t, B).cpu().numpy()[0]
+        g = dev[t] = r.read_tensor(t, B).cpu().numpy()[0]
         assert np.array_equal(g, tens[t]), f"{name}: tensor {t} ({net.tensors[t].name}) differs in {(g != tens[t]).sum()}"
+    # ... and directly against what the reference's own device program produced for this model and image
+    H.assert_reference_hashes(name, net, dev)
     kinds = set(nw.layer_kernels())
     assert ("mma" in kinds) == (variant != capi.VARIANT_SHIFT)
     nw.CleanUp()

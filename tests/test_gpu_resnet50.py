@@ -42,9 +42,12 @@ def test_resnet50_matches_oracle(resnet_model, variant):
     assert np.array_equal(t0_dev, t0)
     # every intermediate feature map and every INT32 accumulator of image 0
     tens, accs = H.oracle_tensors(net, model, t0[0])
+    dev = {}
     for t in range(1, len(net.tensors)):
-        g = r.read_tensor(t, B).cpu().numpy()[0]
+        g = dev[t] = r.read_tensor(t, B).cpu().numpy()[0]
         assert np.array_equal(g, tens[t]), f"tensor {t} ({net.tensors[t].name}) differs in {(g != tens[t]).sum()}"
+    # ... and directly against what the reference's own device program produced for this model and image
+    H.assert_reference_hashes("resnet50", net, dev)
     for l in (0, 1, 3, 4, 13, 26, 45, 52, 53):
         g = r.dump_acc(l, B).cpu().numpy()[0]
         assert np.array_equal(g, accs[l]), f"layer {l} accumulators differ"
