@@ -304,11 +304,15 @@ def ref_run_network(net_name: str, x: np.ndarray, model):
     Returns (per_layer, final, stats): per_layer[l] = int8 [N][PH][PW] the feature writer sent to the
     on-chip cache for layer l (after add / ReLU; [N][1][1] from full_size_pool for end-pool layers; None
     when the layer writes no cache), final = the last layer's map read back from feature_ddr."""
-    Lh = ref_host_lib(net_name)
-    p = os.path.join(_HERE, "_ref", f"libtf2ref_net_{net_name}.so")
-    if Lh is None or not os.path.exists(p):
-        raise FileNotFoundError(p)
-    Ln = C.CDLL(p)
+    if isinstance(net_name, tuple):          # (libhost, libnet) of a generated network (ref_device/multi_layer.py)
+        Lh, Ln = net_name
+    else:
+        Lh = ref_host_lib(net_name)
+        p = os.path.join(_HERE, "_ref", f"libtf2ref_net_{net_name}.so")
+        if Lh is None or not os.path.exists(p):
+            raise FileNotFoundError(p)
+        Ln = C.CDLL(p)
+    Lh.ref_filter_layer_stride.restype = C.c_longlong
     for fn in ("net_ddr_bytes", "net_output_offset", "net_layer_info"):
         getattr(Ln, fn).restype = C.c_longlong
     Lh.ref_input_device_size.restype = C.c_longlong

@@ -42,6 +42,10 @@
  *     retriever.cl:328-329), the ipool feed (retriever.cl:285-302), the DDR residual ping-pong and concat
  *     offsets; 0 mismatches on every layer (tests/test_whole_net_ref.py, tests/golden/whole_net_golden.json).
  *
+ *   - networks the reference ships no tables for (VGG16, SqueezeNet fire modules, pool probes) through the
+ *     same device program built against a generated table header (oracle/ref_device/multi_layer.py;
+ *     tests/test_generated_nets_ref.py, tests/golden/generated_nets_golden.json).
+ *
  * Layouts follow the reference host side: features [C][H][W] int8, codes [N][C][FH][FW] uint8.
  */
 #ifndef TF2_ORACLE_H

@@ -129,12 +129,13 @@ def layer_output_hashes(net: NetDesc, tens):
     return out
 
 
-def assert_reference_hashes(case, net: NetDesc, tens):
+def assert_reference_hashes(case, net: NetDesc, tens, golden="whole_net_golden.json"):
     """`tens` (tensor id -> int8 [C][H][W] of image 0, from the oracle or read back from the GPU) against
-    what the reference's own device program produced for this case (tests/golden/whole_net_golden.json)."""
+    what the reference's own device program produced for this case (tests/golden/whole_net_golden.json,
+    generated_nets_golden.json)."""
     import json
     import os
-    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "whole_net_golden.json")) as f:
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", golden)) as f:
         g = json.load(f)[case]
     got = layer_output_hashes(net, tens)
     assert len(got) == len(g["layers"])

@@ -54,9 +54,13 @@ def test_vgg16_lite_matches_oracle_on_gpu(variant):
     got = r.run_device(torch.from_numpy(x).cuda()).cpu().numpy()
     assert np.array_equal(got, exp), f"logits differ in {(got != exp).sum()} of {exp.size}"
     tens, _ = H.oracle_tensors(net, model, x[0])
+    dev = {}
     for t in range(1, len(net.tensors)):
-        g = r.read_tensor(t, B).cpu().numpy()[0]
+        g = dev[t] = r.read_tensor(t, B).cpu().numpy()[0]
         assert np.array_equal(g, tens[t]), f"tensor {t} differs in {(g != tens[t]).sum()}"
+    # ... and directly against what the reference's own device program produced for this model and image
+    # (tests/test_generated_nets_ref.py: case vgg16_div8)
+    H.assert_reference_hashes("vgg16_div8", net, dev, golden="generated_nets_golden.json")
     if variant == capi.VARIANT_AUTO:
         assert "mma" in nw.layer_kernels()
     nw.CleanUp()
