@@ -22,6 +22,30 @@ def test_shard_range_partitions():
         shard_range(4, 2, 2)
 
 
+class _FakeNetWork:
+    """Stands in for tf2_b200.network.NetWork (which needs a GPU): the packed weight blob is 3000 bytes
+    derived from the model handed to rank 0."""
+
+    def __init__(self):
+        self.calls, self.blob = [], None
+
+    def InitFromCodes(self, model, q, max_images, variant):
+        self.calls.append(("codes", max_images, variant))
+        self.blob = (np.arange(3000, dtype=np.int64) * model % 251).astype(np.uint8)
+
+    def weight_blob_bytes(self):
+        return self.blob.size
+
+    def export_weight_blob(self, ptr):
+        import ctypes
+        ctypes.memmove(ptr, self.blob.ctypes.data, self.blob.size)
+
+    def InitFromBlob(self, ptr, max_images, variant):
+        import ctypes
+        self.calls.append(("blob", max_images, variant))
+        self.blob = np.frombuffer(ctypes.string_at(ptr, 3000), dtype=np.uint8).copy()
+
+
 def _worker(rank, world, port, q):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -45,6 +69,11 @@ def _worker(rank, world, port, q):
             dist.all_gather(gathered, pad)
             parts = [gathered[r][:shard_range(9, r, world)[1] - shard_range(9, r, world)[0]] for r in range(world)]
         ok = ok and bool(torch.equal(torch.cat(parts), data * 2))
+        # init_network_distributed: rank 0 loads the model, the others import the broadcast blob
+        from tf2_b200.dist import init_network_distributed
+        nw = init_network_distributed(_FakeNetWork(), dist, "cpu", model=7 if rank == 0 else None, q=None, max_images=4, variant=1)
+        ok = ok and nw.calls == [("codes" if rank == 0 else "blob", 4, 1)]
+        ok = ok and np.array_equal(nw.blob, (np.arange(3000, dtype=np.int64) * 7 % 251).astype(np.uint8))
         # device-timed numbers are combined as the max over ranks
         t = torch.tensor([1.0 + rank])
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

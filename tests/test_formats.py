@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 from oracle import oracle as O
-from tests.conftest import GOLDEN
+from tests.conftest import GOLDEN, REFERENCE
 from tf2_b200 import formats, nets, synth
 
 # Get_real known answers from the reference compiled as-is
@@ -155,3 +155,35 @@ def test_4bit_blob_roundtrip():
         codes = formats.codes_from_nibbles(nib, min_exp, q_in, q_out)
         expand = (15 + q_in.astype(np.int32)[None, :] - q_out.astype(np.int32)[:, None]).astype(np.int8)
         assert np.array_equal(codes, formats.get_real(w, expand[:, :, None, None]))
+
+
+def test_load_input_image_matches_reference(tmp_path):
+    """LoadInputImage (input_loader.cpp:76-118: read float [3][224][224], feature_trans each plane, crop
+    115 -> 114) compiled unmodified vs load_image_bin + feature_trans — on a seeded synthetic image file and,
+    where the reference tree is present, on its two shipped test images."""
+    L = O.ref_host_lib("resnet50")
+    if L is None:
+        pytest.skip("oracle/_ref not built (reference tree absent)")
+    import ctypes as C
+    from tf2_b200 import synth
+    files = []
+    img = synth.synth_images(1, seed=99)[0]
+    p = tmp_path / "img.bin"
+    img.astype("<f4").tofile(p)
+    files.append(str(p))
+    for name in ("resnet50_data_label_100.bin", "googlenet_data_label_391.bin"):
+        f = os.path.join(REFERENCE, "Runtime_Engine", "cnn", "host", "test_images", name)
+        if os.path.exists(f):
+            files.append(f)
+    L.ref_load_input_image.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p]
+    for f in files:
+        input_raw = np.full(27 * 114 * 114 + 64, np.float32(7.5), np.float32)
+        raw_images = np.zeros(3 * 224 * 224, np.float32)
+        L.ref_load_input_image(f.encode(), input_raw.ctypes.data, raw_images.ctypes.data)
+        mine = formats.load_image_bin(f)
+        assert np.array_equal(mine.reshape(-1), raw_images)
+        assert np.array_equal(formats.feature_trans(mine).reshape(-1), input_raw[:27 * 114 * 114])
+        assert np.all(input_raw[27 * 114 * 114:] == np.float32(7.5))          # nothing written past the 27x114x114 image
+    with pytest.raises(ValueError):
+        (tmp_path / "short.bin").write_bytes(b"\0" * 100)
+        formats.load_image_bin(str(tmp_path / "short.bin"))
