@@ -1,0 +1,104 @@
+// Microbenchmark (for the next round): where should the epilogue read its per-channel requantisation
+// parameters (A = alpha << nshift, B = folded bias / beta / rounding) from?  Today every epilogue warp reads
+// them from shared memory with LDS.128 broadcasts — 41 % of the LSU data-pipe load on the 64 -> 256 layers
+// (profiles/r01_ncu_lsu_breakdown_v5.txt).  A warp's channels are warp-uniform (lane = output row), so the
+// parameters can come through the CONSTANT bank instead: the whole per-layer table (<= 2048 channels x 8 B =
+// 16 KB) passed BY VALUE as a __grid_constant__ kernel argument and indexed with a warp-uniform index
+// (LDC / LDCU with a uniform register: no LSU traffic, no smem staging, no per-tile param copy).
+//   0  params from shared memory, LDS.128 broadcast (today)
+//   1  params from the kernel-argument constant bank, warp-uniform index
+//   2  same, 64-bit loads (A and B interleaved)
+//   3  same as 1 with the warp's channel slice a COMPILE-TIME constant (four copies of the loop body selected by
+//      the warp index): the index is CTA-uniform, so the parameters can be constant-bank OPERANDS of the IMADs
+// One CTA per SM, 16 warps; a "tile" = each lane requantises 32 accumulators (its row, the warp's 32
+// channels) held in registers, like the hi32 path: y = hi32(acc * A + B), ReLU, pack, one 32-byte store.
+// Reports cycles per tile; check the SASS for LDS vs LDC/LDCU/ULDC (cuobjdump -sass).
+#include <cstdio>
+#include <cstdlib>
+#include <cuda_runtime.h>
+#include <type_traits>
+constexpr int MAXC = 2048;
+struct Params { int v[2 * MAXC]; };   // 16 KB: planar (a = v[i], b = v[MAXC + i]) or interleaved (v[2i], v[2i + 1])
+__device__ __forceinline__ int requant(int acc, int a, int b) {
+  long long t = (long long)acc * a + ((long long)b << 32 >> 3); // hi32 form: high word is the result
+  return (int)(t >> 32);
+}
+__device__ __forceinline__ unsigned pack4(int y0, int y1, int y2, int y3) {
+  unsigned lo, r;
+  asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, 0;" : "=r"(lo) : "r"(y1), "r"(y0));
+  asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(y3), "r"(y2), "r"(lo));
+  return r;
+}
+template <int METHOD>
+__global__ void __launch_bounds__(512, 1) k(const __grid_constant__ Params pc, const int* acc_in,
+                                            signed char* out, int n_channels, int tiles, long long* clk) {
+  __shared__ __align__(16) int sA[256], sB[256];
+  const int lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform for the compiler
+  const int q = warp & 3, s = warp >> 2;
+  int acc[32];
+#pragma unroll
+  for (int j = 0; j < 32; j++) acc[j] = acc_in[(threadIdx.x * 32 + j) & 8191];
+  long long t0 = clock64();
+  for (int t = 0; t < tiles; t++) {
+    const int n0 = ((t * gridDim.x + blockIdx.x) * 128) % n_channels;   // the tile's first channel (CTA-uniform)
+    if (METHOD == 0) {
+      __syncthreads();
+      if (threadIdx.x < 128) { sA[threadIdx.x] = pc.v[n0 + threadIdx.x]; sB[threadIdx.x] = pc.v[MAXC + n0 + threadIdx.x]; }
+      __syncthreads();
+    }
+    unsigned w[8];
+    auto body = [&](auto S) {
+      constexpr int kS = decltype(S)::value;          // compile-time slice for METHOD 3, ignored otherwise
+      const int sl = METHOD == 3 ? kS : s;
+#pragma unroll
+      for (int g = 0; g < 8; g++) {
+        int y[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          const int j = 4 * g + e;
+          int a, b;
+          if (METHOD == 0) {
+            a = sA[32 * s + j]; b = sB[32 * s + j];
+          } else if (METHOD == 2) {
+            const int2 ab = reinterpret_cast<const int2*>(pc.v)[n0 + 32 * s + j]; a = ab.x; b = ab.y;
+          } else {
+            a = pc.v[n0 + 32 * sl + j]; b = pc.v[MAXC + n0 + 32 * sl + j];
+          }
+          y[e] = max(requant(acc[j] + t, a, b), 0);
+        }
+        w[g] = pack4(y[0], y[1], y[2], y[3]);
+      }
+    };
+    if (METHOD != 3) body(std::integral_constant<int, 0>{});
+    else if (s == 0) body(std::integral_constant<int, 0>{});
+    else if (s == 1) body(std::integral_constant<int, 1>{});
+    else if (s == 2) body(std::integral_constant<int, 2>{});
+    else body(std::integral_constant<int, 3>{});
+    signed char* p = out + ((size_t)((t * gridDim.x + blockIdx.x) * 128 + 32 * q + lane)) * 256 + 32 * s;
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]),
+                 "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) clk[blockIdx.x] = clock64() - t0;
+}
+int main() {
+  const int tiles = 64, grid = 148, n_channels = 1024;
+  static Params pc;
+  for (int i = 0; i < 2 * MAXC; i++) pc.v[i] = 1000 + 37 * i;
+  int* acc; signed char* out; long long* d;
+  cudaMalloc(&acc, 8192 * 4); cudaMemset(acc, 1, 8192 * 4);
+  cudaMalloc(&out, (size_t)tiles * grid * 128 * 256); cudaMalloc(&d, 148 * 8);
+  auto run = [&](auto kern, const char* name) {
+    for (int rep = 0; rep < 3; rep++) { kern<<<grid, 512>>>(pc, acc, out, n_channels, tiles, d); cudaDeviceSynchronize(); }
+    cudaError_t e = cudaGetLastError();
+    long long h[148]; cudaMemcpy(h, d, sizeof h, cudaMemcpyDeviceToHost);
+    double avg = 0; for (int i = 0; i < grid; i++) avg += (double)h[i] / grid;
+    printf("%-52s %8.0f clk/tile  (%s)\n", name, avg / tiles, cudaGetErrorString(e));
+  };
+  run(k<0>, "0 params from smem (LDS broadcast)");
+  run(k<1>, "1 params from kernel-arg constant bank");
+  run(k<2>, "2 same, interleaved int2 (LDC.64)");
+  run(k<3>, "3 constant-bank operands, compile-time slice");
+  return 0;
+}
