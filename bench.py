@@ -165,7 +165,8 @@ def main():
                 "data": "synthetic", "config": {"workload": workload, "images_per_step": per_step},
                 "cpu_baseline": {"value": val, "unit": "images/sec", "cores": cores, "kind": "port",
                                  "sample": f"{per_step} images per step, whole ResNet50, oracle/tf2_oracle.c (C restatement "
-                                           f"of the reference device kernels; the FPGA emulator path cannot run here)"},
+                                           f"of the reference device kernels, pinned against them compiled and executed; the reference's own "
+                                           f"device program as C is a cycle-level emulation, ~0.03 images/s, DESIGN.md 5)"},
                 "e2e": {"value": val, "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line), flush=True)
         return 0
