@@ -82,6 +82,25 @@ __global__ void __launch_bounds__(512, 1) k(const __grid_constant__ Params pc, c
   __syncthreads();
   if (threadIdx.x == 0) clk[blockIdx.x] = clock64() - t0;
 }
+// launch cost of a big by-value argument: back-to-back launches of an (almost) empty kernel
+struct Small { int v[16]; };
+struct Big24 { int v[6 * 1024]; };   // 24 KB: A (int32) + B (int64) for 2048 channels
+template <typename P>
+__global__ void touch(const __grid_constant__ P p, int* sink) {
+  if (threadIdx.x == 0 && blockIdx.x == 0 && p.v[0] == 123456789) *sink = p.v[1];
+}
+template <typename P>
+static void launch_cost(const char* name, int* sink) {
+  static P p;
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  for (int i = 0; i < 200; i++) touch<P><<<148, 128>>>(p, sink);
+  cudaDeviceSynchronize();
+  cudaEventRecord(e0);
+  for (int i = 0; i < 2000; i++) touch<P><<<148, 128>>>(p, sink);
+  cudaEventRecord(e1); cudaEventSynchronize(e1);
+  float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+  printf("launch cost, %-28s %6.2f us per launch (%zu-byte argument)\n", name, 1e3 * ms / 2000, sizeof(P));
+}
 int main() {
   const int tiles = 64, grid = 148, n_channels = 1024;
   static Params pc;
@@ -100,5 +119,8 @@ int main() {
   run(k<1>, "1 params from kernel-arg constant bank");
   run(k<2>, "2 same, interleaved int2 (LDC.64)");
   run(k<3>, "3 constant-bank operands, compile-time slice");
+  launch_cost<Small>("64 B", (int*)d);
+  launch_cost<Params>("16 KB", (int*)d);
+  launch_cost<Big24>("24 KB", (int*)d);
   return 0;
 }
