@@ -67,3 +67,46 @@ def test_quantum_range_rejects_a_late_outlier():
     w = np.array([0.5, 0.25, 3.0], np.float64)
     with pytest.raises(ValueError):
         Z.quantum_range(w, np.array([0, 0, 1]))
+
+
+def test_float_model_to_served_int8_model():
+    """An arbitrary float param.bin -> INQ grid (quantize_blob) -> calibrated Q -> LoadModel -> oracle: the
+    whole offline path of TransForm_Kit in one go; the INT8 network tracks the float network it came from."""
+    from oracle import oracle as O
+    from tf2_b200 import calibrate as K
+    from tf2_b200 import nets, synth
+    net = nets.vgg16(width_div=16)
+    base = synth.synth_float_blob(net, seed=9)
+    # knock the synthetic power-of-two weights off the grid: a float model as a training framework would save it
+    rng = np.random.default_rng(4)
+    arr = np.frombuffer(base, dtype="<f4").copy()
+    pos = 0
+    for ld in net.layers:
+        cnt = ld.N * ld.C * ld.k * ld.k
+        arr[pos:pos + cnt] *= rng.uniform(0.8, 1.3, cnt).astype(np.float32)
+        pos += cnt + (ld.N if ld.bias_en else 0) + ((4 * ld.N + 1) if ld.bn_en else 0)
+    assert pos == arr.size
+    float_blob = arr.astype("<f4").tobytes()
+    qblob, min_exps = Z.quantize_blob(net, float_blob)
+    assert len(qblob) == len(float_blob) and len(min_exps) == net.num_layers
+    qa = np.frombuffer(qblob, dtype="<f4")
+    pos = 0
+    for ld, me in zip(net.layers, min_exps):
+        cnt = ld.N * ld.C * ld.k * ld.k
+        w = qa[pos:pos + cnt]
+        nib = formats.weights_to_nibbles(w.reshape(ld.N, ld.C, ld.k, ld.k), me)        # raises unless on the 7-level grid
+        assert np.array_equal(formats.nibbles_to_weights(nib, me).reshape(-1), w)
+        pos += cnt + (ld.N if ld.bias_en else 0) + ((4 * ld.N + 1) if ld.bn_en else 0)
+    imgs = synth.synth_images(2, seed=8)
+    qtext, _ = K.calibrate(net, qblob, imgs)
+    q = formats.parse_q_text(net, qtext)
+    model = formats.load_float_blob(net, qblob, q)
+    y = O.run_network(net, model, formats.quantize_input(imgs, int(q[0, 0])))
+    deq = y.reshape(2, -1).astype(np.float64) * np.exp2(q[net.num_layers, :1000].astype(np.float64))
+    ref_q = K.float_forward(net, qblob, imgs)[0][net.result_tensor()].reshape(2, -1)
+    ref_f = K.float_forward(net, float_blob, imgs)[0][net.result_tensor()].reshape(2, -1)
+    for b in range(2):
+        assert np.corrcoef(ref_q[b], deq[b])[0, 1] > 0.99         # INT8 engine arithmetic vs the float net on the grid (0.9997)
+        assert np.corrcoef(ref_f[b], deq[b])[0, 1] > 0.8          # ... and vs the original float model, no retraining (0.94)
+    with pytest.raises(ValueError):
+        Z.quantize_blob(net, float_blob[:-4])

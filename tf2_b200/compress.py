@@ -77,3 +77,37 @@ def quantize_layer(w: np.ndarray, num_quantum_values: int = NUM_QUANTUM_VALUES) 
     max_exp, min_exp = quantum_range(w, mask, num_quantum_values)
     q, _ = shape_into_two_power(w, mask, 0.0, 1.0, max_exp, min_exp)
     return q.astype(np.float32), min_exp
+
+
+def quantize_blob(net, blob: bytes, num_quantum_values: int = NUM_QUANTUM_VALUES):
+    """A float `param.bin` (blob order of model_loader.cpp:154-231) with arbitrary float convolution weights ->
+    (the same blob with every layer's weights on its own INQ grid, list of per-layer min_exp; None for ipool
+    layers).  Biases and BatchNorm / Scale parameters pass through untouched.  The result loads through
+    LoadModel (`Get_real` needs exact powers of two) and packs into the 4-bit format."""
+    buf = memoryview(blob)
+    out = bytearray(blob)
+    pos = 0
+    min_exps = []
+    for ld in net.layers:
+        if ld.ipool:
+            min_exps.append(None)
+            continue
+        if ld.first_layer_7x7:
+            cnt = ld.N * net.input_c * 49
+        else:
+            cnt = ld.N * ld.C * ld.k * ld.k
+        end = pos + 4 * cnt
+        if end > len(buf):
+            raise ValueError("model blob too short")
+        w = np.frombuffer(buf[pos:end], dtype="<f4")
+        q, me = quantize_layer(w, num_quantum_values)
+        out[pos:end] = q.astype("<f4").tobytes()
+        min_exps.append(me)
+        pos = end
+        if ld.bias_en:
+            pos += 4 * ld.N
+        if ld.bn_en:
+            pos += 4 * (4 * ld.N + 1)
+    if pos != len(buf):
+        raise ValueError(f"model blob has {len(buf) - pos} trailing bytes")
+    return bytes(out), min_exps
