@@ -2,7 +2,7 @@
 compiled as C, all kernels running as coroutines: oracle/ref_device/net_harness.c) sends to the on-chip cache
 for every layer, and of the final map it leaves in feature_ddr, for the seeded whole-network cases of
 tests/test_whole_net_ref.py.  Build container only (needs /root/reference + oracle/build_ref.sh):
-    python tests/make_whole_net_golden.py"""
+    python tests/golden/make_whole_net_golden.py"""
 import hashlib
 import json
 import os
@@ -11,7 +11,7 @@ import time
 
 import numpy as np
 
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
 from oracle import oracle as O  # noqa: E402
 from tests.test_whole_net_ref import CASES, build_case  # noqa: E402
 
@@ -28,7 +28,7 @@ for case in CASES:
         "kernels_finished": st["done"], "tiles": st["tap_counts"], "seconds": round(time.time() - t, 1),
     }
     print(case, out[case]["seconds"], "s", flush=True)
-path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "whole_net_golden.json")
+path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "whole_net_golden.json")
 with open(path, "w") as f:
     json.dump(out, f, indent=1)
 print("wrote", path)

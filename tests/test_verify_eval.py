@@ -1,6 +1,6 @@
 """Verify() / Evaluation() and the feature_ddr tile layout they read, against the reference's own
 network_helper.cpp compiled unmodified (oracle/_ref/libtf2ref_host_<net>.so) — live when the build
-container has it, and against tests/golden/eval_golden.json (made by tests/make_eval_golden.py)."""
+container has it, and against tests/golden/eval_golden.json (made by tests/golden/make_eval_golden.py)."""
 import ctypes as C
 import json
 import os

@@ -11,7 +11,7 @@ concat offsets across layers.  The oracle must equal it on every layer.
 The cases are the very models and image the GPU parity tests run (tests/helpers.py: synth_case), so
 "CUDA == oracle" (pytest -m gpu) and "oracle == compiled reference" (here) meet on the same tensors.
 Live where oracle/_ref is built (~80 s); the SHA-256 of the reference's outputs is committed
-(tests/golden/whole_net_golden.json, tests/make_whole_net_golden.py) so the pin travels."""
+(tests/golden/whole_net_golden.json, tests/golden/make_whole_net_golden.py) so the pin travels."""
 import os
 
 import numpy as np
