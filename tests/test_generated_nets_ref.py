@@ -10,13 +10,15 @@ coroutines.  Pinned here, every layer against the oracle:
   * SqueezeNet's fire modules (BASELINE configs[0]): squeeze -> expand1x1 | expand3x3 into one concat
     buffer, stride-2 pools fused into both expand layers, the 1x1 classifier over the whole map — on
     56/28/14-wide maps, see below;
-  * what a fused 3x3/s2 pool means on odd and even maps, with and without kPoolPad.
+  * thirteen probes of fused pools (stride 1 / 2, kPoolPad 0 / 1) and conv strides on odd and even maps.
 
 Finding (by executing the reference): its pool_tail emits ceil(H / 2) rows for a stride-2 pool whatever
 kPoolOutputHeight says (pool_tail.cl:190-196 lets P + 1 rows through), so tables with the Caffe / PyTorch
 size 55 -> 27 or 27 -> 13 (SqueezeNet at 224) desynchronise pool_tail and feature_writer: the reference
 device cannot execute that geometry at all.  55 -> 28 works and equals the oracle.  The torchvision
-geometry is therefore pinned on even maps, and the 55 / 27 / 13 case is pinned to fail in the reference."""
+geometry is therefore pinned on even maps, and the 55 / 27 / 13 case is pinned to fail in the reference
+(test_geometries_the_reference_device_cannot_run, which also holds the second limit found: map widths on
+which pool_tail never releases the last 7-column tile of a row)."""
 import copy
 import hashlib
 import json
@@ -34,8 +36,13 @@ GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "gener
 REF = os.environ.get("TF2_REFERENCE", "/root/reference")
 have_ref = os.path.isdir(os.path.join(REF, "Runtime_Engine", "cnn", "device", "src"))
 
-POOL_PROBES = [(56, 1, 0, 0, 28), (55, 1, 0, 0, 28), (55, 3, 1, 0, 28), (27, 1, 0, 0, 14), (13, 3, 1, 0, 7), (55, 1, 0, 1, 28), (28, 3, 1, 1, 14)]
-CASES = ["vgg16_div8", "squeezenet_fire_even"] + ["pool_%d_k%d_p%d_pp%d_%d" % p for p in POOL_PROBES]
+# (IH, k, pad, conv stride, pool, pool stride, kPoolPad, PH): fused pools and strides on odd / even maps
+PROBES = [(56, 1, 0, 1, 1, 2, 0, 28), (55, 1, 0, 1, 1, 2, 0, 28), (55, 3, 1, 1, 1, 2, 0, 28), (27, 1, 0, 1, 1, 2, 0, 14),
+          (13, 3, 1, 1, 1, 2, 0, 7), (55, 1, 0, 1, 1, 2, 1, 28), (28, 3, 1, 1, 1, 2, 1, 14), (14, 1, 0, 1, 1, 1, 1, 14),
+          (13, 3, 1, 1, 1, 1, 1, 13), (27, 3, 1, 1, 1, 2, 0, 14), (28, 5, 2, 1, 1, 2, 0, 14), (17, 3, 1, 2, 0, 1, 0, 9),
+          (16, 3, 0, 1, 1, 2, 0, 7)]
+PROBE_NAME = "probe_%d_k%d_p%d_s%d_pool%d_ps%d_pp%d_%d"
+CASES = ["vgg16_div8", "squeezenet_fire_even"] + [PROBE_NAME % p for p in PROBES]
 
 
 def tail_net(net, first):
@@ -63,16 +70,18 @@ def resize_maps(net, size_map):
     return n
 
 
-def pool_probe_net(IH, k, pad, pool_pad, PH, C=16, N=16):
+def probe_net(IH, k, pad, stride, pool, pool_stride, pool_pad, PH, C=16, N=16, follow_k=3):
+    """The probed layer followed by a small `follow_k` x `follow_k` layer (so that the probed output goes
+    through the on-chip cache like any inner layer)."""
+    OH = (IH + 2 * pad - k) // stride + 1
     t = [TensorDesc(C, IH, IH, 0, "in"), TensorDesc(N, PH, PH, 1, "t1"), TensorDesc(16, PH, PH, 2, "t2")]
-
-    def layer(i, o, C_, N_, k_, p_, ih, pool, pp, ph):
-        oh = ih + 2 * p_ - k_ + 1
-        return LayerDesc(name=f"l{o}", in_tensor=i, out_tensor=o, out_ch0=0, add_tensor=-1, C=C_, N=N_, k=k_, pad=p_, stride=1,
-                         OH=oh, OW=oh, relu=1, pool=pool, pool_stride=2 if pool else 1, pool_pad=pp, PH=ph, PW=ph, add_relu=0,
-                         gap=0, ipool=0, bias_en=1, bn_en=1, q_in_row=i, q_out_row=o)
-    return NetDesc(name=f"pool{IH}_{k}_{pool_pad}_{PH}", tensors=t, max_out_channel=1024, num_q_rows=3,
-                   layers=[layer(0, 1, C, N, k, pad, IH, 1, pool_pad, PH), layer(1, 2, N, 16, 1, 0, PH, 0, 0, PH)])
+    common = dict(out_ch0=0, add_tensor=-1, add_relu=0, gap=0, ipool=0, bias_en=1, bn_en=1, relu=1)
+    l0 = LayerDesc(name="l0", in_tensor=0, out_tensor=1, C=C, N=N, k=k, pad=pad, stride=stride, OH=OH, OW=OH, pool=pool,
+                   pool_stride=pool_stride, pool_pad=pool_pad, PH=PH, PW=PH, q_in_row=0, q_out_row=1, **common)
+    fp = (follow_k - 1) // 2
+    l1 = LayerDesc(name="l1", in_tensor=1, out_tensor=2, C=N, N=16, k=follow_k, pad=fp, stride=1, OH=PH, OW=PH, pool=0,
+                   pool_stride=1, pool_pad=0, PH=PH, PW=PH, q_in_row=1, q_out_row=2, **common)
+    return NetDesc(name="probe", tensors=t, layers=[l0, l1], max_out_channel=1024, num_q_rows=3)
 
 
 def build_case(case):
@@ -88,10 +97,10 @@ def build_case(case):
         t0 = net.tensors[0]
         x = H.random_input(rng, t0.C, t0.H, t0.W, nonneg=True)
         return net, H.random_model(net, rng, x[None]), x
-    IH, k, pad, pp, PH = [p for p in POOL_PROBES if "pool_%d_k%d_p%d_pp%d_%d" % p == case][0]
-    net = pool_probe_net(IH, k, pad, pp, PH)
-    rng = np.random.default_rng(IH * 100 + PH)
-    x = H.random_input(rng, 16, IH, IH, nonneg=True)
+    p = [p for p in PROBES if PROBE_NAME % p == case][0]
+    net = probe_net(*p)
+    rng = np.random.default_rng(p[0] * 100 + p[7])
+    x = H.random_input(rng, 16, p[0], p[0], nonneg=False)
     return net, H.random_model(net, rng, x[None]), x
 
 
@@ -114,6 +123,7 @@ def test_oracle_equals_reference_live(case):
     per, final, st = run_reference(net, model, x)
     assert st["fifo_bytes_left"] == 0 and st["tap_dropped"] == 0 and st["tap_used"] == st["tap_counts"]
     assert st["parked_ids"] in ([], [24])              # only full_size_pool may be left waiting (no end-pool layer)
+    assert st["done"] >= 24
     tens, _ = H.oracle_tensors(net, model, x)
     for l, ld in enumerate(net.layers[:-1]):
         want = tens[ld.out_tensor][ld.out_ch0:ld.out_ch0 + ld.N]
@@ -124,16 +134,27 @@ def test_oracle_equals_reference_live(case):
 
 
 @pytest.mark.skipif(not have_ref, reason="reference tree absent")
-@pytest.mark.parametrize("probe", [(55, 1, 0, 0, 27), (27, 1, 0, 0, 13)])
-def test_reference_cannot_run_floor_sized_pools_on_odd_maps(probe):
-    """SqueezeNet-at-224's pools (55 -> 27, 27 -> 13): the reference's pool_tail emits one row more than
-    kPoolOutputHeight announces, its feature_writer runs out of step and never finishes."""
-    net = pool_probe_net(*probe)
+@pytest.mark.parametrize("probe,why", [
+    ((55, 1, 0, 1, 1, 2, 0, 27, 16, 16, 1), "floor-sized pool on an odd map"),
+    ((27, 1, 0, 1, 1, 2, 0, 13, 16, 16, 1), "floor-sized pool on an odd map"),
+    ((9, 1, 0, 1, 0, 1, 0, 9, 16, 16, 1), "1x1 layer on a map whose width leaves 1..5 columns in the last group of 7"),
+    ((15, 1, 0, 1, 0, 1, 0, 15, 16, 16, 1), "1x1 layer on a map whose width leaves 1..5 columns in the last group of 7"),
+    ((22, 3, 1, 1, 0, 1, 0, 22, 16, 16, 3), "3x3 layer (steps of 5 columns) on a 22-wide map: 3 releases for 4 tiles")])
+def test_geometries_the_reference_device_cannot_run(probe, why):
+    """Found by executing the reference.  (1) SqueezeNet-at-224's pools (55 -> 27, 27 -> 13): pool_tail emits one
+    row more than kPoolOutputHeight announces.  (2) A layer walks its rows in steps of 7 (1x1) or 5 (k x k) columns up to
+    kOwEndWithOffset = W + 2 (tf2_auto_param.cpp:1662-1668) while its data leaves pool.cl two columns late, and
+    pool_tail releases at most one 7-column tile per step plus one at the end of the row: on many widths (1x1:
+    W mod 7 in 1..5; 3x3: 8, 15, 16, 17, 22, ...) the last tile of every row is never released (the shipped
+    networks only have 7- / 14- / 28- / 56- / 112-wide maps; 13, 27 and 55 happen to work).  In both cases the
+    feature_writer runs out of step and never finishes; the engine and the oracle define these by the plain
+    arithmetic."""
+    net = probe_net(*probe)
     rng = np.random.default_rng(1)
     x = H.random_input(rng, 16, probe[0], probe[0], nonneg=True)
     model = H.random_model(net, rng, x[None])
     per, final, st = run_reference(net, model, x)
-    assert 23 in st["parked_ids"]                      # feature_writer still waiting when everything else has stopped
+    assert 23 in st["parked_ids"], why                 # feature_writer still waiting when everything else has stopped
     tens, _ = H.oracle_tensors(net, model, x)
     assert not np.array_equal(per[0], tens[1])
 
