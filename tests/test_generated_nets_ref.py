@@ -77,7 +77,7 @@ def probe_net(IH, k, pad, stride, pool, pool_stride, pool_pad, PH, C=16, N=16, f
     t = [TensorDesc(C, IH, IH, 0, "in"), TensorDesc(N, PH, PH, 1, "t1"), TensorDesc(16, PH, PH, 2, "t2")]
     common = dict(out_ch0=0, add_tensor=-1, add_relu=0, gap=0, ipool=0, bias_en=1, bn_en=1, relu=1)
     l0 = LayerDesc(name="l0", in_tensor=0, out_tensor=1, C=C, N=N, k=k, pad=pad, stride=stride, OH=OH, OW=OH, pool=pool,
-                   pool_stride=pool_stride, pool_pad=pool_pad, PH=PH, PW=PH, q_in_row=0, q_out_row=1, **common)
+                   pool_stride=pool_stride, pool_pad=pool_pad, PH=PH, PW=PH, q_in_row=0, q_out_row=1, in_may_be_m128=1, **common)
     fp = (follow_k - 1) // 2
     l1 = LayerDesc(name="l1", in_tensor=1, out_tensor=2, C=N, N=16, k=follow_k, pad=fp, stride=1, OH=PH, OW=PH, pool=0,
                    pool_stride=1, pool_pad=0, PH=PH, PW=PH, q_in_row=1, q_out_row=2, **common)
