@@ -11,7 +11,8 @@ import pytest
 from tests import helpers as H
 from tests.test_generated_nets_ref import CASES, build_case
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="new, not yet run on a GPU (round-1 budget spent)")]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(180),
+              pytest.mark.xfail(strict=False, reason="new, not yet run on a GPU (round-1 budget spent)")]
 
 
 @pytest.mark.parametrize("case", [c for c in CASES if c != "vgg16_div8"])
