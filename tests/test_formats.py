@@ -187,3 +187,27 @@ def test_load_input_image_matches_reference(tmp_path):
     with pytest.raises(ValueError):
         (tmp_path / "short.bin").write_bytes(b"\0" * 100)
         formats.load_image_bin(str(tmp_path / "short.bin"))
+
+
+def test_4bit_model_file_roundtrip():
+    """Whole-model 4-bit file (4bit_data_format.txt: short-coded weights, float records for everything else):
+    param.bin -> 4-bit -> param.bin is the identity on an INQ-grid model, the file is ~7x smaller, and the
+    shift codes LoadModel derives from either are the same."""
+    for name, seed in (("resnet50", 3), ("googlenet", 5)):
+        net = nets.load(name)
+        q = formats.parse_q_file(net, os.path.join(GOLDEN, f"{name}_Q"))
+        blob = synth.synth_float_blob(net, seed=seed, q=q)
+        m4 = formats.float_blob_to_4bit(net, blob)
+        assert len(m4) < len(blob) / 6
+        back = formats.float_blob_from_4bit(net, m4)
+        assert back == blob
+        with pytest.raises(ValueError):
+            formats.float_blob_from_4bit(net, m4[:-2])
+        with pytest.raises(ValueError):
+            formats.float_blob_from_4bit(net, m4 + b"\\0\\0")
+    # weights off the grid are refused (the packer is not a quantiser: tf2_b200.compress is)
+    net = nets.vgg16(width_div=16)
+    blob = bytearray(synth.synth_float_blob(net, seed=1))
+    blob[0:4] = np.float32(0.3).tobytes()
+    with pytest.raises(ValueError):
+        formats.float_blob_to_4bit(net, bytes(blob))

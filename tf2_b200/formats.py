@@ -329,6 +329,81 @@ def unpack4_layer(buf: memoryview, pos: int) -> Tuple[np.ndarray, int, int]:
     return nib, min_exp, pos
 
 
+def _float_record(a: np.ndarray) -> bytes:
+    """dtype 1 record (non-convolution parameters stay float): header + float32 values."""
+    a = np.asarray(a, dtype="<f4")
+    dims = list(a.shape) + [1] * (4 - a.ndim)
+    return struct.pack("<bbhhhh", 0, 1, *dims) + a.tobytes()
+
+
+def _blob_fields(net: NetDesc):
+    """The fields of a float param.bin in file order (model_loader.cpp:154-231): (layer, kind, shape)."""
+    for l, ld in enumerate(net.layers):
+        if ld.ipool:
+            continue
+        if ld.first_layer_7x7:
+            yield l, "weight", (ld.N, net.input_c, 7, 7)
+        else:
+            yield l, "weight", (ld.N, ld.C, ld.k, ld.k)
+        if ld.bias_en:
+            yield l, "bias", (ld.N,)
+        if ld.bn_en:
+            for kind, shape in (("mean", (ld.N,)), ("var", (ld.N,)), ("scale_factor", (1,)), ("gamma", (ld.N,)), ("beta", (ld.N,))):
+                yield l, kind, shape
+
+
+def float_blob_to_4bit(net: NetDesc, blob: bytes) -> bytes:
+    """A float param.bin whose convolution weights sit on a 7-level power-of-two grid per layer (INQ output,
+    tf2_b200.compress) -> the 4-bit model file of 4bit_data_format.txt: one record per blob, in param.bin order —
+    weights short-coded (dtype 0), biases and BatchNorm / Scale parameters as float records (dtype 1)."""
+    buf = memoryview(blob)
+    pos = 0
+    out = []
+    for l, kind, shape in _blob_fields(net):
+        a, pos = _read_f32(buf, pos, int(np.prod(shape)))
+        if kind == "weight":
+            nz = a[a != 0]
+            min_exp = int(np.round(np.log2(np.abs(nz).min()))) if nz.size else 0
+            out.append(pack4_layer(weights_to_nibbles(a.reshape(shape), min_exp), min_exp))
+        else:
+            out.append(_float_record(a.reshape(shape)))
+    if pos != len(buf):
+        raise ValueError(f"model blob has {len(buf) - pos} trailing bytes")
+    return b"".join(out)
+
+
+def float_blob_from_4bit(net: NetDesc, data: bytes) -> bytes:
+    """Inverse of float_blob_to_4bit: the float param.bin a 4-bit model file stands for (bit-exact: every
+    weight is a power of two), ready for load_float_blob / LoadModel."""
+    buf = memoryview(data)
+    pos = 0
+    out = []
+    for l, kind, shape in _blob_fields(net):
+        if pos + 10 > len(buf):
+            raise ValueError("4-bit model file too short")
+        dtype = struct.unpack_from("<b", buf, pos + 1)[0]
+        if kind == "weight":
+            if dtype != 0:
+                raise ValueError(f"layer {l}: expected a short-coded weight record")
+            nib, min_exp, pos = unpack4_layer(buf, pos)
+            if nib.shape != tuple(shape):
+                raise ValueError(f"layer {l}: weight record {nib.shape} does not match the tables {tuple(shape)}")
+            out.append(nibbles_to_weights(nib, min_exp).astype("<f4").tobytes())
+        else:
+            if dtype != 1:
+                raise ValueError(f"layer {l}: expected a float record for {kind}")
+            dims = struct.unpack_from("<hhhh", buf, pos + 2)
+            cnt = int(np.prod(shape))
+            if int(np.prod(dims)) != cnt:
+                raise ValueError(f"layer {l}: {kind} record {dims} does not match the tables {tuple(shape)}")
+            pos += 10
+            a, pos = _read_f32(buf, pos, cnt)
+            out.append(a.astype("<f4").tobytes())
+    if pos != len(buf):
+        raise ValueError(f"4-bit model file has {len(buf) - pos} trailing bytes")
+    return b"".join(out)
+
+
 def nibbles_dense(nib: np.ndarray) -> np.ndarray:
     """[N][C][H][W] 4-bit codes -> dense bytes, two per byte, low nibble first (C-ABI layout)."""
     flat = np.asarray(nib, dtype=np.uint8).reshape(-1)

@@ -76,6 +76,14 @@ class NetWork:
         self._upload(max_images, variant)
         return True
 
+    def Init4bit(self, model4_file: str, q_file: str, max_images: int = 1, variant: int = capi.VARIANT_AUTO):
+        """Like Init, from the 4-bit model file of TransForm_Kit/Compression/compress_net/4bit_data_format.txt
+        (formats.float_blob_to_4bit writes one): short-coded power-of-two weights, float biases / BatchNorm."""
+        with open(model4_file, "rb") as f:
+            blob = formats.float_blob_from_4bit(self.net, f.read())
+        with open(q_file, "r") as f:
+            return self.InitFromMemory(blob, f.read(), max_images, variant)
+
     def InitFromCodes(self, model, q: Optional[np.ndarray], max_images: int = 1,
                       variant: int = capi.VARIANT_AUTO):
         """`model`: per layer (codes uint8 [N][C][k][k], params int32 [N][3]) or (None, None)."""
