@@ -29,3 +29,45 @@ def test_engine_equals_reference_device_program(case):
         dev = {t: r.read_tensor(t, 1).cpu().numpy()[0] for t in range(1, len(net.tensors))}
         H.assert_reference_hashes(case, net, dev, golden="generated_nets_golden.json")
         nw.CleanUp()
+
+
+def test_packed4_entry_point_equals_codes_entry_point():
+    """tf2b_load_layer_packed4 (4-bit nibbles + Q rows, expanded on the host side of the C ABI like Get_real)
+    gives the same engine as tf2b_load_layer fed with formats.codes_from_nibbles — and both equal the oracle."""
+    import torch
+    from oracle import oracle as O
+    from tf2_b200 import capi, formats, nets
+    from tf2_b200.network import NetWork, Runner
+    net = nets.chain((16, 14, 14), [dict(N=32, k=3, pad=1), dict(N=24, k=1), dict(N=16, k=5, pad=2)], "packed4")
+    rng = np.random.default_rng(44)
+    B = 2
+    x = H.random_input(rng, 16, 14, 14, nonneg=False, B=B)
+    tens = {0: x[0]}
+    model, packed = [], []
+    for l, ld in enumerate(net.layers):
+        tin = net.tensors[ld.in_tensor]
+        nib = rng.integers(0, 15, (ld.N, ld.C, ld.k, ld.k)).astype(np.uint8)          # 7 = zero, 15 never
+        min_exp = int(rng.integers(-12, -5))
+        q_in = rng.integers(-4, 1, ld.C).astype(np.int8)
+        q_out = rng.integers(-4, 1, ld.N).astype(np.int8)
+        codes = formats.codes_from_nibbles(nib, min_exp, q_in, q_out)
+        params = H.fit_params(rng, ld, tin, tens[ld.in_tensor], codes)
+        tens[ld.out_tensor] = O.layer_forward(ld, tin, tens[ld.in_tensor], codes, params)
+        model.append((codes, params))
+        packed.append((formats.nibbles_dense(nib), min_exp, q_in, q_out, np.ascontiguousarray(params, dtype=np.int32)))
+    exp = O.run_network(net, model, x)
+    a = NetWork(net, 0)
+    a.InitFromCodes(model, None, max_images=B)
+    got_a = Runner(a).run_device(torch.from_numpy(x).cuda()).cpu().numpy()
+    b = NetWork(net, 0)
+    for l, (dense, min_exp, q_in, q_out, params) in enumerate(packed):
+        b._check(b._lib.tf2b_load_layer_packed4(b.handle, l, dense.ctypes.data, min_exp, q_in.ctypes.data, q_out.ctypes.data,
+                                                params.ctypes.data))
+    b._check(b._lib.tf2b_set_variant(b.handle, capi.VARIANT_AUTO))
+    b._check(b._lib.tf2b_finalize(b.handle, B))
+    b.max_images = B
+    got_b = Runner(b).run_device(torch.from_numpy(x).cuda()).cpu().numpy()
+    assert np.array_equal(got_a, exp) and np.array_equal(got_b, exp)
+    assert exp.std() > 3
+    a.CleanUp()
+    b.CleanUp()
