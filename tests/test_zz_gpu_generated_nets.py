@@ -71,3 +71,34 @@ def test_packed4_entry_point_equals_codes_entry_point():
     assert exp.std() > 3
     a.CleanUp()
     b.CleanUp()
+
+
+def test_set_result_returns_an_inner_tensor():
+    """tf2b_set_result: the run calls hand back any tensor of the graph (device and host entry points)."""
+    import torch
+    from tf2_b200 import nets
+    from tf2_b200.network import NetWork, Runner
+    net = nets.chain((16, 14, 14), [dict(N=32, k=3, pad=1), dict(N=24, k=1), dict(N=16, k=3, pad=1, stride=2)], "setres")
+    rng = np.random.default_rng(8)
+    B = 3
+    x = H.random_input(rng, 16, 14, 14, nonneg=False, B=B)
+    model = H.random_model(net, rng, x)
+    nw = NetWork(net, 0)
+    nw.InitFromCodes(model, None, max_images=B)
+    r = Runner(nw)
+    last = r.run_device(torch.from_numpy(x).cuda()).cpu().numpy()
+    assert last.shape == (B, 16, 7, 7)
+    for t in (1, 2):
+        nw.set_result(t)
+        td = net.tensors[t]
+        got = r.run_device(torch.from_numpy(x).cuda()).cpu().numpy()
+        assert got.shape == (B, td.C, td.H, td.W)
+        assert np.array_equal(got, r.read_tensor(t, B).cpu().numpy())
+        assert np.array_equal(r.run_host(x), got)
+        for b in range(B):
+            assert np.array_equal(got[b], H.oracle_tensors(net, model, x[b])[0][t])
+    nw.set_result(net.result_tensor())
+    assert np.array_equal(r.run_device(torch.from_numpy(x).cuda()).cpu().numpy(), last)
+    with pytest.raises(Exception):
+        nw.set_result(99)
+    nw.CleanUp()

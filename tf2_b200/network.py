@@ -50,6 +50,7 @@ class NetWork:
         if rc != capi.TF2B_OK:
             raise Tf2bError(rc, self._lib.tf2b_last_error(None).decode())
         self.max_images = 0
+        self._result_tensor: Optional[int] = None
 
     # -- error plumbing -------------------------------------------------------------------
     def _check(self, rc: int):
@@ -116,6 +117,12 @@ class NetWork:
     def set_variant(self, variant: int):
         self._check(self._lib.tf2b_set_variant(self._h, variant))
 
+    def set_result(self, tensor: int):
+        """Which tensor the run calls return (default: the last layer's output) — the reference's way of
+        verifying an inner layer is to rebuild with a shorter table (CONCAT_LAYER_DEBUG, network_helper.cpp:19-23)."""
+        self._check(self._lib.tf2b_set_result(self._h, tensor))
+        self._result_tensor = tensor
+
     def layer_kernels(self) -> List[str]:
         return [self._lib.tf2b_layer_kernel(self._h, l).decode() for l in range(self.net.num_layers)]
 
@@ -170,7 +177,8 @@ class Runner:
         return self.network.net
 
     def result_shape(self):
-        t = self.net.tensors[self.net.result_tensor()]
+        tid = getattr(self.network, "_result_tensor", None)
+        t = self.net.tensors[self.net.result_tensor() if tid is None else tid]
         return (t.C, t.H, t.W)
 
     # -- device-resident path ---------------------------------------------------------------
