@@ -139,6 +139,25 @@ static void conv_acc_channel(const tf2o_layer* L, const int8_t* X, const uint8_t
   const int OH = L->OH, OW = L->OW;
   uint32_t* a = (uint32_t*)acc;
   for (int i = 0; i < OH * OW; i++) a[i] = (uint32_t)bias;
+  if (k == 1 && s == 1 && pad == 0) {
+    /* 1x1: the map is one contiguous run of OH*OW pixels per channel (same arithmetic, longer vector loops) */
+    const int HW = OH * OW;
+    for (int c = 0; c < C; c++) {
+      const uint8_t cd = code_n[c];
+      if (cd & 0x40) continue;
+      const int sh = cd & 0x1f;
+      const int8_t* xr = X + (size_t)c * HW;
+      if (cd & 0x80) {
+        for (int i = 0; i < HW; i++) {
+          int8_t f = (int8_t)(uint8_t)(0u - (uint8_t)xr[i]); /* pe.cl:32-34 */
+          a[i] += (uint32_t)(int32_t)f << sh;
+        }
+      } else {
+        for (int i = 0; i < HW; i++) a[i] += (uint32_t)(int32_t)xr[i] << sh;
+      }
+    }
+    return;
+  }
   for (int c = 0; c < C; c++) {
     const int8_t* Xc = X + (size_t)c * IH * IW;
     for (int fh = 0; fh < k; fh++) {
