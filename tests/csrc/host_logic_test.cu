@@ -1,0 +1,168 @@
+// CPU test driver for the HOST logic of the product library (no GPU, no CUDA call): it #includes
+// tf2_b200/csrc/api.cu, so the code under test is the shipped translation unit itself — weight preparation
+// (LoadModel codes -> per-channel base shift + power-of-two planes for both kernel families, the negated-copy
+// handling of the int8 -128 quirk, the unscaled low plane, the pixel-pair K layout), the range analysis that
+// selects the folded / hi32 epilogue, and the 4-bit expansion of tf2b_load_layer_packed4.
+//
+// Input: a case file written by tests/test_host_logic.py (layer descriptors as the C ABI structs, codes as
+// formats.codes_from_nibbles / the synthetic models produce them, nibbles + Q rows, BiasBnParam).  For every
+// layer the driver loads the codes, rebuilds every weight from the prepared planes and compares it with the
+// code it came from; loads the same layer through the packed4 entry point and compares the whole prepared
+// state; prints one line per layer.  Exit code 0 = all equal.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../tf2_b200/csrc/api.cu"
+
+static std::vector<unsigned char> read_all(const char* path) {
+  FILE* f = fopen(path, "rb");
+  if (!f) { perror(path); exit(2); }
+  fseek(f, 0, SEEK_END);
+  long n = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  std::vector<unsigned char> b((size_t)n);
+  if (fread(b.data(), 1, (size_t)n, f) != (size_t)n) exit(2);
+  fclose(f);
+  return b;
+}
+
+struct Reader {
+  const unsigned char* p;
+  int32_t i32() { int32_t v; memcpy(&v, p, 4); p += 4; return v; }
+  const unsigned char* bytes(size_t n) { const unsigned char* q = p; p += n; return q; }
+};
+
+// value the code stands for, as (sign, shift); zero codes -> shift = -1
+static void decode(uint8_t cd, int& sign, int& shift) {
+  if (cd & 0x40) { sign = 0; shift = -1; return; }
+  sign = (cd & 0x80) ? -1 : 1;
+  shift = cd & 0x1f;
+}
+
+static long long check_planes(const tf2b_net* net, const LayerState& S, const uint8_t* codes, char* why) {
+  const tf2b_layer_desc& d = S.d;
+  const int C = d.C, N = d.N, k = d.k;
+  const bool quirk = d.in_may_be_m128 != 0;
+  long long bad = 0;
+  // ---- shift-kernel planes (int16): weight = sum_p w16[p] << plane_shift_s[p] << base[n]; with the quirk the
+  //      odd planes multiply the int8-negated activation, i.e. stand for negative weights
+  {
+    size_t nz = 0, nz_codes = 0;
+    for (size_t i = 0; i < S.h_w16.size(); i++) nz += S.h_w16[i] != 0;
+    for (int n = 0; n < N; n++)
+      for (int c = 0; c < C; c++)
+        for (int t = 0; t < k * k; t++) {
+          int sign, shift;
+          decode(codes[((size_t)n * C + c) * k * k + t], sign, shift);
+          long long pos = 0, neg = 0;   // magnitude carried for the plain / negated activation
+          const size_t kidx = (size_t)t * S.Cp + c;
+          for (int p = 0; p < S.planes_s; p++) {
+            long long v = S.h_w16[((size_t)p * S.Npad_s + n) * S.Kp_s + kidx];
+            v = v * (1ll << S.plane_shift_s[p]) * (1ll << S.h_nshift[n]);
+            if (S.plane_neg_s[p]) neg += v; else pos += v;
+          }
+          long long want_pos = 0, want_neg = 0;
+          if (shift >= 0) {
+            nz_codes++;
+            if (quirk) { if (sign > 0) want_pos = 1ll << shift; else want_neg = 1ll << shift; }
+            else want_pos = sign * (1ll << shift);
+          }
+          if (pos != want_pos || neg != want_neg) { if (!bad) snprintf(why, 200, "w16 n=%d c=%d t=%d", n, c, t); bad++; }
+        }
+    if (nz != nz_codes) { if (!bad) snprintf(why, 200, "w16 holds %zu non-zeros for %zu codes", nz, nz_codes); bad++; }
+  }
+  // ---- tensor-core planes (int8)
+  if (S.mma_ok) {
+    const bool dual = quirk;
+    const int in_pitch = net->tpitch[d.in_tensor];
+    const bool pair = tf2b::mma_pair_mode(k, d.stride, d.pad, S.Cp_m, in_pitch, d.OW, d.OH, N, S.planes_m);
+    const int Cpm = pair ? ((k + 1) / 2) * 128 : round_up(S.Cp_m, tf2b::mma_pick_bk(S.Cp_m));
+    size_t nz = 0, nz_codes = 0;
+    for (size_t i = 0; i < S.h_w8.size(); i++) nz += S.h_w8[i] != 0;
+    for (int n = 0; n < N; n++)
+      for (int c = 0; c < C; c++)
+        for (int t = 0; t < k * k; t++) {
+          int sign, shift;
+          decode(codes[((size_t)n * C + c) * k * k + t], sign, shift);
+          long long got[2] = {0, 0};   // [0]: multiplies channel c, [1]: multiplies the negated copy Cp + c
+          for (int half = 0; half < (dual ? 2 : 1); half++) {
+            const int cc = half ? S.Cp + c : c;
+            size_t kidx = (size_t)t * Cpm + cc;
+            if (pair) {
+              const int fh = t / k, fw = t - fh * k;
+              kidx = (size_t)fh * Cpm + (size_t)(fw / 2) * 128 + (size_t)(fw & 1) * 64 + cc;
+            }
+            for (int p = 0; p < S.planes_m; p++) {
+              long long v = S.h_w8[((size_t)p * S.Npad_m + n) * S.Kp_m + kidx];
+              if (v && (v & (v - 1)) && ((-v) & (-v - 1))) { if (!bad) snprintf(why, 200, "w8 not a power of two"); bad++; }
+              if (v > 64 || v < -64) { if (!bad) snprintf(why, 200, "w8 magnitude above 2^6"); bad++; }
+              v *= 1ll << S.plane_shift_m[p];
+              if (p != S.low_plane_m) v *= 1ll << S.h_nshift_m[n];
+              got[half] += v;
+            }
+          }
+          long long want[2] = {0, 0};
+          if (shift >= 0) {
+            nz_codes++;
+            if (dual && sign < 0) want[1] = 1ll << shift; else want[0] = sign * (1ll << shift);
+          }
+          if (got[0] != want[0] || got[1] != want[1]) { if (!bad) snprintf(why, 200, "w8 n=%d c=%d t=%d", n, c, t); bad++; }
+        }
+    if (nz != nz_codes) { if (!bad) snprintf(why, 200, "w8 holds %zu non-zeros for %zu codes", nz, nz_codes); bad++; }
+  }
+  return bad;
+}
+
+static bool same_state(const LayerState& a, const LayerState& b) {
+  return a.h_w16 == b.h_w16 && a.h_w8 == b.h_w8 && a.h_nshift == b.h_nshift && a.h_nshift_m == b.h_nshift_m &&
+         a.h_bias == b.h_bias && a.h_alpha == b.h_alpha && a.h_beta == b.h_beta && a.planes_s == b.planes_s &&
+         a.planes_m == b.planes_m && a.mma_ok == b.mma_ok && a.fast_requant == b.fast_requant &&
+         a.low_plane_m == b.low_plane_m && a.Kp_m == b.Kp_m && a.Kp_s == b.Kp_s;
+}
+
+int main(int argc, char** argv) {
+  if (argc < 2) return 2;
+  std::vector<unsigned char> file = read_all(argv[1]);
+  Reader r{file.data()};
+  const int n_tensors = r.i32(), n_layers = r.i32();
+  tf2b_net net;                                  // built by hand: tf2b_create needs a CUDA device
+  net.tensors.resize(n_tensors);
+  memcpy(net.tensors.data(), r.bytes(sizeof(tf2b_tensor_desc) * n_tensors), sizeof(tf2b_tensor_desc) * n_tensors);
+  net.tpitch.resize(n_tensors);
+  for (int t = 0; t < n_tensors; t++) net.tpitch[t] = round_up(net.tensors[t].C, 16);
+  net.t0_neg_off = round_up(net.tensors[0].C, 16);   // as tf2b_create
+  net.tpitch[0] = 2 * net.t0_neg_off;
+  net.layers.resize(n_layers);
+  tf2b_net net4 = net;
+  int rc_all = 0;
+  for (int l = 0; l < n_layers; l++) {
+    tf2b_layer_desc d;
+    memcpy(&d, r.bytes(sizeof d), sizeof d);
+    net.layers[l].d = d;
+    net4.layers[l].d = d;
+    if (d.ipool) continue;                       // pseudo layer: no weights follow in the case file
+    const size_t cnt = (size_t)d.N * d.C * d.k * d.k;
+    const uint8_t* codes = r.bytes(cnt);
+    const tf2b_bias_bn* params = (const tf2b_bias_bn*)r.bytes(sizeof(tf2b_bias_bn) * d.N);
+    const int has4 = r.i32();
+    int rc = tf2b_load_layer(&net, l, codes, params);
+    char why[200] = "";
+    long long bad = rc == TF2B_OK ? check_planes(&net, net.layers[l], codes, why) : -1;
+    int same4 = -1;
+    if (has4) {
+      const int min_exp = r.i32();
+      const uint8_t* nib = r.bytes((cnt + 1) / 2);
+      const int8_t* q_in = (const int8_t*)r.bytes(d.C);
+      const int8_t* q_out = (const int8_t*)r.bytes(d.N);
+      int rc4 = tf2b_load_layer_packed4(&net4, l, nib, min_exp, q_in, q_out, params);
+      same4 = rc4 == TF2B_OK && same_state(net.layers[l], net4.layers[l]);
+    }
+    const LayerState& S = net.layers[l];
+    printf("layer %d rc=%d bad=%lld planes_s=%d planes_m=%d low=%d mma_ok=%d fast_requant=%d packed4_same=%d %s\n", l, rc, bad,
+           S.planes_s, S.planes_m, S.low_plane_m, (int)S.mma_ok, S.fast_requant, same4, why);
+    if (rc != TF2B_OK || bad != 0 || same4 == 0) rc_all = 1;
+  }
+  return rc_all;
+}
