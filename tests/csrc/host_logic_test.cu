@@ -135,6 +135,10 @@ int main(int argc, char** argv) {
   net.t0_neg_off = round_up(net.tensors[0].C, 16);   // as tf2b_create
   net.tpitch[0] = 2 * net.t0_neg_off;
   net.layers.resize(n_layers);
+  const int B = argc > 2 ? atoi(argv[2]) : 256;
+  net.tbuf.resize(n_tensors);
+  for (int t = 0; t < n_tensors; t++) net.tbuf[t] = reinterpret_cast<int8_t*>((uintptr_t)0x100000000ull + (uintptr_t)t * 0x10000000ull);
+  net.scratch0 = reinterpret_cast<int8_t*>((uintptr_t)0x4000000000ull);
   tf2b_net net4 = net;
   int rc_all = 0;
   for (int l = 0; l < n_layers; l++) {
@@ -160,8 +164,21 @@ int main(int argc, char** argv) {
       same4 = rc4 == TF2B_OK && same_state(net.layers[l], net4.layers[l]);
     }
     const LayerState& S = net.layers[l];
-    printf("layer %d rc=%d bad=%lld planes_s=%d planes_m=%d low=%d mma_ok=%d fast_requant=%d packed4_same=%d %s\n", l, rc, bad,
-           S.planes_s, S.planes_m, S.low_plane_m, (int)S.mma_ok, S.fast_requant, same4, why);
+    // launch plan of the tensor-core path for a batch of B images: what tf2b_layer_mode reports after finalize
+    // (geometry only: the buffer addresses are placeholders, nothing is dereferenced)
+    std::string mode = "shift";
+    if (rc == TF2B_OK && S.mma_ok) {
+      const bool to_scratch = d.pool || d.gap;
+      int8_t* dst = to_scratch ? net.scratch0 : net.tbuf[d.out_tensor] + d.out_ch0;
+      const int dstC = to_scratch ? round_up(d.N, 16) : net.tpitch[d.out_tensor];
+      const int8_t* res = (d.add_tensor >= 0 && !d.pool) ? net.tbuf[d.add_tensor] : nullptr;
+      const int resC = (d.add_tensor >= 0 && !d.pool) ? net.tpitch[d.add_tensor] : 0;
+      ConvParams p = conv_params(&net, S, B, dst, dstC, res, resC, true);
+      mode = tf2b::mma_describe(p, S.planes_m);
+      for (auto& ch : mode) if (ch == ' ') ch = '_';
+    }
+    printf("layer %d rc=%d bad=%lld planes_s=%d planes_m=%d low=%d mma_ok=%d fast_requant=%d packed4_same=%d mode=%s %s\n", l, rc,
+           bad, S.planes_s, S.planes_m, S.low_plane_m, (int)S.mma_ok, S.fast_requant, same4, mode.c_str(), why);
     if (rc != TF2B_OK || bad != 0 || same4 == 0) rc_all = 1;
   }
   return rc_all;

@@ -60,12 +60,12 @@ def _case_file(path, net, model, packed=None):
                 f.write(np.ascontiguousarray(q_out, dtype=np.int8).tobytes())
 
 
-def _run(exe, path):
-    r = subprocess.run([exe, path], capture_output=True, text=True, timeout=600)
+def _run(exe, path, batch=256):
+    r = subprocess.run([exe, path, str(batch)], capture_output=True, text=True, timeout=600)
     rows = []
     for line in r.stdout.splitlines():
-        kv = dict(tok.split("=") for tok in line.split()[2:] if "=" in tok)
-        rows.append({k: int(v) for k, v in kv.items()})
+        kv = dict(tok.split("=", 1) for tok in line.split()[2:] if "=" in tok)
+        rows.append({k: (v if k == "mode" else int(v)) for k, v in kv.items()})
     return r.returncode, rows, r.stdout
 
 
@@ -117,6 +117,17 @@ def test_shipped_networks_weight_preparation(name, seed, tmp_path):
         assert all(r["fast_requant"] >= 2 for r in rows)              # range analysis: folded epilogue everywhere (bench.py
                                                                       # reports "fold": 53 — conv1's low plane keeps the literal form)
         assert sum(r["fast_requant"] == 3 for r in rows) >= 40        # most layers: every base shift >= 3 -> hi32
+        # the launch plan at the BASELINE batch (what tf2b_layer_mode reports on the GPU) is the one the committed
+        # bench line was measured with (profiles/r01_bench_auto_v5.json: roofline.staging_modes)
+        import collections
+        import json
+        plan = collections.Counter(tok for r in rows for tok in r["mode"].split("_"))
+        with open(os.path.join(ROOT, "profiles", "r01_bench_auto_v5.json")) as f:
+            measured = json.load(f)["roofline"]["staging_modes"]
+        assert {k: plan[k] for k in measured} == measured, (dict(plan), measured)
+        assert rows[0]["mode"] == "mma_BN64_BK64_planes2_halo_wres_stages4"                  # conv1: halo tile, literal epilogue
+        assert rows[1]["mode"] == "mma_BN128_BK64_planes2_flat_wres_fold_hi32_stages8"
+        assert plan["mma"] == 54 and plan["hi32"] == 53
         assert rows[0]["low"] >= 0                                    # conv1's code-0 taps sit in the unscaled low plane
 
 
