@@ -160,3 +160,24 @@ def test_random_layers_weight_preparation(tmp_path):
     assert rows[1]["planes_s"] >= 4
     assert rows[4]["fast_requant"] == 0
     assert all(r["mma_ok"] == 1 for i, r in enumerate(rows) if i != 1)
+
+
+def test_every_layer_of_the_baseline_networks_is_planned_on_the_tensor_cores(tmp_path):
+    """BASELINE configs[3] (VGG16, batch 1024 over 8 GPUs = 128 per GPU) and configs[0] (SqueezeNet, one image):
+    full-size tables, random codes — the weight preparation is exact for every layer (25 088-deep fc6 included)
+    and no layer falls back to the shift-accumulate kernel.  (ResNet50 and GoogLeNet: see above.)"""
+    exe = _driver()
+    rng = np.random.default_rng(1)
+    for net, batch in ((nets.vgg16(), 128), (nets.squeezenet(), 1)):
+        model = []
+        for ld in net.layers:
+            params = np.zeros((ld.N, 3), np.int32)
+            params[:, 1] = 1 << 10
+            model.append((H.random_codes(rng, ld.N, ld.C, ld.k), params))
+        path = str(tmp_path / f"{net.name}.bin")
+        _case_file(path, net, model)
+        rc, rows, out = _run(exe, path, batch)
+        assert rc == 0, out[-2000:]
+        assert len(rows) == net.num_layers and all(r["bad"] == 0 and r["mma_ok"] == 1 for r in rows)
+        assert all(r["mode"].startswith("mma_") for r in rows)
+        assert net.layers[0].in_may_be_m128 == 1           # the 3-channel stems see -128: negated copy of tensor 0
