@@ -20,3 +20,6 @@ timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__byte
 # one whole step of conv_mma launches (54) after the warm-up step
 timeout 1500 ncu --set full --clock-control none --import-source on -k regex:conv_mma -s 54 -c 54 -o gpurun_out/prof_mma -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1; echo "ncu full rc=$?"
 fi
+if [ -n "${MICRO}" ]; then
+NCU=${NCU} bash tools/gpu_micro.sh
+fi
