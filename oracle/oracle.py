@@ -296,7 +296,13 @@ def ref_full_layer0(net_name: str, x: np.ndarray, codes: np.ndarray, params: np.
 
 
 # ---- compiled reference device program over ALL layers (oracle/_ref/libtf2ref_net_<net>.so) -------
-def ref_run_network(net_name: str, x: np.ndarray, model):
+def ref_run_frames(net_name, xs: np.ndarray, model):
+    """`xs` int8 [F][C0][H0][W0]: F images through the reference's device program BACK TO BACK in one run
+    (frame_num = F, as Runner::Run does for num_images > 1).  Returns (finals [F] of int8 [N][PH][PW], stats)."""
+    return ref_run_network(net_name, xs, model, _frames=True)
+
+
+def ref_run_network(net_name: str, x: np.ndarray, model, _frames: bool = False):
     """Runs the reference's whole device program (cnn.cl compiled as C, kernels as coroutines:
     oracle/ref_device/net_harness.c) for one image through every layer of a shipped network.
     x int8 [C0][H0][W0] (tensor 0: the transformed, quantised image); model: per layer (codes uint8
@@ -320,11 +326,15 @@ def ref_run_network(net_name: str, x: np.ndarray, model):
     nl = Ln.net_num_layer()
     assert nl == len(model)
     isz, fsz, mb, stride = Lh.ref_input_device_size(), Lh.ref_filter_device_size(), Lh.ref_max_bias_size(), Lh.ref_filter_layer_stride()
-    inp_f = np.zeros(isz, np.float32)
-    xr = np.ascontiguousarray(x, dtype=np.float32)
+    frames = x.shape[0] if _frames else 1
     Lh.ref_input_convert.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
-    Lh.ref_input_convert(xr.ctypes.data, inp_f.ctypes.data, 1)
-    inp = inp_f.astype(np.int8)
+    parts = []
+    for f in range(frames):                      # InputConvert lays out ONE image (input_loader.cpp:123-155 ignores n on the source side)
+        inp_f = np.zeros(isz, np.float32)
+        xr = np.ascontiguousarray(x[f] if _frames else x, dtype=np.float32)
+        Lh.ref_input_convert(xr.ctypes.data, inp_f.ctypes.data, 1)
+        parts.append(inp_f.astype(np.int8))
+    inp = np.concatenate(parts)
     fraw = np.full(fsz, 64, np.uint8)
     bb = np.zeros((nl * mb + 16, 3), np.int32)
     for l, (codes, params) in enumerate(model):
@@ -336,16 +346,16 @@ def ref_run_network(net_name: str, x: np.ndarray, model):
     scratch = np.zeros(fsz, np.uint8)
     Lh.ref_filter_convert.argtypes = [C.c_void_p] * 3
     Lh.ref_filter_convert(scratch.ctypes.data, fraw.ctypes.data, freal.ctypes.data)
-    ddr = np.zeros(Ln.net_ddr_bytes() + (1 << 20), np.int8)
+    ddr = np.zeros(Ln.net_ddr_bytes() + frames * Ln.net_output_offset() + (1 << 20), np.int8)
     info = lambda l, w: Ln.net_layer_info(l, w)
-    total = sum(info(l, 2) for l in range(nl)) + 4096
+    total = frames * sum(info(l, 2) for l in range(nl)) + 4096
     rb, do = Ln.net_tap_record_bytes(), Ln.net_tap_data_offset()
     tap = np.zeros(total * rb, np.uint8)
     ntap = C.c_longlong(0)
     stats = np.zeros(64, np.int64)
-    Ln.net_run.argtypes = [C.c_void_p] * 5 + [C.c_longlong, C.c_void_p, C.c_void_p]
-    rc = Ln.net_run(inp.ctypes.data, freal.ctypes.data, bb.ctypes.data, ddr.ctypes.data, tap.ctypes.data, total,
-                    C.byref(ntap), stats.ctypes.data)
+    Ln.net_run_frames.argtypes = [C.c_int] + [C.c_void_p] * 5 + [C.c_longlong, C.c_void_p, C.c_void_p]
+    rc = Ln.net_run_frames(frames, inp.ctypes.data, freal.ctypes.data, bb.ctypes.data, ddr.ctypes.data, tap.ctypes.data, total,
+                           C.byref(ntap), stats.ctypes.data)
     if rc != 0:
         raise RuntimeError(f"net_run failed: {rc}")
     rec = tap[: ntap.value * rb].reshape(ntap.value, rb)
@@ -375,9 +385,15 @@ def ref_run_network(net_name: str, x: np.ndarray, model):
     nvec, ph, pwv, N, pw = info(l, 9), info(l, 10), info(l, 11), info(l, 12), info(l, 13)
     if info(l, 1):
         ph = pw = pwv = 1
-    base = Ln.net_output_offset() + info(l, 4)
-    final = untile(ddr[base: base + nvec * ph * pwv * 128].copy(), nvec, ph, pwv, N, pw)
+    finals = []
+    for f in range(frames):
+        base = Ln.net_output_offset() * (1 + f) + info(l, 4)
+        finals.append(untile(ddr[base: base + nvec * ph * pwv * 128].copy(), nvec, ph, pwv, N, pw))
+    final = finals[0]
     st = {"done": int(stats[0]), "parked": int(stats[1]), "parked_ids": [int(v) for v in stats[8:8 + int(stats[1])]],
           "switches": int(stats[2]), "tap_dropped": int(stats[3]), "fifo_bytes_left": int(stats[4]),
           "tap_used": pos, "tap_counts": [int(t.shape[0]) for t in tiles], "ddr": ddr}
+    if _frames:
+        st["tap_per_frame"] = [c // frames for c in st["tap_counts"]]
+        return finals, st
     return per_layer, final, st

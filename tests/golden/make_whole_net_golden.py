@@ -28,6 +28,14 @@ for case in CASES:
         "kernels_finished": st["done"], "tiles": st["tap_counts"], "seconds": round(time.time() - t, 1),
     }
     print(case, out[case]["seconds"], "s", flush=True)
+from tests.test_whole_net_ref import _frame_hashes, frames_case  # noqa: E402
+net, model, t0 = frames_case()
+t = time.time()
+finals, st = O.ref_run_frames("googlenet", t0, model)
+assert st["parked"] == 0 and st["fifo_bytes_left"] == 0, st
+out["googlenet_frames"] = {"finals": _frame_hashes(finals), "kernels_finished": st["done"], "tiles": st["tap_counts"],
+                           "seconds": round(time.time() - t, 1)}
+print("googlenet_frames", out["googlenet_frames"]["seconds"], "s", flush=True)
 path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "whole_net_golden.json")
 with open(path, "w") as f:
     json.dump(out, f, indent=1)

@@ -76,3 +76,44 @@ def test_oracle_equals_reference_live(case):
     want = tens[ld.out_tensor][ld.out_ch0:ld.out_ch0 + ld.N]
     assert np.array_equal(final, want.reshape(final.shape))
     assert sum(p is None for p in per) <= 5
+
+
+# ---- images back to back: the premise of sharding a batch over GPUs -------------------------------------
+def frames_case():
+    """GoogLeNet (synthetic model of the GPU tests) on three different images."""
+    from tf2_b200 import formats, synth
+    net, q, model, _ = H.synth_case("googlenet")
+    _, t0 = formats.prepare_input(net, synth.synth_images(3, seed=23), q)
+    return net, model, t0
+
+
+def _frame_hashes(maps):
+    import hashlib
+    return [hashlib.sha256(np.ascontiguousarray(m, dtype=np.int8).tobytes()).hexdigest() for m in maps]
+
+
+def test_frames_back_to_back_hashes():
+    """The reference runs num_images frames through ONE invocation of its kernels (runner.cpp:61-176: frame_num),
+    re-using the on-chip cache, the DDR pages and the filter double buffer from frame to frame.  Every frame's
+    result equals the oracle's result for that image alone: images are independent, which is what lets a batch
+    be sharded over GPUs with no data-path collective."""
+    import json
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "whole_net_golden.json")) as f:
+        g = json.load(f)["googlenet_frames"]
+    net, model, t0 = frames_case()
+    exp = O.run_network(net, model, t0)
+    assert _frame_hashes(exp) == g["finals"]
+    assert len(set(g["finals"])) == 3 and g["kernels_finished"] == 25
+
+
+def test_frames_back_to_back_live():
+    if not _have_ref("googlenet"):
+        pytest.skip("oracle/_ref not built (reference tree absent)")
+    net, model, t0 = frames_case()
+    finals, st = O.ref_run_frames("googlenet", t0, model)
+    assert st["done"] == 25 and st["parked"] == 0 and st["fifo_bytes_left"] == 0
+    assert st["tap_counts"] == [3 * c for c in st["tap_per_frame"]]
+    exp = O.run_network(net, model, t0)
+    for f in range(3):
+        assert np.array_equal(finals[f].reshape(-1), exp[f].reshape(-1)), f"frame {f}"
+    assert exp.std() > 3 and not np.array_equal(exp[0], exp[1])
