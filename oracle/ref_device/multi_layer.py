@@ -140,7 +140,11 @@ def build(net) -> str:
     """Returns the directory holding libhost.so / libnet.so for this network (built on demand)."""
     if not os.path.isdir(os.path.join(REF, "Runtime_Engine")):
         raise FileNotFoundError(REF)
-    key = hashlib.sha1(json.dumps(net.to_json(), sort_keys=True).encode()).hexdigest()[:12]
+    h = hashlib.sha1(json.dumps(net.to_json(), sort_keys=True).encode())
+    for src in ("net_harness.c", "fifo_shim.h", "multi_layer.py", "one_layer.py", os.path.join("..", "ref_host_shim.cpp")):
+        with open(os.path.join(_HERE, src), "rb") as f:      # a changed harness must not meet a cached library
+            h.update(f.read())
+    key = h.hexdigest()[:12]
     out = os.path.join(os.path.dirname(_HERE), "_ref", f"net_{key}")
     if os.path.exists(os.path.join(out, "libnet.so")) and os.path.exists(os.path.join(out, "libhost.so")):
         return out

@@ -81,7 +81,11 @@ def build(cfg: Dict[str, int]) -> str:
     """Returns the directory holding libhost.so / libdev.so for this layer geometry (built on demand)."""
     if not os.path.isdir(os.path.join(REF, "Runtime_Engine")):
         raise FileNotFoundError(REF)
-    key = hashlib.sha1(repr(sorted(cfg.items())).encode()).hexdigest()[:12]
+    h = hashlib.sha1(repr(sorted(cfg.items())).encode())
+    for src in ("full_harness.c", "fifo_shim.h", "one_layer.py", os.path.join("..", "ref_host_shim.cpp")):
+        with open(os.path.join(_HERE, src), "rb") as f:      # a changed harness must not meet a cached library
+            h.update(f.read())
+    key = h.hexdigest()[:12]
     out = os.path.join(os.path.dirname(_HERE), "_ref", f"one_{key}")
     if os.path.exists(os.path.join(out, "libdev.so")) and os.path.exists(os.path.join(out, "libhost.so")):
         return out
