@@ -1,0 +1,60 @@
+"""torch model -> param.bin -> (INQ projection -> calibrated Q -> LoadModel -> oracle): SURVEY.md 8f-3 on a
+torchvision ResNet50 (random initialisation: there is no network for pretrained weights).  The blob order, the
+BatchNorm folding and the table topology are checked by comparing the float forward pass over the blob with the
+torch model itself."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+torchvision = pytest.importorskip("torchvision")
+
+from tf2_b200 import calibrate as K  # noqa: E402
+from tf2_b200 import compress as Z  # noqa: E402
+from tf2_b200 import formats, from_torch, nets, synth  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def torch_resnet50():
+    torch.manual_seed(7)
+    m = torchvision.models.resnet50(weights=None)
+    g = torch.Generator().manual_seed(8)
+    for mod in m.modules():                                 # BatchNorm statistics as after training, not 0 / 1
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            mod.running_mean.copy_(torch.randn(mod.num_features, generator=g) * 0.1)
+            mod.running_var.copy_(torch.rand(mod.num_features, generator=g) * 0.5 + 0.75)
+            mod.weight.data.copy_(torch.rand(mod.num_features, generator=g) * 0.5 + 0.75)
+            mod.bias.data.copy_(torch.randn(mod.num_features, generator=g) * 0.1)
+    return m.eval()
+
+
+def test_blob_of_a_torchvision_resnet50_computes_the_same_function(torch_resnet50):
+    net = nets.resnet50()
+    blob = from_torch.blob_from_modules(net, from_torch.torchvision_resnet50(torch_resnet50))
+    assert len(blob) == formats.float_blob_size(net)
+    imgs = synth.synth_images(2, seed=1) / 50.0
+    with torch.no_grad():
+        want = torch_resnet50(torch.from_numpy(imgs)).numpy()
+    got = K.float_forward(net, blob, imgs)[0][net.result_tensor()].reshape(2, -1)
+    assert np.allclose(got, want, rtol=1e-3, atol=1e-3 * np.abs(want).max())
+    with pytest.raises(ValueError):
+        from_torch.blob_from_modules(net, from_torch.torchvision_resnet50(torch_resnet50)[:-1])
+
+
+def test_torch_model_to_served_int8_model(torch_resnet50):
+    from oracle import oracle as O
+    net = nets.resnet50()
+    blob = from_torch.blob_from_modules(net, from_torch.torchvision_resnet50(torch_resnet50))
+    qblob, min_exps = Z.quantize_blob(net, blob)            # INQ projection, no retraining
+    imgs = synth.synth_images(2, seed=2) / 50.0
+    qtext, _ = K.calibrate(net, qblob, imgs)
+    q = formats.parse_q_text(net, qtext)
+    model = formats.load_float_blob(net, qblob, q)
+    raw, t0 = formats.prepare_input(net, imgs, q)
+    y = O.run_network(net, model, t0).reshape(2, -1).astype(np.float64)
+    deq = y * np.exp2(q[net.num_layers, :1000].astype(np.float64))
+    ref = K.float_forward(net, qblob, imgs)[0][net.result_tensor()].reshape(2, -1)
+    for b in range(2):
+        assert np.corrcoef(ref[b], deq[b])[0, 1] > 0.9
+    # the 4-bit model file of this network: an eighth of the float blob, identity round trip
+    m4 = formats.float_blob_to_4bit(net, qblob)
+    assert len(m4) < len(qblob) / 6 and formats.float_blob_from_4bit(net, m4) == qblob
