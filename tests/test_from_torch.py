@@ -58,3 +58,21 @@ def test_torch_model_to_served_int8_model(torch_resnet50):
     # the 4-bit model file of this network: an eighth of the float blob, identity round trip
     m4 = formats.float_blob_to_4bit(net, qblob)
     assert len(m4) < len(qblob) / 6 and formats.float_blob_from_4bit(net, m4) == qblob
+
+
+def test_squeezenet_tables_compute_torchvision_squeezenet1_1():
+    """nets.squeezenet() (BASELINE configs[0]; the reference ships no SqueezeNet tables) against torchvision's own
+    SqueezeNet 1.1: stride-2 stem with its pool, fire-module concats, the stride-2 pools fused into both expand
+    layers, the 1x1 classifier with ReLU over the 13x13 map."""
+    torch.manual_seed(3)
+    m = torchvision.models.squeezenet1_1(weights=None).eval()
+    net = nets.squeezenet()
+    blob = from_torch.blob_from_modules(net, from_torch.torchvision_squeezenet1_1(m))
+    assert len(blob) == formats.float_blob_size(net)
+    imgs = synth.synth_images(2, seed=5) / 50.0
+    with torch.no_grad():
+        x = m.features(torch.from_numpy(imgs))
+        want = m.classifier[2](m.classifier[1](x)).numpy()             # conv + ReLU, before the 13x13 average
+    got = K.float_forward(net, blob, imgs)[0][net.result_tensor()]
+    assert got.shape == want.shape == (2, 1000, 13, 13)
+    assert np.allclose(got, want, rtol=1e-3, atol=1e-3 * np.abs(want).max())

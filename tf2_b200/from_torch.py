@@ -65,3 +65,17 @@ def torchvision_resnet50(model) -> List[Tuple[object, Optional[object]]]:
             mods += [(blk.conv1, blk.bn1), (blk.conv2, blk.bn2), (blk.conv3, blk.bn3)]
     mods.append((model.fc, None))
     return mods
+
+
+def torchvision_squeezenet1_1(model) -> List[Tuple[object, Optional[object]]]:
+    """Module list of a torchvision SqueezeNet 1.1 in the layer order of `nets.squeezenet()`: conv1, then squeeze /
+    expand1x1 / expand3x3 of every fire module, then the 1x1 classifier convolution (its ReLU is the layer's; the
+    13x13 average after it is outside the runtime: full_size_pool.cl is a 7x7 average)."""
+    import torch
+    mods = [(model.features[0], None)]
+    for f in model.features:
+        if hasattr(f, "squeeze"):
+            mods += [(f.squeeze, None), (f.expand1x1, None), (f.expand3x3, None)]
+    conv = [c for c in model.classifier if isinstance(c, torch.nn.Conv2d)]
+    mods.append((conv[0], None))
+    return mods
