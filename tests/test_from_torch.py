@@ -76,3 +76,26 @@ def test_squeezenet_tables_compute_torchvision_squeezenet1_1():
     got = K.float_forward(net, blob, imgs)[0][net.result_tensor()]
     assert got.shape == want.shape == (2, 1000, 13, 13)
     assert np.allclose(got, want, rtol=1e-3, atol=1e-3 * np.abs(want).max())
+
+
+def test_vgg16_tables_compute_a_torch_vgg16():
+    """nets.vgg16() (BASELINE configs[3]) against a torchvision VGG16 at a quarter of the width whose 2x2 pools are
+    replaced by the runtime's 3x3 / stride-2 window (pool.cl knows no other; 224 -> 112 needs ceil mode): the 13
+    convolutions, the five pools, fc6 as a 7x7 convolution in torch's flatten order, fc7, fc8."""
+    from torchvision.models.vgg import make_layers
+    torch.manual_seed(11)
+    cfg = [16, 16, "M", 32, 32, "M", 64, 64, 64, "M", 128, 128, 128, "M", 128, 128, 128, "M"]
+    features = make_layers(cfg)
+    for i, mod in enumerate(features):
+        if isinstance(mod, torch.nn.MaxPool2d):
+            features[i] = torch.nn.MaxPool2d(3, 2, ceil_mode=True)
+    classifier = torch.nn.Sequential(torch.nn.Linear(128 * 7 * 7, 1024), torch.nn.ReLU(), torch.nn.Linear(1024, 1024),
+                                     torch.nn.ReLU(), torch.nn.Linear(1024, 1000))
+    net = nets.vgg16(width_div=4)
+    blob = from_torch.blob_from_modules(net, from_torch.vgg_modules(features, classifier))
+    assert len(blob) == formats.float_blob_size(net)
+    imgs = synth.synth_images(2, seed=6) / 50.0
+    with torch.no_grad():
+        want = classifier(torch.flatten(features.eval()(torch.from_numpy(imgs)), 1)).numpy()
+    got = K.float_forward(net, blob, imgs)[0][net.result_tensor()].reshape(2, -1)
+    assert np.allclose(got, want, rtol=1e-3, atol=1e-3 * np.abs(want).max())

@@ -79,3 +79,21 @@ def torchvision_squeezenet1_1(model) -> List[Tuple[object, Optional[object]]]:
     conv = [c for c in model.classifier if isinstance(c, torch.nn.Conv2d)]
     mods.append((conv[0], None))
     return mods
+
+
+def vgg_modules(features, classifier) -> List[Tuple[object, Optional[object]]]:
+    """Module list of a torchvision-style VGG (`features`: Conv2d / ReLU / pool sequence, `classifier`: Linear /
+    ReLU / Dropout sequence) in the layer order of `nets.vgg16()`: the convolutions, then fc6 as a 7x7 convolution
+    over the last map (torch flattens [C][H][W], which is the convolution's own weight order), fc7, fc8."""
+    import torch
+
+    class _AsConv:
+        def __init__(self, lin, c, k):
+            self.weight = lin.weight.reshape(lin.out_features, c, k, k)
+            self.bias = lin.bias
+
+    convs = [m for m in features if isinstance(m, torch.nn.Conv2d)]
+    lins = [m for m in classifier if isinstance(m, torch.nn.Linear)]
+    c_last = convs[-1].out_channels
+    k = int(round((lins[0].in_features // c_last) ** 0.5))
+    return [(c, None) for c in convs] + [(_AsConv(lins[0], c_last, k), None)] + [(l, None) for l in lins[1:]]
