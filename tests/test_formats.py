@@ -211,3 +211,26 @@ def test_4bit_model_file_roundtrip():
     blob[0:4] = np.float32(0.3).tobytes()
     with pytest.raises(ValueError):
         formats.float_blob_to_4bit(net, bytes(blob))
+
+
+def test_every_shipped_q_file_parses_like_the_reference():
+    """The four Q files the reference ships (host/model/: resnet50_Q, pytorch_resnet50_q, resnet50_pruned_Q,
+    googlenet_Q) through its own Quantization() (quantization.cpp:25-55, compiled unmodified) vs parse_q_file."""
+    model_dir = os.path.join(REFERENCE, "Runtime_Engine", "cnn", "host", "model")
+    if not os.path.isdir(model_dir) or O.ref_host_lib("resnet50") is None:
+        pytest.skip("reference tree / oracle/_ref absent")
+    seen = 0
+    for fname, name in (("resnet50_Q", "resnet50"), ("pytorch_resnet50_q", "resnet50"), ("resnet50_pruned_Q", "resnet50_pruned"),
+                        ("googlenet_Q", "googlenet")):
+        path = os.path.join(model_dir, fname)
+        L = O.ref_host_lib(name)
+        net = nets.load(name)
+        nq, mo = L.ref_num_q_layers(), L.ref_max_out_channel()
+        qref = np.zeros((nq + 2) * mo, dtype=np.int8)
+        L.ref_quantization(qref.ctypes.data, path.encode())
+        q = formats.parse_q_file(net, path)
+        assert q.shape == (nq, mo) and np.array_equal(q, qref[:nq * mo].reshape(nq, mo)), fname
+        with open(path) as f:
+            assert len(f.read().split()) == formats.q_file_value_count(net), fname
+        seen += 1
+    assert seen == 4
