@@ -107,12 +107,16 @@ int tf2b_set_variant(tf2b_net* net, int variant);
  * and the others receive it with a single NCCL broadcast. */
 int64_t tf2b_weight_blob_bytes(tf2b_net* net);
 int tf2b_export_weight_blob(tf2b_net* net, void* dev_dst, void* stream);
-int tf2b_import_weight_blob(tf2b_net* net, const void* dev_src, void* stream);
+/* `blob_bytes` = length of the buffer at dev_src; the header carries a hash of the layer/tensor tables and
+ * the arena size, every offset is checked against them before anything is read. */
+int tf2b_import_weight_blob(tf2b_net* net, const void* dev_src, int64_t blob_bytes, void* stream);
 
 /* Replaces Runner::Run's enqueue of the finite kernels (runner.cpp:166-183) with inputs already on
  * the device.  `in_dev`: int8 tensor-0 images in `in_layout`; `out_dev`: int8 result tensor
  * (`result_tensor` of tf2b_set_result, default = the last layer's output) in `out_layout`.
- * Asynchronous on `stream` (a cudaStream_t, may be NULL). */
+ * Asynchronous on `stream` (a cudaStream_t, may be NULL).
+ * A handle owns ONE set of feature-map buffers: run calls on one handle must be issued from one thread and
+ * onto one stream at a time (or ordered by the caller with events); use one handle per concurrent stream. */
 int tf2b_run(tf2b_net* net, const int8_t* in_dev, int in_layout, int n_images, int8_t* out_dev,
              int out_layout, void* stream);
 
@@ -132,6 +136,9 @@ int tf2b_run_raw224_host(tf2b_net* net, const int8_t* raw_host, int n_images, in
  * Host buffers should be pinned; they must stay valid until tf2b_wait returns. */
 int tf2b_submit_raw224_host(tf2b_net* net, const int8_t* raw_host, int n_images, int8_t* out_host,
                             int out_layout, int slot);
+/* Same for tensor-0 images in `in_layout` (networks without the 7x7 -> 3x3 stem transform). */
+int tf2b_submit_host(tf2b_net* net, const int8_t* in_host, int in_layout, int n_images, int8_t* out_host,
+                     int out_layout, int slot);
 int tf2b_wait(tf2b_net* net, int slot);
 
 int tf2b_run_host(tf2b_net* net, const int8_t* in_host, int in_layout, int n_images,

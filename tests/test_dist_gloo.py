@@ -31,6 +31,7 @@ class _FakeNetWork:
 
     def InitFromCodes(self, model, q, max_images, variant):
         self.calls.append(("codes", max_images, variant))
+        self.q = q
         self.blob = (np.arange(3000, dtype=np.int64) * model % 251).astype(np.uint8)
 
     def weight_blob_bytes(self):
@@ -40,10 +41,11 @@ class _FakeNetWork:
         import ctypes
         ctypes.memmove(ptr, self.blob.ctypes.data, self.blob.size)
 
-    def InitFromBlob(self, ptr, max_images, variant):
+    def InitFromBlob(self, ptr, nbytes, max_images, variant, q=None):
         import ctypes
         self.calls.append(("blob", max_images, variant))
-        self.blob = np.frombuffer(ctypes.string_at(ptr, 3000), dtype=np.uint8).copy()
+        self.q = q
+        self.blob = np.frombuffer(ctypes.string_at(ptr, nbytes), dtype=np.uint8).copy()
 
 
 def _worker(rank, world, port, q):
@@ -71,8 +73,11 @@ def _worker(rank, world, port, q):
         ok = ok and bool(torch.equal(torch.cat(parts), data * 2))
         # init_network_distributed: rank 0 loads the model, the others import the broadcast blob
         from tf2_b200.dist import init_network_distributed
-        nw = init_network_distributed(_FakeNetWork(), dist, "cpu", model=7 if rank == 0 else None, q=None, max_images=4, variant=1)
+        qtab = (np.arange(6 * 11, dtype=np.int64) % 9 - 5).astype(np.int8).reshape(6, 11)
+        nw = init_network_distributed(_FakeNetWork(), dist, "cpu", model=7 if rank == 0 else None,
+                                      q=qtab if rank == 0 else None, max_images=4, variant=1)
         ok = ok and nw.calls == [("codes" if rank == 0 else "blob", 4, 1)]
+        ok = ok and np.array_equal(nw.q, qtab)          # every rank ends up with rank 0's Q table
         ok = ok and np.array_equal(nw.blob, (np.arange(3000, dtype=np.int64) * 7 % 251).astype(np.uint8))
         # device-timed numbers are combined as the max over ranks
         t = torch.tensor([1.0 + rank])

@@ -113,7 +113,7 @@ def test_weight_blob_roundtrip():
     ya = Runner(a).run_device(torch.from_numpy(x).cuda()).cpu().numpy()
     for variant in (capi.VARIANT_AUTO, capi.VARIANT_SHIFT):
         b = NetWork(net, 0)
-        b.InitFromBlob(blob.data_ptr(), max_images=2, variant=variant)
+        b.InitFromBlob(blob.data_ptr(), int(blob.numel()), max_images=2, variant=variant)
         yb = Runner(b).run_device(torch.from_numpy(x).cuda()).cpu().numpy()
         assert np.array_equal(ya, yb)
         if variant == capi.VARIANT_AUTO:

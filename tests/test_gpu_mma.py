@@ -104,12 +104,24 @@ def test_mma_parity(name, chw, specs, B, ckw):
     r = Runner(nw)
     out = r.run_device(torch.from_numpy(x).cuda()).cpu().numpy()
     for b in range(B):
-        tens, _ = H.oracle_tensors(net, model, x[b])
+        tens, accs = H.oracle_tensors(net, model, x[b])
         for t in range(1, len(net.tensors)):
             got = r.read_tensor(t, B).cpu().numpy()[b]
             bad = (got != tens[t])
             assert not bad.any(), f"{name}: image {b} tensor {t} differs in {bad.sum()} of {bad.size} (first {np.argwhere(bad)[:4].tolist()})"
         assert np.array_equal(out[b], tens[net.result_tensor()])
+        if b == 0:
+            # the INT32 accumulators of the tensor-core kernel itself (pe.cl:196-199's tap): the same launch plan
+            # with the exact epilogue writing bias + sum of shifted features before requantisation
+            for l in range(1, net.num_layers):
+                if kern[l] != "mma":
+                    continue
+                g = r.dump_acc(l, B).cpu().numpy()
+                for bb in range(B):
+                    want = accs[l] if bb == 0 else H.oracle_tensors(net, model, x[bb])[1][l]
+                    assert np.array_equal(g[bb], want), f"{name}: layer {l} image {bb} INT32 accumulators differ in {(g[bb] != want).sum()}"
+            # the tap must leave the feature maps of the run untouched
+            assert np.array_equal(r.read_tensor(net.result_tensor(), B).cpu().numpy(), out)
     # a second run with fewer images than max_images (tiles past the batch end)
     if B > 1:
         out1 = r.run_device(torch.from_numpy(x[:1].copy()).cuda()).cpu().numpy()
@@ -164,6 +176,11 @@ def test_mma_modes(name, chw, spec, B, ckw, want):
         tens, _ = H.oracle_tensors(net, model, x[b])
         bad = out[b] != tens[net.result_tensor()]
         assert not bad.any(), f"{name} [{plan}]: image {b} differs in {bad.sum()} of {bad.size} (first {np.argwhere(bad)[:4].tolist()})"
+    # INT32 accumulators of this very launch plan (CTA pairs / halo tiles included)
+    g = r.dump_acc(1, B).cpu().numpy()
+    for b in range(B):
+        want = H.oracle_tensors(net, model, x[b])[1][1]
+        assert np.array_equal(g[b], want), f"{name} [{plan}]: image {b} INT32 accumulators differ in {(g[b] != want).sum()}"
     # fewer images than max_images: other tile counts (pairs with a missing partner, ragged last tile)
     for nb in {1, max(1, B - 1)}:
         o = r.run_device(torch.from_numpy(x[:nb].copy()).cuda()).cpu().numpy()

@@ -82,3 +82,49 @@ def test_resnet50_batch256_properties(resnet_model):
     assert np.array_equal(a, a2)         # deterministic
     assert a.std() > 1.0                 # the synthetic model keeps the logits alive
     nw.CleanUp()
+
+
+def test_resnet50_batch256_plan_matches_oracle(resnet_model):
+    """The BENCHMARKED configuration itself (B = 256, variant AUTO: 30 layers run as CTA pairs, which a B = 2 run
+    never selects on the 7x7 / 14x14 maps) against the oracle and the executed reference: image 0 is the image of
+    tests/golden/whole_net_golden.json, every one of its 55 tensors is compared with the oracle and with the
+    hashes of what the reference's own device program produced; the first, a middle and the last image of the
+    batch are compared at the logits and at the INT32 accumulators of CTA-pair / halo / flat layers."""
+    import torch
+    from oracle import oracle as O
+    from tf2_b200.network import NetWork, Runner
+    net, q, model = resnet_model
+    B = 256
+    rng = np.random.default_rng(5)
+    raw = rng.integers(-128, 128, size=(B, 3, 224, 224), dtype=np.int8)
+    raw0, _ = formats.prepare_input(net, synth.synth_images(1, seed=11), q)      # the golden case's image
+    raw[0] = raw0[0]
+    nw = NetWork(net, 0)
+    nw.InitFromCodes(model, q, max_images=B, variant=capi.VARIANT_AUTO)
+    modes = nw.layer_modes(B)
+    assert sum("ctapair" in m for m in modes) >= 20, modes          # the plan under test IS the CTA-pair plan
+    assert any("halo" in m for m in modes) and all(k == "mma" for k in nw.layer_kernels())
+    r = Runner(nw)
+    got = r.run_device(torch.from_numpy(raw).cuda(), raw224=True).cpu().numpy()
+    pick = [0, 131, 255]
+    t0 = formats.feature_trans(raw[pick]).reshape(len(pick), -1, 114, 114)
+    exp = O.run_network(net, model, t0)
+    for i, b in enumerate(pick):
+        assert np.array_equal(got[b], exp[i]), f"image {b}: logits differ in {(got[b] != exp[i]).sum()} of {exp[i].size}"
+    # every tensor of image 0: oracle and reference-device hashes
+    tens, accs = H.oracle_tensors(net, model, t0[0])
+    dev = {}
+    for t in range(1, len(net.tensors)):
+        g = dev[t] = r.read_tensor(t, 1).cpu().numpy()[0]
+        assert np.array_equal(g, tens[t]), f"tensor {t} ({net.tensors[t].name}) differs in {(g != tens[t]).sum()}"
+    H.assert_reference_hashes("resnet50", net, dev)
+    # INT32 accumulators out of the tensor-core kernel in this launch plan: conv1 (halo, low plane), a halo 3x3,
+    # flat + residual, CTA-pair 1x1 / 3x3 / stride 2, the last bottleneck and the fc layer
+    _, accs_last = H.oracle_tensors(net, model, t0[2])
+    for l in (0, 3, 4, 13, 26, 29, 45, 47, 52, 53):
+        g = r.dump_acc(l, B).cpu().numpy()
+        assert np.array_equal(g[0], accs[l]), f"layer {l} [{modes[l]}]: image 0 accumulators differ in {(g[0] != accs[l]).sum()}"
+        assert np.array_equal(g[255], accs_last[l]), f"layer {l} [{modes[l]}]: image 255 accumulators differ"
+    # the taps left the run's feature maps alone
+    assert np.array_equal(r.read_tensor(net.result_tensor(), B).cpu().numpy(), got)
+    nw.CleanUp()

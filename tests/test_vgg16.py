@@ -64,3 +64,37 @@ def test_vgg16_lite_matches_oracle_on_gpu(variant):
     if variant == capi.VARIANT_AUTO:
         assert "mma" in nw.layer_kernels()
     nw.CleanUp()
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(900)
+def test_vgg16_full_size_matches_oracle_on_gpu():
+    """BASELINE configs[3]'s network at FULL width (15.47 GMAC per image, 138 M weights: the arena holds them as
+    int8 planes for the tensor cores and int16 planes for the shift kernel), B = 3, against the oracle: every
+    tensor of image 0, the logits of all images, INT32 accumulators of the stem (which sees -128), a 224-wide 3x3,
+    a CTA-pair 3x3 and the 7x7 fc6 convolution."""
+    import torch
+    from oracle import oracle as O
+    from tf2_b200.network import NetWork, Runner
+    net = nets.vgg16()
+    rng = np.random.default_rng(12)
+    B = 3
+    x = H.random_input(rng, 3, 224, 224, nonneg=False, B=B)
+    model = H.random_model(net, rng, x)
+    exp = O.run_network(net, model, x)
+    nw = NetWork(net, 0)
+    nw.InitFromCodes(model, None, max_images=B, variant=capi.VARIANT_AUTO)
+    kern = nw.layer_kernels()
+    assert kern.count("mma") >= 15, kern
+    r = Runner(nw)
+    got = r.run_device(torch.from_numpy(x).cuda()).cpu().numpy()
+    assert np.array_equal(got, exp), f"logits differ in {(got != exp).sum()} of {exp.size}"
+    tens, accs = H.oracle_tensors(net, model, x[0])
+    for t in range(1, len(net.tensors)):
+        g = r.read_tensor(t, 1).cpu().numpy()[0]
+        assert np.array_equal(g, tens[t]), f"tensor {t} differs in {(g != tens[t]).sum()}"
+    for l in (0, 1, 7, 13, 15):
+        g = r.dump_acc(l, B).cpu().numpy()[0]
+        assert np.array_equal(g, accs[l]), f"layer {l} ({kern[l]}): INT32 accumulators differ in {(g != accs[l]).sum()}"
+    assert np.array_equal(r.run_host(x), exp)
+    nw.CleanUp()

@@ -2,17 +2,14 @@
 tests/test_generated_nets_ref.py (SqueezeNet fire modules on even maps, the pool / stride probes): the golden
 hashes come from the executed reference, so this is CUDA vs compiled reference without the oracle in between.
 
-Written after the round's GPU minutes were spent: not yet run on a B200, hence the non-strict xfail (an
-unexpected pass is reported as XPASS) and the file name that sorts it last.  The VGG16 case of the same
-golden file is checked inside tests/test_vgg16.py, which has run."""
+The VGG16 case of the same golden file is checked inside tests/test_vgg16.py."""
 import numpy as np
 import pytest
 
 from tests import helpers as H
 from tests.test_generated_nets_ref import CASES, build_case
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(180),
-              pytest.mark.xfail(strict=False, reason="new, not yet run on a GPU (round-1 budget spent)")]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(180)]
 
 
 @pytest.mark.parametrize("case", [c for c in CASES if c != "vgg16_div8"])

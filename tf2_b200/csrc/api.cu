@@ -31,7 +31,8 @@ cudaError_t launch_gap(const int8_t*, int8_t*, int, int, int, int, int, cudaStre
 // tensor-core path (conv_mma.cu)
 bool mma_layer_supported(const tf2b_layer_desc& L, int in_pitch, int planes8);
 cudaError_t launch_conv_mma(const ConvParams& p, const int8_t* wgt8, int planes8,
-                            const int* plane8_shift, void* tmaps, cudaStream_t stream);
+                            const int* plane8_shift, void* tmaps, int num_sms, cudaStream_t stream);
+cudaError_t mma_prepare_device(int* num_sms);
 size_t mma_tmap_bytes();
 std::string mma_describe(const ConvParams& p, int planes8);
 int mma_build_tmaps(void* host_tmaps, const ConvParams& p, const int8_t* wgt8, int planes8,
@@ -83,6 +84,7 @@ struct BlobLayerMeta {  // fixed-size, trivially copyable: travels inside the we
 
 struct tf2b_net {
   int device = 0;
+  int num_sms = 0;          // of `device` (grids of the persistent kernels)
   std::vector<tf2b_tensor_desc> tensors;
   std::vector<int> tpitch;  // channel pitch of each tensor (C rounded up to 16)
   int t0_neg_off = 0;       // channel offset of the negated copy inside tensor 0
@@ -133,7 +135,11 @@ static int fail(tf2b_net* n, int code, const char* fmt, ...) {
                   __FILE__, __LINE__);                                                     \
   } while (0)
 
-static std::string g_create_err;
+// tf2b_create has no handle to hang its error text on: one slot per calling thread
+static thread_local std::string g_create_err;
+extern "C" {
+static int ensure_io(tf2b_net* net);
+}
 
 // ------------------------------------------------------------------------------------------------
 // weight preparation: LoadModel codes -> per-channel base shift + power-of-two weight planes
@@ -488,6 +494,10 @@ int tf2b_set_result(tf2b_net* net, int tensor) {
   if (!net) return TF2B_ERR_ARG;
   if (tensor < 0 || tensor >= (int)net->tensors.size()) return fail(net, TF2B_ERR_ARG, "tensor out of range");
   net->result_tensor = tensor;
+  if (net->finalized) {
+    CUDA_TRY(net, cudaSetDevice(net->device));
+    return ensure_io(net);
+  }
   return TF2B_OK;
 }
 
@@ -508,8 +518,20 @@ static size_t layout_arena(tf2b_net* net) {
   return off;
 }
 
+constexpr size_t kBlobFixed = 32;   // magic, layer count, hash of the layer / tensor tables, arena bytes
 static size_t blob_header_bytes(const tf2b_net* net) {
-  return align256(16 + net->layers.size() * sizeof(BlobLayerMeta));
+  return align256(kBlobFixed + net->layers.size() * sizeof(BlobLayerMeta));
+}
+// FNV-1a over the tensor and layer tables: a blob only fits an engine created from the same tables
+static uint64_t tables_hash(const tf2b_net* net) {
+  uint64_t h = 1469598103934665603ull;
+  auto mix = [&](const void* p, size_t n) {
+    const unsigned char* b = (const unsigned char*)p;
+    for (size_t i = 0; i < n; i++) { h ^= b[i]; h *= 1099511628211ull; }
+  };
+  for (auto& t : net->tensors) mix(&t, sizeof t);
+  for (auto& S : net->layers) mix(&S.d, sizeof S.d);
+  return h;
 }
 
 int64_t tf2b_weight_blob_bytes(tf2b_net* net) {
@@ -528,6 +550,7 @@ int tf2b_finalize(tf2b_net* net, int max_images) {
     if (!net->layers[l].d.ipool && !net->layers[l].loaded)
       return fail(net, TF2B_ERR_STATE, "layer %zu has no weights loaded", l);
   CUDA_TRY(net, cudaSetDevice(net->device));
+  CUDA_TRY(net, tf2b::mma_prepare_device(&net->num_sms));
   net->max_images = max_images;
   net->arena_bytes = layout_arena(net);
   CUDA_TRY(net, cudaMalloc(&net->arena, std::max<size_t>(net->arena_bytes, 256)));
@@ -582,6 +605,47 @@ static ConvParams conv_params(tf2b_net* net, const LayerState& S, int B, int8_t*
   return p;
 }
 
+// Staging of the host-buffer entry points, allocated when the plan is frozen (never inside a run call):
+// the synchronous pair io_in / io_out and the two slots of the pipelined call with their copy streams and
+// events.  Inputs are sized for max_images raw or tensor-0 images, outputs for the RESULT tensor; a later
+// tf2b_set_result to a larger tensor grows the output side.
+static int ensure_io(tf2b_net* net) {
+  const size_t B = (size_t)net->max_images;
+  const size_t in_b = std::max((size_t)3 * 224 * 224, (size_t)net->tensors[0].C * net->tensors[0].H * net->tensors[0].W) * B;
+  const tf2b_tensor_desc& tr = net->tensors[net->result_tensor];
+  const size_t out_b = std::max((size_t)tr.C * tr.H * tr.W * B, (size_t)256);
+  if (!net->s_h2d) {
+    CUDA_TRY(net, cudaStreamCreateWithFlags(&net->s_h2d, cudaStreamNonBlocking));
+    CUDA_TRY(net, cudaStreamCreateWithFlags(&net->s_d2h, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+      CUDA_TRY(net, cudaEventCreateWithFlags(&net->ev_h2d[i], cudaEventDisableTiming));
+      CUDA_TRY(net, cudaEventCreateWithFlags(&net->ev_comp[i], cudaEventDisableTiming));
+      CUDA_TRY(net, cudaEventCreateWithFlags(&net->ev_d2h[i], cudaEventDisableTiming));
+    }
+  }
+  if (in_b > net->io_in_bytes) {
+    CUDA_TRY(net, cudaDeviceSynchronize());
+    int8_t** bufs[3] = {&net->io_in, &net->slot_in[0], &net->slot_in[1]};
+    for (auto b : bufs) {
+      if (*b) CUDA_TRY(net, cudaFree(*b));
+      *b = nullptr;
+      CUDA_TRY(net, cudaMalloc(b, in_b));
+    }
+    net->io_in_bytes = in_b;
+  }
+  if (out_b > net->io_out_bytes) {
+    CUDA_TRY(net, cudaDeviceSynchronize());
+    int8_t** bufs[3] = {&net->io_out, &net->slot_out[0], &net->slot_out[1]};
+    for (auto b : bufs) {
+      if (*b) CUDA_TRY(net, cudaFree(*b));
+      *b = nullptr;
+      CUDA_TRY(net, cudaMalloc(b, out_b));
+    }
+    net->io_out_bytes = out_b;
+  }
+  return TF2B_OK;
+}
+
 static int alloc_runtime(tf2b_net* net) {
   const int B = net->max_images;
   net->tbuf.assign(net->tensors.size(), nullptr);
@@ -600,14 +664,10 @@ static int alloc_runtime(tf2b_net* net) {
   net->scratch_bytes = sc;
   CUDA_TRY(net, cudaMalloc(&net->scratch0, sc));
   CUDA_TRY(net, cudaMalloc(&net->scratch1, sc));
-  // staging for host entry points: largest of tensor 0 / raw image, and the result tensor
-  size_t in_b = std::max((size_t)3 * 224 * 224, (size_t)net->tensors[0].C * net->tensors[0].H * net->tensors[0].W) * B;
-  size_t out_b = 0;
-  for (auto& t : net->tensors) out_b = std::max(out_b, (size_t)t.C * t.H * t.W * B);
-  net->io_in_bytes = in_b;
-  net->io_out_bytes = out_b;
-  CUDA_TRY(net, cudaMalloc(&net->io_in, in_b));
-  CUDA_TRY(net, cudaMalloc(&net->io_out, out_b));
+  {
+    int rc = ensure_io(net);
+    if (rc != TF2B_OK) return rc;
+  }
   // tensor maps of the tensor-core path depend on buffer addresses: build them now
   for (auto& S : net->layers) {
     if (!S.mma_ok) continue;
@@ -655,19 +715,21 @@ static int run_layers(tf2b_net* net, int B, cudaStream_t st, int only_layer, int
       }
       continue;
     }
-    const bool to_scratch = d.pool || d.gap;
+    // the accumulator tap re-runs one convolution with its feature map diverted to scratch; everything
+    // else of the layer's launch plan (kernel family, staging mode, CTA pairs, residual) stays as it is
+    const bool to_scratch = d.pool || d.gap || acc_dump != nullptr;
     const int Np16 = round_up(d.N, 16);
     int8_t* cdst = to_scratch ? net->scratch0 : out;
     const int cdstC = to_scratch ? Np16 : outC;
     // the residual add sits after the pool (pool_tail -> feature_writer): fuse it into the conv
     // epilogue only when there is no pool
     const int8_t* cres = d.pool ? nullptr : res;
-    bool use_mma = S.kernel == 2 && S.mma_ok && acc_dump == nullptr;
+    bool use_mma = S.kernel == 2 && S.mma_ok;
     ConvParams p = conv_params(net, S, B, cdst, cdstC, cres, resC, use_mma);
     p.acc_dump = acc_dump;
     if (use_mma) {
       CUDA_TRY(net, tf2b::launch_conv_mma(p, reinterpret_cast<const int8_t*>(net->arena + S.off_w8),
-                                          S.planes_m, S.plane_shift_m, S.h_tmaps.data(), st));
+                                          S.planes_m, S.plane_shift_m, S.h_tmaps.data(), net->num_sms, st));
     } else {
       CUDA_TRY(net, tf2b::launch_conv_shift(p, reinterpret_cast<const int16_t*>(net->arena + S.off_w16), st));
     }
@@ -775,37 +837,29 @@ int tf2b_run_raw224_host(tf2b_net* net, const int8_t* raw_host, int n_images, in
   return TF2B_OK;
 }
 
-// Pipelined form of tf2b_run_raw224_host: the reference's host also only *enqueues* its finite
+// Pipelined form of the host-buffer calls: the reference's host also only *enqueues* its finite
 // kernels (Runner::EnqueueKernels, runner.cpp:32) and waits later (WaitForAllKernels).  Two slots:
 // while batch i computes, the H2D copy of batch i+1 and the D2H copy of batch i-1 run on their own
-// copy engines.  tf2b_wait(slot) returns when that slot's result is in out_host.
-int tf2b_submit_raw224_host(tf2b_net* net, const int8_t* raw_host, int n_images, int8_t* out_host, int out_layout,
-                            int slot) {
+// copy engines.  tf2b_wait(slot) returns when that slot's result is in out_host.  All staging buffers,
+// streams and events exist since tf2b_finalize (ensure_io): nothing is allocated here.
+static int submit_common(tf2b_net* net, const int8_t* in_host, bool raw224, int in_layout, int n_images,
+                         int8_t* out_host, int out_layout, int slot) {
   int rc = check_run(net, n_images);
   if (rc) return rc;
-  if (!raw_host || !out_host || slot < 0 || slot > 1) return fail(net, TF2B_ERR_ARG, "bad pointer or slot");
+  if (!in_host || !out_host || slot < 0 || slot > 1) return fail(net, TF2B_ERR_ARG, "bad pointer or slot");
   CUDA_TRY(net, cudaSetDevice(net->device));
-  if (!net->s_h2d) {
-    CUDA_TRY(net, cudaStreamCreateWithFlags(&net->s_h2d, cudaStreamNonBlocking));
-    CUDA_TRY(net, cudaStreamCreateWithFlags(&net->s_d2h, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; i++) {
-      CUDA_TRY(net, cudaMalloc(&net->slot_in[i], net->io_in_bytes));
-      CUDA_TRY(net, cudaMalloc(&net->slot_out[i], net->io_out_bytes));
-      CUDA_TRY(net, cudaEventCreateWithFlags(&net->ev_h2d[i], cudaEventDisableTiming));
-      CUDA_TRY(net, cudaEventCreateWithFlags(&net->ev_comp[i], cudaEventDisableTiming));
-      CUDA_TRY(net, cudaEventCreateWithFlags(&net->ev_d2h[i], cudaEventDisableTiming));
-    }
-  }
+  const tf2b_tensor_desc& t0 = net->tensors[0];
   const tf2b_tensor_desc& tr = net->tensors[net->result_tensor];
+  const size_t in_bytes = (size_t)n_images * (raw224 ? (size_t)3 * 224 * 224 : (size_t)t0.C * t0.H * t0.W);
   cudaStream_t sc = net->own_stream;
   // the slot's input staging buffer is free once the previous batch that used it has been consumed
   if (net->slot_used[slot]) CUDA_TRY(net, cudaStreamWaitEvent(net->s_h2d, net->ev_comp[slot], 0));
-  CUDA_TRY(net, cudaMemcpyAsync(net->slot_in[slot], raw_host, (size_t)n_images * 3 * 224 * 224, cudaMemcpyHostToDevice,
-                                net->s_h2d));
+  CUDA_TRY(net, cudaMemcpyAsync(net->slot_in[slot], in_host, in_bytes, cudaMemcpyHostToDevice, net->s_h2d));
   CUDA_TRY(net, cudaEventRecord(net->ev_h2d[slot], net->s_h2d));
   CUDA_TRY(net, cudaStreamWaitEvent(sc, net->ev_h2d[slot], 0));
   if (net->slot_used[slot]) CUDA_TRY(net, cudaStreamWaitEvent(sc, net->ev_d2h[slot], 0));  // slot_out still being read back
-  rc = tf2b_run_raw224(net, net->slot_in[slot], n_images, net->slot_out[slot], out_layout, sc);
+  rc = raw224 ? tf2b_run_raw224(net, net->slot_in[slot], n_images, net->slot_out[slot], out_layout, sc)
+              : tf2b_run(net, net->slot_in[slot], in_layout, n_images, net->slot_out[slot], out_layout, sc);
   if (rc) return rc;
   CUDA_TRY(net, cudaEventRecord(net->ev_comp[slot], sc));
   CUDA_TRY(net, cudaStreamWaitEvent(net->s_d2h, net->ev_comp[slot], 0));
@@ -814,6 +868,16 @@ int tf2b_submit_raw224_host(tf2b_net* net, const int8_t* raw_host, int n_images,
   CUDA_TRY(net, cudaEventRecord(net->ev_d2h[slot], net->s_d2h));
   net->slot_used[slot] = true;
   return TF2B_OK;
+}
+
+int tf2b_submit_raw224_host(tf2b_net* net, const int8_t* raw_host, int n_images, int8_t* out_host, int out_layout,
+                            int slot) {
+  return submit_common(net, raw_host, true, TF2B_LAYOUT_CHW, n_images, out_host, out_layout, slot);
+}
+
+int tf2b_submit_host(tf2b_net* net, const int8_t* in_host, int in_layout, int n_images, int8_t* out_host,
+                     int out_layout, int slot) {
+  return submit_common(net, in_host, false, in_layout, n_images, out_host, out_layout, slot);
 }
 
 int tf2b_wait(tf2b_net* net, int slot) {
@@ -858,21 +922,18 @@ int tf2b_dump_acc(tf2b_net* net, int layer, int n_images, int32_t* acc_dev, void
   // feature maps of the last run are left untouched
   LayerState& S = net->layers[layer];
   if (S.d.ipool) return fail(net, TF2B_ERR_ARG, "ipool layer has no accumulators");
-  tf2b_layer_desc saved = S.d;
   size_t need = (size_t)n_images * S.d.OH * S.d.OW * round_up(S.d.N, 16);
   if (need > net->scratch_bytes) {
     // layers that normally write straight to their tensor may exceed the scratch: grow it
+    CUDA_TRY(net, cudaDeviceSynchronize());
     CUDA_TRY(net, cudaFree(net->scratch0));
     CUDA_TRY(net, cudaFree(net->scratch1));
+    net->scratch0 = net->scratch1 = nullptr;
     net->scratch_bytes = need;
     CUDA_TRY(net, cudaMalloc(&net->scratch0, need));
     CUDA_TRY(net, cudaMalloc(&net->scratch1, need));
   }
-  S.d.pool = 1;  // forces the convolution output into scratch0; only the conv launch runs
-  S.d.add_tensor = -1;
-  int rc2 = run_layers(net, n_images, (cudaStream_t)stream, layer, acc_dev);
-  S.d = saved;
-  return rc2;
+  return run_layers(net, n_images, (cudaStream_t)stream, layer, acc_dev);
 }
 
 int tf2b_export_weight_blob(tf2b_net* net, void* dev_dst, void* stream) {
@@ -881,9 +942,11 @@ int tf2b_export_weight_blob(tf2b_net* net, void* dev_dst, void* stream) {
   CUDA_TRY(net, cudaSetDevice(net->device));
   const size_t hb = blob_header_bytes(net);
   std::vector<unsigned char> hdr(hb, 0);
-  uint64_t magic = 0x54463242424c4f42ull, nl = net->layers.size();
+  uint64_t magic = 0x54463242424c4f42ull, nl = net->layers.size(), th = tables_hash(net), ab = net->arena_bytes;
   memcpy(hdr.data(), &magic, 8);
   memcpy(hdr.data() + 8, &nl, 8);
+  memcpy(hdr.data() + 16, &th, 8);
+  memcpy(hdr.data() + 24, &ab, 8);
   for (size_t l = 0; l < net->layers.size(); l++) {
     const LayerState& S = net->layers[l];
     BlobLayerMeta m;
@@ -896,7 +959,7 @@ int tf2b_export_weight_blob(tf2b_net* net, void* dev_dst, void* stream) {
     m.off_w16 = S.off_w16; m.off_w8 = S.off_w8; m.off_bias = S.off_bias; m.off_alpha = S.off_alpha;
     m.off_beta = S.off_beta; m.off_nshift = S.off_nshift; m.off_nshift_m = S.off_nshift_m;
     m.low_plane_m = S.low_plane_m; m.nshift_m_len = (int32_t)S.h_nshift_m.size(); m.fast_requant = S.fast_requant;
-    memcpy(hdr.data() + 16 + l * sizeof m, &m, sizeof m);
+    memcpy(hdr.data() + kBlobFixed + l * sizeof m, &m, sizeof m);
   }
   cudaStream_t st = (cudaStream_t)stream;
   CUDA_TRY(net, cudaMemcpyAsync(dev_dst, hdr.data(), hb, cudaMemcpyHostToDevice, st));
@@ -907,24 +970,30 @@ int tf2b_export_weight_blob(tf2b_net* net, void* dev_dst, void* stream) {
 
 // Import = the receiving side of the init-time NCCL broadcast: engine created from the same layer
 // tables, no model file read; call instead of tf2b_load_layer, then tf2b_finalize.
-int tf2b_import_weight_blob(tf2b_net* net, const void* dev_src, void* stream) {
+int tf2b_import_weight_blob(tf2b_net* net, const void* dev_src, int64_t blob_bytes, void* stream) {
   if (!net || !dev_src) return TF2B_ERR_ARG;
   if (net->finalized) return fail(net, TF2B_ERR_STATE, "import must precede tf2b_finalize");
   CUDA_TRY(net, cudaSetDevice(net->device));
   const size_t hb = blob_header_bytes(net);
+  if (blob_bytes < (int64_t)hb) return fail(net, TF2B_ERR_ARG, "weight blob of %lld bytes is shorter than its header", (long long)blob_bytes);
   std::vector<unsigned char> hdr(hb);
   cudaStream_t st = (cudaStream_t)stream;
   CUDA_TRY(net, cudaMemcpyAsync(hdr.data(), dev_src, hb, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(net, cudaStreamSynchronize(st));
-  uint64_t magic, nl;
+  uint64_t magic, nl, th, ab;
   memcpy(&magic, hdr.data(), 8);
   memcpy(&nl, hdr.data() + 8, 8);
-  if (magic != 0x54463242424c4f42ull || nl != net->layers.size())
-    return fail(net, TF2B_ERR_ARG, "weight blob does not match this network");
+  memcpy(&th, hdr.data() + 16, 8);
+  memcpy(&ab, hdr.data() + 24, 8);
+  if (magic != 0x54463242424c4f42ull || nl != net->layers.size() || th != tables_hash(net))
+    return fail(net, TF2B_ERR_ARG, "weight blob does not match this network (magic / layer count / table hash)");
+  if ((uint64_t)blob_bytes != hb + ab)
+    return fail(net, TF2B_ERR_ARG, "weight blob is %lld bytes, its header says %llu", (long long)blob_bytes,
+                (unsigned long long)(hb + ab));
   for (size_t l = 0; l < net->layers.size(); l++) {
     LayerState& S = net->layers[l];
     BlobLayerMeta m;
-    memcpy(&m, hdr.data() + 16 + l * sizeof m, sizeof m);
+    memcpy(&m, hdr.data() + kBlobFixed + l * sizeof m, sizeof m);
     if (S.d.ipool) continue;
     if (!m.loaded) return fail(net, TF2B_ERR_ARG, "blob layer %zu has no weights", l);
     S.loaded = true; S.Cp = m.Cp; S.Cp_m = m.Cp_m; S.Npad_s = m.Npad_s; S.Kp_s = m.Kp_s; S.planes_s = m.planes_s;
@@ -934,6 +1003,8 @@ int tf2b_import_weight_blob(tf2b_net* net, const void* dev_src, void* stream) {
     }
     // pull the arrays back to the host so finalize() can lay out and upload them uniformly
     auto pull = [&](auto& vec, size_t count, int64_t off) -> cudaError_t {
+      // every array must lie inside the arena part of the blob the caller handed over
+      if (off < 0 || count > (size_t)1 << 40 || (uint64_t)off + count * sizeof(vec[0]) > ab) return cudaErrorInvalidValue;
       vec.resize(count);
       if (!count) return cudaSuccess;
       return cudaMemcpy(vec.data(), (const unsigned char*)dev_src + hb + off, count * sizeof(vec[0]), cudaMemcpyDeviceToHost);

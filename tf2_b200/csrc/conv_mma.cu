@@ -48,6 +48,18 @@ constexpr bool kExp = true;
 constexpr bool kExp = false;
 #endif
 
+// Mode switches (TF2B_MMA_HALO, _FOLD, _HI32, _CG2, _PAIR, _BRES, _RESTMA, _RBUFS, _BN256, _DIRECT, _PDL,
+// _STAGES) are read from the environment only in experiment builds; the shipped library has no getenv.
+inline int env_int(const char* name, int dflt) {
+#ifdef TF2B_EXPERIMENTS
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+#else
+  (void)name;
+  return dflt;
+#endif
+}
+
 constexpr int MMA_M = 128;
 constexpr int NUM_EPI_WARPS = 16;
 constexpr int NUM_THREADS = 32 * (2 + NUM_EPI_WARPS);
@@ -1025,7 +1037,14 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
                   const int j = 4 * j4 + u;
-                  yy[u] = requant_raw((int)(tot[j] * (unsigned)mm[u] + (unsigned)bb[u] + low[j]), aa[u], ee[u]);
+                  const int a32 = (int)(tot[j] * (unsigned)mm[u] + (unsigned)bb[u] + low[j]);
+                  // INT32 accumulator tap (pe.cl:196-199 prints this value): [image][N][OH][OW]
+                  if (c.acc_dump != nullptr && dvalid && ncolp + cc + j < c.N) {
+                    const int hw = c.OH * c.OW;
+                    const int bimg = (int)(dpix / hw);
+                    c.acc_dump[((size_t)bimg * c.N + (ncolp + cc + j)) * hw + (int)(dpix - (long long)bimg * hw)] = a32;
+                  }
+                  yy[u] = requant_raw(a32, aa[u], ee[u]);
                 }
               }
             }
@@ -1137,7 +1156,7 @@ int pick_bn(int planes8, int N);
 // position-space row (OW + k - 1) that fits the 128 accumulator rows.  One TMA box per tile instead
 // of one per filter tap; measured: the 64-channel layers were bound by the number of TMA boxes/rows.
 bool halo_mode(int k, int stride, int Cp, int OW, int OH, int N, int planes8) {
-  static const bool allow = getenv("TF2B_MMA_HALO") == nullptr || atoi(getenv("TF2B_MMA_HALO")) != 0;
+  static const bool allow = env_int("TF2B_MMA_HALO", 1) != 0;
   if (!allow || k < 2 || stride != 1 || OW + k - 1 > MMA_M) return false;
   const int BK = pick_bk(Cp), BN = pick_bn(planes8, N);
   const int kchunks = (Cp + BK - 1) / BK, n_tiles = (N + BN - 1) / BN;
@@ -1152,14 +1171,14 @@ bool halo_mode(int k, int stride, int Cp, int OW, int OH, int N, int planes8) {
 }
 
 bool pair_mode(int k, int stride, int pad, int Cp, int xC, int OW) {
-  static const bool allow = getenv("TF2B_MMA_PAIR") == nullptr || atoi(getenv("TF2B_MMA_PAIR")) != 0;
+  static const bool allow = env_int("TF2B_MMA_PAIR", 1) != 0;
   return allow && k >= 2 && stride == 1 && pad == 0 && Cp == 64 && xC == 64 && OW <= MMA_M;
 }
 
 // N tile: 256 for single-plane layers (one A tile feeds twice the MMA work; TMEM 2 x 256 columns),
 // 128 up to two planes, else 64 (TMEM: 2 buffers x planes x BN <= 512 columns)
 int pick_bn(int planes8, int N) {
-  static const bool allow256 = getenv("TF2B_MMA_BN256") == nullptr || atoi(getenv("TF2B_MMA_BN256")) != 0;
+  static const bool allow256 = env_int("TF2B_MMA_BN256", 1) != 0;
   if (planes8 == 1 && N >= 256 && allow256) return 256;
   if (planes8 <= 2 && N >= 128) return 128;
   return 64;
@@ -1169,7 +1188,7 @@ int pick_bn(int planes8, int N) {
 // the folded requantisation (one IMAD.HI per output) applies: range analysis passed, <= 2 scaled planes,
 // no unscaled low plane
 bool fold_applies(const ConvParams& c, int planes8) {
-  static const bool allow_fold = getenv("TF2B_MMA_FOLD") == nullptr || atoi(getenv("TF2B_MMA_FOLD")) != 0;
+  static const bool allow_fold = env_int("TF2B_MMA_FOLD", 1) != 0;
   return allow_fold && c.fast_requant >= 2 && c.low_plane < 0 && planes8 <= 2;
 }
 
@@ -1226,21 +1245,21 @@ void fill_geometry(MmaParams& P, const ConvParams& c, int planes8) {
   P.b_bytes = P.BN * P.BK;
   // weight-stationary when the CTA's slab is small and the grid can be a multiple of n_tiles
   {
-    static const bool allow = getenv("TF2B_MMA_BRES") == nullptr || atoi(getenv("TF2B_MMA_BRES")) != 0;
+    static const bool allow = env_int("TF2B_MMA_BRES", 1) != 0;
     const long long slab = (long long)P.taps * P.kchunks * planes8 * P.b_bytes;
     P.b_resident = P.halo || (allow && slab <= 96 * 1024 && P.taps * P.kchunks * planes8 <= 64 && P.n_tiles <= 16);
     P.res_bytes = P.b_resident ? (int)slab : 0;
   }
   const int stage_bytes = P.a_stage_bytes + (P.b_resident ? 0 : planes8 * P.b_bytes);
   {
-    static const bool allow = getenv("TF2B_MMA_RESTMA") == nullptr || atoi(getenv("TF2B_MMA_RESTMA")) != 0;
+    static const bool allow = env_int("TF2B_MMA_RESTMA", 1) != 0;
     P.res_tma = allow && c.r != nullptr && P.mode == 0 && P.BN >= 128 && (c.rC % 16 == 0);
     P.res_bufs = 2;
     if (P.res_tma) {
       // The residual operand streams from HBM once; what hides its latency is the number of tiles in
       // flight (measured: with two buffers the producer idles on the ring).  Split shared memory into
       // whole tiles in flight: (activation stages of one tile + one residual tile) each.
-      static const int cap = getenv("TF2B_MMA_RBUFS") ? atoi(getenv("TF2B_MMA_RBUFS")) : 2;   // measured: deeper rings do not help
+      static const int cap = env_int("TF2B_MMA_RBUFS", 2);   // measured: deeper rings do not help
       const int budget = 224 * 1024 - EPI_BYTES - P.res_bytes;
       const int per_tile = P.kchunks * stage_bytes + P.BN * 128;
       int t = budget / per_tile;
@@ -1259,7 +1278,7 @@ void fill_geometry(MmaParams& P, const ConvParams& c, int planes8) {
   P.b_stage_bytes = planes8 * P.b_bytes;
   P.cg2 = 0;
   {
-    static const bool allow = getenv("TF2B_MMA_CG2") == nullptr || atoi(getenv("TF2B_MMA_CG2")) != 0;
+    static const bool allow = env_int("TF2B_MMA_CG2", 1) != 0;
     if (allow && !P.halo && !P.pair && !P.b_resident && !P.res_tma && planes8 * P.BN == 256 && planes8 <= 2 &&
         P.m_tiles >= 4 && P.BK == 128 && fold_applies(c, planes8)) {
       P.cg2 = 1;
@@ -1270,7 +1289,7 @@ void fill_geometry(MmaParams& P, const ConvParams& c, int planes8) {
   int st = (224 * 1024 - EPI_BYTES - P.res_bytes - rres_bytes) / stage_bytes_final;
   P.stages = st > MAX_STAGES ? MAX_STAGES : (st < 2 ? 2 : st);
   {
-    static const int cap = getenv("TF2B_MMA_STAGES") ? atoi(getenv("TF2B_MMA_STAGES")) : 0;   // experiment switch
+    static const int cap = env_int("TF2B_MMA_STAGES", 0);   // experiment switch
     if (cap >= 1 && P.stages > cap) P.stages = cap;
   }
   // instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): c_format S32 (2) at bit 4,
@@ -1284,20 +1303,20 @@ void fill_geometry(MmaParams& P, const ConvParams& c, int planes8) {
   P.d_tiles_w = make_fastdiv(P.tiles_w);
   P.d_tiles_h = make_fastdiv(P.tiles_h);
   {
-    static const int poll = getenv("TF2B_MMA_POLL0") ? atoi(getenv("TF2B_MMA_POLL0")) : 0;
-    static const int top = getenv("TF2B_MMA_TOP") ? atoi(getenv("TF2B_MMA_TOP")) : 0;
+    static const int poll = env_int("TF2B_MMA_POLL0", 0);
+    static const int top = env_int("TF2B_MMA_TOP", 0);
     P.poll_lane0 = poll;
     P.roles_top = top;
-    static const int noepi = getenv("TF2B_MMA_NOEPI") ? atoi(getenv("TF2B_MMA_NOEPI")) : 0;
+    static const int noepi = env_int("TF2B_MMA_NOEPI", 0);
     P.noepi = noepi;
-    static const int l2pf = getenv("TF2B_MMA_L2PF") ? atoi(getenv("TF2B_MMA_L2PF")) : 0;
+    static const int l2pf = env_int("TF2B_MMA_L2PF", 0);
     P.l2_prefetch = l2pf;
   }
   P.idx32 = ((long long)c.B * c.OH * c.OW * c.yC < (1ll << 31)) && ((long long)c.B * c.OH * c.OW * (c.rC > 0 ? c.rC : 1) < (1ll << 31));
   P.direct256 = (c.yC % 32 == 0) && (((unsigned long long)c.y) % 32 == 0) &&
                 (c.r == nullptr || ((c.rC % 32 == 0) && (((unsigned long long)c.r) % 32 == 0)));
   {
-    static const bool allow = getenv("TF2B_MMA_DIRECT") == nullptr || atoi(getenv("TF2B_MMA_DIRECT")) != 0;
+    static const bool allow = env_int("TF2B_MMA_DIRECT", 1) != 0;
     if (!allow) P.direct256 = 0;
   }
 }
@@ -1425,22 +1444,15 @@ int mma_build_tmaps(void* host_tmaps, const ConvParams& c, const int8_t* wgt8, i
   return 0;
 }
 
-cudaError_t launch_conv_mma(const ConvParams& c, const int8_t* /*wgt8*/, int planes8, const int* plane8_shift,
-                            void* tmaps, cudaStream_t stream) {
-  static int num_sms = 0;
-  static bool attr_set = false;
-  if (!num_sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-  }
-  MmaParams P;
-  fill_geometry(P, c, planes8);
-  for (int i = 0; i < kMaxPlanes; i++) P.plane8_shift[i] = plane8_shift[i];
-  const int stage_bytes = P.a_stage_bytes + (P.b_resident ? 0 : P.b_stage_bytes);
-  const size_t smem = (size_t)P.res_bytes + (size_t)P.stages * stage_bytes + EPI_BYTES +
-                      (P.res_tma ? (size_t)P.res_bufs * P.BN * 128 : 0) + 1024;
-  using KernelFn = void (*)(MmaParams, TmapPair);
+namespace {
+using KernelFn = void (*)(MmaParams, TmapPair);
+constexpr int kEpiVariants = 21;   // index = EPI + 1 for EPI <= 15; 17..20 = the hi32 forms of 8, 9, 12, 13
+struct KernelTables {
+  KernelFn single[3][2][kEpiVariants];   // [BN 64/128/256][mode][epilogue]
+  KernelFn pair[2][2][2][2];             // CTA pairs: [BN 128 two planes / 256 one plane][mode][residual][hi32]
+  KernelFn pair_exact[2][2];             // CTA pairs with the exact epilogue (accumulator tap)
+};
+const KernelTables& kernel_tables() {
 #define TF2B_EPI_ROW(BN_, MODE_)                                                                              \
   {conv_mma_kernel<BN_, MODE_, -1>, conv_mma_kernel<BN_, MODE_, 0>, conv_mma_kernel<BN_, MODE_, 1>,            \
    conv_mma_kernel<BN_, MODE_, 2>,  conv_mma_kernel<BN_, MODE_, 3>, conv_mma_kernel<BN_, MODE_, 4>,            \
@@ -1449,25 +1461,57 @@ cudaError_t launch_conv_mma(const ConvParams& c, const int8_t* /*wgt8*/, int pla
    conv_mma_kernel<BN_, MODE_, 12>, conv_mma_kernel<BN_, MODE_, 13>, nullptr, nullptr,                         \
    conv_mma_kernel<BN_, MODE_, 24>, conv_mma_kernel<BN_, MODE_, 25>, conv_mma_kernel<BN_, MODE_, 28>,          \
    conv_mma_kernel<BN_, MODE_, 29>}
-  constexpr int kEpiVariants = 21;   // index = EPI + 1 for EPI <= 15; 17..20 = the hi32 forms of 8, 9, 12, 13
-  static const KernelFn table[3][2][kEpiVariants] = {{TF2B_EPI_ROW(64, 0), TF2B_EPI_ROW(64, 1)},
-                                                     {TF2B_EPI_ROW(128, 0), TF2B_EPI_ROW(128, 1)},
-                                                     {TF2B_EPI_ROW(256, 0), TF2B_EPI_ROW(256, 1)}};
+  static const KernelTables T = {
+      {{TF2B_EPI_ROW(64, 0), TF2B_EPI_ROW(64, 1)}, {TF2B_EPI_ROW(128, 0), TF2B_EPI_ROW(128, 1)},
+       {TF2B_EPI_ROW(256, 0), TF2B_EPI_ROW(256, 1)}},
+      {{{{conv_mma_kernel<128, 0, 9, true>, conv_mma_kernel<128, 0, 25, true>},
+         {conv_mma_kernel<128, 0, 13, true>, conv_mma_kernel<128, 0, 29, true>}},
+        {{conv_mma_kernel<128, 1, 9, true>, conv_mma_kernel<128, 1, 25, true>},
+         {conv_mma_kernel<128, 1, 13, true>, conv_mma_kernel<128, 1, 29, true>}}},
+       {{{conv_mma_kernel<256, 0, 8, true>, conv_mma_kernel<256, 0, 24, true>},
+         {conv_mma_kernel<256, 0, 12, true>, conv_mma_kernel<256, 0, 28, true>}},
+        {{conv_mma_kernel<256, 1, 8, true>, conv_mma_kernel<256, 1, 24, true>},
+         {conv_mma_kernel<256, 1, 12, true>, conv_mma_kernel<256, 1, 28, true>}}}},
+      {{conv_mma_kernel<128, 0, -1, true>, conv_mma_kernel<128, 1, -1, true>},
+       {conv_mma_kernel<256, 0, -1, true>, conv_mma_kernel<256, 1, -1, true>}}};
 #undef TF2B_EPI_ROW
-  if (!attr_set) {
-    const int lim = 226 * 1024;
-    for (int a = 0; a < 3; a++)
-      for (int b = 0; b < 2; b++)
-        for (int f = 0; f < kEpiVariants; f++) {
-          if (!table[a][b][f]) continue;
-          cudaError_t e = cudaFuncSetAttribute(table[a][b][f], cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
-          if (e != cudaSuccess) return e;
-        }
-    attr_set = true;
+  return T;
+}
+}  // namespace
+
+// Per-device set-up of the tensor-core kernels: the > 48 KB dynamic shared memory opt-in is a per-device
+// function attribute, so every engine calls this from tf2b_finalize after cudaSetDevice(its device).
+cudaError_t mma_prepare_device(int* num_sms) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  e = cudaDeviceGetAttribute(num_sms, cudaDevAttrMultiProcessorCount, dev);
+  if (e != cudaSuccess) return e;
+  const KernelTables& T = kernel_tables();
+  const KernelFn* all = &T.single[0][0][0];
+  const int n_all = (int)(sizeof(KernelTables) / sizeof(KernelFn));
+  for (int i = 0; i < n_all; i++) {
+    if (!all[i]) continue;
+    e = cudaFuncSetAttribute(all[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    if (e != cudaSuccess) return e;
   }
-  // the fast requantisation needs at most two scaled planes (+ the optional low plane)
+  return cudaSuccess;
+}
+
+cudaError_t launch_conv_mma(const ConvParams& c, const int8_t* /*wgt8*/, int planes8, const int* plane8_shift,
+                            void* tmaps, int num_sms, cudaStream_t stream) {
+  MmaParams P;
+  fill_geometry(P, c, planes8);
+  for (int i = 0; i < kMaxPlanes; i++) P.plane8_shift[i] = plane8_shift[i];
+  const int stage_bytes = P.a_stage_bytes + (P.b_resident ? 0 : P.b_stage_bytes);
+  const size_t smem = (size_t)P.res_bytes + (size_t)P.stages * stage_bytes + EPI_BYTES +
+                      (P.res_tma ? (size_t)P.res_bufs * P.BN * 128 : 0) + 1024;
+  // the fast requantisation needs at most two scaled planes (+ the optional low plane); the INT32
+  // accumulator tap lives in the exact epilogue (EPI < 0), which sees the very TMEM accumulators the
+  // fast forms would
   const int scaled_planes = planes8 - (c.low_plane >= 0 ? 1 : 0);
-  const bool fast = c.fast_requant != 0 && scaled_planes <= 2 && (c.low_plane < 0 || c.low_plane == planes8 - 1);
+  const bool fast = c.acc_dump == nullptr && c.fast_requant != 0 && scaled_planes <= 2 &&
+                    (c.low_plane < 0 || c.low_plane == planes8 - 1);
   // folded form (one IMAD.HI per output): additionally needs alpha << nshift in int32 and an accumulator
   // that cannot wrap (fast_requant == 2, api.cu), and no unscaled low plane
   const bool fold = fast && fold_applies(c, planes8);
@@ -1476,7 +1520,7 @@ cudaError_t launch_conv_mma(const ConvParams& c, const int8_t* /*wgt8*/, int pla
                        : 0;
   // (a variant with two epilogue groups of 8 warps taking alternate tiles was measured: no gain on the
   // epilogue-bound layers, slower with a residual operand — the epilogue is throughput bound, L1TEX ~72 %)
-  static const bool allow_hi32 = getenv("TF2B_MMA_HI32") == nullptr || atoi(getenv("TF2B_MMA_HI32")) != 0;
+  static const bool allow_hi32 = env_int("TF2B_MMA_HI32", 1) != 0;
   const bool hi32 = fold && allow_hi32 && c.fast_requant >= 3;
   int epi_idx = epi;
   if (hi32) {
@@ -1484,32 +1528,16 @@ cudaError_t launch_conv_mma(const ConvParams& c, const int8_t* /*wgt8*/, int pla
     epi_idx = 17 + ((bits & 1) | ((bits & 4) >> 1));
   }
   P.egroups = 1;
-  KernelFn kfn = table[P.BN == 256 ? 2 : (P.BN == 128 ? 1 : 0)][P.mode][epi_idx];
-  // CTA-pair kernels exist for the folded epilogues of 256-wide MMAs: BN = 256 single plane, BN = 128 two planes
-  static const KernelFn pair_table[2][2][2][2] = {
-      {{{conv_mma_kernel<128, 0, 9, true>, conv_mma_kernel<128, 0, 25, true>},
-        {conv_mma_kernel<128, 0, 13, true>, conv_mma_kernel<128, 0, 29, true>}},
-       {{conv_mma_kernel<128, 1, 9, true>, conv_mma_kernel<128, 1, 25, true>},
-        {conv_mma_kernel<128, 1, 13, true>, conv_mma_kernel<128, 1, 29, true>}}},
-      {{{conv_mma_kernel<256, 0, 8, true>, conv_mma_kernel<256, 0, 24, true>},
-        {conv_mma_kernel<256, 0, 12, true>, conv_mma_kernel<256, 0, 28, true>}},
-       {{conv_mma_kernel<256, 1, 8, true>, conv_mma_kernel<256, 1, 24, true>},
-        {conv_mma_kernel<256, 1, 12, true>, conv_mma_kernel<256, 1, 28, true>}}}};
-  static bool pair_attr_set = false;
-  if (!pair_attr_set) {
-    for (int a = 0; a < 2; a++)
-      for (int b = 0; b < 2; b++)
-        for (int f = 0; f < 2; f++)
-          for (int h = 0; h < 2; h++) {
-            cudaError_t e = cudaFuncSetAttribute(pair_table[a][b][f][h], cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
-            if (e != cudaSuccess) return e;
-          }
-    pair_attr_set = true;
-  }
+  const KernelTables& T = kernel_tables();
+  KernelFn kfn = T.single[P.BN == 256 ? 2 : (P.BN == 128 ? 1 : 0)][P.mode][epi_idx];
   if (P.cg2) {
-    if (!fold) return cudaErrorInvalidValue;   // fill_geometry() only picks pair mode for folded epilogues
-    kfn = pair_table[P.BN == 256 ? 1 : 0][P.mode][c.r != nullptr ? 1 : 0][hi32 ? 1 : 0];
+    // fill_geometry() only picks pair mode for layers whose run-time epilogue is folded; the accumulator
+    // tap runs the same CTA-pair main loop with the exact epilogue
+    if (!fold && c.acc_dump == nullptr) return cudaErrorInvalidValue;
+    kfn = fold ? T.pair[P.BN == 256 ? 1 : 0][P.mode][c.r != nullptr ? 1 : 0][hi32 ? 1 : 0]
+               : T.pair_exact[P.BN == 256 ? 1 : 0][P.mode];
   }
+  if (!kfn) return cudaErrorInvalidValue;
   const int num_tiles = P.m_tiles * P.n_tiles;
   int grid = num_tiles < num_sms ? num_tiles : num_sms;
   if (P.b_resident) {
@@ -1524,7 +1552,7 @@ cudaError_t launch_conv_mma(const ConvParams& c, const int8_t* /*wgt8*/, int pla
   }
   const TmapPair* tp = reinterpret_cast<const TmapPair*>(tmaps);
   P.dbg = nullptr;
-  static const bool debug = getenv("TF2B_MMA_DEBUG") != nullptr;
+  static const bool debug = env_int("TF2B_MMA_DEBUG", 0) != 0;
   static long long* dbg_dev = nullptr;
   if (debug) {
     if (!dbg_dev) cudaMalloc(&dbg_dev, sizeof(long long) * 8 * 148);
@@ -1532,7 +1560,7 @@ cudaError_t launch_conv_mma(const ConvParams& c, const int8_t* /*wgt8*/, int pla
     P.dbg = dbg_dev;
   }
   {
-    static const bool use_pdl = getenv("TF2B_MMA_PDL") == nullptr || atoi(getenv("TF2B_MMA_PDL")) != 0;
+    static const bool use_pdl = env_int("TF2B_MMA_PDL", 1) != 0;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof cfg);
     cfg.gridDim = dim3(grid);

@@ -29,9 +29,30 @@ def broadcast_bytes(buf, dist, src: int = 0):
     return buf
 
 
+def broadcast_q(q, dist, device, src: int = 0):
+    """The parsed Q table (int8 [rows][max_out_channel], a few KB) from `src` to every rank."""
+    import numpy as np
+    import torch
+    if dist.get_rank() == src:
+        has = torch.tensor([0 if q is None else 1, 0 if q is None else q.shape[0], 0 if q is None else q.shape[1]],
+                           dtype=torch.int64, device=device)
+    else:
+        has = torch.zeros(3, dtype=torch.int64, device=device)
+    dist.broadcast(has, src)
+    if int(has[0]) == 0:
+        return None
+    if dist.get_rank() == src:
+        buf = torch.from_numpy(np.ascontiguousarray(q, dtype=np.int8).view(np.uint8).reshape(-1)).to(device)
+    else:
+        buf = torch.empty(int(has[1]) * int(has[2]), dtype=torch.uint8, device=device)
+    dist.broadcast(buf, src)
+    return buf.cpu().numpy().view(np.int8).reshape(int(has[1]), int(has[2])).copy()
+
+
 def init_network_distributed(nw, dist, device, model=None, q=None, max_images: int = 1, variant: int = 0):
     """Rank 0 loads the model (`model` = LoadModel output), every other rank receives the packed
-    weights through one broadcast and imports them (tf2b_import_weight_blob)."""
+    weights through one broadcast and imports them (tf2b_import_weight_blob).  Rank 0's Q table travels
+    too (Runner.Run needs its first entry to quantise float images on every rank)."""
     import torch
     rank = dist.get_rank()
     if rank == 0:
@@ -41,6 +62,7 @@ def init_network_distributed(nw, dist, device, model=None, q=None, max_images: i
     else:
         blob = torch.empty(0, dtype=torch.uint8, device=device)
     blob = broadcast_bytes(blob, dist, 0)
+    q = broadcast_q(q, dist, device, 0)
     if rank != 0:
-        nw.InitFromBlob(blob.data_ptr(), max_images=max_images, variant=variant)
+        nw.InitFromBlob(blob.data_ptr(), int(blob.numel()), max_images=max_images, variant=variant, q=q)
     return nw

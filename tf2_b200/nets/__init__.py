@@ -17,6 +17,10 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def load(name: str) -> NetDesc:
+    if name == "vgg16":
+        return vgg16()
+    if name == "squeezenet":
+        return squeezenet()
     p = os.path.join(_HERE, name + ".json")
     if not os.path.exists(p):
         raise KeyError(f"unknown built-in network {name!r}")

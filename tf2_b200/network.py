@@ -107,9 +107,12 @@ class NetWork:
         self._check(self._lib.tf2b_finalize(self._h, max_images))
         self.max_images = max_images
 
-    def InitFromBlob(self, blob_dev_ptr: int, max_images: int, variant: int = capi.VARIANT_AUTO, stream: int = 0):
-        """Receiving side of the init-time weight broadcast (no model file on this rank)."""
-        self._check(self._lib.tf2b_import_weight_blob(self._h, blob_dev_ptr, stream))
+    def InitFromBlob(self, blob_dev_ptr: int, blob_bytes: int, max_images: int, variant: int = capi.VARIANT_AUTO,
+                     stream: int = 0, q: Optional[np.ndarray] = None):
+        """Receiving side of the init-time weight broadcast (no model file on this rank).  `q` = the Q table
+        (Runner.Run needs its first entry to quantise float images)."""
+        self.q = q
+        self._check(self._lib.tf2b_import_weight_blob(self._h, blob_dev_ptr, blob_bytes, stream))
         self._check(self._lib.tf2b_set_variant(self._h, variant))
         self._check(self._lib.tf2b_finalize(self._h, max_images))
         self.max_images = max_images
@@ -181,18 +184,41 @@ class Runner:
         t = self.net.tensors[self.net.result_tensor() if tid is None else tid]
         return (t.C, t.H, t.W)
 
+    def _check_input_shape(self, shape, raw224: bool, in_layout: int):
+        """The C ABI takes plain pointers: a wrong-shaped buffer would be read out of bounds."""
+        t0 = self.net.tensors[0]
+        if raw224:
+            want = (3, 224, 224)
+        else:
+            want = (t0.C, t0.H, t0.W) if in_layout == capi.LAYOUT_CHW else (t0.H, t0.W, t0.C)
+        if tuple(shape) != want:
+            raise ValueError(f"input images have shape {tuple(shape)}, the network expects {want}")
+
+    def _check_out_size(self, out, B: int):
+        C_, H_, W_ = self.result_shape()
+        n = out.numel() if hasattr(out, "numel") else np.asarray(out).size
+        if n != B * C_ * H_ * W_:
+            raise ValueError(f"output buffer holds {n} values, the result of {B} images has {B * C_ * H_ * W_}")
+
     # -- device-resident path ---------------------------------------------------------------
     def run_device(self, x, out=None, raw224: bool = False, in_layout: int = capi.LAYOUT_CHW,
                    out_layout: int = capi.LAYOUT_CHW, stream=None):
         """x: torch int8 CUDA tensor, either raw quantised images [B,3,224,224] (raw224=True; the
         device applies feature_trans) or tensor-0 images [B,C,H,W] / [B,H,W,C]."""
         import torch
-        assert x.is_cuda and x.dtype == torch.int8 and x.is_contiguous()
+        if not (x.is_cuda and x.dtype == torch.int8 and x.is_contiguous()):
+            raise ValueError("run_device: x must be a contiguous int8 CUDA tensor")
+        if x.device.index != self.network.device:
+            raise ValueError(f"run_device: x lives on {x.device}, the engine on cuda:{self.network.device}")
         B = x.shape[0]
+        self._check_input_shape(tuple(x.shape[1:]), raw224, in_layout)
         C_, H_, W_ = self.result_shape()
         if out is None:
             shape = (B, C_, H_, W_) if out_layout == capi.LAYOUT_CHW else (B, H_, W_, C_)
             out = torch.empty(shape, dtype=torch.int8, device=x.device)
+        elif not (out.is_cuda and out.device == x.device and out.dtype == torch.int8 and out.is_contiguous()
+                  and out.numel() == B * C_ * H_ * W_):
+            raise ValueError(f"run_device: out must be a contiguous int8 tensor of {B * C_ * H_ * W_} elements on {x.device}")
         st = stream if stream is not None else torch.cuda.current_stream(x.device)
         sp = C.c_void_p(st.cuda_stream)
         if raw224:
@@ -207,10 +233,12 @@ class Runner:
                  out_layout: int = capi.LAYOUT_CHW):
         """x_host / out_host: int8 numpy arrays or CPU torch tensors (pinned for async copies)."""
         xp, B = _host_ptr(x_host)
+        self._check_input_shape(tuple(x_host.shape[1:]), raw224, in_layout)
         C_, H_, W_ = self.result_shape()
         if out_host is None:
             out_host = np.empty((B, C_, H_, W_) if out_layout == capi.LAYOUT_CHW else (B, H_, W_, C_), dtype=np.int8)
         op, _ = _host_ptr(out_host)
+        self._check_out_size(out_host, B)
         if raw224:
             rc = self._lib.tf2b_run_raw224_host(self.network.handle, xp, B, op, out_layout)
         else:
@@ -219,11 +247,19 @@ class Runner:
         return out_host
 
     # -- pipelined host path: EnqueueKernels now, WaitForAllKernels later (runner.cpp:32,183) ------
-    def submit_host(self, x_host, out_host, slot: int, out_layout: int = capi.LAYOUT_CHW):
-        """Enqueue H2D + run + D2H of one raw int8 batch on `slot` (0/1); pinned buffers."""
+    def submit_host(self, x_host, out_host, slot: int, out_layout: int = capi.LAYOUT_CHW, raw224: bool = True,
+                    in_layout: int = capi.LAYOUT_CHW):
+        """Enqueue H2D + run + D2H of one int8 batch on `slot` (0/1); pinned buffers.  raw224: raw quantised
+        3x224x224 images (the device applies feature_trans), else tensor-0 images in `in_layout`."""
         xp, B = _host_ptr(x_host)
+        self._check_input_shape(tuple(x_host.shape[1:]), raw224, in_layout)
         op, _ = _host_ptr(out_host)
-        self.network._check(self._lib.tf2b_submit_raw224_host(self.network.handle, xp, B, op, out_layout, slot))
+        self._check_out_size(out_host, B)
+        if raw224:
+            rc = self._lib.tf2b_submit_raw224_host(self.network.handle, xp, B, op, out_layout, slot)
+        else:
+            rc = self._lib.tf2b_submit_host(self.network.handle, xp, in_layout, B, op, out_layout, slot)
+        self.network._check(rc)
 
     def wait(self, slot: int):
         self.network._check(self._lib.tf2b_wait(self.network.handle, slot))
