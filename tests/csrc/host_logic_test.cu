@@ -46,32 +46,50 @@ static long long check_planes(const tf2b_net* net, const LayerState& S, const ui
   const int C = d.C, N = d.N, k = d.k;
   const bool quirk = d.in_may_be_m128 != 0;
   long long bad = 0;
-  // ---- shift-kernel planes (int16): weight = sum_p w16[p] << plane_shift_s[p] << base[n]; with the quirk the
-  //      odd planes multiply the int8-negated activation, i.e. stand for negative weights
+  // ---- shift-accumulate kernel: packed 4-bit codes in segments.  weight = +-2^e << seg_shift << base[n]; a segment
+  //      flagged "neg" multiplies the int8-negated activation (stands for negative weights of a layer whose input may
+  //      hold -128), and for tensor 0 the negative weights sit as magnitudes on the channels of its negated copy
   {
+    const bool dual = quirk && d.in_tensor == 0;
+    const int KC = tf2b::sa_kc(S.Cp_s);
+    const int cchunks = (S.Cp_s + KC - 1) / KC;
+    const size_t row_bytes = (size_t)S.Kp_s / 2;
+    if ((size_t)S.nseg_s * S.Npad_s * row_bytes != S.h_w4.size()) { snprintf(why, 200, "w4 size"); return 1; }
     size_t nz = 0, nz_codes = 0;
-    for (size_t i = 0; i < S.h_w16.size(); i++) nz += S.h_w16[i] != 0;
+    for (size_t i = 0; i < S.h_w4.size(); i++) nz += ((S.h_w4[i] & 7) != 7) + (((S.h_w4[i] >> 4) & 7) != 7);
+    for (int g = 1; g < S.nseg_s; g++)
+      if (S.seg_shift_s[g] > S.seg_shift_s[g - 1]) { if (!bad) snprintf(why, 200, "segments not in descending shift order"); bad++; }
     for (int n = 0; n < N; n++)
       for (int c = 0; c < C; c++)
         for (int t = 0; t < k * k; t++) {
           int sign, shift;
           decode(codes[((size_t)n * C + c) * k * k + t], sign, shift);
-          long long pos = 0, neg = 0;   // magnitude carried for the plain / negated activation
-          const size_t kidx = (size_t)t * S.Cp + c;
-          for (int p = 0; p < S.planes_s; p++) {
-            long long v = S.h_w16[((size_t)p * S.Npad_s + n) * S.Kp_s + kidx];
-            v = v * (1ll << S.plane_shift_s[p]) * (1ll << S.h_nshift[n]);
-            if (S.plane_neg_s[p]) neg += v; else pos += v;
+          long long pos[2] = {0, 0}, neg[2] = {0, 0};   // [half]: plain / negated-copy channel; pos / neg: plain / negating segment
+          for (int half = 0; half < (dual ? 2 : 1); half++) {
+            const size_t kidx = (size_t)t * cchunks * KC + (half ? S.Cp + c : c);
+            for (int g = 0; g < S.nseg_s; g++) {
+              const uint8_t byte = S.h_w4[((size_t)g * S.Npad_s + n) * row_bytes + kidx / 2];
+              const unsigned nib = (kidx & 1) ? (byte >> 4) : (byte & 15);
+              if ((nib & 7) == 7) { if (nib & 8) { if (!bad) snprintf(why, 200, "negative zero code"); bad++; } continue; }
+              long long v = (1ll << (nib & 7)) * (1ll << S.seg_shift_s[g]) * (1ll << S.h_nshift[n]);
+              if (nib & 8) v = -v;
+              if (S.seg_neg_s[g]) neg[half] += v; else pos[half] += v;
+            }
           }
-          long long want_pos = 0, want_neg = 0;
+          long long want_pos[2] = {0, 0}, want_neg[2] = {0, 0};
           if (shift >= 0) {
             nz_codes++;
-            if (quirk) { if (sign > 0) want_pos = 1ll << shift; else want_neg = 1ll << shift; }
-            else want_pos = sign * (1ll << shift);
+            if (!quirk) want_pos[0] = sign * (1ll << shift);
+            else if (sign > 0) want_pos[0] = 1ll << shift;
+            else if (dual) want_pos[1] = 1ll << shift;
+            else want_neg[0] = 1ll << shift;
           }
-          if (pos != want_pos || neg != want_neg) { if (!bad) snprintf(why, 200, "w16 n=%d c=%d t=%d", n, c, t); bad++; }
+          if (pos[0] != want_pos[0] || pos[1] != want_pos[1] || neg[0] != want_neg[0] || neg[1] != want_neg[1]) {
+            if (!bad) snprintf(why, 200, "w4 n=%d c=%d t=%d", n, c, t);
+            bad++;
+          }
         }
-    if (nz != nz_codes) { if (!bad) snprintf(why, 200, "w16 holds %zu non-zeros for %zu codes", nz, nz_codes); bad++; }
+    if (nz != nz_codes) { if (!bad) snprintf(why, 200, "w4 holds %zu non-zeros for %zu codes", nz, nz_codes); bad++; }
   }
   // ---- tensor-core planes (int8)
   if (S.mma_ok) {
@@ -116,8 +134,8 @@ static long long check_planes(const tf2b_net* net, const LayerState& S, const ui
 }
 
 static bool same_state(const LayerState& a, const LayerState& b) {
-  return a.h_w16 == b.h_w16 && a.h_w8 == b.h_w8 && a.h_nshift == b.h_nshift && a.h_nshift_m == b.h_nshift_m &&
-         a.h_bias == b.h_bias && a.h_alpha == b.h_alpha && a.h_beta == b.h_beta && a.planes_s == b.planes_s &&
+  return a.h_w4 == b.h_w4 && a.h_w8 == b.h_w8 && a.h_nshift == b.h_nshift && a.h_nshift_m == b.h_nshift_m &&
+         a.h_bias == b.h_bias && a.h_alpha == b.h_alpha && a.h_beta == b.h_beta && a.nseg_s == b.nseg_s &&
          a.planes_m == b.planes_m && a.mma_ok == b.mma_ok && a.fast_requant == b.fast_requant &&
          a.low_plane_m == b.low_plane_m && a.Kp_m == b.Kp_m && a.Kp_s == b.Kp_s;
 }
@@ -177,8 +195,8 @@ int main(int argc, char** argv) {
       mode = tf2b::mma_describe(p, S.planes_m);
       for (auto& ch : mode) if (ch == ' ') ch = '_';
     }
-    printf("layer %d rc=%d bad=%lld planes_s=%d planes_m=%d low=%d mma_ok=%d fast_requant=%d packed4_same=%d mode=%s %s\n", l, rc,
-           bad, S.planes_s, S.planes_m, S.low_plane_m, (int)S.mma_ok, S.fast_requant, same4, mode.c_str(), why);
+    printf("layer %d rc=%d bad=%lld segs_s=%d planes_m=%d low=%d mma_ok=%d fast_requant=%d packed4_same=%d mode=%s %s\n", l, rc,
+           bad, S.nseg_s, S.planes_m, S.low_plane_m, (int)S.mma_ok, S.fast_requant, same4, mode.c_str(), why);
     if (rc != TF2B_OK || bad != 0 || same4 == 0) rc_all = 1;
   }
   return rc_all;

@@ -19,7 +19,7 @@ from tf2_b200.network import _layer_descs
 
 SRC = os.path.join(ROOT, "tests", "csrc", "host_logic_test.cu")
 EXE = os.path.join(ROOT, "tests", "_build", "host_logic_test")
-OBJS = [os.path.join(ROOT, "tf2_b200", "lib", f"{n}.o") for n in ("conv_mma", "conv_shift", "aux_kernels")]
+OBJS = [os.path.join(ROOT, "tf2_b200", "lib", f"{n}.o") for n in ("conv_mma", "conv_sa", "aux_kernels")]
 DEPS = [SRC, os.path.join(ROOT, "tf2_b200", "csrc", "api.cu"), os.path.join(ROOT, "tf2_b200", "csrc", "common.cuh"),
         os.path.join(ROOT, "include", "tf2b200.h")] + OBJS
 
@@ -155,9 +155,9 @@ def test_random_layers_weight_preparation(tmp_path):
     rc, rows, out = _run(exe, path)
     assert rc == 0, out
     assert all(r["rc"] == 0 and r["bad"] == 0 for r in rows), out
-    assert net.layers[0].in_may_be_m128 == 1 and rows[0]["planes_s"] % 2 == 0      # plain + negated planes
+    assert net.layers[0].in_may_be_m128 == 1 and rows[0]["segs_s"] >= 1            # tensor 0: negated copy = extra channels
     assert net.layers[1].in_may_be_m128 == 1 and rows[1]["mma_ok"] == 0            # -128 beyond tensor 0: exact kernel only
-    assert rows[1]["planes_s"] >= 4
+    assert rows[1]["segs_s"] >= 4                                                  # three exponent levels x (plain, negating)
     assert rows[4]["fast_requant"] == 0
     assert all(r["mma_ok"] == 1 for i, r in enumerate(rows) if i != 1)
 

@@ -18,9 +18,17 @@
 #include "common.cuh"
 
 namespace tf2b {
-cudaError_t launch_conv_shift(const ConvParams& p, const int16_t* wgt, cudaStream_t stream);
-int conv_shift_bn();
-int conv_shift_kc();
+// CUDA-core shift-accumulate path (conv_sa.cu)
+cudaError_t launch_conv_sa(const ConvParams& p, int nseg, const int* seg_shift, const int* seg_neg, const void* tmaps,
+                           int ksplit, int num_sms, cudaStream_t stream);
+cudaError_t sa_prepare_device();
+int sa_kc(int Cp);
+int sa_npad(int N);
+int sa_max_segments();
+size_t sa_tmap_bytes();
+int sa_ksplit(const ConvParams& p, int num_sms);
+std::string sa_describe(const ConvParams& p, int nseg, int ksplit);
+int sa_build_tmaps(void* host_tmaps, const ConvParams& p, const uint8_t* wgt4, int nseg, int ksplit, std::string* err);
 cudaError_t launch_chw_to_hwc(const int8_t*, int8_t*, int, int, int, int, int, int, cudaStream_t);
 cudaError_t launch_hwc_to_chw(const int8_t*, int8_t*, int, int, int, int, int, cudaStream_t);
 cudaError_t launch_hwc_repitch(const int8_t*, int8_t*, size_t, int, int, int, int, cudaStream_t);
@@ -51,11 +59,12 @@ struct LayerState {
   bool loaded = false;
   int Cp = 0;  // reduction channels padded to 16
   int Cp_m = 0;  // reduction channels seen by the tensor-core path (2*Cp when it reads the negated copy)
-  // --- shift kernel (int16 planes) ---
-  int Npad_s = 0, Kp_s = 0, planes_s = 0;
-  int plane_shift_s[tf2b::kMaxPlanes] = {0, 0, 0, 0};
-  int plane_neg_s[tf2b::kMaxPlanes] = {0, 0, 0, 0};
-  std::vector<int16_t> h_w16;
+  // --- shift-accumulate kernel: packed 4-bit codes, one row block per segment (exponent level x sign-quirk) ---
+  int Npad_s = 0, Kp_s = 0, Cp_s = 0, nseg_s = 0, ksplit_s = 0;
+  int seg_shift_s[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // descending: the kernel combines the segment sums by Horner's rule
+  int seg_neg_s[8] = {0, 0, 0, 0, 0, 0, 0, 0};     // 1: the segment multiplies the int8-negated activations
+  std::vector<uint8_t> h_w4;
+  std::vector<unsigned char> h_tmaps_s;
   // --- mma kernel (int8 planes) ---
   int Npad_m = 0, Kp_m = 0, planes_m = 0;
   int plane_shift_m[tf2b::kMaxPlanes] = {0, 0, 0, 0};
@@ -69,7 +78,7 @@ struct LayerState {
   std::vector<int32_t> h_bias, h_alpha, h_beta;
   std::vector<uint8_t> h_nshift;
   // device views inside the arena
-  size_t off_w16 = 0, off_w8 = 0, off_bias = 0, off_alpha = 0, off_beta = 0, off_nshift = 0, off_nshift_m = 0;
+  size_t off_w4 = 0, off_w8 = 0, off_bias = 0, off_alpha = 0, off_beta = 0, off_nshift = 0, off_nshift_m = 0;
   int kernel = 0;  // 0 none (ipool), 1 shift, 2 mma
   std::vector<unsigned char> h_tmaps;  // CUtensorMap blobs for the mma path (host copy)
   std::string mode_desc;               // tf2b_layer_mode() text
@@ -77,9 +86,9 @@ struct LayerState {
 };
 
 struct BlobLayerMeta {  // fixed-size, trivially copyable: travels inside the weight blob
-  int32_t loaded, Cp, Cp_m, Npad_s, Kp_s, planes_s, plane_shift_s[4], plane_neg_s[4];
+  int32_t loaded, Cp, Cp_m, Npad_s, Kp_s, Cp_s, nseg_s, seg_shift_s[8], seg_neg_s[8];
   int32_t Npad_m, Kp_m, planes_m, plane_shift_m[4], mma_ok, Npar, low_plane_m, nshift_m_len, fast_requant;
-  int64_t off_w16, off_w8, off_bias, off_alpha, off_beta, off_nshift, off_nshift_m;
+  int64_t off_w4, off_w8, off_bias, off_alpha, off_beta, off_nshift, off_nshift_m;
 };
 
 struct tf2b_net {
@@ -167,44 +176,57 @@ static int prepare_layer(tf2b_net* net, LayerState& S, const uint8_t* codes,
     max_rel = std::max(max_rel, mx - mn);
   }
   const bool quirk = d.in_may_be_m128 != 0;
-  // ---- shift kernel planes: int16 +-2^e, e in 0..14 ----
+  // ---- shift-accumulate kernel: 4-bit codes (bit 3 = negative, bits 0..2 = exponent e in 0..6, 7 = zero) in
+  //      segments of 7 exponent levels: shift = base[n] + 7 * level + e.  The int8 negate quirk (pe.cl:32-34) is
+  //      carried either by the negated copy of tensor 0 (extra channels, positive magnitudes) or, for any other
+  //      tensor that may hold -128, by segments that multiply the byte-negated activations.
   {
-    const int lv = 15;
+    const int lv = 7;
     const int np = max_rel / lv + 1;
-    S.planes_s = np * (quirk ? 2 : 1);
-    if (S.planes_s > tf2b::kMaxPlanes)
-      return fail(net, TF2B_ERR_ARG, "layer needs %d int16 planes (> %d)", S.planes_s, tf2b::kMaxPlanes);
-    S.Npad_s = round_up(N, tf2b::conv_shift_bn());
-    S.Kp_s = round_up(Ktot, tf2b::conv_shift_kc());
-    S.h_w16.assign((size_t)S.planes_s * S.Npad_s * S.Kp_s, 0);
-    for (int p = 0; p < np; p++) {
-      if (quirk) {
-        S.plane_shift_s[2 * p] = S.plane_shift_s[2 * p + 1] = lv * p;
-        S.plane_neg_s[2 * p] = 0;
-        S.plane_neg_s[2 * p + 1] = 1;
-      } else {
-        S.plane_shift_s[p] = lv * p;
-        S.plane_neg_s[p] = 0;
+    const bool dual_s = quirk && d.in_tensor == 0 && S.Cp == net->t0_neg_off;
+    const bool negseg = quirk && !dual_s;
+    S.Cp_s = dual_s ? 2 * S.Cp : S.Cp;
+    const int KC = tf2b::sa_kc(S.Cp_s);
+    const int cchunks = (S.Cp_s + KC - 1) / KC;
+    S.Npad_s = tf2b::sa_npad(N);
+    S.Kp_s = k * k * cchunks * KC;
+    // candidate segments (level, negated) in descending shift order; empty ones are dropped
+    std::vector<std::vector<uint8_t>> rows;
+    S.nseg_s = 0;
+    for (int lvl = np - 1; lvl >= 0; lvl--)
+      for (int ng = 0; ng < (negseg ? 2 : 1); ng++) {
+        std::vector<uint8_t> w4((size_t)S.Npad_s * (S.Kp_s / 2), 0x77);
+        bool any = false;
+        for (int n = 0; n < N; n++)
+          for (int c = 0; c < C; c++)
+            for (int t = 0; t < k * k; t++) {
+              const uint8_t cd = codes[((size_t)n * C + c) * k * k + t];
+              if (cd & 0x40) continue;
+              const int rel = (cd & 0x1f) - base[n];
+              if (rel / lv != lvl) continue;
+              const bool negw = (cd & 0x80) != 0;
+              if (negseg && (negw ? 1 : 0) != ng) continue;
+              int cc = c;
+              unsigned nib = (unsigned)(rel - lvl * lv);
+              if (negw) {
+                if (dual_s) cc = S.Cp + c;          // magnitude times the negated copy
+                else if (!negseg) nib |= 8u;        // plain negative weight
+              }
+              const size_t kidx = ((size_t)t * cchunks * KC) + cc;
+              uint8_t& byte = w4[(size_t)n * (S.Kp_s / 2) + kidx / 2];
+              byte = (kidx & 1) ? (uint8_t)((byte & 0x0f) | (nib << 4)) : (uint8_t)((byte & 0xf0) | nib);
+              any = true;
+            }
+        if (!any && !(lvl == 0 && ng == 0 && S.nseg_s == 0)) continue;   // keep one segment for an all-zero layer
+        if (S.nseg_s >= tf2b::sa_max_segments())
+          return fail(net, TF2B_ERR_ARG, "layer needs more than %d weight segments", tf2b::sa_max_segments());
+        S.seg_shift_s[S.nseg_s] = lv * lvl;
+        S.seg_neg_s[S.nseg_s] = ng;
+        S.nseg_s++;
+        rows.push_back(std::move(w4));
       }
-    }
-    for (int n = 0; n < N; n++) {
-      for (int c = 0; c < C; c++) {
-        for (int t = 0; t < k * k; t++) {
-          uint8_t cd = codes[((size_t)n * C + c) * k * k + t];
-          if (cd & 0x40) continue;
-          int rel = (cd & 0x1f) - base[n];
-          int p = rel / lv, e = rel - p * lv;
-          bool negw = (cd & 0x80) != 0;
-          size_t kidx = (size_t)t * S.Cp + c;
-          if (quirk) {
-            int pl = 2 * p + (negw ? 1 : 0);
-            S.h_w16[((size_t)pl * S.Npad_s + n) * S.Kp_s + kidx] = (int16_t)(1 << e);
-          } else {
-            S.h_w16[((size_t)p * S.Npad_s + n) * S.Kp_s + kidx] = (int16_t)(negw ? -(1 << e) : (1 << e));
-          }
-        }
-      }
-    }
+    S.h_w4.clear();
+    for (auto& r : rows) S.h_w4.insert(S.h_w4.end(), r.begin(), r.end());
   }
   // ---- mma kernel planes: int8 +-2^e, e in 0..6.  A layer whose input may hold -128 can use the
   //      tensor cores only when that input is tensor 0 (which carries the negated copy): positive
@@ -283,7 +305,7 @@ static int prepare_layer(tf2b_net* net, LayerState& S, const uint8_t* codes,
             }
             S.h_w8[((size_t)p * S.Npad_m + n) * S.Kp_m + kidx] = (int8_t)v;
           }
-      S.h_nshift_m.assign(round_up(std::max(round_up(N, tf2b::conv_shift_bn()), S.Npad_m), 16), 0);
+      S.h_nshift_m.assign(round_up(std::max(tf2b::sa_npad(N), S.Npad_m), 16), 0);
       for (int n = 0; n < N; n++) S.h_nshift_m[n] = bm[n];
       S.mma_ok = true;
     }
@@ -507,7 +529,7 @@ static size_t layout_arena(tf2b_net* net) {
   size_t off = 0;
   for (auto& S : net->layers) {
     if (S.d.ipool || !S.loaded) continue;
-    S.off_w16 = off; off = align256(off + S.h_w16.size() * 2);
+    S.off_w4 = off; off = align256(off + S.h_w4.size());
     S.off_w8 = off; off = align256(off + S.h_w8.size());
     S.off_bias = off; off = align256(off + (size_t)S.Npar * 4);
     S.off_alpha = off; off = align256(off + (size_t)S.Npar * 4);
@@ -551,6 +573,7 @@ int tf2b_finalize(tf2b_net* net, int max_images) {
       return fail(net, TF2B_ERR_STATE, "layer %zu has no weights loaded", l);
   CUDA_TRY(net, cudaSetDevice(net->device));
   CUDA_TRY(net, tf2b::mma_prepare_device(&net->num_sms));
+  CUDA_TRY(net, tf2b::sa_prepare_device());
   net->max_images = max_images;
   net->arena_bytes = layout_arena(net);
   CUDA_TRY(net, cudaMalloc(&net->arena, std::max<size_t>(net->arena_bytes, 256)));
@@ -560,7 +583,7 @@ int tf2b_finalize(tf2b_net* net, int max_images) {
       if (!bytes) return cudaSuccess;
       return cudaMemcpy(net->arena + off, src, bytes, cudaMemcpyHostToDevice);
     };
-    CUDA_TRY(net, up(S.off_w16, S.h_w16.data(), S.h_w16.size() * 2));
+    CUDA_TRY(net, up(S.off_w4, S.h_w4.data(), S.h_w4.size()));
     CUDA_TRY(net, up(S.off_w8, S.h_w8.data(), S.h_w8.size()));
     CUDA_TRY(net, up(S.off_bias, S.h_bias.data(), (size_t)S.Npar * 4));
     CUDA_TRY(net, up(S.off_alpha, S.h_alpha.data(), (size_t)S.Npar * 4));
@@ -599,8 +622,7 @@ static ConvParams conv_params(tf2b_net* net, const LayerState& S, int B, int8_t*
     p.Npad = S.Npad_m; p.Kp = S.Kp_m; p.Ktot = S.Kp_m; p.planes = S.planes_m;
     for (int i = 0; i < tf2b::kMaxPlanes; i++) { p.plane_shift[i] = S.plane_shift_m[i]; p.plane_neg[i] = 0; }
   } else {
-    p.Npad = S.Npad_s; p.Kp = S.Kp_s; p.Ktot = d.k * d.k * S.Cp; p.planes = S.planes_s;
-    for (int i = 0; i < tf2b::kMaxPlanes; i++) { p.plane_shift[i] = S.plane_shift_s[i]; p.plane_neg[i] = S.plane_neg_s[i]; }
+    p.Npad = S.Npad_s; p.Kp = S.Kp_s; p.Ktot = S.Kp_s; p.planes = S.nseg_s; p.Cp = S.Cp_s;
   }
   return p;
 }
@@ -688,6 +710,17 @@ static int alloc_runtime(tf2b_net* net) {
       net->err = "mma tensor map: " + err;
     }
   }
+  // ... and those of the shift-accumulate path (every convolution has one: it is the exact fallback)
+  for (auto& S : net->layers) {
+    if (S.d.ipool) continue;
+    const tf2b_layer_desc& d = S.d;
+    ConvParams p = conv_params(net, S, B, net->scratch0, round_up(d.N, 16), nullptr, 0, false);
+    S.ksplit_s = tf2b::sa_ksplit(p, net->num_sms);
+    S.h_tmaps_s.assign(tf2b::sa_tmap_bytes(), 0);
+    std::string err;
+    int rc = tf2b::sa_build_tmaps(S.h_tmaps_s.data(), p, net->arena + S.off_w4, S.nseg_s, S.ksplit_s, &err);
+    if (rc != 0) return fail(net, TF2B_ERR_CUDA, "shift-accumulate tensor map: %s", err.c_str());
+  }
   return TF2B_OK;
 }
 
@@ -731,7 +764,8 @@ static int run_layers(tf2b_net* net, int B, cudaStream_t st, int only_layer, int
       CUDA_TRY(net, tf2b::launch_conv_mma(p, reinterpret_cast<const int8_t*>(net->arena + S.off_w8),
                                           S.planes_m, S.plane_shift_m, S.h_tmaps.data(), net->num_sms, st));
     } else {
-      CUDA_TRY(net, tf2b::launch_conv_shift(p, reinterpret_cast<const int16_t*>(net->arena + S.off_w16), st));
+      CUDA_TRY(net, tf2b::launch_conv_sa(p, S.nseg_s, S.seg_shift_s, S.seg_neg_s, S.h_tmaps_s.data(), S.ksplit_s,
+                                         net->num_sms, st));
     }
     launches++;
     if (prof) CUDA_TRY(net, cudaEventRecord(net->ev[3 * l + 1], st));
@@ -951,12 +985,11 @@ int tf2b_export_weight_blob(tf2b_net* net, void* dev_dst, void* stream) {
     const LayerState& S = net->layers[l];
     BlobLayerMeta m;
     memset(&m, 0, sizeof m);
-    m.loaded = S.loaded; m.Cp = S.Cp; m.Cp_m = S.Cp_m; m.Npad_s = S.Npad_s; m.Kp_s = S.Kp_s; m.planes_s = S.planes_s;
+    m.loaded = S.loaded; m.Cp = S.Cp; m.Cp_m = S.Cp_m; m.Npad_s = S.Npad_s; m.Kp_s = S.Kp_s; m.Cp_s = S.Cp_s; m.nseg_s = S.nseg_s;
     m.Npad_m = S.Npad_m; m.Kp_m = S.Kp_m; m.planes_m = S.planes_m; m.mma_ok = S.planes_m > 0; m.Npar = S.Npar;
-    for (int i = 0; i < 4; i++) {
-      m.plane_shift_s[i] = S.plane_shift_s[i]; m.plane_neg_s[i] = S.plane_neg_s[i]; m.plane_shift_m[i] = S.plane_shift_m[i];
-    }
-    m.off_w16 = S.off_w16; m.off_w8 = S.off_w8; m.off_bias = S.off_bias; m.off_alpha = S.off_alpha;
+    for (int i = 0; i < 4; i++) m.plane_shift_m[i] = S.plane_shift_m[i];
+    for (int i = 0; i < 8; i++) { m.seg_shift_s[i] = S.seg_shift_s[i]; m.seg_neg_s[i] = S.seg_neg_s[i]; }
+    m.off_w4 = S.off_w4; m.off_w8 = S.off_w8; m.off_bias = S.off_bias; m.off_alpha = S.off_alpha;
     m.off_beta = S.off_beta; m.off_nshift = S.off_nshift; m.off_nshift_m = S.off_nshift_m;
     m.low_plane_m = S.low_plane_m; m.nshift_m_len = (int32_t)S.h_nshift_m.size(); m.fast_requant = S.fast_requant;
     memcpy(hdr.data() + kBlobFixed + l * sizeof m, &m, sizeof m);
@@ -996,11 +1029,12 @@ int tf2b_import_weight_blob(tf2b_net* net, const void* dev_src, int64_t blob_byt
     memcpy(&m, hdr.data() + kBlobFixed + l * sizeof m, sizeof m);
     if (S.d.ipool) continue;
     if (!m.loaded) return fail(net, TF2B_ERR_ARG, "blob layer %zu has no weights", l);
-    S.loaded = true; S.Cp = m.Cp; S.Cp_m = m.Cp_m; S.Npad_s = m.Npad_s; S.Kp_s = m.Kp_s; S.planes_s = m.planes_s;
+    S.loaded = true; S.Cp = m.Cp; S.Cp_m = m.Cp_m; S.Npad_s = m.Npad_s; S.Kp_s = m.Kp_s; S.Cp_s = m.Cp_s; S.nseg_s = m.nseg_s;
     S.Npad_m = m.Npad_m; S.Kp_m = m.Kp_m; S.planes_m = m.planes_m; S.mma_ok = m.mma_ok != 0; S.Npar = m.Npar;
-    for (int i = 0; i < 4; i++) {
-      S.plane_shift_s[i] = m.plane_shift_s[i]; S.plane_neg_s[i] = m.plane_neg_s[i]; S.plane_shift_m[i] = m.plane_shift_m[i];
-    }
+    if (S.nseg_s < 1 || S.nseg_s > 8 || S.planes_m < 0 || S.planes_m > tf2b::kMaxPlanes)
+      return fail(net, TF2B_ERR_ARG, "blob layer %zu: segment / plane counts out of range", l);
+    for (int i = 0; i < 4; i++) S.plane_shift_m[i] = m.plane_shift_m[i];
+    for (int i = 0; i < 8; i++) { S.seg_shift_s[i] = m.seg_shift_s[i]; S.seg_neg_s[i] = m.seg_neg_s[i]; }
     // pull the arrays back to the host so finalize() can lay out and upload them uniformly
     auto pull = [&](auto& vec, size_t count, int64_t off) -> cudaError_t {
       // every array must lie inside the arena part of the blob the caller handed over
@@ -1009,7 +1043,7 @@ int tf2b_import_weight_blob(tf2b_net* net, const void* dev_src, int64_t blob_byt
       if (!count) return cudaSuccess;
       return cudaMemcpy(vec.data(), (const unsigned char*)dev_src + hb + off, count * sizeof(vec[0]), cudaMemcpyDeviceToHost);
     };
-    CUDA_TRY(net, pull(S.h_w16, (size_t)S.planes_s * S.Npad_s * S.Kp_s, m.off_w16));
+    CUDA_TRY(net, pull(S.h_w4, (size_t)S.nseg_s * S.Npad_s * (S.Kp_s / 2), m.off_w4));
     CUDA_TRY(net, pull(S.h_w8, (size_t)S.planes_m * S.Npad_m * S.Kp_m, m.off_w8));
     CUDA_TRY(net, pull(S.h_bias, (size_t)S.Npar, m.off_bias));
     CUDA_TRY(net, pull(S.h_alpha, (size_t)S.Npar, m.off_alpha));
@@ -1059,8 +1093,12 @@ const char* tf2b_layer_mode(tf2b_net* net, int layer, int n_images) {
   if (!net || !net->finalized || layer < 0 || layer >= (int)net->layers.size()) return "none";
   LayerState& S = net->layers[layer];
   if (S.d.ipool) return "pool";
-  if (!(S.kernel == 2 && S.mma_ok)) return "shift";
   const tf2b_layer_desc& d = S.d;
+  if (!(S.kernel == 2 && S.mma_ok)) {
+    ConvParams ps = conv_params(net, S, n_images > 0 ? n_images : net->max_images, net->scratch0, round_up(d.N, 16), nullptr, 0, false);
+    S.mode_desc = tf2b::sa_describe(ps, S.nseg_s, S.ksplit_s);
+    return S.mode_desc.c_str();
+  }
   const bool to_scratch = d.pool || d.gap;
   int8_t* dst = to_scratch ? net->scratch0 : net->tbuf[d.out_tensor] + d.out_ch0;
   const int dstC = to_scratch ? round_up(d.N, 16) : net->tpitch[d.out_tensor];

@@ -8,7 +8,7 @@ NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC
        --expt-relaxed-constexpr -cudart static)
 objs=()
-for f in conv_shift aux_kernels conv_mma api; do
+for f in conv_sa aux_kernels conv_mma api; do
   o="$out/$f.o"
   if [ ! -f "$o" ] || [ "$here/$f.cu" -nt "$o" ] || [ "$here/common.cuh" -nt "$o" ] || [ "$here/../../include/tf2b200.h" -nt "$o" ]; then
     "$NVCC" "${FLAGS[@]}" ${PTXAS_V:+-Xptxas -v} ${TF2B_EXPERIMENTS:+-DTF2B_EXPERIMENTS=1} -c "$here/$f.cu" -o "$o"
