@@ -126,7 +126,7 @@ def test_shipped_networks_weight_preparation(name, seed, tmp_path):
             measured = json.load(f)["roofline"]["staging_modes"]
         assert {k: plan[k] for k in measured} == measured, (dict(plan), measured)
         assert rows[0]["mode"] == "mma_BN64_BK64_planes2_halo_wres_stages4"                  # conv1: halo tile, literal epilogue
-        assert rows[1]["mode"] == "mma_BN128_BK64_planes2_flat_wres_fold_hi32_stages8"
+        assert rows[1]["mode"] == "mma_BN128_BK64_planes2_flat_wres_fold_hi32_tmastore_stages8"
         assert plan["mma"] == 54 and plan["hi32"] == 53
         assert rows[0]["low"] >= 0                                    # conv1's code-0 taps sit in the unscaled low plane
 

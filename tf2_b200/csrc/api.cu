@@ -38,7 +38,13 @@ cudaError_t launch_maxpool3x3(const int8_t*, int8_t*, const int8_t*, int, int, i
 cudaError_t launch_gap(const int8_t*, int8_t*, int, int, int, int, int, cudaStream_t);
 // tensor-core path (conv_mma.cu)
 bool mma_layer_supported(const tf2b_layer_desc& L, int in_pitch, int planes8);
-cudaError_t launch_conv_mma(const ConvParams& p, const int8_t* wgt8, int planes8,
+struct MmaHostParams {
+  const int32_t* bias;
+  const int32_t* alpha;
+  const int32_t* beta;
+  const uint8_t* nshift;
+};
+cudaError_t launch_conv_mma(const ConvParams& p, const MmaHostParams& hp, int planes8,
                             const int* plane8_shift, void* tmaps, int num_sms, cudaStream_t stream);
 cudaError_t mma_prepare_device(int* num_sms);
 size_t mma_tmap_bytes();
@@ -121,6 +127,11 @@ struct tf2b_net {
   bool slot_used[2] = {false, false};
   int last_launches = 0;
   int last_images = 0;
+  // CUDA-graph executor: the layer sequence of a batch size is captured once (programmatic-dependent-launch
+  // edges included) and replayed; key = number of images
+  bool use_graph = true;
+  struct GraphEntry { int B; int launches; cudaGraphExec_t exec; };
+  std::vector<GraphEntry> graphs;
   bool profile = false;
   std::vector<cudaEvent_t> ev;  // 3 per layer: layer start, conv end, layer end
   std::string err;
@@ -501,10 +512,23 @@ int tf2b_load_layer_packed4(tf2b_net* net, int layer, const uint8_t* nibbles, in
   return tf2b_load_layer(net, layer, codes.data(), params);
 }
 
+static void drop_graphs(tf2b_net* net) {
+  for (auto& g : net->graphs) cudaGraphExecDestroy(g.exec);
+  net->graphs.clear();
+}
+
+int tf2b_set_graph(tf2b_net* net, int on) {
+  if (!net) return TF2B_ERR_ARG;
+  net->use_graph = on != 0;
+  if (!on) drop_graphs(net);
+  return TF2B_OK;
+}
+
 int tf2b_set_variant(tf2b_net* net, int variant) {
   if (!net) return TF2B_ERR_ARG;
   if (variant < 0 || variant > 2) return fail(net, TF2B_ERR_ARG, "unknown variant %d", variant);
   net->variant = variant;
+  drop_graphs(net);   // captured graphs hold the kernels of the old plan
   for (auto& S : net->layers) {
     if (S.d.ipool) { S.kernel = 0; continue; }
     S.kernel = (variant != TF2B_VARIANT_SHIFT && S.mma_ok) ? 2 : 1;
@@ -563,6 +587,7 @@ int64_t tf2b_weight_blob_bytes(tf2b_net* net) {
 }
 
 static int alloc_runtime(tf2b_net* net);
+static int build_tmaps(tf2b_net* net);
 
 int tf2b_finalize(tf2b_net* net, int max_images) {
   if (!net) return TF2B_ERR_ARG;
@@ -690,7 +715,13 @@ static int alloc_runtime(tf2b_net* net) {
     int rc = ensure_io(net);
     if (rc != TF2B_OK) return rc;
   }
-  // tensor maps of the tensor-core path depend on buffer addresses: build them now
+  return build_tmaps(net);
+}
+
+// Tensor maps depend on buffer addresses (tensors, scratch, arena): built when the plan is frozen and again
+// whenever a buffer moves (tf2b_dump_acc growing the scratch).
+static int build_tmaps(tf2b_net* net) {
+  const int B = net->max_images;
   for (auto& S : net->layers) {
     if (!S.mma_ok) continue;
     const tf2b_layer_desc& d = S.d;
@@ -761,8 +792,8 @@ static int run_layers(tf2b_net* net, int B, cudaStream_t st, int only_layer, int
     ConvParams p = conv_params(net, S, B, cdst, cdstC, cres, resC, use_mma);
     p.acc_dump = acc_dump;
     if (use_mma) {
-      CUDA_TRY(net, tf2b::launch_conv_mma(p, reinterpret_cast<const int8_t*>(net->arena + S.off_w8),
-                                          S.planes_m, S.plane_shift_m, S.h_tmaps.data(), net->num_sms, st));
+      const tf2b::MmaHostParams hp = {S.h_bias.data(), S.h_alpha.data(), S.h_beta.data(), S.h_nshift_m.data()};
+      CUDA_TRY(net, tf2b::launch_conv_mma(p, hp, S.planes_m, S.plane_shift_m, S.h_tmaps.data(), net->num_sms, st));
     } else {
       CUDA_TRY(net, tf2b::launch_conv_sa(p, S.nseg_s, S.seg_shift_s, S.seg_neg_s, S.h_tmaps_s.data(), S.ksplit_s,
                                          net->num_sms, st));
@@ -787,6 +818,54 @@ static int run_layers(tf2b_net* net, int B, cudaStream_t st, int only_layer, int
     if (prof) CUDA_TRY(net, cudaEventRecord(net->ev[3 * l + 2], st));
   }
   net->last_launches += launches;
+  return TF2B_OK;
+}
+
+// Runs the layer sequence for B images on `st`: replays the captured CUDA graph of this batch size (captured on
+// first use), or launches kernel by kernel when graphs are off, the stream cannot capture (legacy default
+// stream), or per-layer profiling is on.
+static int run_layers_exec(tf2b_net* net, int B, cudaStream_t st) {
+  if (!net->use_graph || net->profile || st == nullptr || st == cudaStreamLegacy) return run_layers(net, B, st, -1, nullptr);
+  for (auto& g : net->graphs)
+    if (g.B == B) {
+      CUDA_TRY(net, cudaGraphLaunch(g.exec, st));
+      net->last_launches += g.launches;
+      return TF2B_OK;
+    }
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone)
+    return run_layers(net, B, st, -1, nullptr);   // the caller is capturing already: become part of its graph
+  if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+    cudaGetLastError();
+    return run_layers(net, B, st, -1, nullptr);
+  }
+  const int before = net->last_launches;
+  int rc = run_layers(net, B, st, -1, nullptr);
+  cudaGraph_t graph = nullptr;
+  cudaError_t ce = cudaStreamEndCapture(st, &graph);
+  const int launches = net->last_launches - before;
+  if (rc != TF2B_OK || ce != cudaSuccess || !graph) {
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    net->use_graph = false;                      // capture is not possible here: stay with plain launches
+    net->last_launches = before;
+    return rc != TF2B_OK ? rc : run_layers(net, B, st, -1, nullptr);
+  }
+  cudaGraphExec_t exec = nullptr;
+  ce = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ce != cudaSuccess || !exec) {
+    cudaGetLastError();
+    net->use_graph = false;
+    net->last_launches = before;
+    return run_layers(net, B, st, -1, nullptr);
+  }
+  if (net->graphs.size() >= 8) {                 // a handful of batch sizes at most
+    cudaGraphExecDestroy(net->graphs.front().exec);
+    net->graphs.erase(net->graphs.begin());
+  }
+  net->graphs.push_back({B, launches, exec});
+  CUDA_TRY(net, cudaGraphLaunch(exec, st));
   return TF2B_OK;
 }
 
@@ -832,7 +911,7 @@ int tf2b_run(tf2b_net* net, const int8_t* in_dev, int in_layout, int n_images, i
     return fail(net, TF2B_ERR_ARG, "unknown layout %d", in_layout);
   }
   net->last_launches++;
-  rc = run_layers(net, n_images, st, -1, nullptr);
+  rc = run_layers_exec(net, n_images, st);
   if (rc) return rc;
   return write_result(net, net->result_tensor, n_images, out_dev, out_layout, st);
 }
@@ -851,7 +930,7 @@ int tf2b_run_raw224(tf2b_net* net, const int8_t* raw_dev, int n_images, int8_t* 
   net->last_images = n_images;
   CUDA_TRY(net, tf2b::launch_raw224_to_s2d(raw_dev, net->tbuf[0], n_images, 1, st));
   net->last_launches++;
-  rc = run_layers(net, n_images, st, -1, nullptr);
+  rc = run_layers_exec(net, n_images, st);
   if (rc) return rc;
   return write_result(net, net->result_tensor, n_images, out_dev, out_layout, st);
 }
@@ -963,9 +1042,12 @@ int tf2b_dump_acc(tf2b_net* net, int layer, int n_images, int32_t* acc_dev, void
     CUDA_TRY(net, cudaFree(net->scratch0));
     CUDA_TRY(net, cudaFree(net->scratch1));
     net->scratch0 = net->scratch1 = nullptr;
+    drop_graphs(net);   // captured graphs hold the old scratch addresses
     net->scratch_bytes = need;
     CUDA_TRY(net, cudaMalloc(&net->scratch0, need));
     CUDA_TRY(net, cudaMalloc(&net->scratch1, need));
+    int rcb = build_tmaps(net);   // layers that write to the scratch carry its address in their tensor maps
+    if (rcb != TF2B_OK) return rcb;
   }
   return run_layers(net, n_images, (cudaStream_t)stream, layer, acc_dev);
 }
@@ -1112,6 +1194,7 @@ const char* tf2b_layer_mode(tf2b_net* net, int layer, int n_images) {
 void tf2b_destroy(tf2b_net* net) {
   if (!net) return;
   cudaSetDevice(net->device);
+  drop_graphs(net);
   for (auto p : net->tbuf) if (p) cudaFree(p);
   if (net->arena) cudaFree(net->arena);
   if (net->scratch0) cudaFree(net->scratch0);

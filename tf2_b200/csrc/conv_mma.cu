@@ -37,6 +37,14 @@
 
 namespace tf2b {
 
+// host copies of a layer's per-channel parameters (the launcher builds the constant-bank table from them)
+struct MmaHostParams {
+  const int32_t* bias;
+  const int32_t* alpha;
+  const int32_t* beta;
+  const uint8_t* nshift;
+};
+
 namespace {
 
 // Experiment switches (TF2B_MMA_DEBUG role counters, TF2B_MMA_NOEPI, TF2B_MMA_POLL0, TF2B_MMA_TOP,
@@ -125,13 +133,18 @@ struct MmaParams {
   int b_stage_bytes;        // bytes of weights one CTA stages per k-iteration
   int egroups;              // epilogue warp groups (1: all 16 warps share every tile; 2: 8 warps per tile,
                             // the groups take alternate tiles = alternate TMEM buffers)
+  int n_tile0;              // first n-tile of this launch (channel window of the parameter table); n_tiles counts
+                            // the n-tiles of the launch
+  int tstore;               // flat layers, folded epilogue: finished int8 rows leave through per-warp TMA stores
 };
 
 struct TmapPair {
   CUtensorMap a;
   CUtensorMap b;
-  CUtensorMap r;   // residual operand (flat layers): [pixels][channels], 128 x 128-byte boxes
+  CUtensorMap r;   // residual operand (flat layers): [pixels][channels], 128 x 128-byte boxes; CTA pairs: weight half tile
+  CUtensorMap y;   // output of flat layers with the folded epilogue: [pixels][channels], per-warp 32-row boxes (TMA store)
 };
+
 
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -210,6 +223,15 @@ __device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* map, int c0, 
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
+
+// TMA store of a finished shared-memory tile (bulk async-group of the issuing thread)
+__device__ __forceinline__ void tma_store_2d(unsigned smem, const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(smem), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 
 __device__ __forceinline__ void tmem_alloc(unsigned smem_dst, unsigned ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
@@ -338,7 +360,7 @@ __device__ __forceinline__ TileCoord decode_tile(const MmaParams& P, int tile) {
   TileCoord t;
   const int mt = fdiv(tile, P.d_ntiles);
   const int nt = tile - mt * P.n_tiles;
-  t.n0 = nt * P.BN;
+  t.n0 = (P.n_tile0 + nt) * P.BN;
   t.m0 = mt * MMA_M;
   t.b0 = t.oh0 = t.ow0 = 0;
   if (P.mode == 1) {
@@ -735,7 +757,8 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
     constexpr bool CT_LOW = FAST && (EPI & 2);
     constexpr bool CT_RES = FAST && (EPI & 4);
     constexpr bool FOLD = FAST && (EPI & 8);
-    constexpr bool HI32 = FOLD && (EPI & 16);   // every channel has nshift >= 3: y = hi32(tot*(alpha<<(nshift-3)) + (B>>3))
+    constexpr bool HI32 = FOLD && (EPI & 16);
+    constexpr bool TSTORE_GLOBAL = FOLD && MODE == 0;   // every channel has nshift >= 3: y = hi32(tot*(alpha<<(nshift-3)) + (B>>3))
     constexpr int G = 1;                  // epilogue groups; group g owns the tiles with local index % G == g
     constexpr int SLICES = 4 / G;         // column slices of a tile (one warp per lane quarter and slice)
     constexpr int WT = BN / SLICES;       // columns per warp: 16..128
@@ -754,7 +777,9 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
     // epilogue scratch lives behind the pipeline stages in dynamic shared memory
     unsigned char* epi_base = smem_raw + (smem_base - smem_u32(smem_raw)) + P.stages * stage_bytes;
     unsigned char* stage = epi_base + ew * EPI_WARP_BYTES;                         // int8 staging tile [32][EPI_ROW]
-    int* prm = reinterpret_cast<int*>(stage + 32 * EPI_ROW);                       // [6][PSTR] per-channel params
+    // per-channel params: [6][PSTR] int32 behind the staging tile; the folded form needs 768 bytes ({A} [64] int32,
+    // {B} [64] int64) and sits behind the two 1 KB staging tiles of the TMA-store path instead
+    int* prm = reinterpret_cast<int*>(stage + (FOLD ? 2048 : 32 * EPI_ROW));
     // coalesced mapping (constant per thread): iteration it -> row rl[it], 16-byte segment sg
     const int sg = lane % SEGS;
     int rl[SEGS];
@@ -825,6 +850,7 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
     unsigned e_tfull, e_tempty;
     asm volatile("mov.u32 %0, %1;" : "=r"(e_tfull) : "r"(tfull_bar));
     asm volatile("mov.u32 %0, %1;" : "=r"(e_tempty) : "r"(tempty_bar));
+    int tsel = 0;   // staging buffer parity of the TMA-store path (advances by PASSES per tile)
     int e_mt = 0, e_nt = 0;
     const int step_mt = fdiv(G * q_step, P.d_ntiles), step_nt = G * q_step - step_mt * P.n_tiles;
     int li = group;   // CTA-local tile index
@@ -859,7 +885,7 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
       }
       TileCoord t;
       if (MODE == 0 && !cg2) {
-        t.n0 = e_nt * BN;
+        t.n0 = (P.n_tile0 + e_nt) * BN;
         t.m0 = e_mt * MMA_M;
         t.b0 = t.oh0 = t.ow0 = 0;
       } else {
@@ -908,12 +934,22 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
       res_pixel(t, rvalid, rpix);
       const bool dvalid = rvalid;
       const long long dpix = rpix;
-      const bool direct = (SEGS == 2) && P.direct256 != 0;
+      // flat layers with the folded epilogue: the warp's finished 32 rows x W bytes go to a swizzled staging tile in
+      // shared memory and leave through ONE TMA store per pass (full lines, no LSU store wavefronts); the last,
+      // partial m-tile of a run keeps the guarded direct stores (rows past the batch end must not be written)
+      constexpr bool TSTORE_OK = FOLD && MODE == 0;
+      const bool tstore = TSTORE_OK && P.tstore != 0 && (t.m0 + MMA_M <= M);
+      const bool direct = (SEGS == 2) && P.direct256 != 0 && !tstore;
+      if (TSTORE_OK && !tstore && !direct) {
+        // the generic staging tile below shares memory with the TMA staging tiles: earlier stores must have read them
+        if (lane == 0) tma_store_wait_read<0>();
+        __syncwarp();
+      }
       long long opix[SEGS];
 #pragma unroll
       for (int it = 0; it < SEGS; it++) {
         opix[it] = -1;
-        if (direct) continue;   // the direct path stores this thread's own row (dvalid / dpix)
+        if (direct || tstore) continue;   // these paths store this thread's own row (dvalid / dpix)
         bool valid;
         long long pix;
         if (MODE == 0) {
@@ -1054,7 +1090,13 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
             if (has_res) y4 = add_relu ? add_res_s8x4<true>(y4, rw[j4]) : add_res_s8x4<false>(y4, rw[j4]);
             packed[j4] = y4;
           }
-          if (direct) {
+          if (tstore) {
+            // staging tile of this pass: [32 rows][W bytes], 16-byte chunk index XOR-swizzled like the tensor map
+            // (SWIZZLE_32B: chunk ^= bit 7 of the address = (row >> 2) & 1): conflict-free 16-byte stores
+            unsigned char* sbuf = stage + ((tsel + pass) & 1) * 1024;
+            const int chunk = (W == 32) ? ((cc >> 4) ^ ((lane >> 2) & 1)) : 0;
+            *reinterpret_cast<uint4*>(sbuf + lane * W + chunk * 16) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+          } else if (direct) {
             if (cc == 0) out_lo = make_uint4(packed[0], packed[1], packed[2], packed[3]);
             else out_hi = make_uint4(packed[0], packed[1], packed[2], packed[3]);
           } else {
@@ -1073,6 +1115,19 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
           if (!direct) __syncwarp();
           if (has_res && res_tma) lds_res(slice * WT + (pass + 1) * W, resq);
           else load_res(rvalid, rpix, ncolp + W, resq);   // prefetch the next pass's residual
+        }
+        if (tstore) {
+          // generic-proxy writes -> async proxy, then one lane issues the store and commits its bulk group
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(smem_u32(stage + ((tsel + pass) & 1) * 1024), &maps.y, ncolp, t.m0 + quarter * 32);
+            tma_store_commit();
+            // the buffer written next (the other one) must have been read out by its previous store
+            tma_store_wait_read<1>();
+          }
+          __syncwarp();
+          continue;
         }
         if (direct) {
           // this lane's own row: 32 contiguous bytes = one sector
@@ -1109,7 +1164,9 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
         __syncwarp();
         if (lane == 0) mbar_arrive(rempty_bar + 8 * rb);
       }
+      tsel = (tsel + PASSES) & 1;
     }
+    if (TSTORE_GLOBAL && lane == 0) tma_store_wait_read<0>();   // staging memory must outlive its last store
     if (dbg && lane == 0) {
       P.dbg[blockIdx.x * 8 + 5] = w_tfull;
       P.dbg[blockIdx.x * 8 + 6] = clock64() - t_start;
@@ -1312,6 +1369,15 @@ void fill_geometry(MmaParams& P, const ConvParams& c, int planes8) {
     static const int l2pf = env_int("TF2B_MMA_L2PF", 0);
     P.l2_prefetch = l2pf;
   }
+  P.n_tile0 = 0;
+  // per-warp TMA stores: flat layers whose run-time epilogue is the folded one (the accumulator tap runs the exact
+  // epilogue and keeps the guarded direct stores)
+  {
+    const int scaled = planes8 - (c.low_plane >= 0 ? 1 : 0);
+    const bool fast = c.acc_dump == nullptr && c.fast_requant != 0 && scaled <= 2 && (c.low_plane < 0 || c.low_plane == planes8 - 1);
+    static const bool allow = env_int("TF2B_MMA_TSTORE", 1) != 0;
+    P.tstore = (allow && P.mode == 0 && fast && fold_applies(c, planes8)) ? 1 : 0;
+  }
   P.idx32 = ((long long)c.B * c.OH * c.OW * c.yC < (1ll << 31)) && ((long long)c.B * c.OH * c.OW * (c.rC > 0 ? c.rC : 1) < (1ll << 31));
   P.direct256 = (c.yC % 32 == 0) && (((unsigned long long)c.y) % 32 == 0) &&
                 (c.r == nullptr || ((c.rC % 32 == 0) && (((unsigned long long)c.r) % 32 == 0)));
@@ -1352,10 +1418,10 @@ std::string mma_describe(const ConvParams& c, int planes8) {
   MmaParams P;
   fill_geometry(P, c, planes8);
   char b[192];
-  snprintf(b, sizeof b, "mma BN%d BK%d planes%d %s%s%s%s%s stages%d", P.BN, P.BK, planes8,
+  snprintf(b, sizeof b, "mma BN%d BK%d planes%d %s%s%s%s%s%s stages%d", P.BN, P.BK, planes8,
            P.mode == 0 ? "flat" : (P.halo ? "halo" : (P.pair ? "pixelpair" : "box")), P.b_resident ? " wres" : "",
            P.res_tma ? " restma" : "", fold_applies(c, planes8) ? (c.fast_requant >= 3 ? " fold hi32" : " fold") : "",
-           P.cg2 ? " ctapair" : "", P.stages);
+           P.tstore ? " tmastore" : "", P.cg2 ? " ctapair" : "", P.stages);
   return std::string(b);
 }
 
@@ -1429,6 +1495,22 @@ int mma_build_tmaps(void* host_tmaps, const ConvParams& c, const int8_t* wgt8, i
       return -1;
     }
   }
+  memset(&tp->y, 0, sizeof tp->y);
+  if (P.tstore) {
+    // the warp (quarter, slice) of the epilogue owns 32 rows x W = min(32, BN / 4) channels per pass
+    const int W = P.BN / 4 > 32 ? 32 : P.BN / 4;
+    cuuint64_t dims[2] = {(cuuint64_t)c.N, (cuuint64_t)c.B * c.OH * c.OW};
+    cuuint64_t strides[1] = {(cuuint64_t)c.yC};
+    cuuint32_t box[2] = {(cuuint32_t)W, 32};
+    cuuint32_t es[2] = {1, 1};
+    r = enc(&tp->y, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)c.y, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            W == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      if (err) *err = "cuTensorMapEncodeTiled(Y) failed with CUresult " + std::to_string((int)r);
+      return -1;
+    }
+  }
   if (P.res_tma) {
     cuuint64_t dims[2] = {(cuuint64_t)c.N, (cuuint64_t)c.B * c.OH * c.OW};
     cuuint64_t strides[1] = {(cuuint64_t)c.rC};
@@ -1498,7 +1580,7 @@ cudaError_t mma_prepare_device(int* num_sms) {
   return cudaSuccess;
 }
 
-cudaError_t launch_conv_mma(const ConvParams& c, const int8_t* /*wgt8*/, int planes8, const int* plane8_shift,
+cudaError_t launch_conv_mma(const ConvParams& c, const MmaHostParams& /*hp*/, int planes8, const int* plane8_shift,
                             void* tmaps, int num_sms, cudaStream_t stream) {
   MmaParams P;
   fill_geometry(P, c, planes8);
@@ -1538,18 +1620,6 @@ cudaError_t launch_conv_mma(const ConvParams& c, const int8_t* /*wgt8*/, int pla
                : T.pair_exact[P.BN == 256 ? 1 : 0][P.mode];
   }
   if (!kfn) return cudaErrorInvalidValue;
-  const int num_tiles = P.m_tiles * P.n_tiles;
-  int grid = num_tiles < num_sms ? num_tiles : num_sms;
-  if (P.b_resident) {
-    // every CTA must keep one n-tile: grid = multiple of n_tiles
-    grid = (grid / P.n_tiles) * P.n_tiles;
-    if (grid < P.n_tiles) grid = P.n_tiles;
-  }
-  if (P.cg2) {
-    // pairs of CTAs (one cluster per TPC pair); work items = pairs of m-tiles x n-tiles
-    const int items = ((P.m_tiles + 1) / 2) * P.n_tiles;
-    grid = 2 * std::min(items, num_sms / 2);
-  }
   const TmapPair* tp = reinterpret_cast<const TmapPair*>(tmaps);
   P.dbg = nullptr;
   static const bool debug = env_int("TF2B_MMA_DEBUG", 0) != 0;
@@ -1559,7 +1629,20 @@ cudaError_t launch_conv_mma(const ConvParams& c, const int8_t* /*wgt8*/, int pla
     cudaMemsetAsync(dbg_dev, 0, sizeof(long long) * 8 * 148, stream);
     P.dbg = dbg_dev;
   }
+  int grid = 0, num_tiles = 0;
   {
+    num_tiles = P.m_tiles * P.n_tiles;
+    grid = num_tiles < num_sms ? num_tiles : num_sms;
+    if (P.b_resident) {
+      // every CTA must keep one n-tile: grid = multiple of n_tiles
+      grid = (grid / P.n_tiles) * P.n_tiles;
+      if (grid < P.n_tiles) grid = P.n_tiles;
+    }
+    if (P.cg2) {
+      // pairs of CTAs (one cluster per TPC pair); work items = pairs of m-tiles x n-tiles
+      const int items = ((P.m_tiles + 1) / 2) * P.n_tiles;
+      grid = 2 * std::min(items, num_sms / 2);
+    }
     static const bool use_pdl = env_int("TF2B_MMA_PDL", 1) != 0;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof cfg);

@@ -120,6 +120,10 @@ class NetWork:
     def set_variant(self, variant: int):
         self._check(self._lib.tf2b_set_variant(self._h, variant))
 
+    def set_graph(self, on: bool):
+        """CUDA-graph executor on (default) / off (kernel-by-kernel launches)."""
+        self._check(self._lib.tf2b_set_graph(self._h, 1 if on else 0))
+
     def set_result(self, tensor: int):
         """Which tensor the run calls return (default: the last layer's output) — the reference's way of
         verifying an inner layer is to rebuild with a shorter table (CONCAT_LAYER_DEBUG, network_helper.cpp:19-23)."""
