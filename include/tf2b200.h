@@ -103,10 +103,13 @@ int tf2b_finalize(tf2b_net* net, int max_images);
 
 int tf2b_set_variant(tf2b_net* net, int variant);
 
-/* Executor: by default the layer sequence of a batch size is captured once into a CUDA graph (the
- * programmatic-dependent-launch edges between consecutive layers included) and replayed by every later run
- * of that size — the counterpart of the reference enqueueing all its kernels once per frame batch
- * (Runner::EnqueueKernels, runner.cpp:32).  on = 0 launches kernel by kernel (A/B measurements, debugging). */
+/* Executor: by default (on = 1) the layer sequence of a batch size is captured once into a CUDA graph (the
+ * programmatic-dependent-launch edges between consecutive layers included) and replayed by every later run of
+ * that size — the counterpart of the reference enqueueing all its kernels once per frame batch
+ * (Runner::EnqueueKernels, runner.cpp:32) — and independent branches of the layer graph (inception branches,
+ * the shortcut convolution of a residual block) run concurrently on the engine's side streams.
+ * on = 0: kernel by kernel on the caller's stream; 2: graph, one stream; 3: several streams, no graph
+ * (A/B measurements, debugging). */
 int tf2b_set_graph(tf2b_net* net, int on);
 
 /* Copies packed device weights/params from/to a flat device buffer so one rank can load the model

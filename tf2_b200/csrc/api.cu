@@ -129,6 +129,17 @@ struct tf2b_net {
   int last_images = 0;
   // CUDA-graph executor: the layer sequence of a batch size is captured once (programmatic-dependent-launch
   // edges included) and replayed; key = number of images
+  // layer schedule over streams (finalize): independent branches (inception branches, the shortcut convolution of a
+  // residual block) run concurrently; lane 0 is the caller's stream, lanes 1.. are the engine's side streams
+  static constexpr int kLanes = 4;
+  std::vector<int> lane;                       // per layer
+  std::vector<std::vector<int>> wait_on;       // per layer: layers on other lanes it must wait for
+  std::vector<char> need_event;                // per layer: another lane waits for it
+  std::vector<cudaEvent_t> ev_layer;
+  cudaStream_t side[kLanes] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[kLanes] = {nullptr, nullptr, nullptr, nullptr};
+  bool lane_used[kLanes] = {true, false, false, false};
+  bool multi_stream = true;
   bool use_graph = true;
   struct GraphEntry { int B; int launches; cudaGraphExec_t exec; };
   std::vector<GraphEntry> graphs;
@@ -519,8 +530,9 @@ static void drop_graphs(tf2b_net* net) {
 
 int tf2b_set_graph(tf2b_net* net, int on) {
   if (!net) return TF2B_ERR_ARG;
-  net->use_graph = on != 0;
-  if (!on) drop_graphs(net);
+  net->use_graph = on == 1 || on == 2;
+  net->multi_stream = on == 1 || on == 3;
+  drop_graphs(net);
   return TF2B_OK;
 }
 
@@ -588,6 +600,7 @@ int64_t tf2b_weight_blob_bytes(tf2b_net* net) {
 
 static int alloc_runtime(tf2b_net* net);
 static int build_tmaps(tf2b_net* net);
+static int build_schedule(tf2b_net* net);
 
 int tf2b_finalize(tf2b_net* net, int max_images) {
   if (!net) return TF2B_ERR_ARG;
@@ -617,6 +630,8 @@ int tf2b_finalize(tf2b_net* net, int max_images) {
     CUDA_TRY(net, up(S.off_nshift_m, S.h_nshift_m.data(), S.h_nshift_m.size()));
   }
   int rc = alloc_runtime(net);
+  if (rc != TF2B_OK) return rc;
+  rc = build_schedule(net);
   if (rc != TF2B_OK) return rc;
   net->finalized = true;
   return tf2b_set_variant(net, net->variant);
@@ -755,12 +770,71 @@ static int build_tmaps(tf2b_net* net) {
   return TF2B_OK;
 }
 
-static int run_layers(tf2b_net* net, int B, cudaStream_t st, int only_layer, int32_t* acc_dump) {
+// Dependency schedule of the layer graph over kLanes streams.  A layer depends on every earlier layer that writes
+// its input tensor (all branch tails of a concat buffer) or its residual operand, and on the previous user of the
+// shared pool / gap scratch.  It continues the lane of a producer that is still the tail of its lane (so that
+// programmatic dependent launch keeps working along chains), else it opens the next lane round robin.
+static int build_schedule(tf2b_net* net) {
+  const int L = (int)net->layers.size();
+  net->lane.assign(L, 0);
+  net->wait_on.assign(L, {});
+  net->need_event.assign(L, 0);
+  for (int i = 0; i < tf2b_net::kLanes; i++) net->lane_used[i] = i == 0;
+  std::vector<int> tail(tf2b_net::kLanes, -1);
+  int last_scratch = -1, rr = 0;
+  for (int l = 0; l < L; l++) {
+    const tf2b_layer_desc& d = net->layers[l].d;
+    std::vector<int> deps;
+    for (int j = 0; j < l; j++) {
+      const tf2b_layer_desc& e = net->layers[j].d;
+      if (e.out_tensor == d.in_tensor || (d.add_tensor >= 0 && e.out_tensor == d.add_tensor)) deps.push_back(j);
+      // a slice of a concat buffer is written once, but keep writers of the same tensor ordered with later readers
+    }
+    const bool scratch = !d.ipool && (d.pool || d.gap);
+    if (scratch && last_scratch >= 0) deps.push_back(last_scratch);
+    int ln = -1;
+    for (int j : deps)
+      if (tail[net->lane[j]] == j && (ln < 0 || j == l - 1)) ln = net->lane[j];
+    if (ln < 0) {
+      if (deps.empty()) ln = 0;
+      else { rr = rr % (tf2b_net::kLanes - 1) + 1; ln = rr; }
+    }
+    net->lane[l] = ln;
+    net->lane_used[ln] = true;
+    for (int j : deps)
+      if (net->lane[j] != ln) { net->wait_on[l].push_back(j); net->need_event[j] = 1; }
+    tail[ln] = l;
+    if (scratch) last_scratch = l;
+  }
+  CUDA_TRY(net, cudaEventCreateWithFlags(&net->ev_fork, cudaEventDisableTiming));
+  for (int i = 1; i < tf2b_net::kLanes; i++) {
+    CUDA_TRY(net, cudaStreamCreateWithFlags(&net->side[i], cudaStreamNonBlocking));
+    CUDA_TRY(net, cudaEventCreateWithFlags(&net->ev_join[i], cudaEventDisableTiming));
+  }
+  net->ev_layer.assign(L, nullptr);
+  for (int l = 0; l < L; l++)
+    if (net->need_event[l]) CUDA_TRY(net, cudaEventCreateWithFlags(&net->ev_layer[l], cudaEventDisableTiming));
+  return TF2B_OK;
+}
+
+static int run_layers(tf2b_net* net, int B, cudaStream_t st0, int only_layer, int32_t* acc_dump) {
   int launches = 0;
   const bool prof = net->profile && only_layer < 0 && !net->ev.empty();
+  // several lanes only for whole-network runs outside the per-layer profiler
+  const bool lanes = net->multi_stream && !prof && only_layer < 0 && !net->lane.empty();
+  if (lanes) {
+    CUDA_TRY(net, cudaEventRecord(net->ev_fork, st0));
+    for (int i = 1; i < tf2b_net::kLanes; i++)
+      if (net->lane_used[i]) CUDA_TRY(net, cudaStreamWaitEvent(net->side[i], net->ev_fork, 0));
+  }
   for (size_t l = 0; l < net->layers.size(); l++) {
     if (only_layer >= 0 && (int)l != only_layer) continue;
     LayerState& S = net->layers[l];
+    cudaStream_t st = st0;
+    if (lanes) {
+      if (net->lane[l] > 0) st = net->side[net->lane[l]];
+      for (int j : net->wait_on[l]) CUDA_TRY(net, cudaStreamWaitEvent(st, net->ev_layer[j], 0));
+    }
     if (prof) CUDA_TRY(net, cudaEventRecord(net->ev[3 * l], st));
     const tf2b_layer_desc& d = S.d;
     const tf2b_tensor_desc& ti = net->tensors[d.in_tensor];
@@ -777,6 +851,7 @@ static int run_layers(tf2b_net* net, int B, cudaStream_t st, int only_layer, int
         CUDA_TRY(net, cudaEventRecord(net->ev[3 * l + 1], st));
         CUDA_TRY(net, cudaEventRecord(net->ev[3 * l + 2], st));
       }
+      if (lanes && net->need_event[l]) CUDA_TRY(net, cudaEventRecord(net->ev_layer[l], st));
       continue;
     }
     // the accumulator tap re-runs one convolution with its feature map diverted to scratch; everything
@@ -816,6 +891,14 @@ static int run_layers(tf2b_net* net, int B, cudaStream_t st, int only_layer, int
       launches++;
     }
     if (prof) CUDA_TRY(net, cudaEventRecord(net->ev[3 * l + 2], st));
+    if (lanes && net->need_event[l]) CUDA_TRY(net, cudaEventRecord(net->ev_layer[l], st));
+  }
+  if (lanes) {
+    for (int i = 1; i < tf2b_net::kLanes; i++)
+      if (net->lane_used[i]) {
+        CUDA_TRY(net, cudaEventRecord(net->ev_join[i], net->side[i]));
+        CUDA_TRY(net, cudaStreamWaitEvent(st0, net->ev_join[i], 0));
+      }
   }
   net->last_launches += launches;
   return TF2B_OK;
@@ -1212,6 +1295,12 @@ void tf2b_destroy(tf2b_net* net) {
   if (net->s_h2d) cudaStreamDestroy(net->s_h2d);
   if (net->s_d2h) cudaStreamDestroy(net->s_d2h);
   for (auto e : net->ev) cudaEventDestroy(e);
+  for (auto e : net->ev_layer) if (e) cudaEventDestroy(e);
+  if (net->ev_fork) cudaEventDestroy(net->ev_fork);
+  for (int i = 1; i < tf2b_net::kLanes; i++) {
+    if (net->ev_join[i]) cudaEventDestroy(net->ev_join[i]);
+    if (net->side[i]) cudaStreamDestroy(net->side[i]);
+  }
   delete net;
 }
 

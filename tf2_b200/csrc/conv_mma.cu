@@ -260,6 +260,16 @@ __device__ __forceinline__ void tmem_ld16(unsigned taddr, unsigned (&v)[16]) {
         "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld32(unsigned taddr, unsigned (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---- CTA-pair (cta_group::2) forms.  Shared-memory window addresses carry the CTA rank of the pair in
@@ -925,6 +935,84 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
             prm[4 * PSTR + i] = 1 << nsh;                                   // (x << s) == x * 2^s  (mod 2^32)
             prm[5 * PSTR + i] = (nsh + 7 < 32) ? (1 << (nsh + 7)) : 0;      // second plane: x * 2^(s+7)
           }
+        }
+      }
+      // ---- lean path: flat layers with the folded epilogue on a full m-tile.  Nothing here depends on the lane's
+      //      pixel: the residual tile comes from the TMA ring, the finished rows leave through a TMA store, so the
+      //      warp does no address arithmetic at all.  The W accumulators of a pass are read in one tcgen05.ld and
+      //      the TMEM buffer goes back to the MMA warp BEFORE the arithmetic of the last pass.
+      if constexpr (FOLD && MODE == 0) {
+        const bool lean_res_ok = !has_res || res_tma;
+        if (P.tstore != 0 && (t.m0 + MMA_M <= M) && lean_res_ok && !(kExp && P.noepi)) {
+          mbar_wait_timed(e_tfull + 8 * buf, tph, w_tfull, dbg, 0);
+          tc_fence_after();
+          if (has_res) mbar_wait_warp(rfull_bar + 8 * rb, rphase, 0);
+          const unsigned t_row0 = tmem_base + ((unsigned)(quarter * 32) << 16) + buf * acc_cols + slice * WT;
+#pragma unroll
+          for (int pass = 0; pass < PASSES; pass++) {
+            unsigned tot[W], tot1[W];
+            if constexpr (W == 32) {
+              tmem_ld32(t_row0 + pass * W, tot);
+              if (CT_TWO) tmem_ld32(t_row0 + BN + pass * W, tot1);
+            } else {
+              tmem_ld16(t_row0 + pass * W, tot);
+              if (CT_TWO) tmem_ld16(t_row0 + BN + pass * W, tot1);
+            }
+            tmem_ld_wait();
+            if (pass == PASSES - 1) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) {
+                if constexpr (cg2) mbar_arrive_leader(e_tempty + 8 * buf);
+                else mbar_arrive(e_tempty + 8 * buf);
+              }
+            }
+            uint4 resq[SEGS];
+            if (has_res) lds_res(slice * WT + pass * W, resq);
+            unsigned char* sbuf = stage + ((tsel + pass) & 1) * 1024;
+#pragma unroll
+            for (int cc = 0; cc < W; cc += 16) {
+              const uint4 rq = has_res ? resq[cc / 16] : make_uint4(0, 0, 0, 0);
+              const unsigned rw[4] = {rq.x, rq.y, rq.z, rq.w};
+              unsigned packed[4];
+              const int pc = pass * W + cc;
+#pragma unroll
+              for (int j4 = 0; j4 < 4; j4++) {
+                const int4 pa = *reinterpret_cast<const int4*>(prm + pc + 4 * j4);
+                const longlong2 pb0 = *reinterpret_cast<const longlong2*>(prm + PSTR + 2 * (pc + 4 * j4));
+                const longlong2 pb1 = *reinterpret_cast<const longlong2*>(prm + PSTR + 2 * (pc + 4 * j4) + 4);
+                const int aa[4] = {pa.x, pa.y, pa.z, pa.w};
+                const long long bq[4] = {pb0.x, pb0.y, pb1.x, pb1.y};
+                int yy[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                  const int j = cc + 4 * j4 + u;
+                  const int tt = CT_TWO ? (int)(tot1[j] * 128u + tot[j]) : (int)tot[j];
+                  const long long tq = (long long)tt * (long long)aa[u] + bq[u];   // IMAD.HI with the 64-bit addend
+                  yy[u] = HI32 ? (int)(tq >> 32) : (int)(tq >> 35);
+                }
+                unsigned y4 = pack_sat4(yy[0], yy[1], yy[2], yy[3]);
+                if (conv_relu) y4 = relu_s8x4(y4);
+                if (has_res) y4 = add_relu ? add_res_s8x4<true>(y4, rw[j4]) : add_res_s8x4<false>(y4, rw[j4]);
+                packed[j4] = y4;
+              }
+              const int chunk = (W == 32) ? ((cc >> 4) ^ ((lane >> 2) & 1)) : 0;
+              *reinterpret_cast<uint4*>(sbuf + lane * W + chunk * 16) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(smem_u32(sbuf), &maps.y, ncolw + pass * W, t.m0 + quarter * 32);
+              tma_store_commit();
+              tma_store_wait_read<1>();   // the other staging tile (written next) has been read out
+            }
+            __syncwarp();
+          }
+          if (has_res) {
+            if (lane == 0) mbar_arrive(rempty_bar + 8 * rb);
+          }
+          tsel = (tsel + PASSES) & 1;
+          continue;
         }
       }
       // ---- (1b) this thread's accumulator row -> pixel (for the residual), and the pixels of its
