@@ -234,7 +234,11 @@ def main():
     in_bytes = int(np.prod(in_shape))
     out = torch.empty(out_shape, dtype=torch.int8, device=dev)
     out_host = torch.empty(out_shape, dtype=torch.int8).pin_memory()
-    stream = torch.cuda.current_stream(dev)
+    # a stream of our own: the engine's default executor (CUDA graph replay) needs a capturable stream, which the
+    # legacy default stream is not; every device-timed launch and both timing events go to this stream
+    torch.cuda.synchronize(dev)              # the input batches were copied on the default stream
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
 
     def barrier():
         if world > 1:

@@ -8,7 +8,8 @@ import ctypes as C
 import os
 from typing import Optional
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libtf2b200.so")
+# TF2B_LIB: development override (A/B builds of the same sources under tools/); the product is lib/libtf2b200.so
+_LIB_PATH = os.environ.get("TF2B_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libtf2b200.so")
 
 TF2B_OK = 0
 VARIANT_AUTO, VARIANT_SHIFT, VARIANT_MMA = 0, 1, 2

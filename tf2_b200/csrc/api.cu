@@ -30,8 +30,8 @@ int sa_ksplit(const ConvParams& p, int num_sms);
 std::string sa_describe(const ConvParams& p, int nseg, int ksplit);
 int sa_build_tmaps(void* host_tmaps, const ConvParams& p, const uint8_t* wgt4, int nseg, int ksplit, std::string* err);
 cudaError_t launch_chw_to_hwc(const int8_t*, int8_t*, int, int, int, int, int, int, cudaStream_t);
-cudaError_t launch_hwc_to_chw(const int8_t*, int8_t*, int, int, int, int, int, cudaStream_t);
-cudaError_t launch_hwc_repitch(const int8_t*, int8_t*, size_t, int, int, int, int, cudaStream_t);
+cudaError_t launch_hwc_to_chw(const int8_t*, int8_t*, int, int, int, int, int, const int*, cudaStream_t);
+cudaError_t launch_hwc_repitch(const int8_t*, int8_t*, size_t, int, int, int, int, const int*, cudaStream_t);
 cudaError_t launch_raw224_to_s2d(const int8_t*, int8_t*, int, int, cudaStream_t);
 cudaError_t launch_maxpool3x3(const int8_t*, int8_t*, const int8_t*, int, int, int, int, int, int,
                               int, int, int, int, int, int, cudaStream_t);
@@ -62,7 +62,10 @@ static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
 struct LayerState {
   tf2b_layer_desc d;
-  bool loaded = false;
+  bool loaded = false;     // weights were handed over (tf2b_load_layer*) or imported with a blob
+  bool prepared = false;   // device-side weight forms have been built (prepare_network / blob import)
+  std::vector<uint8_t> h_codes;          // LoadModel's codes [N][C][k][k], kept until tf2b_finalize
+  std::vector<tf2b_bias_bn> h_params;    // [N]
   int Cp = 0;  // reduction channels padded to 16
   int Cp_m = 0;  // reduction channels seen by the tensor-core path (2*Cp when it reads the negated copy)
   // --- shift-accumulate kernel: packed 4-bit codes, one row block per segment (exponent level x sign-quirk) ---
@@ -103,6 +106,12 @@ struct tf2b_net {
   std::vector<tf2b_tensor_desc> tensors;
   std::vector<int> tpitch;  // channel pitch of each tensor (C rounded up to 16)
   int t0_neg_off = 0;       // channel offset of the negated copy inside tensor 0
+  // Channel order of a tensor in memory (empty = natural): tpos[t][c] = position of logical channel c.  Chosen at
+  // tf2b_finalize so that channels whose weights share a power-of-two offset sit next to each other in K (the
+  // producers' weight rows and the consumers' weight columns are laid out accordingly: free at run time); reads
+  // at the boundary (tf2b_read_tensor, the result) and the accumulator tap undo it.
+  std::vector<std::vector<int>> tpos;
+  std::vector<size_t> off_tpos, off_tinv;   // device copies inside the arena (int32 [C]): logical->position, position->logical
   std::vector<LayerState> layers;
   int variant = TF2B_VARIANT_AUTO;
   int max_images = 0;
@@ -140,6 +149,7 @@ struct tf2b_net {
   cudaEvent_t ev_fork = nullptr, ev_join[kLanes] = {nullptr, nullptr, nullptr, nullptr};
   bool lane_used[kLanes] = {true, false, false, false};
   bool multi_stream = true;
+  bool permute = true;      // choose_permutations at finalize (off: natural channel order everywhere)
   bool use_graph = true;
   struct GraphEntry { int B; int launches; cudaGraphExec_t exec; };
   std::vector<GraphEntry> graphs;
@@ -179,6 +189,11 @@ static int prepare_layer(tf2b_net* net, LayerState& S, const uint8_t* codes,
                          const tf2b_bias_bn* params) {
   const tf2b_layer_desc& d = S.d;
   const int C = d.C, N = d.N, k = d.k;
+  // positions of the logical input / output channels in their tensors (natural order when the tensor has none)
+  const std::vector<int>* vin = (d.in_tensor < (int)net->tpos.size() && !net->tpos[d.in_tensor].empty()) ? &net->tpos[d.in_tensor] : nullptr;
+  const std::vector<int>* vout = (d.out_tensor < (int)net->tpos.size() && !net->tpos[d.out_tensor].empty()) ? &net->tpos[d.out_tensor] : nullptr;
+  auto pin = [&](int c) { return vin ? (*vin)[c] : c; };
+  auto pout = [&](int n) { return vout ? (*vout)[n] : n; };
   S.Cp = round_up(C, 16);
   const int Ktot = k * k * S.Cp;
   // per-channel base shift = smallest shift among the channel's non-zero codes
@@ -228,14 +243,14 @@ static int prepare_layer(tf2b_net* net, LayerState& S, const uint8_t* codes,
               if (rel / lv != lvl) continue;
               const bool negw = (cd & 0x80) != 0;
               if (negseg && (negw ? 1 : 0) != ng) continue;
-              int cc = c;
+              int cc = pin(c);
               unsigned nib = (unsigned)(rel - lvl * lv);
               if (negw) {
-                if (dual_s) cc = S.Cp + c;          // magnitude times the negated copy
+                if (dual_s) cc = S.Cp + c;          // magnitude times the negated copy (tensor 0 keeps its order)
                 else if (!negseg) nib |= 8u;        // plain negative weight
               }
               const size_t kidx = ((size_t)t * cchunks * KC) + cc;
-              uint8_t& byte = w4[(size_t)n * (S.Kp_s / 2) + kidx / 2];
+              uint8_t& byte = w4[(size_t)pout(n) * (S.Kp_s / 2) + kidx / 2];
               byte = (kidx & 1) ? (uint8_t)((byte & 0x0f) | (nib << 4)) : (uint8_t)((byte & 0xf0) | nib);
               any = true;
             }
@@ -316,7 +331,7 @@ static int prepare_layer(tf2b_net* net, LayerState& S, const uint8_t* codes,
               e = rel - p * lv;
             }
             int v = 1 << e;
-            int cc = c;
+            int cc = pin(c);
             if (cd & 0x80) {
               if (dual) cc = S.Cp + c; else v = -v;
             }
@@ -325,10 +340,10 @@ static int prepare_layer(tf2b_net* net, LayerState& S, const uint8_t* codes,
               const int fh = t / k, fw = t - fh * k;
               kidx = (size_t)fh * Cpm + (size_t)(fw / 2) * 128 + (size_t)(fw & 1) * 64 + cc;
             }
-            S.h_w8[((size_t)p * S.Npad_m + n) * S.Kp_m + kidx] = (int8_t)v;
+            S.h_w8[((size_t)p * S.Npad_m + pout(n)) * S.Kp_m + kidx] = (int8_t)v;
           }
       S.h_nshift_m.assign(round_up(std::max(tf2b::sa_npad(N), S.Npad_m), 16), 0);
-      for (int n = 0; n < N; n++) S.h_nshift_m[n] = bm[n];
+      for (int n = 0; n < N; n++) S.h_nshift_m[pout(n)] = bm[n];
       S.mma_ok = true;
     }
   }
@@ -357,14 +372,14 @@ static int prepare_layer(tf2b_net* net, LayerState& S, const uint8_t* codes,
       for (int i = 0; i < C * k * k; i++)
         if (!(cn[i] & 0x40)) sum += 128.0L * (long double)(1ull << (cn[i] & 0x1f));
       if (sum >= 2147483647.0L) fold = false;
-      const long double a = fabsl((long double)params[n].alpha) * (long double)(1ull << S.h_nshift_m[n]);
+      const long double a = fabsl((long double)params[n].alpha) * (long double)(1ull << S.h_nshift_m[pout(n)]);
       if (a >= 2147483647.0L) fold = false;
     }
     if (fold) {
       S.fast_requant = 2;
       // every base shift >= 3: the epilogue can drop the final shift (conv_mma.cu HI32)
       bool hi = true;
-      for (int n = 0; n < N; n++) hi = hi && S.h_nshift_m[n] >= 3;
+      for (int n = 0; n < N; n++) hi = hi && S.h_nshift_m[pout(n)] >= 3;
       if (hi) S.fast_requant = 3;
     }
   }
@@ -374,12 +389,105 @@ static int prepare_layer(tf2b_net* net, LayerState& S, const uint8_t* codes,
   S.h_beta.assign(S.Npar, 0);
   S.h_nshift.assign(round_up(S.Npar, 16), 0);
   for (int n = 0; n < N; n++) {
-    S.h_bias[n] = params[n].bias;
-    S.h_alpha[n] = params[n].alpha;
-    S.h_beta[n] = params[n].beta;
-    S.h_nshift[n] = base[n];
+    S.h_bias[pout(n)] = params[n].bias;
+    S.h_alpha[pout(n)] = params[n].alpha;
+    S.h_beta[pout(n)] = params[n].beta;
+    S.h_nshift[pout(n)] = base[n];
   }
-  S.loaded = true;
+  S.prepared = true;
+  return TF2B_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// channel order of the inner tensors
+// ------------------------------------------------------------------------------------------------
+// Per input channel of a layer: the smallest shift, relative to each output channel's base shift, any of its
+// weights carries.  With TF2's per-channel Q tables this is (Q_in[c] - min Q_in): shift = 15 + q_in[c] - q_out[n]
+// - exponent (model_loader.cpp:159-168).
+static std::vector<int> channel_offsets(const LayerState& S) {
+  const tf2b_layer_desc& d = S.d;
+  const int C = d.C, N = d.N, kk = d.k * d.k;
+  std::vector<int> base(N, 0), off(C, 99);
+  for (int n = 0; n < N; n++) {
+    int mn = 99;
+    const uint8_t* cn = S.h_codes.data() + (size_t)n * C * kk;
+    for (int i = 0; i < C * kk; i++)
+      if (!(cn[i] & 0x40)) mn = std::min(mn, cn[i] & 0x1f);
+    base[n] = mn == 99 ? 0 : mn;
+  }
+  for (int n = 0; n < N; n++) {
+    const uint8_t* cn = S.h_codes.data() + (size_t)n * C * kk;
+    for (int c = 0; c < C; c++)
+      for (int t = 0; t < kk; t++) {
+        const uint8_t cd = cn[(size_t)c * kk + t];
+        if (!(cd & 0x40)) off[c] = std::min(off[c], (cd & 0x1f) - base[n]);
+      }
+  }
+  for (int c = 0; c < C; c++)
+    if (off[c] == 99) off[c] = 0;
+  return off;
+}
+
+// Tensors joined by a residual add share one order (feature_writer.cl:124-127 adds element by element); concat
+// buffers, tensors touched by an ipool pseudo layer and tensor 0 keep the natural order.  Within a class the
+// channels are sorted (stably) by the offset its heaviest consumer sees, so that channels of equal offset are
+// contiguous in that consumer's K dimension.
+static void choose_permutations(tf2b_net* net) {
+  const int T = (int)net->tensors.size();
+  net->tpos.assign(T, {});
+  std::vector<int> parent(T);
+  for (int t = 0; t < T; t++) parent[t] = t;
+  auto find = [&](int x) { while (parent[x] != x) x = parent[x] = parent[parent[x]]; return x; };
+  std::vector<char> ok(T, 1);
+  std::vector<int> writers(T, 0);
+  ok[0] = 0;
+  for (auto& S : net->layers) {
+    const tf2b_layer_desc& d = S.d;
+    writers[d.out_tensor]++;
+    if (d.ipool) { ok[d.in_tensor] = ok[d.out_tensor] = 0; continue; }
+    if (d.out_ch0 != 0 || d.N != net->tensors[d.out_tensor].C) ok[d.out_tensor] = 0;
+    if (d.C != net->tensors[d.in_tensor].C) ok[d.in_tensor] = 0;
+    if (!S.loaded || S.h_codes.empty()) ok[d.in_tensor] = ok[d.out_tensor] = 0;
+    if (d.add_tensor >= 0) parent[find(d.out_tensor)] = find(d.add_tensor);
+  }
+  for (int t = 0; t < T; t++)
+    if (writers[t] != 1) ok[t] = 0;
+  std::vector<char> class_ok(T, 1);
+  for (int t = 0; t < T; t++)
+    if (!ok[t]) class_ok[find(t)] = 0;
+  for (int root = 0; root < T; root++) {
+    if (find(root) != root || !class_ok[root]) continue;
+    const LayerState* best = nullptr;
+    double best_work = -1.0;
+    for (auto& S : net->layers) {
+      if (S.d.ipool || find(S.d.in_tensor) != root) continue;
+      const double w = (double)S.d.k * S.d.k * S.d.C * S.d.N * S.d.OH * S.d.OW;
+      if (w > best_work) { best_work = w; best = &S; }
+    }
+    if (!best) continue;
+    const std::vector<int> off = channel_offsets(*best);
+    const int C = (int)off.size();
+    if (*std::min_element(off.begin(), off.end()) == *std::max_element(off.begin(), off.end())) continue;
+    std::vector<int> order(C);
+    for (int c = 0; c < C; c++) order[c] = c;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return off[a] < off[b]; });
+    std::vector<int> pos(C);
+    for (int p = 0; p < C; p++) pos[order[p]] = p;
+    for (int t = 0; t < T; t++)
+      if (find(t) == root) net->tpos[t] = pos;
+  }
+}
+
+// Builds the device-side weight forms of every loaded layer (tf2b_finalize; the CPU test driver calls it directly).
+static int prepare_network(tf2b_net* net, bool permute) {
+  if (permute) choose_permutations(net);
+  else net->tpos.assign(net->tensors.size(), {});
+  for (auto& S : net->layers) {
+    if (S.d.ipool || S.prepared) continue;
+    if (S.h_codes.empty()) return fail(net, TF2B_ERR_STATE, "a layer has no weights loaded");
+    int rc = prepare_layer(net, S, S.h_codes.data(), S.h_params.data());
+    if (rc != TF2B_OK) return rc;
+  }
   return TF2B_OK;
 }
 
@@ -480,7 +588,14 @@ int tf2b_load_layer(tf2b_net* net, int layer, const uint8_t* codes, const tf2b_b
   LayerState& S = net->layers[layer];
   if (S.d.ipool) return fail(net, TF2B_ERR_ARG, "layer %d is an ipool pseudo layer (no weights)", layer);
   if (!codes || !params) return fail(net, TF2B_ERR_ARG, "null codes/params");
-  return prepare_layer(net, S, codes, params);
+  // The device-side weight forms depend on the channel order chosen for the tensors, which needs every layer's
+  // codes: keep a copy, build everything in tf2b_finalize (prepare_network)
+  const size_t cnt = (size_t)S.d.N * S.d.C * S.d.k * S.d.k;
+  S.h_codes.assign(codes, codes + cnt);
+  S.h_params.assign(params, params + S.d.N);
+  S.loaded = true;
+  S.prepared = false;
+  return TF2B_OK;
 }
 
 int tf2b_load_layer_packed4(tf2b_net* net, int layer, const uint8_t* nibbles, int min_exp,
@@ -573,12 +688,23 @@ static size_t layout_arena(tf2b_net* net) {
     S.off_nshift = off; off = align256(off + S.h_nshift.size());
     S.off_nshift_m = off; off = align256(off + S.h_nshift_m.size());
   }
+  net->off_tpos.assign(net->tensors.size(), 0);
+  net->off_tinv.assign(net->tensors.size(), 0);
+  for (size_t t = 0; t < net->tensors.size(); t++) {
+    if (t >= net->tpos.size() || net->tpos[t].empty()) continue;
+    net->off_tpos[t] = off; off = align256(off + net->tpos[t].size() * 4);
+    net->off_tinv[t] = off; off = align256(off + net->tpos[t].size() * 4);
+  }
   return off;
 }
 
 constexpr size_t kBlobFixed = 32;   // magic, layer count, hash of the layer / tensor tables, arena bytes
+struct BlobTensorMeta {             // channel order of a tensor (position of every logical channel), if it has one
+  int64_t off_pos, off_inv;
+  int32_t channels, has_order;
+};
 static size_t blob_header_bytes(const tf2b_net* net) {
-  return align256(kBlobFixed + net->layers.size() * sizeof(BlobLayerMeta));
+  return align256(kBlobFixed + net->layers.size() * sizeof(BlobLayerMeta) + net->tensors.size() * sizeof(BlobTensorMeta));
 }
 // FNV-1a over the tensor and layer tables: a blob only fits an engine created from the same tables
 static uint64_t tables_hash(const tf2b_net* net) {
@@ -613,6 +739,16 @@ int tf2b_finalize(tf2b_net* net, int max_images) {
   CUDA_TRY(net, tf2b::mma_prepare_device(&net->num_sms));
   CUDA_TRY(net, tf2b::sa_prepare_device());
   net->max_images = max_images;
+  {
+    bool any_raw = false;
+    for (auto& S : net->layers) any_raw = any_raw || (!S.d.ipool && !S.prepared);
+    if (any_raw) {   // (an imported blob brings prepared layers and their channel orders)
+      int rcp = prepare_network(net, net->permute);
+      if (rcp != TF2B_OK) return rcp;
+    }
+    if (net->tpos.size() != net->tensors.size()) net->tpos.assign(net->tensors.size(), {});
+    for (auto& S : net->layers) { S.h_codes.clear(); S.h_codes.shrink_to_fit(); }
+  }
   net->arena_bytes = layout_arena(net);
   CUDA_TRY(net, cudaMalloc(&net->arena, std::max<size_t>(net->arena_bytes, 256)));
   for (auto& S : net->layers) {
@@ -628,6 +764,13 @@ int tf2b_finalize(tf2b_net* net, int max_images) {
     CUDA_TRY(net, up(S.off_beta, S.h_beta.data(), (size_t)S.Npar * 4));
     CUDA_TRY(net, up(S.off_nshift, S.h_nshift.data(), S.h_nshift.size()));
     CUDA_TRY(net, up(S.off_nshift_m, S.h_nshift_m.data(), S.h_nshift_m.size()));
+  }
+  for (size_t t = 0; t < net->tensors.size(); t++) {
+    if (net->tpos[t].empty()) continue;
+    std::vector<int> inv(net->tpos[t].size());
+    for (size_t c = 0; c < inv.size(); c++) inv[net->tpos[t][c]] = (int)c;
+    CUDA_TRY(net, cudaMemcpy(net->arena + net->off_tpos[t], net->tpos[t].data(), inv.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(net, cudaMemcpy(net->arena + net->off_tinv[t], inv.data(), inv.size() * 4, cudaMemcpyHostToDevice));
   }
   int rc = alloc_runtime(net);
   if (rc != TF2B_OK) return rc;
@@ -866,6 +1009,8 @@ static int run_layers(tf2b_net* net, int B, cudaStream_t st0, int only_layer, in
     bool use_mma = S.kernel == 2 && S.mma_ok;
     ConvParams p = conv_params(net, S, B, cdst, cdstC, cres, resC, use_mma);
     p.acc_dump = acc_dump;
+    p.acc_perm = (acc_dump != nullptr && !net->tpos[d.out_tensor].empty())
+                     ? reinterpret_cast<const int*>(net->arena + net->off_tinv[d.out_tensor]) : nullptr;
     if (use_mma) {
       const tf2b::MmaHostParams hp = {S.h_bias.data(), S.h_alpha.data(), S.h_beta.data(), S.h_nshift_m.data()};
       CUDA_TRY(net, tf2b::launch_conv_mma(p, hp, S.planes_m, S.plane_shift_m, S.h_tmaps.data(), net->num_sms, st));
@@ -963,10 +1108,12 @@ static int check_run(tf2b_net* net, int n_images) {
 static int write_result(tf2b_net* net, int tensor, int B, int8_t* out_dev, int layout, cudaStream_t st) {
   const tf2b_tensor_desc& t = net->tensors[tensor];
   const int Cp = net->tpitch[tensor];
+  // logical channel c lives at position pos[c] of the stored tensor
+  const int* pos = net->tpos[tensor].empty() ? nullptr : reinterpret_cast<const int*>(net->arena + net->off_tpos[tensor]);
   if (layout == TF2B_LAYOUT_CHW) {
-    CUDA_TRY(net, tf2b::launch_hwc_to_chw(net->tbuf[tensor], out_dev, B, t.C, t.H, t.W, Cp, st));
+    CUDA_TRY(net, tf2b::launch_hwc_to_chw(net->tbuf[tensor], out_dev, B, t.C, t.H, t.W, Cp, pos, st));
   } else if (layout == TF2B_LAYOUT_HWC) {
-    CUDA_TRY(net, tf2b::launch_hwc_repitch(net->tbuf[tensor], out_dev, (size_t)B * t.H * t.W, t.C, Cp, t.C, 0, st));
+    CUDA_TRY(net, tf2b::launch_hwc_repitch(net->tbuf[tensor], out_dev, (size_t)B * t.H * t.W, t.C, Cp, t.C, 0, pos, st));
   } else {
     return fail(net, TF2B_ERR_ARG, "unknown layout %d", layout);
   }
@@ -989,7 +1136,7 @@ int tf2b_run(tf2b_net* net, const int8_t* in_dev, int in_layout, int n_images, i
                                           net->t0_neg_off, st));
   } else if (in_layout == TF2B_LAYOUT_HWC) {
     CUDA_TRY(net, tf2b::launch_hwc_repitch(in_dev, net->tbuf[0], (size_t)n_images * t0.H * t0.W, t0.C, t0.C,
-                                           net->tpitch[0], net->t0_neg_off, st));
+                                           net->tpitch[0], net->t0_neg_off, nullptr, st));
   } else {
     return fail(net, TF2B_ERR_ARG, "unknown layout %d", in_layout);
   }
@@ -1159,6 +1306,15 @@ int tf2b_export_weight_blob(tf2b_net* net, void* dev_dst, void* stream) {
     m.low_plane_m = S.low_plane_m; m.nshift_m_len = (int32_t)S.h_nshift_m.size(); m.fast_requant = S.fast_requant;
     memcpy(hdr.data() + kBlobFixed + l * sizeof m, &m, sizeof m);
   }
+  for (size_t t = 0; t < net->tensors.size(); t++) {
+    BlobTensorMeta tm;
+    memset(&tm, 0, sizeof tm);
+    tm.has_order = net->tpos[t].empty() ? 0 : 1;
+    tm.channels = (int32_t)net->tpos[t].size();
+    tm.off_pos = (int64_t)net->off_tpos[t];
+    tm.off_inv = (int64_t)net->off_tinv[t];
+    memcpy(hdr.data() + kBlobFixed + net->layers.size() * sizeof(BlobLayerMeta) + t * sizeof tm, &tm, sizeof tm);
+  }
   cudaStream_t st = (cudaStream_t)stream;
   CUDA_TRY(net, cudaMemcpyAsync(dev_dst, hdr.data(), hb, cudaMemcpyHostToDevice, st));
   CUDA_TRY(net, cudaMemcpyAsync((unsigned char*)dev_dst + hb, net->arena, net->arena_bytes, cudaMemcpyDeviceToDevice, st));
@@ -1217,6 +1373,24 @@ int tf2b_import_weight_blob(tf2b_net* net, const void* dev_src, int64_t blob_byt
     CUDA_TRY(net, pull(S.h_nshift_m, (size_t)m.nshift_m_len, m.off_nshift_m));
     S.low_plane_m = m.low_plane_m;
     S.fast_requant = m.fast_requant;
+    S.prepared = true;
+  }
+  net->tpos.assign(net->tensors.size(), {});
+  for (size_t t = 0; t < net->tensors.size(); t++) {
+    BlobTensorMeta tm;
+    memcpy(&tm, hdr.data() + kBlobFixed + net->layers.size() * sizeof(BlobLayerMeta) + t * sizeof tm, sizeof tm);
+    if (!tm.has_order) continue;
+    if (tm.channels != net->tensors[t].C || tm.off_pos < 0 || (uint64_t)tm.off_pos + (uint64_t)tm.channels * 4 > ab)
+      return fail(net, TF2B_ERR_ARG, "blob tensor %zu: channel order out of range", t);
+    net->tpos[t].resize(tm.channels);
+    CUDA_TRY(net, cudaMemcpy(net->tpos[t].data(), (const unsigned char*)dev_src + hb + tm.off_pos, (size_t)tm.channels * 4,
+                             cudaMemcpyDeviceToHost));
+    std::vector<char> seen(tm.channels, 0);
+    for (int c = 0; c < tm.channels; c++) {
+      const int ppos = net->tpos[t][c];
+      if (ppos < 0 || ppos >= tm.channels || seen[ppos]) return fail(net, TF2B_ERR_ARG, "blob tensor %zu: not a permutation", t);
+      seen[ppos] = 1;
+    }
   }
   return TF2B_OK;
 }

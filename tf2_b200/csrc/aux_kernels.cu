@@ -39,8 +39,9 @@ __global__ void chw_to_hwc_kernel(const int8_t* __restrict__ src, int8_t* __rest
 }
 
 // [B][H][W][Cp] (first C channels) -> [B][C][H][W]
+// pos != nullptr: logical channel c is stored at position pos[c]
 __global__ void hwc_to_chw_kernel(const int8_t* __restrict__ src, int8_t* __restrict__ dst, int B,
-                                  int C, int H, int W, int Cp) {
+                                  int C, int H, int W, int Cp, const int* __restrict__ pos) {
   size_t total = (size_t)B * C * H * W;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
        i += (size_t)gridDim.x * blockDim.x) {
@@ -50,13 +51,13 @@ __global__ void hwc_to_chw_kernel(const int8_t* __restrict__ src, int8_t* __rest
     t /= H;
     int c = (int)(t % C);
     int b = (int)(t / C);
-    dst[i] = src[(((size_t)b * H + h) * W + w) * Cp + c];
+    dst[i] = src[(((size_t)b * H + h) * W + w) * Cp + (pos ? pos[c] : c)];
   }
 }
 
 // [B][H][W][Cs] (first C channels) -> [B][H][W][Cd] dense copy with re-pitch (zero fill)
 __global__ void hwc_repitch_kernel(const int8_t* __restrict__ src, int8_t* __restrict__ dst,
-                                   size_t npix, int C, int Cs, int Cd, int neg_off) {
+                                   size_t npix, int C, int Cs, int Cd, int neg_off, const int* __restrict__ pos) {
   size_t total = npix * Cd;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
        i += (size_t)gridDim.x * blockDim.x) {
@@ -64,7 +65,7 @@ __global__ void hwc_repitch_kernel(const int8_t* __restrict__ src, int8_t* __res
     size_t pix = i / Cd;
     bool ng = neg_off > 0 && c >= neg_off;
     if (ng) c -= neg_off;
-    unsigned char x = c < C ? (unsigned char)src[pix * Cs + c] : (unsigned char)0;
+    unsigned char x = c < C ? (unsigned char)src[pix * Cs + (pos ? pos[c] : c)] : (unsigned char)0;
     if (ng) x = (unsigned char)(0u - x);
     dst[i] = (int8_t)x;
   }
@@ -200,15 +201,15 @@ cudaError_t launch_chw_to_hwc(const int8_t* src, int8_t* dst, int B, int C, int 
   return cudaGetLastError();
 }
 cudaError_t launch_hwc_to_chw(const int8_t* src, int8_t* dst, int B, int C, int H, int W, int Cp,
-                              cudaStream_t s) {
+                              const int* pos, cudaStream_t s) {
   size_t total = (size_t)B * C * H * W;
-  hwc_to_chw_kernel<<<grid_for(total, 256), 256, 0, s>>>(src, dst, B, C, H, W, Cp);
+  hwc_to_chw_kernel<<<grid_for(total, 256), 256, 0, s>>>(src, dst, B, C, H, W, Cp, pos);
   return cudaGetLastError();
 }
 cudaError_t launch_hwc_repitch(const int8_t* src, int8_t* dst, size_t npix, int C, int Cs, int Cd,
-                               int neg_off, cudaStream_t s) {
+                               int neg_off, const int* pos, cudaStream_t s) {
   size_t total = npix * Cd;
-  hwc_repitch_kernel<<<grid_for(total, 256), 256, 0, s>>>(src, dst, npix, C, Cs, Cd, neg_off);
+  hwc_repitch_kernel<<<grid_for(total, 256), 256, 0, s>>>(src, dst, npix, C, Cs, Cd, neg_off, pos);
   return cudaGetLastError();
 }
 cudaError_t launch_raw224_to_s2d(const int8_t* raw, int8_t* dst, int B, int dual, cudaStream_t s) {

@@ -20,6 +20,7 @@ struct ConvParams {
   const int32_t* beta;    // [Npad]
   const uint8_t* nshift;  // [Npad]  per-output-channel base shift factored out of the codes
   int32_t* acc_dump;      // optional [B][N][OH][OW] int32 accumulators (debug tap)
+  const int* acc_perm;    // tap: logical channel of output row n (the tensor's stored channel order), or nullptr
   int B, IH, IW, Cp, xC;
   int OH, OW, N, Npad, yC, rC;
   int k, pad, stride;

@@ -769,7 +769,12 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
     constexpr bool FOLD = FAST && (EPI & 8);
     constexpr bool HI32 = FOLD && (EPI & 16);
     constexpr bool TSTORE_GLOBAL = FOLD && MODE == 0;   // every channel has nshift >= 3: y = hi32(tot*(alpha<<(nshift-3)) + (B>>3))
-    constexpr int G = 1;                  // epilogue groups; group g owns the tiles with local index % G == g
+#ifndef TF2B_EPI_GROUPS
+#define TF2B_EPI_GROUPS 1
+#endif
+    // epilogue groups; group g owns the tiles with local index % G == g (two groups: the TMEM reads of one tile
+    // overlap the arithmetic of the other).  Flat folded layers only; everything else runs one group.
+    constexpr int G = (FOLD && MODE == 0 && !CG2 && BN == 128) ? TF2B_EPI_GROUPS : 1;
     constexpr int SLICES = 4 / G;         // column slices of a tile (one warp per lane quarter and slice)
     constexpr int WT = BN / SLICES;       // columns per warp: 16..128
     constexpr int W = WT > 32 ? 32 : WT;  // columns per pass (staging tile width)
@@ -1166,7 +1171,8 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
                   if (c.acc_dump != nullptr && dvalid && ncolp + cc + j < c.N) {
                     const int hw = c.OH * c.OW;
                     const int bimg = (int)(dpix / hw);
-                    c.acc_dump[((size_t)bimg * c.N + (ncolp + cc + j)) * hw + (int)(dpix - (long long)bimg * hw)] = a32;
+                    const int nl = c.acc_perm ? c.acc_perm[ncolp + cc + j] : ncolp + cc + j;
+                    c.acc_dump[((size_t)bimg * c.N + nl) * hw + (int)(dpix - (long long)bimg * hw)] = a32;
                   }
                   yy[u] = requant_raw(a32, aa[u], ee[u]);
                 }
@@ -1404,7 +1410,13 @@ void fill_geometry(MmaParams& P, const ConvParams& c, int planes8) {
       // The residual operand streams from HBM once; what hides its latency is the number of tiles in
       // flight (measured: with two buffers the producer idles on the ring).  Split shared memory into
       // whole tiles in flight: (activation stages of one tile + one residual tile) each.
-      static const int cap = env_int("TF2B_MMA_RBUFS", 2);   // measured: deeper rings do not help
+#ifndef TF2B_RBUFS_CAP
+#define TF2B_RBUFS_CAP 4
+#endif
+      // ring depth: the residual tile streams from HBM, and a slot is re-requested only when the epilogue has
+      // consumed it, so depth x tile bytes in flight have to cover the DRAM latency (with the lean epilogue the
+      // per-tile time of the 64 -> 256 layers was (latency + epilogue) / depth)
+      static const int cap = env_int("TF2B_MMA_RBUFS", TF2B_RBUFS_CAP);
       const int budget = 224 * 1024 - EPI_BYTES - P.res_bytes;
       const int per_tile = P.kchunks * stage_bytes + P.BN * 128;
       int t = budget / per_tile;
@@ -1697,7 +1709,7 @@ cudaError_t launch_conv_mma(const ConvParams& c, const MmaHostParams& /*hp*/, in
     const int bits = epi - 1;   // 8, 9, 12 or 13
     epi_idx = 17 + ((bits & 1) | ((bits & 4) >> 1));
   }
-  P.egroups = 1;
+  P.egroups = (fold && P.mode == 0 && !P.cg2 && P.BN == 128) ? TF2B_EPI_GROUPS : 1;
   const KernelTables& T = kernel_tables();
   KernelFn kfn = T.single[P.BN == 256 ? 2 : (P.BN == 128 ? 1 : 0)][P.mode][epi_idx];
   if (P.cg2) {

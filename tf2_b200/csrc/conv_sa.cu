@@ -339,7 +339,7 @@ conv_sa_kernel(const __grid_constant__ SaParams P, const __grid_constant__ SaMap
           const int row = ty + TYN * i;
           const int a32 = (int)((unsigned)bias + ((unsigned)acc[i][j] << nsh));
           if (c.acc_dump != nullptr && n < c.N && dump_off[i] >= 0)
-            c.acc_dump[(size_t)dump_off[i] + (size_t)n * (size_t)(c.OH * c.OW)] = a32;
+            c.acc_dump[(size_t)dump_off[i] + (size_t)(c.acc_perm ? c.acc_perm[n] : n) * (size_t)(c.OH * c.OW)] = a32;
           int y = requant(a32, alpha, beta);
           if (c.relu) y = max(y, 0);
           Cs[row * CS_STRIDE + tx + 16 * j] = (unsigned char)(signed char)y;

@@ -33,3 +33,22 @@ for r in body:
 print("total warp instructions", tot)
 for op, n in ops.most_common(top):
     print(f"{op:16s} {n:12d} {100.0*n/tot:5.1f}%  samples {samples[op]}")
+# hottest individual SASS lines by warp-stall samples (where the warps sit), with the stall-reason columns the
+# source page carries
+stall_cols = [h for h in hdr if h.lower().startswith("stall_") or "stall" in h.lower()]
+tot_s = sum(int(r[ix["# Samples"]] or 0) for r in body)
+print(f"total samples {tot_s}; stall columns: {stall_cols[:24]}")
+order = sorted(range(len(body)), key=lambda i: -int(body[i][ix["# Samples"]] or 0))[:top]
+for i in order:
+    r = body[i]
+    s = int(r[ix["# Samples"]] or 0)
+    why = []
+    for h in stall_cols:
+        try:
+            v = int(r[ix[h]] or 0)
+        except ValueError:
+            continue
+        if v > 0 and h != "# Samples":
+            why.append((v, h))
+    why = " ".join(f"{h}={v}" for v, h in sorted(why, reverse=True)[:3])
+    print(f"{i:6d} samples {s:7d} ({100.0*s/max(1,tot_s):4.1f}%) exec {r[ix['Instructions Executed']]:>9s}  {r[ix['Source']].strip()[:70]:70s} {why}")
