@@ -46,6 +46,15 @@ static long long check_planes(const tf2b_net* net, const LayerState& S, const ui
   const int C = d.C, N = d.N, k = d.k;
   const bool quirk = d.in_may_be_m128 != 0;
   long long bad = 0;
+  // stored position of a logical input / output channel (the engine may reorder the channels of inner tensors)
+  const std::vector<int>* vin = net->tpos[d.in_tensor].empty() ? nullptr : &net->tpos[d.in_tensor];
+  const std::vector<int>* vout = net->tpos[d.out_tensor].empty() ? nullptr : &net->tpos[d.out_tensor];
+  auto pin = [&](int c) { return vin ? (*vin)[c] : c; };
+  auto pout = [&](int n) { return vout ? (*vout)[n] : n; };
+  if (vin) {   // a permutation, and sorted by the consumer-side offset classes it was derived for
+    std::vector<char> seen(vin->size(), 0);
+    for (int v : *vin) { if (v < 0 || v >= (int)vin->size() || seen[v]) { snprintf(why, 200, "input order is not a permutation"); return 1; } seen[v] = 1; }
+  }
   // ---- shift-accumulate kernel: packed 4-bit codes in segments.  weight = +-2^e << seg_shift << base[n]; a segment
   //      flagged "neg" multiplies the int8-negated activation (stands for negative weights of a layer whose input may
   //      hold -128), and for tensor 0 the negative weights sit as magnitudes on the channels of its negated copy
@@ -66,12 +75,12 @@ static long long check_planes(const tf2b_net* net, const LayerState& S, const ui
           decode(codes[((size_t)n * C + c) * k * k + t], sign, shift);
           long long pos[2] = {0, 0}, neg[2] = {0, 0};   // [half]: plain / negated-copy channel; pos / neg: plain / negating segment
           for (int half = 0; half < (dual ? 2 : 1); half++) {
-            const size_t kidx = (size_t)t * cchunks * KC + (half ? S.Cp + c : c);
+            const size_t kidx = (size_t)t * cchunks * KC + (half ? S.Cp + c : pin(c));
             for (int g = 0; g < S.nseg_s; g++) {
-              const uint8_t byte = S.h_w4[((size_t)g * S.Npad_s + n) * row_bytes + kidx / 2];
+              const uint8_t byte = S.h_w4[((size_t)g * S.Npad_s + pout(n)) * row_bytes + kidx / 2];
               const unsigned nib = (kidx & 1) ? (byte >> 4) : (byte & 15);
               if ((nib & 7) == 7) { if (nib & 8) { if (!bad) snprintf(why, 200, "negative zero code"); bad++; } continue; }
-              long long v = (1ll << (nib & 7)) * (1ll << S.seg_shift_s[g]) * (1ll << S.h_nshift[n]);
+              long long v = (1ll << (nib & 7)) * (1ll << S.seg_shift_s[g]) * (1ll << S.h_nshift[pout(n)]);
               if (nib & 8) v = -v;
               if (S.seg_neg_s[g]) neg[half] += v; else pos[half] += v;
             }
@@ -106,18 +115,18 @@ static long long check_planes(const tf2b_net* net, const LayerState& S, const ui
           decode(codes[((size_t)n * C + c) * k * k + t], sign, shift);
           long long got[2] = {0, 0};   // [0]: multiplies channel c, [1]: multiplies the negated copy Cp + c
           for (int half = 0; half < (dual ? 2 : 1); half++) {
-            const int cc = half ? S.Cp + c : c;
+            const int cc = half ? S.Cp + c : pin(c);
             size_t kidx = (size_t)t * Cpm + cc;
             if (pair) {
               const int fh = t / k, fw = t - fh * k;
               kidx = (size_t)fh * Cpm + (size_t)(fw / 2) * 128 + (size_t)(fw & 1) * 64 + cc;
             }
             for (int p = 0; p < S.planes_m; p++) {
-              long long v = S.h_w8[((size_t)p * S.Npad_m + n) * S.Kp_m + kidx];
+              long long v = S.h_w8[((size_t)p * S.Npad_m + pout(n)) * S.Kp_m + kidx];
               if (v && (v & (v - 1)) && ((-v) & (-v - 1))) { if (!bad) snprintf(why, 200, "w8 not a power of two"); bad++; }
               if (v > 64 || v < -64) { if (!bad) snprintf(why, 200, "w8 magnitude above 2^6"); bad++; }
               v *= 1ll << S.plane_shift_m[p];
-              if (p != S.low_plane_m) v *= 1ll << S.h_nshift_m[n];
+              if (p != S.low_plane_m) v *= 1ll << S.h_nshift_m[pout(n)];
               got[half] += v;
             }
           }
@@ -158,7 +167,8 @@ int main(int argc, char** argv) {
   for (int t = 0; t < n_tensors; t++) net.tbuf[t] = reinterpret_cast<int8_t*>((uintptr_t)0x100000000ull + (uintptr_t)t * 0x10000000ull);
   net.scratch0 = reinterpret_cast<int8_t*>((uintptr_t)0x4000000000ull);
   tf2b_net net4 = net;
-  int rc_all = 0;
+  struct Case { const uint8_t* codes; const tf2b_bias_bn* params; int has4; int rc; int rc4; };
+  std::vector<Case> cases(n_layers, Case{nullptr, nullptr, 0, 0, 0});
   for (int l = 0; l < n_layers; l++) {
     tf2b_layer_desc d;
     memcpy(&d, r.bytes(sizeof d), sizeof d);
@@ -166,21 +176,34 @@ int main(int argc, char** argv) {
     net4.layers[l].d = d;
     if (d.ipool) continue;                       // pseudo layer: no weights follow in the case file
     const size_t cnt = (size_t)d.N * d.C * d.k * d.k;
-    const uint8_t* codes = r.bytes(cnt);
-    const tf2b_bias_bn* params = (const tf2b_bias_bn*)r.bytes(sizeof(tf2b_bias_bn) * d.N);
-    const int has4 = r.i32();
-    int rc = tf2b_load_layer(&net, l, codes, params);
-    char why[200] = "";
-    long long bad = rc == TF2B_OK ? check_planes(&net, net.layers[l], codes, why) : -1;
-    int same4 = -1;
-    if (has4) {
+    cases[l].codes = r.bytes(cnt);
+    cases[l].params = (const tf2b_bias_bn*)r.bytes(sizeof(tf2b_bias_bn) * d.N);
+    cases[l].has4 = r.i32();
+    cases[l].rc = tf2b_load_layer(&net, l, cases[l].codes, cases[l].params);
+    if (cases[l].has4) {
       const int min_exp = r.i32();
       const uint8_t* nib = r.bytes((cnt + 1) / 2);
       const int8_t* q_in = (const int8_t*)r.bytes(d.C);
       const int8_t* q_out = (const int8_t*)r.bytes(d.N);
-      int rc4 = tf2b_load_layer_packed4(&net4, l, nib, min_exp, q_in, q_out, params);
-      same4 = rc4 == TF2B_OK && same_state(net.layers[l], net4.layers[l]);
+      cases[l].rc4 = tf2b_load_layer_packed4(&net4, l, nib, min_exp, q_in, q_out, cases[l].params);
+    } else {
+      cases[l].rc4 = tf2b_load_layer(&net4, l, cases[l].codes, cases[l].params);
     }
+  }
+  // what tf2b_finalize does before anything touches the device: channel orders, then every layer's weight forms
+  const int rcp = prepare_network(&net, true), rcp4 = prepare_network(&net4, true);
+  int rc_all = (rcp != TF2B_OK || rcp4 != TF2B_OK) ? 1 : 0;
+  int n_ordered = 0;
+  for (auto& v : net.tpos) n_ordered += !v.empty();
+  printf("prepare rc=%d rc4=%d ordered_tensors=%d %s\n", rcp, rcp4, n_ordered, net.err.c_str());
+  for (int l = 0; l < n_layers; l++) {
+    const tf2b_layer_desc d = net.layers[l].d;
+    if (d.ipool) continue;
+    const int rc = cases[l].rc != TF2B_OK ? cases[l].rc : rcp;
+    char why[200] = "";
+    long long bad = rc == TF2B_OK ? check_planes(&net, net.layers[l], cases[l].codes, why) : -1;
+    int same4 = -1;
+    if (cases[l].has4) same4 = cases[l].rc4 == TF2B_OK && same_state(net.layers[l], net4.layers[l]) && net.tpos == net4.tpos;
     const LayerState& S = net.layers[l];
     // launch plan of the tensor-core path for a batch of B images: what tf2b_layer_mode reports after finalize
     // (geometry only: the buffer addresses are placeholders, nothing is dereferenced)

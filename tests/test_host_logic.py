@@ -64,6 +64,8 @@ def _run(exe, path, batch=256):
     r = subprocess.run([exe, path, str(batch)], capture_output=True, text=True, timeout=600)
     rows = []
     for line in r.stdout.splitlines():
+        if not line.startswith("layer "):
+            continue
         kv = dict(tok.split("=", 1) for tok in line.split()[2:] if "=" in tok)
         rows.append({k: (v if k == "mode" else int(v)) for k, v in kv.items()})
     return r.returncode, rows, r.stdout

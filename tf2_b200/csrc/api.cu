@@ -19,8 +19,8 @@
 
 namespace tf2b {
 // CUDA-core shift-accumulate path (conv_sa.cu)
-cudaError_t launch_conv_sa(const ConvParams& p, int nseg, const int* seg_shift, const int* seg_neg, const void* tmaps,
-                           int ksplit, int num_sms, cudaStream_t stream);
+cudaError_t launch_conv_sa(const ConvParams& p, int nseg, const int* seg_shift, const int* seg_neg, const int* seg_cbeg,
+                           const int* seg_cend, const void* tmaps, int ksplit, int num_sms, cudaStream_t stream);
 cudaError_t sa_prepare_device();
 int sa_kc(int Cp);
 int sa_npad(int N);
@@ -72,6 +72,8 @@ struct LayerState {
   int Npad_s = 0, Kp_s = 0, Cp_s = 0, nseg_s = 0, ksplit_s = 0;
   int seg_shift_s[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // descending: the kernel combines the segment sums by Horner's rule
   int seg_neg_s[8] = {0, 0, 0, 0, 0, 0, 0, 0};     // 1: the segment multiplies the int8-negated activations
+  int seg_cbeg_s[8] = {0, 0, 0, 0, 0, 0, 0, 0};    // channel chunks [cbeg, cend) of every tap the segment spans
+  int seg_cend_s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   std::vector<uint8_t> h_w4;
   std::vector<unsigned char> h_tmaps_s;
   // --- mma kernel (int8 planes) ---
@@ -95,7 +97,7 @@ struct LayerState {
 };
 
 struct BlobLayerMeta {  // fixed-size, trivially copyable: travels inside the weight blob
-  int32_t loaded, Cp, Cp_m, Npad_s, Kp_s, Cp_s, nseg_s, seg_shift_s[8], seg_neg_s[8];
+  int32_t loaded, Cp, Cp_m, Npad_s, Kp_s, Cp_s, nseg_s, seg_shift_s[8], seg_neg_s[8], seg_cbeg_s[8], seg_cend_s[8];
   int32_t Npad_m, Kp_m, planes_m, plane_shift_m[4], mma_ok, Npar, low_plane_m, nshift_m_len, fast_requant;
   int64_t off_w4, off_w8, off_bias, off_alpha, off_beta, off_nshift, off_nshift_m;
 };
@@ -214,12 +216,16 @@ static int prepare_layer(tf2b_net* net, LayerState& S, const uint8_t* codes,
   }
   const bool quirk = d.in_may_be_m128 != 0;
   // ---- shift-accumulate kernel: 4-bit codes (bit 3 = negative, bits 0..2 = exponent e in 0..6, 7 = zero) in
-  //      segments of 7 exponent levels: shift = base[n] + 7 * level + e.  The int8 negate quirk (pe.cl:32-34) is
-  //      carried either by the negated copy of tensor 0 (extra channels, positive magnitudes) or, for any other
-  //      tensor that may hold -128, by segments that multiply the byte-negated activations.
+  //      segments: shift = base[n] + D + e with one D per segment.  Two ways to pick D, the cheaper one wins:
+  //        plain levels    D = 7 * floor(rel / 7): every segment walks the whole K range;
+  //        offset classes  D = off[c] + 7 * floor((rel - off[c]) / 7) with off[c] the input channel's own offset
+  //                        (q_in[c] - min q_in): when the tensor's channels are ordered by that offset a segment
+  //                        only spans the chunks of its class and K is walked ONCE in total.
+  //      The int8 negate quirk (pe.cl:32-34) is carried either by the negated copy of tensor 0 (extra channels,
+  //      positive magnitudes) or, for any other tensor that may hold -128, by segments that multiply the
+  //      byte-negated activations.
   {
     const int lv = 7;
-    const int np = max_rel / lv + 1;
     const bool dual_s = quirk && d.in_tensor == 0 && S.Cp == net->t0_neg_off;
     const bool negseg = quirk && !dual_s;
     S.Cp_s = dual_s ? 2 * S.Cp : S.Cp;
@@ -227,43 +233,79 @@ static int prepare_layer(tf2b_net* net, LayerState& S, const uint8_t* codes,
     const int cchunks = (S.Cp_s + KC - 1) / KC;
     S.Npad_s = tf2b::sa_npad(N);
     S.Kp_s = k * k * cchunks * KC;
-    // candidate segments (level, negated) in descending shift order; empty ones are dropped
-    std::vector<std::vector<uint8_t>> rows;
-    S.nseg_s = 0;
-    for (int lvl = np - 1; lvl >= 0; lvl--)
-      for (int ng = 0; ng < (negseg ? 2 : 1); ng++) {
-        std::vector<uint8_t> w4((size_t)S.Npad_s * (S.Kp_s / 2), 0x77);
-        bool any = false;
-        for (int n = 0; n < N; n++)
-          for (int c = 0; c < C; c++)
-            for (int t = 0; t < k * k; t++) {
-              const uint8_t cd = codes[((size_t)n * C + c) * k * k + t];
-              if (cd & 0x40) continue;
-              const int rel = (cd & 0x1f) - base[n];
-              if (rel / lv != lvl) continue;
-              const bool negw = (cd & 0x80) != 0;
-              if (negseg && (negw ? 1 : 0) != ng) continue;
-              int cc = pin(c);
-              unsigned nib = (unsigned)(rel - lvl * lv);
-              if (negw) {
-                if (dual_s) cc = S.Cp + c;          // magnitude times the negated copy (tensor 0 keeps its order)
-                else if (!negseg) nib |= 8u;        // plain negative weight
-              }
-              const size_t kidx = ((size_t)t * cchunks * KC) + cc;
-              uint8_t& byte = w4[(size_t)pout(n) * (S.Kp_s / 2) + kidx / 2];
-              byte = (kidx & 1) ? (uint8_t)((byte & 0x0f) | (nib << 4)) : (uint8_t)((byte & 0xf0) | nib);
-              any = true;
-            }
-        if (!any && !(lvl == 0 && ng == 0 && S.nseg_s == 0)) continue;   // keep one segment for an all-zero layer
-        if (S.nseg_s >= tf2b::sa_max_segments())
-          return fail(net, TF2B_ERR_ARG, "layer needs more than %d weight segments", tf2b::sa_max_segments());
-        S.seg_shift_s[S.nseg_s] = lv * lvl;
-        S.seg_neg_s[S.nseg_s] = ng;
-        S.nseg_s++;
-        rows.push_back(std::move(w4));
-      }
-    S.h_w4.clear();
-    for (auto& r : rows) S.h_w4.insert(S.h_w4.end(), r.begin(), r.end());
+    const int kk = k * k;
+    // per input channel: smallest relative shift of any of its weights
+    std::vector<int> off(C, 99);
+    for (int n = 0; n < N; n++)
+      for (int c = 0; c < C; c++)
+        for (int t = 0; t < kk; t++) {
+          const uint8_t cd = codes[((size_t)n * C + c) * kk + t];
+          if (!(cd & 0x40)) off[c] = std::min(off[c], (cd & 0x1f) - base[n]);
+        }
+    for (int c = 0; c < C; c++) if (off[c] == 99) off[c] = 0;
+    struct Seg { int D, ng, cb, ce; };
+    auto plan = [&](bool classes, std::vector<Seg>& segs) -> long long {
+      segs.clear();
+      for (int n = 0; n < N; n++)
+        for (int c = 0; c < C; c++)
+          for (int t = 0; t < kk; t++) {
+            const uint8_t cd = codes[((size_t)n * C + c) * kk + t];
+            if (cd & 0x40) continue;
+            const int rel = (cd & 0x1f) - base[n];
+            const int o = classes ? off[c] : 0;
+            const int D = o + lv * ((rel - o) / lv);
+            const bool negw = (cd & 0x80) != 0;
+            const int ng = (negseg && negw) ? 1 : 0;
+            const int cc = (negw && dual_s) ? S.Cp + c : pin(c);
+            const int chunk = cc / KC;
+            Seg* f = nullptr;
+            for (auto& sg : segs) if (sg.D == D && sg.ng == ng) { f = &sg; break; }
+            if (!f) { segs.push_back({D, ng, chunk, chunk + 1}); continue; }
+            f->cb = std::min(f->cb, chunk);
+            f->ce = std::max(f->ce, chunk + 1);
+          }
+      if (segs.empty()) segs.push_back({0, 0, 0, cchunks});
+      std::sort(segs.begin(), segs.end(), [](const Seg& a, const Seg& b) { return a.D != b.D ? a.D > b.D : a.ng < b.ng; });
+      long long cost = 0;
+      for (auto& sg : segs) cost += sg.ce - sg.cb;
+      return (int)segs.size() <= tf2b::sa_max_segments() ? cost : -1;
+    };
+    std::vector<Seg> seg_plain, seg_class;
+    const long long cost_plain = plan(false, seg_plain), cost_class = plan(true, seg_class);
+    if (cost_plain < 0 && cost_class < 0)
+      return fail(net, TF2B_ERR_ARG, "layer needs more than %d weight segments", tf2b::sa_max_segments());
+    const bool classes = cost_class >= 0 && (cost_plain < 0 || cost_class < cost_plain);
+    const std::vector<Seg>& segs = classes ? seg_class : seg_plain;
+    S.nseg_s = (int)segs.size();
+    for (int g = 0; g < 8; g++) {
+      S.seg_shift_s[g] = g < S.nseg_s ? segs[g].D : 0;
+      S.seg_neg_s[g] = g < S.nseg_s ? segs[g].ng : 0;
+      S.seg_cbeg_s[g] = g < S.nseg_s ? segs[g].cb : 0;
+      S.seg_cend_s[g] = g < S.nseg_s ? segs[g].ce : 0;
+    }
+    S.h_w4.assign((size_t)S.nseg_s * S.Npad_s * (S.Kp_s / 2), 0x77);
+    for (int n = 0; n < N; n++)
+      for (int c = 0; c < C; c++)
+        for (int t = 0; t < kk; t++) {
+          const uint8_t cd = codes[((size_t)n * C + c) * kk + t];
+          if (cd & 0x40) continue;
+          const int rel = (cd & 0x1f) - base[n];
+          const int o = classes ? off[c] : 0;
+          const int D = o + lv * ((rel - o) / lv);
+          const bool negw = (cd & 0x80) != 0;
+          const int ng = (negseg && negw) ? 1 : 0;
+          int g = 0;
+          while (g < S.nseg_s && !(segs[g].D == D && segs[g].ng == ng)) g++;
+          int cc = pin(c);
+          unsigned nib = (unsigned)(rel - D);
+          if (negw) {
+            if (dual_s) cc = S.Cp + c;          // magnitude times the negated copy (tensor 0 keeps its order)
+            else if (!negseg) nib |= 8u;        // plain negative weight
+          }
+          const size_t kidx = ((size_t)t * cchunks * KC) + cc;
+          uint8_t& byte = S.h_w4[((size_t)g * S.Npad_s + pout(n)) * (S.Kp_s / 2) + kidx / 2];
+          byte = (kidx & 1) ? (uint8_t)((byte & 0x0f) | (nib << 4)) : (uint8_t)((byte & 0xf0) | nib);
+        }
   }
   // ---- mma kernel planes: int8 +-2^e, e in 0..6.  A layer whose input may hold -128 can use the
   //      tensor cores only when that input is tensor 0 (which carries the negated copy): positive
@@ -1015,8 +1057,8 @@ static int run_layers(tf2b_net* net, int B, cudaStream_t st0, int only_layer, in
       const tf2b::MmaHostParams hp = {S.h_bias.data(), S.h_alpha.data(), S.h_beta.data(), S.h_nshift_m.data()};
       CUDA_TRY(net, tf2b::launch_conv_mma(p, hp, S.planes_m, S.plane_shift_m, S.h_tmaps.data(), net->num_sms, st));
     } else {
-      CUDA_TRY(net, tf2b::launch_conv_sa(p, S.nseg_s, S.seg_shift_s, S.seg_neg_s, S.h_tmaps_s.data(), S.ksplit_s,
-                                         net->num_sms, st));
+      CUDA_TRY(net, tf2b::launch_conv_sa(p, S.nseg_s, S.seg_shift_s, S.seg_neg_s, S.seg_cbeg_s, S.seg_cend_s,
+                                         S.h_tmaps_s.data(), S.ksplit_s, net->num_sms, st));
     }
     launches++;
     if (prof) CUDA_TRY(net, cudaEventRecord(net->ev[3 * l + 1], st));
@@ -1300,7 +1342,10 @@ int tf2b_export_weight_blob(tf2b_net* net, void* dev_dst, void* stream) {
     m.loaded = S.loaded; m.Cp = S.Cp; m.Cp_m = S.Cp_m; m.Npad_s = S.Npad_s; m.Kp_s = S.Kp_s; m.Cp_s = S.Cp_s; m.nseg_s = S.nseg_s;
     m.Npad_m = S.Npad_m; m.Kp_m = S.Kp_m; m.planes_m = S.planes_m; m.mma_ok = S.planes_m > 0; m.Npar = S.Npar;
     for (int i = 0; i < 4; i++) m.plane_shift_m[i] = S.plane_shift_m[i];
-    for (int i = 0; i < 8; i++) { m.seg_shift_s[i] = S.seg_shift_s[i]; m.seg_neg_s[i] = S.seg_neg_s[i]; }
+    for (int i = 0; i < 8; i++) {
+      m.seg_shift_s[i] = S.seg_shift_s[i]; m.seg_neg_s[i] = S.seg_neg_s[i];
+      m.seg_cbeg_s[i] = S.seg_cbeg_s[i]; m.seg_cend_s[i] = S.seg_cend_s[i];
+    }
     m.off_w4 = S.off_w4; m.off_w8 = S.off_w8; m.off_bias = S.off_bias; m.off_alpha = S.off_alpha;
     m.off_beta = S.off_beta; m.off_nshift = S.off_nshift; m.off_nshift_m = S.off_nshift_m;
     m.low_plane_m = S.low_plane_m; m.nshift_m_len = (int32_t)S.h_nshift_m.size(); m.fast_requant = S.fast_requant;
@@ -1355,7 +1400,12 @@ int tf2b_import_weight_blob(tf2b_net* net, const void* dev_src, int64_t blob_byt
     if (S.nseg_s < 1 || S.nseg_s > 8 || S.planes_m < 0 || S.planes_m > tf2b::kMaxPlanes)
       return fail(net, TF2B_ERR_ARG, "blob layer %zu: segment / plane counts out of range", l);
     for (int i = 0; i < 4; i++) S.plane_shift_m[i] = m.plane_shift_m[i];
-    for (int i = 0; i < 8; i++) { S.seg_shift_s[i] = m.seg_shift_s[i]; S.seg_neg_s[i] = m.seg_neg_s[i]; }
+    for (int i = 0; i < 8; i++) {
+      S.seg_shift_s[i] = m.seg_shift_s[i]; S.seg_neg_s[i] = m.seg_neg_s[i];
+      S.seg_cbeg_s[i] = m.seg_cbeg_s[i]; S.seg_cend_s[i] = m.seg_cend_s[i];
+      if (i < S.nseg_s && (S.seg_cbeg_s[i] < 0 || S.seg_cend_s[i] <= S.seg_cbeg_s[i] || S.seg_cend_s[i] > 4096))
+        return fail(net, TF2B_ERR_ARG, "blob layer %zu: segment range out of bounds", l);
+    }
     // pull the arrays back to the host so finalize() can lay out and upload them uniformly
     auto pull = [&](auto& vec, size_t count, int64_t off) -> cudaError_t {
       // every array must lie inside the arena part of the blob the caller handed over

@@ -450,7 +450,7 @@ __device__ __forceinline__ unsigned add_res_s8x4(unsigned y4, unsigned r4) {
 // ((beta + 2^14) << 20))) >> 35 with tot = plane0 + (plane1 << 7) — one IMAD.HI per output; bit4 (with
 // bit3) = every nshift >= 3, so alpha << (nshift-3) and the addend >> 3 make the high word the result.
 template <int BN, int MODE, int EPI, bool CG2 = false>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __maxnreg__(112)   // 576 threads x 112 registers = 64 512 of the 65 536 (launch bounds alone cap at 96)
 conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ TmapPair maps) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // carve: [resident weight slab] [stages][A | B planes] (1024-aligned) [epilogue scratch]
@@ -869,7 +869,138 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
     int e_mt = 0, e_nt = 0;
     const int step_mt = fdiv(G * q_step, P.d_ntiles), step_nt = G * q_step - step_mt * P.n_tiles;
     int li = group;   // CTA-local tile index
-    for (int q = q_first + group * q_step; q < q_count; q += G * q_step, li += G) {
+    bool lean_done = false;
+    // ================= lean tile loop: flat layers with the folded epilogue.  Nothing in it depends on the lane's
+    // pixel: the residual tile comes from the TMA ring and the finished rows leave through a TMA store (rows past
+    // the end of the tensor are clipped by the hardware; rows of images beyond this run's batch are don't-cares),
+    // so a warp does no address arithmetic at all.  The W accumulators of a pass are read by ONE tcgen05.ld and
+    // the TMEM buffer goes back to the MMA warp BEFORE the arithmetic of the last pass.
+    if constexpr (FOLD && MODE == 0) {
+      if (P.tstore != 0 && (!CT_RES || res_tma) && !(kExp && (P.noepi != 0 || P.dbg != nullptr))) {
+        lean_done = true;
+        const unsigned t_row_w = tmem_base + ((unsigned)(quarter * 32) << 16) + slice * WT;
+        const int res_bufs = P.res_bufs;
+        int lrb = group % res_bufs;
+        unsigned lrph = (unsigned)(group / res_bufs) & 1u;
+        for (int q = q_first + group * q_step; q < q_count; q += G * q_step, li += G) {
+          const int lbuf = li & 1;
+          const unsigned ltph = (unsigned)(li >> 1) & 1u;
+          int m0, n0;
+          if constexpr (!cg2) {
+            if (li == group) {
+              e_mt = fdiv(q, P.d_ntiles);
+              e_nt = q - e_mt * P.n_tiles;
+            } else {
+              e_mt += step_mt;
+              e_nt += step_nt;
+              if (e_nt >= P.n_tiles) { e_nt -= P.n_tiles; e_mt++; }
+            }
+            m0 = e_mt * MMA_M;
+            n0 = (P.n_tile0 + e_nt) * BN;
+          } else {
+            const TileCoord tc = decode_tile(P, tile_of(q));
+            m0 = tc.m0;
+            n0 = tc.n0;
+          }
+          const int ncolw = n0 + slice * WT;
+          if (ncolw != cached_ncol0) {   // {A, B} of this warp's WT channels -> its private smem slice
+            __syncwarp();
+            cached_ncol0 = ncolw;
+            for (int i = lane; i < WT; i += 32) {
+              const int nn = ncolw + i;
+              const long long al = __ldg(c.alpha + nn), bi = __ldg(c.bias + nn), be = __ldg(c.beta + nn);
+              const int nsh = (int)__ldg(c.nshift + nn);
+              const long long b64 = bi * al + ((be + 16384ll) << 20);
+              prm[i] = HI32 ? (int)((unsigned)al << (nsh - 3)) : (int)((unsigned)al << nsh);
+              reinterpret_cast<long long*>(prm + PSTR)[i] = HI32 ? (b64 >> 3) : b64;
+            }
+            __syncwarp();
+          }
+          mbar_wait(e_tfull + 8 * lbuf, ltph);
+          tc_fence_after();
+          if (CT_RES) mbar_wait(rfull_bar + 8 * lrb, lrph);
+          const unsigned t_row0 = t_row_w + lbuf * acc_cols;
+          const unsigned rbase = smem_rres + lrb * res_tile + my_row * 128;
+#pragma unroll
+          for (int pass = 0; pass < PASSES; pass++) {
+            unsigned tot[W], tot1[W];
+            if constexpr (W == 32) {
+              tmem_ld32(t_row0 + pass * W, tot);
+              if (CT_TWO) tmem_ld32(t_row0 + BN + pass * W, tot1);
+            } else {
+              tmem_ld16(t_row0 + pass * W, tot);
+              if (CT_TWO) tmem_ld16(t_row0 + BN + pass * W, tot1);
+            }
+            tmem_ld_wait();
+            if (pass == PASSES - 1) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) {
+                if constexpr (cg2) mbar_arrive_leader(e_tempty + 8 * lbuf);
+                else mbar_arrive(e_tempty + 8 * lbuf);
+              }
+            }
+            uint4 resq[SEGS];
+            if (CT_RES) {
+              const int col = slice * WT + pass * W;
+              const unsigned rb2 = rbase + (col >> 7) * (128 * 128);
+#pragma unroll
+              for (int sq = 0; sq < SEGS; sq++) {
+                const int chunk = ((col & 127) >> 4) + sq;
+                const unsigned a = rb2 + (unsigned)(((chunk ^ (my_row & 7)) & 7) << 4);
+                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(resq[sq].x), "=r"(resq[sq].y), "=r"(resq[sq].z), "=r"(resq[sq].w) : "r"(a));
+              }
+            }
+            unsigned char* sbuf = stage + ((tsel + pass) & 1) * 1024;
+#pragma unroll
+            for (int cc = 0; cc < W; cc += 16) {
+              const uint4 rq = CT_RES ? resq[cc / 16] : make_uint4(0, 0, 0, 0);
+              const unsigned rw[4] = {rq.x, rq.y, rq.z, rq.w};
+              unsigned packed[4];
+              const int pc = pass * W + cc;
+#pragma unroll
+              for (int j4 = 0; j4 < 4; j4++) {
+                const int4 pa = *reinterpret_cast<const int4*>(prm + pc + 4 * j4);
+                const longlong2 pb0 = *reinterpret_cast<const longlong2*>(prm + PSTR + 2 * (pc + 4 * j4));
+                const longlong2 pb1 = *reinterpret_cast<const longlong2*>(prm + PSTR + 2 * (pc + 4 * j4) + 4);
+                const int aa[4] = {pa.x, pa.y, pa.z, pa.w};
+                const long long bq[4] = {pb0.x, pb0.y, pb1.x, pb1.y};
+                int yy[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                  const int j = cc + 4 * j4 + u;
+                  const int tt = CT_TWO ? (int)(tot1[j] * 128u + tot[j]) : (int)tot[j];
+                  const long long tq = (long long)tt * (long long)aa[u] + bq[u];   // IMAD.HI with the 64-bit addend
+                  yy[u] = HI32 ? (int)(tq >> 32) : (int)(tq >> 35);
+                }
+                unsigned y4 = pack_sat4(yy[0], yy[1], yy[2], yy[3]);
+                if (conv_relu) y4 = relu_s8x4(y4);
+                if (CT_RES) y4 = add_relu ? add_res_s8x4<true>(y4, rw[j4]) : add_res_s8x4<false>(y4, rw[j4]);
+                packed[j4] = y4;
+              }
+              const int chunk = (W == 32) ? ((cc >> 4) ^ ((lane >> 2) & 1)) : 0;
+              *reinterpret_cast<uint4*>(sbuf + lane * W + chunk * 16) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(smem_u32(sbuf), &maps.y, ncolw + pass * W, m0 + quarter * 32);
+              tma_store_commit();
+              tma_store_wait_read<1>();   // the other staging tile (written next) has been read out
+            }
+            __syncwarp();
+          }
+          if (CT_RES) {
+            if (lane == 0) mbar_arrive(rempty_bar + 8 * lrb);
+            lrb += G;
+            if (lrb >= res_bufs) { lrb -= res_bufs; lrph ^= 1u; }
+          }
+          tsel = (tsel + PASSES) & 1;
+        }
+      }
+    }
+    // ================= generic tile loop (every other mode)
+    for (int q = q_first + group * q_step; q < q_count && !lean_done; q += G * q_step, li += G) {
       const int tile = tile_of(q);
       if (G == 1) {
         if (li > 0) {   // next TMEM buffer / residual ring slot
@@ -940,84 +1071,6 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
             prm[4 * PSTR + i] = 1 << nsh;                                   // (x << s) == x * 2^s  (mod 2^32)
             prm[5 * PSTR + i] = (nsh + 7 < 32) ? (1 << (nsh + 7)) : 0;      // second plane: x * 2^(s+7)
           }
-        }
-      }
-      // ---- lean path: flat layers with the folded epilogue on a full m-tile.  Nothing here depends on the lane's
-      //      pixel: the residual tile comes from the TMA ring, the finished rows leave through a TMA store, so the
-      //      warp does no address arithmetic at all.  The W accumulators of a pass are read in one tcgen05.ld and
-      //      the TMEM buffer goes back to the MMA warp BEFORE the arithmetic of the last pass.
-      if constexpr (FOLD && MODE == 0) {
-        const bool lean_res_ok = !has_res || res_tma;
-        if (P.tstore != 0 && (t.m0 + MMA_M <= M) && lean_res_ok && !(kExp && P.noepi)) {
-          mbar_wait_timed(e_tfull + 8 * buf, tph, w_tfull, dbg, 0);
-          tc_fence_after();
-          if (has_res) mbar_wait_warp(rfull_bar + 8 * rb, rphase, 0);
-          const unsigned t_row0 = tmem_base + ((unsigned)(quarter * 32) << 16) + buf * acc_cols + slice * WT;
-#pragma unroll
-          for (int pass = 0; pass < PASSES; pass++) {
-            unsigned tot[W], tot1[W];
-            if constexpr (W == 32) {
-              tmem_ld32(t_row0 + pass * W, tot);
-              if (CT_TWO) tmem_ld32(t_row0 + BN + pass * W, tot1);
-            } else {
-              tmem_ld16(t_row0 + pass * W, tot);
-              if (CT_TWO) tmem_ld16(t_row0 + BN + pass * W, tot1);
-            }
-            tmem_ld_wait();
-            if (pass == PASSES - 1) {
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) {
-                if constexpr (cg2) mbar_arrive_leader(e_tempty + 8 * buf);
-                else mbar_arrive(e_tempty + 8 * buf);
-              }
-            }
-            uint4 resq[SEGS];
-            if (has_res) lds_res(slice * WT + pass * W, resq);
-            unsigned char* sbuf = stage + ((tsel + pass) & 1) * 1024;
-#pragma unroll
-            for (int cc = 0; cc < W; cc += 16) {
-              const uint4 rq = has_res ? resq[cc / 16] : make_uint4(0, 0, 0, 0);
-              const unsigned rw[4] = {rq.x, rq.y, rq.z, rq.w};
-              unsigned packed[4];
-              const int pc = pass * W + cc;
-#pragma unroll
-              for (int j4 = 0; j4 < 4; j4++) {
-                const int4 pa = *reinterpret_cast<const int4*>(prm + pc + 4 * j4);
-                const longlong2 pb0 = *reinterpret_cast<const longlong2*>(prm + PSTR + 2 * (pc + 4 * j4));
-                const longlong2 pb1 = *reinterpret_cast<const longlong2*>(prm + PSTR + 2 * (pc + 4 * j4) + 4);
-                const int aa[4] = {pa.x, pa.y, pa.z, pa.w};
-                const long long bq[4] = {pb0.x, pb0.y, pb1.x, pb1.y};
-                int yy[4];
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                  const int j = cc + 4 * j4 + u;
-                  const int tt = CT_TWO ? (int)(tot1[j] * 128u + tot[j]) : (int)tot[j];
-                  const long long tq = (long long)tt * (long long)aa[u] + bq[u];   // IMAD.HI with the 64-bit addend
-                  yy[u] = HI32 ? (int)(tq >> 32) : (int)(tq >> 35);
-                }
-                unsigned y4 = pack_sat4(yy[0], yy[1], yy[2], yy[3]);
-                if (conv_relu) y4 = relu_s8x4(y4);
-                if (has_res) y4 = add_relu ? add_res_s8x4<true>(y4, rw[j4]) : add_res_s8x4<false>(y4, rw[j4]);
-                packed[j4] = y4;
-              }
-              const int chunk = (W == 32) ? ((cc >> 4) ^ ((lane >> 2) & 1)) : 0;
-              *reinterpret_cast<uint4*>(sbuf + lane * W + chunk * 16) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-            }
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) {
-              tma_store_2d(smem_u32(sbuf), &maps.y, ncolw + pass * W, t.m0 + quarter * 32);
-              tma_store_commit();
-              tma_store_wait_read<1>();   // the other staging tile (written next) has been read out
-            }
-            __syncwarp();
-          }
-          if (has_res) {
-            if (lane == 0) mbar_arrive(rempty_bar + 8 * rb);
-          }
-          tsel = (tsel + PASSES) & 1;
-          continue;
         }
       }
       // ---- (1b) this thread's accumulator row -> pixel (for the residual), and the pixels of its

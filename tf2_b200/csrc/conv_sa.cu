@@ -53,6 +53,8 @@ struct SaParams {
   int nseg;
   int seg_shift[SA_MAXSEG];
   int seg_neg[SA_MAXSEG];
+  int seg_cbeg[SA_MAXSEG];  // channel chunks [cbeg, cend) of every tap the segment covers: with the channels of a tensor
+  int seg_cend[SA_MAXSEG];  // ordered by their power-of-two offset, a segment only spans the chunks of its offset class
   int Npad;                 // rows per segment in the packed weight matrix
   int a_bytes, b_bytes;     // bytes one stage receives
   int ksplit;               // 1: the two half-warps take alternate 16-channel steps, partial sums via shuffles
@@ -184,12 +186,11 @@ conv_sa_kernel(const __grid_constant__ SaParams P, const __grid_constant__ SaMap
   }
   __syncthreads();
   const int num_tiles = P.m_tiles * P.n_tiles;
-  const int chunks_per_seg = P.taps * P.cchunks;
 
   // ---- producer cursor (thread 0): the TMA loads run SA_STAGES - 1 chunks ahead of the MACs, across segment and
   //      tile boundaries (persistent CTAs: the ring never drains).  No "empty" barriers: chunk i + STAGES - 1 goes
   //      into the stage of chunk i - 1, which every warp has left once it is past the CTA barrier of chunk i.
-  int p_tile = blockIdx.x, p_g = 0, p_tap = 0, p_cc = 0, p_stage = 0;
+  int p_tile = blockIdx.x, p_g = 0, p_tap = 0, p_cc = P.seg_cbeg[0], p_stage = 0;
   SaTile p_tc = sa_decode(P, p_tile < num_tiles ? p_tile : 0, BM);
   auto produce = [&]() {
     if (p_tile >= num_tiles) return;
@@ -201,8 +202,7 @@ conv_sa_kernel(const __grid_constant__ SaParams P, const __grid_constant__ SaMap
     else tma_load_4d(sa, &maps.a, fb, p_cc * P.KC, p_tc.ow0 * c.stride - c.pad + fw, p_tc.oh0 * c.stride - c.pad + fh, p_tc.b0);
     tma_load_2d(sa + a_stage, &maps.b, fb, (p_tap * P.cchunks + p_cc) * (P.KC / 2), p_g * P.Npad + p_tc.n0);
     if (++p_stage == SA_STAGES) p_stage = 0;
-    if (++p_cc == P.cchunks) {
-      p_cc = 0;
+    if (++p_cc == P.seg_cend[p_g]) {
       if (++p_tap == P.taps) {
         p_tap = 0;
         if (++p_g == P.nseg) {
@@ -211,6 +211,7 @@ conv_sa_kernel(const __grid_constant__ SaParams P, const __grid_constant__ SaMap
           if (p_tile < num_tiles) p_tc = sa_decode(P, p_tile, BM);
         }
       }
+      p_cc = P.seg_cbeg[p_g];
     }
   };
   if (t == 0)
@@ -236,7 +237,8 @@ conv_sa_kernel(const __grid_constant__ SaParams P, const __grid_constant__ SaMap
       for (int j = 0; j < TN; j++) acc[i][j] = 0;
     for (int g = 0; g < P.nseg; g++) {
       const bool neg = P.seg_neg[g] != 0;
-      for (int ch = 0; ch < chunks_per_seg; ch++) {
+      const int chunks_of_seg = P.taps * (P.seg_cend[g] - P.seg_cbeg[g]);
+      for (int ch = 0; ch < chunks_of_seg; ch++) {
         mbar_wait(full_bar + 8 * stage, phase);
         const unsigned char* As = smem + stage * stage_bytes;
         const unsigned char* Bp = As + a_stage;
@@ -401,7 +403,8 @@ EncodeTiledFn sa_encode_fn(std::string* err) {
   return fn;
 }
 
-void sa_geometry(SaParams& P, const ConvParams& c, int nseg, const int* seg_shift, const int* seg_neg, int ksplit) {
+void sa_geometry(SaParams& P, const ConvParams& c, int nseg, const int* seg_shift, const int* seg_neg, int ksplit,
+                 const int* seg_cbeg = nullptr, const int* seg_cend = nullptr) {
   memset(&P, 0, sizeof P);
   P.c = c;
   P.ksplit = ksplit;
@@ -415,6 +418,8 @@ void sa_geometry(SaParams& P, const ConvParams& c, int nseg, const int* seg_shif
   for (int i = 0; i < SA_MAXSEG; i++) {
     P.seg_shift[i] = (i < nseg && seg_shift) ? seg_shift[i] : 0;
     P.seg_neg[i] = (i < nseg && seg_neg) ? seg_neg[i] : 0;
+    P.seg_cbeg[i] = (i < nseg && seg_cbeg) ? seg_cbeg[i] : 0;
+    P.seg_cend[i] = (i < nseg && seg_cend) ? seg_cend[i] : P.cchunks;
   }
   P.Npad = c.Npad;
   P.n_tiles = (c.N + P.BN - 1) / P.BN;
@@ -525,10 +530,10 @@ cudaError_t sa_prepare_device() {
   return cudaSuccess;
 }
 
-cudaError_t launch_conv_sa(const ConvParams& c, int nseg, const int* seg_shift, const int* seg_neg, const void* tmaps,
-                           int ksplit, int num_sms, cudaStream_t stream) {
+cudaError_t launch_conv_sa(const ConvParams& c, int nseg, const int* seg_shift, const int* seg_neg, const int* seg_cbeg,
+                           const int* seg_cend, const void* tmaps, int ksplit, int num_sms, cudaStream_t stream) {
   SaParams P;
-  sa_geometry(P, c, nseg, seg_shift, seg_neg, ksplit);
+  sa_geometry(P, c, nseg, seg_shift, seg_neg, ksplit, seg_cbeg, seg_cend);
   const int num_tiles = P.m_tiles * P.n_tiles;
   const int BM = ksplit ? 64 : SA_BM;
   const int stage_bytes = BM * P.KC + P.BN * (P.KC / 2);
