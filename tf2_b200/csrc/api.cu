@@ -54,6 +54,7 @@ int mma_build_tmaps(void* host_tmaps, const ConvParams& p, const int8_t* wgt8, i
 int mma_bn();
 int mma_pick_bk(int Cp);
 bool mma_pair_mode(int k, int stride, int pad, int Cp, int xC, int OW, int OH, int N, int planes8);
+bool mma_sparse2_ok(const tf2b_layer_desc& L, int in_pitch, int N);
 }  // namespace tf2b
 
 using tf2b::ConvParams;
@@ -80,6 +81,9 @@ struct LayerState {
   int Npad_m = 0, Kp_m = 0, planes_m = 0;
   int plane_shift_m[tf2b::kMaxPlanes] = {0, 0, 0, 0};
   int low_plane_m = -1;  // index of the plane that holds absolute shifts 0..6 (not scaled by 2^nshift), or -1
+  int sparse2_m = 0;     // two planes whose second one is sparse in K: per (tap, 32-channel block) a 2-bit mask says
+                         // which planes hold weights; the MMA warp issues per plane and skips empty blocks
+  std::vector<uint8_t> h_blkmask;   // [taps][K chunks]: 2 bits per 32-channel block of the chunk
   int fast_requant = 0;  // range analysis: no int32 intermediate of pe.cl:191-194 can wrap for this layer
   std::vector<int8_t> h_w8;
   std::vector<uint8_t> h_nshift_m;  // per-channel base shift of the tensor-core planes
@@ -99,6 +103,8 @@ struct LayerState {
 struct BlobLayerMeta {  // fixed-size, trivially copyable: travels inside the weight blob
   int32_t loaded, Cp, Cp_m, Npad_s, Kp_s, Cp_s, nseg_s, seg_shift_s[8], seg_neg_s[8], seg_cbeg_s[8], seg_cend_s[8];
   int32_t Npad_m, Kp_m, planes_m, plane_shift_m[4], mma_ok, Npar, low_plane_m, nshift_m_len, fast_requant;
+  int32_t sparse2_m, blkmask_len;
+  uint8_t blkmask[320];
   int64_t off_w4, off_w8, off_bias, off_alpha, off_beta, off_nshift, off_nshift_m;
 };
 
@@ -357,6 +363,58 @@ static int prepare_layer(tf2b_net* net, LayerState& S, const uint8_t* codes,
       S.h_w8.assign((size_t)np * S.Npad_m * S.Kp_m, 0);
       for (int p = 0; p < np; p++) S.plane_shift_m[p] = lv * p;
       if (use_low) S.plane_shift_m[np - 1] = 0;
+      // Sparse second plane (two planes, no low plane, no negated copy): the second plane's shift D1 is free, and a
+      // channel whose weights all fit [D1, D1 + 6] can live in plane 1 alone, one whose weights all fit [0, 6] in
+      // plane 0 alone; only the others straddle.  With the tensor's channels ordered by their offset, whole
+      // 32-channel blocks of K then hold weights in ONE plane and the MMA warp skips the other (api: blkmask).
+      // D1 is chosen to minimise the number of (block, plane) pairs that have to be issued.
+      S.sparse2_m = 0;
+      std::vector<char> chan_plane;   // per logical channel: 0 / 1 = that plane only, 2 = per weight (rel <= 6 -> plane 0)
+      if (np == 2 && !use_low && !dual && !pair) {
+        const int kk2 = k * k;
+        std::vector<int> lo(C, 99), hi(C, -1);
+        for (int n = 0; n < N; n++)
+          for (int c = 0; c < C; c++)
+            for (int t = 0; t < kk2; t++) {
+              const uint8_t cd = codes[((size_t)n * C + c) * kk2 + t];
+              if (cd & 0x40) continue;
+              const int rel = (cd & 0x1f) - bm[n];
+              lo[c] = std::min(lo[c], rel);
+              hi[c] = std::max(hi[c], rel);
+            }
+        const int nblk = Cpm / 32;
+        long long best_cost = -1;
+        int best_d1 = lv;
+        std::vector<char> best_plane;
+        for (int d1 = 1; d1 <= lv; d1++) {
+          bool ok = true;
+          std::vector<char> cp(C, 0);
+          std::vector<char> use0(nblk, 0), use1(nblk, 0);
+          for (int c = 0; c < C && ok; c++) {
+            if (hi[c] < 0) continue;                                  // no weights at all
+            const int b = pin(c) / 32;
+            if (hi[c] <= 6) { cp[c] = 0; use0[b] = 1; }
+            else if (lo[c] >= d1 && hi[c] <= d1 + 6) { cp[c] = 1; use1[b] = 1; }
+            else {
+              cp[c] = 2;
+              use0[b] = use1[b] = 1;
+              if (hi[c] > d1 + 6) ok = false;                         // a weight above plane 1's range
+              // weights in (6, d1) cannot exist: d1 <= 7
+            }
+          }
+          if (!ok) continue;
+          long long cost = 0;
+          for (int b = 0; b < nblk; b++) cost += use0[b] + use1[b];
+          if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_d1 = d1; best_plane = cp; }
+        }
+        if (best_cost >= 0 && best_cost * 10 <= (long long)nblk * 2 * 9 && tf2b::mma_sparse2_ok(d, in_pitch, N) &&
+            (size_t)(k * k) * (size_t)(Cpm / tf2b::mma_pick_bk(S.Cp_m)) <= sizeof(((ConvParams*)nullptr)->blkmask)) {
+          S.sparse2_m = 1;
+          S.plane_shift_m[1] = best_d1;
+          chan_plane = best_plane;
+        }
+      }
+      const int d1s = S.plane_shift_m[1];
       for (int n = 0; n < N; n++)
         for (int c = 0; c < C; c++)
           for (int t = 0; t < k * k; t++) {
@@ -367,6 +425,10 @@ static int prepare_layer(tf2b_net* net, LayerState& S, const uint8_t* codes,
             if (use_low && sft < lv) {
               p = np - 1;
               e = sft;
+            } else if (S.sparse2_m) {
+              const int rel = sft - bm[n];
+              p = chan_plane[c] == 2 ? (rel <= 6 ? 0 : 1) : chan_plane[c];
+              e = p ? rel - d1s : rel;
             } else {
               int rel = sft - bm[n];
               p = rel / lv;
@@ -384,6 +446,30 @@ static int prepare_layer(tf2b_net* net, LayerState& S, const uint8_t* codes,
             }
             S.h_w8[((size_t)p * S.Npad_m + pout(n)) * S.Kp_m + kidx] = (int8_t)v;
           }
+      // which planes hold weights in each (tap, 32-channel block): 2 bits per block, one byte per (tap, K chunk)
+      {
+        const int BKm = tf2b::mma_pick_bk(S.Cp_m);
+        const int kch = pair ? pair_chunks : Cpm / BKm;
+        const int ntap = pair ? k : k * k;
+        S.h_blkmask.assign((size_t)ntap * kch, 0);
+        if (S.sparse2_m) {
+          for (int p = 0; p < np; p++)
+            for (int n = 0; n < N; n++) {
+              const int8_t* row = S.h_w8.data() + ((size_t)p * S.Npad_m + pout(n)) * S.Kp_m;
+              for (int kx = 0; kx < S.Kp_m; kx++)
+                if (row[kx]) {
+                  const int tap = kx / Cpm, cc2 = kx - tap * Cpm;
+                  S.h_blkmask[(size_t)tap * kch + cc2 / BKm] |= (uint8_t)(1u << (2 * ((cc2 % BKm) / 32) + p));
+                }
+            }
+          // every plane needs at least one issued block per tile (its first MMA clears the accumulator)
+          for (int p = 0; p < 2; p++) {
+            bool any = false;
+            for (auto m : S.h_blkmask) any = any || (m & (0x55u << p));
+            if (!any) S.h_blkmask[0] |= (uint8_t)(1u << p);
+          }
+        }
+      }
       S.h_nshift_m.assign(round_up(std::max(tf2b::sa_npad(N), S.Npad_m), 16), 0);
       for (int n = 0; n < N; n++) S.h_nshift_m[pout(n)] = bm[n];
       S.mma_ok = true;
@@ -843,7 +929,10 @@ static ConvParams conv_params(tf2b_net* net, const LayerState& S, int B, int8_t*
   p.OH = d.OH; p.OW = d.OW; p.N = d.N; p.yC = dstC; p.rC = resC;
   p.k = d.k; p.pad = d.pad; p.stride = d.stride;
   p.relu = d.relu; p.add_relu = d.add_relu;
+  p.sparse2 = 0;
   if (mma) {
+    p.sparse2 = S.sparse2_m;
+    if (S.sparse2_m) memcpy(p.blkmask, S.h_blkmask.data(), std::min(S.h_blkmask.size(), sizeof p.blkmask));
     p.Npad = S.Npad_m; p.Kp = S.Kp_m; p.Ktot = S.Kp_m; p.planes = S.planes_m;
     for (int i = 0; i < tf2b::kMaxPlanes; i++) { p.plane_shift[i] = S.plane_shift_m[i]; p.plane_neg[i] = 0; }
   } else {
@@ -1349,6 +1438,8 @@ int tf2b_export_weight_blob(tf2b_net* net, void* dev_dst, void* stream) {
     m.off_w4 = S.off_w4; m.off_w8 = S.off_w8; m.off_bias = S.off_bias; m.off_alpha = S.off_alpha;
     m.off_beta = S.off_beta; m.off_nshift = S.off_nshift; m.off_nshift_m = S.off_nshift_m;
     m.low_plane_m = S.low_plane_m; m.nshift_m_len = (int32_t)S.h_nshift_m.size(); m.fast_requant = S.fast_requant;
+    m.sparse2_m = S.sparse2_m; m.blkmask_len = (int32_t)std::min(S.h_blkmask.size(), sizeof m.blkmask);
+    memcpy(m.blkmask, S.h_blkmask.data(), (size_t)m.blkmask_len);
     memcpy(hdr.data() + kBlobFixed + l * sizeof m, &m, sizeof m);
   }
   for (size_t t = 0; t < net->tensors.size(); t++) {
@@ -1423,6 +1514,9 @@ int tf2b_import_weight_blob(tf2b_net* net, const void* dev_src, int64_t blob_byt
     CUDA_TRY(net, pull(S.h_nshift_m, (size_t)m.nshift_m_len, m.off_nshift_m));
     S.low_plane_m = m.low_plane_m;
     S.fast_requant = m.fast_requant;
+    S.sparse2_m = m.sparse2_m;
+    if (m.blkmask_len < 0 || m.blkmask_len > (int32_t)sizeof m.blkmask) return fail(net, TF2B_ERR_ARG, "blob layer %zu: bad block mask", l);
+    S.h_blkmask.assign(m.blkmask, m.blkmask + m.blkmask_len);
     S.prepared = true;
   }
   net->tpos.assign(net->tensors.size(), {});

@@ -133,6 +133,9 @@ struct MmaParams {
   int b_stage_bytes;        // bytes of weights one CTA stages per k-iteration
   int egroups;              // epilogue warp groups (1: all 16 warps share every tile; 2: 8 warps per tile,
                             // the groups take alternate tiles = alternate TMEM buffers)
+  int sparse2;              // two planes issued separately (N = BN each), empty (tap, block, plane) combinations skipped
+  unsigned p1mul;           // 2^shift of the second plane (128 with the plain 7-level planes)
+  unsigned idesc1;          // instruction descriptor of a one-plane MMA (N = BN)
   int n_tile0;              // first n-tile of this launch (channel window of the parameter table); n_tiles counts
                             // the n-tiles of the launch
   int tstore;               // flat layers, folded epilogue: finished int8 rows leave through per-warp TMA stores
@@ -450,7 +453,8 @@ __device__ __forceinline__ unsigned add_res_s8x4(unsigned y4, unsigned r4) {
 // ((beta + 2^14) << 20))) >> 35 with tot = plane0 + (plane1 << 7) — one IMAD.HI per output; bit4 (with
 // bit3) = every nshift >= 3, so alpha << (nshift-3) and the addend >> 3 make the high word the result.
 template <int BN, int MODE, int EPI, bool CG2 = false>
-__global__ void __maxnreg__(112)   // 576 threads x 112 registers = 64 512 of the 65 536 (launch bounds alone cap at 96)
+// (18 warps = 5 on one scheduler: 16 384 registers / (5 warps x 32 lanes) caps the kernel at 96 registers per thread)
+__global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ TmapPair maps) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // carve: [resident weight slab] [stages][A | B planes] (1024-aligned) [epilogue scratch]
@@ -621,11 +625,27 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
           mbar_wait_timed(empty_bar + 8 * stage, phase ^ 1, w_empty, dbg, (kExp ? P.poll_lane0 : 0));
           const unsigned fb = full_bar + 8 * stage;
           const unsigned sa = smem_base + stage * stage_bytes;
+          // sparse second plane: which planes hold weights anywhere in this (tap, K chunk)
+          const unsigned cmask = P.sparse2 ? (unsigned)P.c.blkmask[tap * P.kchunks + kc] : 0xffu;
+          const bool ld0 = (cmask & 0x55u) != 0, ld1 = (cmask & 0xaau) != 0;
           if constexpr (cg2) {
             // Pair mode: both producers signal the LEADER's full barrier (its MMA warp drives both SMs).
             // This CTA stages its own 128 activation rows and its half of the weight tile: plane
-            // `rank` of a two-plane layer, or rows rank*128.. of a 256-wide single plane.
-            if (elect_one()) {
+            // `rank` of a two-plane layer, or rows rank*128.. of a 256-wide single plane — or, with the sparse
+            // second plane, rows rank*64.. of EACH plane that holds weights in this chunk (one-plane MMAs, N = BN,
+            // take half of their rows from either CTA).
+            if (P.sparse2) {
+              if (elect_one()) {
+                const unsigned half = (unsigned)(64 * P.BK);
+                const unsigned bbytes = (ld0 ? half : 0u) + (ld1 ? half : 0u);
+                if (cta_rank == 0) mbar_expect_tx(fb, 2u * ((unsigned)P.a_bytes + bbytes));
+                else mbar_arrive_leader(fb);
+                if (MODE == 0) tma_load_2d_cg2(sa, &maps.a, fb, kc * P.BK, t.m0);
+                else tma_load_4d_cg2(sa, &maps.a, fb, kc * P.BK, t.ow0 * P.c.stride - P.c.pad + fw, t.oh0 * P.c.stride - P.c.pad + fh, t.b0);
+                if (ld0) tma_load_2d_cg2(sa + a_stage, &maps.r, fb, tap * P.Cpm + kc * P.BK, t.n0 + (int)cta_rank * 64);
+                if (ld1) tma_load_2d_cg2(sa + a_stage + half, &maps.r, fb, tap * P.Cpm + kc * P.BK, P.Npad + t.n0 + (int)cta_rank * 64);
+              }
+            } else if (elect_one()) {
               if (cta_rank == 0) mbar_expect_tx(fb, 2u * (unsigned)(P.a_bytes + P.b_stage_bytes));
               else mbar_arrive_leader(fb);
               if (MODE == 0) {
@@ -638,7 +658,8 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
               tma_load_2d_cg2(sa + a_stage, &maps.r, fb, tap * P.Cpm + kc * P.BK, brow);
             }
           } else if (elect_one()) {
-            mbar_expect_tx(fb, (unsigned)(P.a_bytes + (P.b_resident ? 0 : P.planes * P.b_bytes)));
+            const int nld = P.sparse2 ? (int)ld0 + (int)ld1 : P.planes;
+            mbar_expect_tx(fb, (unsigned)(P.a_bytes + (P.b_resident ? 0 : nld * P.b_bytes)));
             if (MODE == 0) {
               tma_load_2d(sa, &maps.a, fb, kc * P.BK, t.m0);
             } else if (P.pair) {
@@ -650,7 +671,8 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
             }
             if (!P.b_resident)
               for (int pl = 0; pl < P.planes; pl++)
-                tma_load_2d(sa + a_stage + pl * b_plane, &maps.b, fb, tap * P.Cpm + kc * P.BK, pl * P.Npad + t.n0);
+                if (!P.sparse2 || (pl == 0 ? ld0 : ld1))
+                  tma_load_2d(sa + a_stage + pl * b_plane, &maps.b, fb, tap * P.Cpm + kc * P.BK, pl * P.Npad + t.n0);
           }
           __syncwarp();
           if (++stage == P.stages) { stage = 0; phase ^= 1; }
@@ -674,6 +696,7 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
       mbar_wait_timed(tempty_bar + 8 * buf, ((unsigned)(li >> 1) & 1u) ^ 1u, w_tempty, dbg, (kExp ? P.poll_lane0 : 0));   // epilogue has drained this accumulator
       tc_fence_after();
       const unsigned d_tmem = tmem_base + buf * acc_cols;
+      unsigned touched0 = 0u, touched1 = 0u;   // sparse second plane: has the plane's accumulator been written in this tile
       for (int it = 0; it < kiters; it++) {
         mbar_wait_timed(full_bar + 8 * stage, phase, w_full, dbg, (kExp ? P.poll_lane0 : 0));
         tc_fence_after();
@@ -718,6 +741,36 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
           const unsigned bsrc = P.b_resident ? smem_res + it * P.planes * b_plane : sa + a_stage;
           const unsigned long long db = make_smem_desc(bsrc, P.sbo16, P.layout_type);
           const unsigned acc0 = it > 0 ? 1u : 0u;
+          if (P.sparse2) {
+            // Sparse second plane: one-plane instructions (N = BN) into each plane's own TMEM columns, issued only
+            // for the (32-channel block, plane) combinations that hold weights.  The first instruction a plane
+            // sees in a tile overwrites its accumulator.
+            const unsigned cmask = (unsigned)P.c.blkmask[it];
+            const unsigned pstride = cg2 ? (unsigned)(64 * P.BK) : (unsigned)b_plane;   // pair: half the rows per CTA
+            const unsigned long long db1 = make_smem_desc(bsrc + pstride, P.sbo16, P.layout_type);
+            const int nblk = P.BK >> 5;
+            for (int kb = 0; kb < nblk; kb++) {
+              const unsigned m2 = (cmask >> (2 * kb)) & 3u;
+              const unsigned long long koff = (unsigned long long)(2 * kb);
+              if (m2 & 1u) {
+                if constexpr (cg2) umma_i8_cg2(d_tmem, da + koff, db + koff, P.idesc1, touched0);
+                else umma_i8(d_tmem, da + koff, db + koff, P.idesc1, touched0);
+                touched0 = 1u;
+              }
+              if (m2 & 2u) {
+                if constexpr (cg2) umma_i8_cg2(d_tmem + BN, da + koff, db1 + koff, P.idesc1, touched1);
+                else umma_i8(d_tmem + BN, da + koff, db1 + koff, P.idesc1, touched1);
+                touched1 = 1u;
+              }
+            }
+            if constexpr (cg2) {
+              umma_commit_cg2(empty_bar + 8 * stage);
+              if (it == kiters - 1) umma_commit_cg2(tfull_bar + 8 * buf);
+            } else {
+              umma_commit(empty_bar + 8 * stage);
+              if (it == kiters - 1) umma_commit(tfull_bar + 8 * buf);
+            }
+          } else
           // advance both descriptors by 32 bytes of K inside the swizzled row
           if constexpr (cg2) {
             // one M = 256 instruction spans both SMs: A = the two CTAs' activation tiles, B = their halves
@@ -787,6 +840,7 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
     const int group = G == 2 ? (ew >> 3) : 0;
     const ConvParams& c = P.c;
     const int M = c.B * c.OH * c.OW;
+    const unsigned p1mul = P.p1mul;           // 2^shift of the second plane
     const bool conv_relu = c.relu != 0;       // relu.cl:54, applied to the packed int8 values
     const bool add_relu = c.add_relu != 0;    // feature_writer.cl:126
     // epilogue scratch lives behind the pipeline stages in dynamic shared memory
@@ -923,23 +977,6 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
           const unsigned rbase = smem_rres + lrb * res_tile + my_row * 128;
 #pragma unroll
           for (int pass = 0; pass < PASSES; pass++) {
-            unsigned tot[W], tot1[W];
-            if constexpr (W == 32) {
-              tmem_ld32(t_row0 + pass * W, tot);
-              if (CT_TWO) tmem_ld32(t_row0 + BN + pass * W, tot1);
-            } else {
-              tmem_ld16(t_row0 + pass * W, tot);
-              if (CT_TWO) tmem_ld16(t_row0 + BN + pass * W, tot1);
-            }
-            tmem_ld_wait();
-            if (pass == PASSES - 1) {
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) {
-                if constexpr (cg2) mbar_arrive_leader(e_tempty + 8 * lbuf);
-                else mbar_arrive(e_tempty + 8 * lbuf);
-              }
-            }
             uint4 resq[SEGS];
             if (CT_RES) {
               const int col = slice * WT + pass * W;
@@ -954,6 +991,19 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
             unsigned char* sbuf = stage + ((tsel + pass) & 1) * 1024;
 #pragma unroll
             for (int cc = 0; cc < W; cc += 16) {
+              unsigned tot[16], tot1[16];
+              tmem_ld16(t_row0 + pass * W + cc, tot);
+              if (CT_TWO) tmem_ld16(t_row0 + BN + pass * W + cc, tot1);
+              tmem_ld_wait();
+              if (pass == PASSES - 1 && cc + 16 >= W) {
+                // the accumulators of this tile are in registers: hand the TMEM buffer back before the arithmetic
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                  if constexpr (cg2) mbar_arrive_leader(e_tempty + 8 * lbuf);
+                  else mbar_arrive(e_tempty + 8 * lbuf);
+                }
+              }
               const uint4 rq = CT_RES ? resq[cc / 16] : make_uint4(0, 0, 0, 0);
               const unsigned rw[4] = {rq.x, rq.y, rq.z, rq.w};
               unsigned packed[4];
@@ -968,8 +1018,8 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
                 int yy[4];
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
-                  const int j = cc + 4 * j4 + u;
-                  const int tt = CT_TWO ? (int)(tot1[j] * 128u + tot[j]) : (int)tot[j];
+                  const int j = 4 * j4 + u;
+                  const int tt = CT_TWO ? (int)(tot1[j] * p1mul + tot[j]) : (int)tot[j];
                   const long long tq = (long long)tt * (long long)aa[u] + bq[u];   // IMAD.HI with the 64-bit addend
                   yy[u] = HI32 ? (int)(tq >> 32) : (int)(tq >> 35);
                 }
@@ -1069,7 +1119,7 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
               prm[2 * PSTR + i] = be;
             }
             prm[4 * PSTR + i] = 1 << nsh;                                   // (x << s) == x * 2^s  (mod 2^32)
-            prm[5 * PSTR + i] = (nsh + 7 < 32) ? (1 << (nsh + 7)) : 0;      // second plane: x * 2^(s+7)
+            prm[5 * PSTR + i] = (nsh + P.plane8_shift[1] < 32) ? (1 << (nsh + P.plane8_shift[1])) : 0;   // second plane: x * 2^(s + its shift)
           }
         }
       }
@@ -1186,7 +1236,7 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
 #pragma unroll
               for (int u = 0; u < 4; u++) {
                 const int j = 4 * j4 + u;
-                const int tt = two ? (int)(tot1[j] * 128u + tot[j]) : (int)tot[j];
+                const int tt = two ? (int)(tot1[j] * p1mul + tot[j]) : (int)tot[j];
                 const long long t = (long long)tt * (long long)aa[u] + bq[u];   // IMAD.HI with the 64-bit addend
                 yy[u] = HI32 ? (int)(t >> 32) : (int)(t >> 35);
               }
@@ -1507,6 +1557,10 @@ void fill_geometry(MmaParams& P, const ConvParams& c, int planes8) {
   // saturate (bit 3) off
   P.idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((unsigned)((P.BN * P.planes) >> 3) << 17) |
             ((unsigned)((P.cg2 ? 2 * MMA_M : MMA_M) >> 4) << 24);
+  P.idesc1 = (2u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(P.BN >> 3) << 17) |
+             ((unsigned)((P.cg2 ? 2 * MMA_M : MMA_M) >> 4) << 24);
+  P.sparse2 = (c.sparse2 && planes8 == 2 && !P.halo && !P.pair && P.BN >= 128) ? 1 : 0;
+  P.p1mul = 1u << (c.plane_shift[1] & 31);
   P.layout_type = (P.BK == 128) ? 2u : 4u;
   P.sbo16 = (unsigned)(8 * P.BK) >> 4;
   P.d_ntiles = make_fastdiv(P.n_tiles);
@@ -1548,6 +1602,13 @@ bool mma_pair_mode(int k, int stride, int pad, int Cp, int xC, int OW, int OH, i
   return !halo_mode(k, stride, Cp, OW, OH, N, planes8) && pair_mode(k, stride, pad, Cp, xC, OW);
 }
 
+// can a two-plane layer of this shape use the sparse second plane (streamed or resident weights, not the halo tile)?
+bool mma_sparse2_ok(const tf2b_layer_desc& L, int in_pitch, int N) {
+  (void)in_pitch;
+  const int Cp = (L.C + 15) / 16 * 16;
+  return pick_bn(2, N) >= 128 && !halo_mode(L.k, L.stride, Cp, L.OW, L.OH, N, 2);
+}
+
 bool mma_layer_supported(const tf2b_layer_desc& L, int in_pitch, int planes8) {
   if (L.ipool) return false;
   if (L.stride < 1 || L.stride > 8) return false;   // TMA traversal stride limit
@@ -1571,10 +1632,10 @@ std::string mma_describe(const ConvParams& c, int planes8) {
   MmaParams P;
   fill_geometry(P, c, planes8);
   char b[192];
-  snprintf(b, sizeof b, "mma BN%d BK%d planes%d %s%s%s%s%s%s stages%d", P.BN, P.BK, planes8,
+  snprintf(b, sizeof b, "mma BN%d BK%d planes%d %s%s%s%s%s%s%s stages%d", P.BN, P.BK, planes8,
            P.mode == 0 ? "flat" : (P.halo ? "halo" : (P.pair ? "pixelpair" : "box")), P.b_resident ? " wres" : "",
            P.res_tma ? " restma" : "", fold_applies(c, planes8) ? (c.fast_requant >= 3 ? " fold hi32" : " fold") : "",
-           P.tstore ? " tmastore" : "", P.cg2 ? " ctapair" : "", P.stages);
+           P.tstore ? " tmastore" : "", P.cg2 ? " ctapair" : "", P.sparse2 ? " sparse2" : "", P.stages);
   return std::string(b);
 }
 
@@ -1639,7 +1700,7 @@ int mma_build_tmaps(void* host_tmaps, const ConvParams& c, const int8_t* wgt8, i
   if (P.cg2) {
     cuuint64_t dims[2] = {(cuuint64_t)c.Kp, (cuuint64_t)planes8 * c.Npad};
     cuuint64_t strides[1] = {(cuuint64_t)c.Kp};
-    cuuint32_t box[2] = {(cuuint32_t)P.BK, 128};
+    cuuint32_t box[2] = {(cuuint32_t)P.BK, (cuuint32_t)(P.sparse2 ? 64 : 128)};   // sparse second plane: half of EACH plane
     cuuint32_t es[2] = {1, 1};
     r = enc(&tp->r, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)wgt8, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
             sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

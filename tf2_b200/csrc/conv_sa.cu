@@ -153,7 +153,7 @@ __device__ __forceinline__ SaTile sa_decode(const SaParams& P, int tile, int BM)
 // TN = output channels per thread (BN = 16 * TN).  KSPLIT (layers with few tiles): the tile is 64 pixels, the two
 // half-warps (lane bit 4) take alternate 16-channel steps of every chunk and their partial sums meet in a
 // warp-shuffle reduction; otherwise the tile is 128 pixels and lane bit 4 is a second pixel group.
-template <int TN, bool KSPLIT>
+template <int TN, bool KSPLIT, int KC>
 __global__ void __launch_bounds__(SA_THREADS, 2)
 conv_sa_kernel(const __grid_constant__ SaParams P, const __grid_constant__ SaMaps maps) {
   constexpr int BN = 16 * TN;
@@ -162,9 +162,9 @@ conv_sa_kernel(const __grid_constant__ SaParams P, const __grid_constant__ SaMap
   constexpr int TYN = BM / TM;                             // row distance between a thread's pixels
   extern __shared__ __align__(128) unsigned char smem[];
   // carve: [stages][A tile | packed B tile]  [2][expanded B tile, reused as the int8 output staging tile]
-  const int a_stage = BM * P.KC;
-  const int b_stage = BN * (P.KC / 2);
-  const int stage_bytes = a_stage + b_stage;
+  constexpr int a_stage = BM * KC;
+  constexpr int b_stage = BN * (KC / 2);
+  constexpr int stage_bytes = a_stage + b_stage;
   unsigned char* const bx_base = smem + SA_STAGES * stage_bytes;
   constexpr int BX_BYTES = BN * SA_BSTRIDE;
   __shared__ __align__(8) unsigned long long bars[SA_STAGES];
@@ -198,9 +198,9 @@ conv_sa_kernel(const __grid_constant__ SaParams P, const __grid_constant__ SaMap
     const unsigned fb = full_bar + 8 * p_stage;
     const unsigned sa = smem_u32(smem) + p_stage * stage_bytes;
     mbar_expect_tx(fb, (unsigned)(P.a_bytes + P.b_bytes));
-    if (P.mode == 0) tma_load_2d(sa, &maps.a, fb, p_cc * P.KC, p_tc.m0);
-    else tma_load_4d(sa, &maps.a, fb, p_cc * P.KC, p_tc.ow0 * c.stride - c.pad + fw, p_tc.oh0 * c.stride - c.pad + fh, p_tc.b0);
-    tma_load_2d(sa + a_stage, &maps.b, fb, (p_tap * P.cchunks + p_cc) * (P.KC / 2), p_g * P.Npad + p_tc.n0);
+    if (P.mode == 0) tma_load_2d(sa, &maps.a, fb, p_cc * KC, p_tc.m0);
+    else tma_load_4d(sa, &maps.a, fb, p_cc * KC, p_tc.ow0 * c.stride - c.pad + fw, p_tc.oh0 * c.stride - c.pad + fh, p_tc.b0);
+    tma_load_2d(sa + a_stage, &maps.b, fb, (p_tap * P.cchunks + p_cc) * (KC / 2), p_g * P.Npad + p_tc.n0);
     if (++p_stage == SA_STAGES) p_stage = 0;
     if (++p_cc == P.seg_cend[p_g]) {
       if (++p_tap == P.taps) {
@@ -225,7 +225,7 @@ conv_sa_kernel(const __grid_constant__ SaParams P, const __grid_constant__ SaMap
   int stage = 0;
   unsigned phase = 0;
   int bxsel = 0;
-  const int ksteps = P.KC / 16;
+  constexpr int ksteps = KC / 16;
   for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
     const SaTile tc = sa_decode(P, tile, BM);
     // ONE accumulator set: segments come in descending shift order and are combined by Horner's rule,
@@ -245,29 +245,34 @@ conv_sa_kernel(const __grid_constant__ SaParams P, const __grid_constant__ SaMap
         unsigned char* Bx = bx_base + bxsel * BX_BYTES;
         // ---- expand the packed weight tile of this chunk: 16 packed bytes -> 32 int8 weights per item
         {
-          const int per_row = P.KC / 32;
-          const int items = BN * per_row;
-          for (int e = t; e < items; e += SA_CONSUMERS) {
-            const int row = e / per_row, part = e - row * per_row;
-            const uint4 pk = *reinterpret_cast<const uint4*>(Bp + row * (P.KC / 2) + part * 16);
-            uint4 o0, o1;
-            expand8(pk.x, o0.x, o0.y);
-            expand8(pk.y, o0.z, o0.w);
-            expand8(pk.z, o1.x, o1.y);
-            expand8(pk.w, o1.z, o1.w);
-            uint4* dst = reinterpret_cast<uint4*>(Bx + row * SA_BSTRIDE + part * 32);
-            dst[0] = o0;
-            dst[1] = o1;
+          constexpr int per_row = KC / 32;
+          constexpr int items = BN * per_row;
+#pragma unroll
+          for (int e0 = 0; e0 < items; e0 += SA_CONSUMERS) {
+            const int e = e0 + t;
+            if (items % SA_CONSUMERS == 0 || e < items) {
+              const int row = e / per_row, part = e % per_row;
+              const uint4 pk = *reinterpret_cast<const uint4*>(Bp + row * (KC / 2) + part * 16);
+              uint4 o0, o1;
+              expand8(pk.x, o0.x, o0.y);
+              expand8(pk.y, o0.z, o0.w);
+              expand8(pk.z, o1.x, o1.y);
+              expand8(pk.w, o1.z, o1.w);
+              uint4* dst = reinterpret_cast<uint4*>(Bx + row * SA_BSTRIDE + part * 32);
+              dst[0] = o0;
+              dst[1] = o1;
+            }
           }
         }
         bar_consumers();
         if (t == 0) produce();   // refills the stage of the previous chunk
         // ---- MACs: 16 channels per step as 4 x IDP.4A per (pixel, channel) pair
+#pragma unroll
         for (int ks = kh; ks < ksteps; ks += (KSPLIT ? 2 : 1)) {
           uint4 a[TM];
 #pragma unroll
           for (int i = 0; i < TM; i++) {
-            a[i] = *reinterpret_cast<const uint4*>(As + (ty + TYN * i) * P.KC + ks * 16);
+            a[i] = *reinterpret_cast<const uint4*>(As + (ty + TYN * i) * KC + ks * 16);
             if (neg) {   // pe.cl:32-34: negate inside int8 (wraps: -(-128) = -128)
               a[i].x = __vneg4(a[i].x); a[i].y = __vneg4(a[i].y); a[i].z = __vneg4(a[i].z); a[i].w = __vneg4(a[i].w);
             }
@@ -514,19 +519,25 @@ int sa_build_tmaps(void* host_tmaps, const ConvParams& c, const uint8_t* wgt4, i
 }
 
 namespace {
-template <int TN, bool KS>
+template <int TN, bool KS, int KC>
 cudaError_t sa_set_attr() {
-  return cudaFuncSetAttribute(conv_sa_kernel<TN, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  return cudaFuncSetAttribute(conv_sa_kernel<TN, KS, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+}
+template <int TN, bool KS, int KC>
+void sa_launch(int grid, size_t smem, cudaStream_t stream, const SaParams& P, const SaMaps& m) {
+  conv_sa_kernel<TN, KS, KC><<<grid, SA_THREADS, smem, stream>>>(P, m);
 }
 }  // namespace
 
 // per-device: opt in to > 48 KB dynamic shared memory (called from tf2b_finalize after cudaSetDevice)
 cudaError_t sa_prepare_device() {
   cudaError_t e;
-  if ((e = sa_set_attr<4, false>()) != cudaSuccess) return e;
-  if ((e = sa_set_attr<8, false>()) != cudaSuccess) return e;
-  if ((e = sa_set_attr<4, true>()) != cudaSuccess) return e;
-  if ((e = sa_set_attr<8, true>()) != cudaSuccess) return e;
+  if ((e = sa_set_attr<4, false, 64>()) != cudaSuccess) return e;
+  if ((e = sa_set_attr<8, false, 64>()) != cudaSuccess) return e;
+  if ((e = sa_set_attr<4, true, 64>()) != cudaSuccess) return e;
+  if ((e = sa_set_attr<8, true, 64>()) != cudaSuccess) return e;
+  if ((e = sa_set_attr<4, false, 32>()) != cudaSuccess) return e;
+  if ((e = sa_set_attr<8, false, 32>()) != cudaSuccess) return e;
   return cudaSuccess;
 }
 
@@ -541,12 +552,17 @@ cudaError_t launch_conv_sa(const ConvParams& c, int nseg, const int* seg_shift, 
   int grid = std::min(num_tiles, 2 * num_sms);
   if (grid < 1) grid = 1;
   const SaMaps* tp = reinterpret_cast<const SaMaps*>(tmaps);
-  if (P.BN == 64) {
-    if (ksplit) conv_sa_kernel<4, true><<<grid, SA_THREADS, smem, stream>>>(P, *tp);
-    else conv_sa_kernel<4, false><<<grid, SA_THREADS, smem, stream>>>(P, *tp);
+  if (P.KC == 64) {
+    if (P.BN == 64) {
+      if (ksplit) sa_launch<4, true, 64>(grid, smem, stream, P, *tp);
+      else sa_launch<4, false, 64>(grid, smem, stream, P, *tp);
+    } else {
+      if (ksplit) sa_launch<8, true, 64>(grid, smem, stream, P, *tp);
+      else sa_launch<8, false, 64>(grid, smem, stream, P, *tp);
+    }
   } else {
-    if (ksplit) conv_sa_kernel<8, true><<<grid, SA_THREADS, smem, stream>>>(P, *tp);
-    else conv_sa_kernel<8, false><<<grid, SA_THREADS, smem, stream>>>(P, *tp);
+    if (P.BN == 64) sa_launch<4, false, 32>(grid, smem, stream, P, *tp);
+    else sa_launch<8, false, 32>(grid, smem, stream, P, *tp);
   }
   return cudaGetLastError();
 }
