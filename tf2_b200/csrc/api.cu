@@ -20,7 +20,8 @@
 namespace tf2b {
 // CUDA-core shift-accumulate path (conv_sa.cu)
 cudaError_t launch_conv_sa(const ConvParams& p, int nseg, const int* seg_shift, const int* seg_neg, const int* seg_cbeg,
-                           const int* seg_cend, const void* tmaps, int ksplit, int num_sms, cudaStream_t stream);
+                           const int* seg_cend, const unsigned char* kmask_dev, const void* tmaps, int ksplit, int num_sms,
+                           cudaStream_t stream);
 cudaError_t sa_prepare_device();
 int sa_kc(int Cp);
 int sa_npad(int N);
@@ -49,8 +50,9 @@ cudaError_t launch_conv_mma(const ConvParams& p, const MmaHostParams& hp, int pl
 cudaError_t mma_prepare_device(int* num_sms);
 size_t mma_tmap_bytes();
 std::string mma_describe(const ConvParams& p, int planes8);
-int mma_build_tmaps(void* host_tmaps, const ConvParams& p, const int8_t* wgt8, int planes8,
+int mma_build_tmaps(void* host_tmaps, const ConvParams& p, const int8_t* wgt8, const uint8_t* wgt4, int planes8,
                     std::string* err);
+long long mma_slab_bytes(int k, int Cp, int N, int planes8);
 int mma_bn();
 int mma_pick_bk(int Cp);
 bool mma_pair_mode(int k, int stride, int pad, int Cp, int xC, int OW, int OH, int N, int planes8);
@@ -76,6 +78,7 @@ struct LayerState {
   int seg_cbeg_s[8] = {0, 0, 0, 0, 0, 0, 0, 0};    // channel chunks [cbeg, cend) of every tap the segment spans
   int seg_cend_s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   std::vector<uint8_t> h_w4;
+  std::vector<uint8_t> h_kmask;   // [nseg][taps * chunks]: 16-channel steps of a (segment, tap, chunk) that hold weights
   std::vector<unsigned char> h_tmaps_s;
   // --- mma kernel (int8 planes) ---
   int Npad_m = 0, Kp_m = 0, planes_m = 0;
@@ -86,6 +89,8 @@ struct LayerState {
   std::vector<uint8_t> h_blkmask;   // [taps][K chunks]: 2 bits per 32-channel block of the chunk
   int fast_requant = 0;  // range analysis: no int32 intermediate of pe.cl:191-194 can wrap for this layer
   std::vector<int8_t> h_w8;
+  std::vector<uint8_t> h_w8p;   // the same planes as 4-bit codes (layers whose weight slab is resident in shared memory)
+  size_t off_w8p = 0;
   std::vector<uint8_t> h_nshift_m;  // per-channel base shift of the tensor-core planes
   bool mma_ok = false;
   // --- per-channel params (padded to max(Npad_s, Npad_m)) ---
@@ -93,6 +98,7 @@ struct LayerState {
   std::vector<int32_t> h_bias, h_alpha, h_beta;
   std::vector<uint8_t> h_nshift;
   // device views inside the arena
+  size_t off_kmask = 0;
   size_t off_w4 = 0, off_w8 = 0, off_bias = 0, off_alpha = 0, off_beta = 0, off_nshift = 0, off_nshift_m = 0;
   int kernel = 0;  // 0 none (ipool), 1 shift, 2 mma
   std::vector<unsigned char> h_tmaps;  // CUtensorMap blobs for the mma path (host copy)
@@ -105,6 +111,7 @@ struct BlobLayerMeta {  // fixed-size, trivially copyable: travels inside the we
   int32_t Npad_m, Kp_m, planes_m, plane_shift_m[4], mma_ok, Npar, low_plane_m, nshift_m_len, fast_requant;
   int32_t sparse2_m, blkmask_len;
   uint8_t blkmask[320];
+  int64_t off_kmask, kmask_len, off_w8p, w8p_len;
   int64_t off_w4, off_w8, off_bias, off_alpha, off_beta, off_nshift, off_nshift_m;
 };
 
@@ -290,6 +297,7 @@ static int prepare_layer(tf2b_net* net, LayerState& S, const uint8_t* codes,
       S.seg_cend_s[g] = g < S.nseg_s ? segs[g].ce : 0;
     }
     S.h_w4.assign((size_t)S.nseg_s * S.Npad_s * (S.Kp_s / 2), 0x77);
+    S.h_kmask.assign((size_t)S.nseg_s * kk * cchunks, 0);
     for (int n = 0; n < N; n++)
       for (int c = 0; c < C; c++)
         for (int t = 0; t < kk; t++) {
@@ -311,6 +319,7 @@ static int prepare_layer(tf2b_net* net, LayerState& S, const uint8_t* codes,
           const size_t kidx = ((size_t)t * cchunks * KC) + cc;
           uint8_t& byte = S.h_w4[((size_t)g * S.Npad_s + pout(n)) * (S.Kp_s / 2) + kidx / 2];
           byte = (kidx & 1) ? (uint8_t)((byte & 0x0f) | (nib << 4)) : (uint8_t)((byte & 0xf0) | nib);
+          S.h_kmask[(size_t)g * kk * cchunks + (size_t)t * cchunks + cc / KC] |= (uint8_t)(1u << ((cc % KC) / 16));
         }
   }
   // ---- mma kernel planes: int8 +-2^e, e in 0..6.  A layer whose input may hold -128 can use the
@@ -468,6 +477,21 @@ static int prepare_layer(tf2b_net* net, LayerState& S, const uint8_t* codes,
             for (auto m : S.h_blkmask) any = any || (m & (0x55u << p));
             if (!any) S.h_blkmask[0] |= (uint8_t)(1u << p);
           }
+        }
+      }
+      // packed 4-bit copy of the planes for the layers that keep their weights resident in shared memory: every
+      // entry of a plane is 0 or +-2^e, e <= 6 — exactly one 4-bit code (bit 3 = negative, bits 0..2 = e, 7 = zero)
+      S.h_w8p.clear();
+      if (!pair && tf2b::mma_slab_bytes(k, S.Cp_m, N, np) > 0 && S.Kp_m % 32 == 0) {
+        S.h_w8p.assign(S.h_w8.size() / 2, 0x77);
+        for (size_t i = 0; i < S.h_w8.size(); i++) {
+          const int v = S.h_w8[i];
+          if (!v) continue;
+          unsigned e = 0;
+          for (int m = v < 0 ? -v : v; m > 1; m >>= 1) e++;
+          const unsigned nib = e | (v < 0 ? 8u : 0u);
+          uint8_t& b8 = S.h_w8p[i >> 1];
+          b8 = (i & 1) ? (uint8_t)((b8 & 0x0f) | (nib << 4)) : (uint8_t)((b8 & 0xf0) | nib);
         }
       }
       S.h_nshift_m.assign(round_up(std::max(tf2b::sa_npad(N), S.Npad_m), 16), 0);
@@ -809,7 +833,9 @@ static size_t layout_arena(tf2b_net* net) {
   for (auto& S : net->layers) {
     if (S.d.ipool || !S.loaded) continue;
     S.off_w4 = off; off = align256(off + S.h_w4.size());
+    S.off_kmask = off; off = align256(off + S.h_kmask.size());
     S.off_w8 = off; off = align256(off + S.h_w8.size());
+    S.off_w8p = off; off = align256(off + S.h_w8p.size());
     S.off_bias = off; off = align256(off + (size_t)S.Npar * 4);
     S.off_alpha = off; off = align256(off + (size_t)S.Npar * 4);
     S.off_beta = off; off = align256(off + (size_t)S.Npar * 4);
@@ -886,7 +912,9 @@ int tf2b_finalize(tf2b_net* net, int max_images) {
       return cudaMemcpy(net->arena + off, src, bytes, cudaMemcpyHostToDevice);
     };
     CUDA_TRY(net, up(S.off_w4, S.h_w4.data(), S.h_w4.size()));
+    CUDA_TRY(net, up(S.off_kmask, S.h_kmask.data(), S.h_kmask.size()));
     CUDA_TRY(net, up(S.off_w8, S.h_w8.data(), S.h_w8.size()));
+    CUDA_TRY(net, up(S.off_w8p, S.h_w8p.data(), S.h_w8p.size()));
     CUDA_TRY(net, up(S.off_bias, S.h_bias.data(), (size_t)S.Npar * 4));
     CUDA_TRY(net, up(S.off_alpha, S.h_alpha.data(), (size_t)S.Npar * 4));
     CUDA_TRY(net, up(S.off_beta, S.h_beta.data(), (size_t)S.Npar * 4));
@@ -930,8 +958,10 @@ static ConvParams conv_params(tf2b_net* net, const LayerState& S, int B, int8_t*
   p.k = d.k; p.pad = d.pad; p.stride = d.stride;
   p.relu = d.relu; p.add_relu = d.add_relu;
   p.sparse2 = 0;
+  p.w4_avail = 0;
   if (mma) {
     p.sparse2 = S.sparse2_m;
+    p.w4_avail = S.h_w8p.empty() ? 0 : 1;
     if (S.sparse2_m) memcpy(p.blkmask, S.h_blkmask.data(), std::min(S.h_blkmask.size(), sizeof p.blkmask));
     p.Npad = S.Npad_m; p.Kp = S.Kp_m; p.Ktot = S.Kp_m; p.planes = S.planes_m;
     for (int i = 0; i < tf2b::kMaxPlanes; i++) { p.plane_shift[i] = S.plane_shift_m[i]; p.plane_neg[i] = 0; }
@@ -1022,8 +1052,8 @@ static int build_tmaps(tf2b_net* net) {
     ConvParams p = conv_params(net, S, B, dst, dstC, res, resC, true);
     S.h_tmaps.assign(tf2b::mma_tmap_bytes(), 0);
     std::string err;
-    int rc = tf2b::mma_build_tmaps(S.h_tmaps.data(), p,
-                                   reinterpret_cast<const int8_t*>(net->arena + S.off_w8), S.planes_m, &err);
+    int rc = tf2b::mma_build_tmaps(S.h_tmaps.data(), p, reinterpret_cast<const int8_t*>(net->arena + S.off_w8),
+                                   S.h_w8p.empty() ? nullptr : net->arena + S.off_w8p, S.planes_m, &err);
     if (rc != 0) {
       // not fatal: fall back to the shift kernel for this layer, remember why
       S.mma_ok = false;
@@ -1147,7 +1177,7 @@ static int run_layers(tf2b_net* net, int B, cudaStream_t st0, int only_layer, in
       CUDA_TRY(net, tf2b::launch_conv_mma(p, hp, S.planes_m, S.plane_shift_m, S.h_tmaps.data(), net->num_sms, st));
     } else {
       CUDA_TRY(net, tf2b::launch_conv_sa(p, S.nseg_s, S.seg_shift_s, S.seg_neg_s, S.seg_cbeg_s, S.seg_cend_s,
-                                         S.h_tmaps_s.data(), S.ksplit_s, net->num_sms, st));
+                                         net->arena + S.off_kmask, S.h_tmaps_s.data(), S.ksplit_s, net->num_sms, st));
     }
     launches++;
     if (prof) CUDA_TRY(net, cudaEventRecord(net->ev[3 * l + 1], st));
@@ -1435,6 +1465,8 @@ int tf2b_export_weight_blob(tf2b_net* net, void* dev_dst, void* stream) {
       m.seg_shift_s[i] = S.seg_shift_s[i]; m.seg_neg_s[i] = S.seg_neg_s[i];
       m.seg_cbeg_s[i] = S.seg_cbeg_s[i]; m.seg_cend_s[i] = S.seg_cend_s[i];
     }
+    m.off_kmask = S.off_kmask; m.kmask_len = (int64_t)S.h_kmask.size();
+    m.off_w8p = S.off_w8p; m.w8p_len = (int64_t)S.h_w8p.size();
     m.off_w4 = S.off_w4; m.off_w8 = S.off_w8; m.off_bias = S.off_bias; m.off_alpha = S.off_alpha;
     m.off_beta = S.off_beta; m.off_nshift = S.off_nshift; m.off_nshift_m = S.off_nshift_m;
     m.low_plane_m = S.low_plane_m; m.nshift_m_len = (int32_t)S.h_nshift_m.size(); m.fast_requant = S.fast_requant;
@@ -1506,7 +1538,11 @@ int tf2b_import_weight_blob(tf2b_net* net, const void* dev_src, int64_t blob_byt
       return cudaMemcpy(vec.data(), (const unsigned char*)dev_src + hb + off, count * sizeof(vec[0]), cudaMemcpyDeviceToHost);
     };
     CUDA_TRY(net, pull(S.h_w4, (size_t)S.nseg_s * S.Npad_s * (S.Kp_s / 2), m.off_w4));
+    if (m.kmask_len < 0 || m.kmask_len > (1 << 20)) return fail(net, TF2B_ERR_ARG, "blob layer %zu: bad step mask", l);
+    CUDA_TRY(net, pull(S.h_kmask, (size_t)m.kmask_len, m.off_kmask));
     CUDA_TRY(net, pull(S.h_w8, (size_t)S.planes_m * S.Npad_m * S.Kp_m, m.off_w8));
+    if (m.w8p_len != 0 && m.w8p_len != (int64_t)S.h_w8.size() / 2) return fail(net, TF2B_ERR_ARG, "blob layer %zu: bad packed planes", l);
+    CUDA_TRY(net, pull(S.h_w8p, (size_t)m.w8p_len, m.off_w8p));
     CUDA_TRY(net, pull(S.h_bias, (size_t)S.Npar, m.off_bias));
     CUDA_TRY(net, pull(S.h_alpha, (size_t)S.Npar, m.off_alpha));
     CUDA_TRY(net, pull(S.h_beta, (size_t)S.Npar, m.off_beta));

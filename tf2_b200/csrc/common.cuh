@@ -33,6 +33,7 @@ struct ConvParams {
   int low_plane;                // tensor-core path: plane added without the per-channel 2^nshift, or -1
   int fast_requant;             // load-time range analysis proved that no int32 intermediate of the
                                 // requantisation can wrap: the fused 64-bit form is exact
+  int w4_avail;                 // tensor-core path: a packed 4-bit copy of the weight planes exists (resident-weight layers)
   int sparse2;                  // tensor-core path, two planes: issue per plane, skip the (tap, 32-channel block, plane)
   unsigned char blkmask[320];   // combinations that hold no weights: [tap][K chunk], 2 bits per block of the chunk
 };

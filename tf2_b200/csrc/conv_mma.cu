@@ -133,6 +133,8 @@ struct MmaParams {
   int b_stage_bytes;        // bytes of weights one CTA stages per k-iteration
   int egroups;              // epilogue warp groups (1: all 16 warps share every tile; 2: 8 warps per tile,
                             // the groups take alternate tiles = alternate TMEM buffers)
+  int b_packed4;            // resident weights arrive as PACKED 4-bit codes (TMA) and are expanded on the fly, once per CTA,
+                            // into the swizzled K-major int8 slab the MMAs read (4bit_data_format.txt's information content)
   int sparse2;              // two planes issued separately (N = BN each), empty (tap, block, plane) combinations skipped
   unsigned p1mul;           // 2^shift of the second plane (128 with the plain 7-level planes)
   unsigned idesc1;          // instruction descriptor of a one-plane MMA (N = BN)
@@ -146,6 +148,7 @@ struct TmapPair {
   CUtensorMap b;
   CUtensorMap r;   // residual operand (flat layers): [pixels][channels], 128 x 128-byte boxes; CTA pairs: weight half tile
   CUtensorMap y;   // output of flat layers with the folded epilogue: [pixels][channels], per-warp 32-row boxes (TMA store)
+  CUtensorMap p;   // packed 4-bit weight planes [planes * Npad][Kp / 2] (resident-weight layers)
 };
 
 
@@ -400,6 +403,21 @@ __device__ __forceinline__ void stg256(void* p, const uint4& lo, const uint4& hi
                : "memory");
 }
 
+// Eight 4-bit codes (code i in bits 4i..4i+3: bit 3 = negative, bits 0..2 = exponent e, 7 = zero) -> eight int8
+// weights +-2^e (lo = weights 0..3, hi = 4..7): PRMT look-up of the magnitude, PRMT sign-replicate for the mask,
+// -m = ~m + 1 per byte (m >= 1 wherever the mask is set: no carry between bytes)
+__device__ __forceinline__ void expand8(unsigned w, unsigned& lo, unsigned& hi) {
+  const unsigned T0 = 0x08040201u, T1 = 0x00402010u;
+  const unsigned w4 = w << 4;
+  unsigned mlo, mhi, slo, shi;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(mlo) : "r"(T0), "r"(T1), "r"(w & 0x7777u));
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(mhi) : "r"(T0), "r"(T1), "r"((w >> 16) & 0x7777u));
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(slo) : "r"(w), "r"(w4), "r"(0x9D8Cu));
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(shi) : "r"(w), "r"(w4), "r"(0xBFAEu));
+  lo = (mlo ^ slo) + (slo & 0x01010101u);
+  hi = (mhi ^ shi) + (shi & 0x01010101u);
+}
+
 // saturating pack of four int32 into int8x4 (y0 in byte 0): cvt.pack.sat clamps to [-128,127]
 __device__ __forceinline__ unsigned pack_sat4(int y0, int y1, int y2, int y3) {
   unsigned hi, r;
@@ -542,6 +560,44 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
   // prefetch, row LUT) overlaps the tail of the previous layer's kernel; from here on this grid
   // reads what that kernel wrote, so wait for it to complete and flush.  The next layer's grid may
   // be scheduled as soon as SMs free up (it blocks at its own wait).
+  // Resident weights from PACKED 4-bit tiles (weights do not depend on the previous layer, so this whole block
+  // overlaps that layer's tail under programmatic dependent launch): one thread TMA-loads the CTA's slab as
+  // nibbles (bit 3 = negative, bits 0..2 = exponent, 7 = zero) into the still idle pipeline ring, every thread
+  // expands 16 codes at a time into the swizzled K-major int8 layout the UMMA descriptors expect, and a proxy
+  // fence hands the slab to the tensor core.
+  if (P.b_packed4 && (int)blockIdx.x < num_tiles) {
+    const int n0p = decode_tile(P, blockIdx.x).n0;
+    const int ntile = P.taps * P.kchunks * P.planes;
+    const int ptile = b_plane >> 1;   // bytes of one packed tile
+    if (warp == 0) {
+      if (elect_one()) {
+        mbar_expect_tx(bres_bar, (unsigned)(ntile * ptile));
+        for (int tap = 0; tap < P.taps; tap++)
+          for (int kc = 0; kc < P.kchunks; kc++)
+            for (int pl = 0; pl < P.planes; pl++)
+              tma_load_2d(smem_base + ((tap * P.kchunks + kc) * P.planes + pl) * ptile, &maps.p, bres_bar,
+                          (tap * P.Cpm + kc * P.BK) >> 1, pl * P.Npad + n0p);
+      }
+      __syncwarp();
+    }
+    mbar_wait(bres_bar, 0);
+    const int cpr = P.BK >> 4;                  // 16-byte output chunks per row
+    const int cpt = BN * cpr;                   // ... per tile
+    const unsigned char* pk_base = smem_raw + (smem_base - smem_u32(smem_raw));
+    unsigned char* out_base = smem_raw + (smem_res - smem_u32(smem_raw));
+    for (int idx = threadIdx.x; idx < ntile * cpt; idx += NUM_THREADS) {
+      const int ti = idx / cpt, rem = idx - ti * cpt;
+      const int row = rem / cpr, j = rem - row * cpr;
+      const uint2 pk = *reinterpret_cast<const uint2*>(pk_base + ti * ptile + row * (P.BK >> 1) + j * 8);
+      uint4 o;
+      expand8(pk.x, o.x, o.y);
+      expand8(pk.y, o.z, o.w);
+      const int swz = (P.BK == 128) ? (row & 7) : ((row >> 1) & 3);   // SWIZZLE_128B / SWIZZLE_64B of the address bits
+      *reinterpret_cast<uint4*>(out_base + ti * b_plane + row * P.BK + ((j ^ swz) << 4)) = o;
+    }
+    fence_proxy_async();
+    __syncthreads();   // slab complete; the ring is free for the activation tiles from here on
+  }
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
@@ -551,7 +607,7 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
     unsigned phase = 0;
     const bool dbg = kExp && P.dbg != nullptr;
     long long w_empty = 0, t_start = clock64();
-    if (P.b_resident && (int)blockIdx.x < num_tiles) {
+    if (P.b_resident && !P.b_packed4 && (int)blockIdx.x < num_tiles) {
       // weight-stationary: every tile of this CTA has the same n-tile (grid is a multiple of
       // n_tiles), so its whole weight slab is fetched once
       const int n0 = decode_tile(P, blockIdx.x).n0;
@@ -791,7 +847,7 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
             umma_i8(d_tmem, da, db, P.idesc, acc0);
             umma_i8(d_tmem, da + 2ull, db + 2ull, P.idesc, 1u);
           }
-          if (!cg2) {
+          if (!cg2 && !P.sparse2) {
             umma_commit(empty_bar + 8 * stage);             // frees the smem stage when the MMAs retire
             if (it == kiters - 1) umma_commit(tfull_bar + 8 * buf);   // accumulators complete -> epilogue
           }
@@ -1557,6 +1613,10 @@ void fill_geometry(MmaParams& P, const ConvParams& c, int planes8) {
   // saturate (bit 3) off
   P.idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((unsigned)((P.BN * P.planes) >> 3) << 17) |
             ((unsigned)((P.cg2 ? 2 * MMA_M : MMA_M) >> 4) << 24);
+  {
+    static const bool allow = env_int("TF2B_MMA_PACKED4", 1) != 0;
+    P.b_packed4 = (allow && c.w4_avail && P.b_resident && P.res_bytes / 2 <= P.stages * stage_bytes_final) ? 1 : 0;
+  }
   P.idesc1 = (2u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(P.BN >> 3) << 17) |
              ((unsigned)((P.cg2 ? 2 * MMA_M : MMA_M) >> 4) << 24);
   P.sparse2 = (c.sparse2 && planes8 == 2 && !P.halo && !P.pair && P.BN >= 128) ? 1 : 0;
@@ -1602,6 +1662,14 @@ bool mma_pair_mode(int k, int stride, int pad, int Cp, int xC, int OW, int OH, i
   return !halo_mode(k, stride, Cp, OW, OH, N, planes8) && pair_mode(k, stride, pad, Cp, xC, OW);
 }
 
+// bytes of the resident weight slab of one n-tile (0 when the layer streams its weights): api.cu keeps a packed
+// 4-bit copy of the planes for the layers that have one
+long long mma_slab_bytes(int k, int Cp, int N, int planes8) {
+  const int BK = pick_bk(Cp), BN = pick_bn(planes8, N);
+  const long long slab = (long long)k * k * ((Cp + BK - 1) / BK) * planes8 * BN * BK;
+  return slab <= 112 * 1024 ? slab : 0;
+}
+
 // can a two-plane layer of this shape use the sparse second plane (streamed or resident weights, not the halo tile)?
 bool mma_sparse2_ok(const tf2b_layer_desc& L, int in_pitch, int N) {
   (void)in_pitch;
@@ -1632,14 +1700,15 @@ std::string mma_describe(const ConvParams& c, int planes8) {
   MmaParams P;
   fill_geometry(P, c, planes8);
   char b[192];
-  snprintf(b, sizeof b, "mma BN%d BK%d planes%d %s%s%s%s%s%s%s stages%d", P.BN, P.BK, planes8,
+  snprintf(b, sizeof b, "mma BN%d BK%d planes%d %s%s%s%s%s%s%s%s stages%d", P.BN, P.BK, planes8,
            P.mode == 0 ? "flat" : (P.halo ? "halo" : (P.pair ? "pixelpair" : "box")), P.b_resident ? " wres" : "",
            P.res_tma ? " restma" : "", fold_applies(c, planes8) ? (c.fast_requant >= 3 ? " fold hi32" : " fold") : "",
-           P.tstore ? " tmastore" : "", P.cg2 ? " ctapair" : "", P.sparse2 ? " sparse2" : "", P.stages);
+           P.tstore ? " tmastore" : "", P.cg2 ? " ctapair" : "", P.sparse2 ? " sparse2" : "", P.b_packed4 ? " packed4" : "", P.stages);
   return std::string(b);
 }
 
-int mma_build_tmaps(void* host_tmaps, const ConvParams& c, const int8_t* wgt8, int planes8, std::string* err) {
+int mma_build_tmaps(void* host_tmaps, const ConvParams& c, const int8_t* wgt8, const uint8_t* wgt4, int planes8,
+                    std::string* err) {
   EncodeTiledFn enc = get_encode_fn(err);
   if (!enc) return -1;
   MmaParams P;
@@ -1706,6 +1775,19 @@ int mma_build_tmaps(void* host_tmaps, const ConvParams& c, const int8_t* wgt8, i
             sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
       if (err) *err = "cuTensorMapEncodeTiled(B half) failed with CUresult " + std::to_string((int)r);
+      return -1;
+    }
+  }
+  memset(&tp->p, 0, sizeof tp->p);
+  if (P.b_packed4) {
+    cuuint64_t dims[2] = {(cuuint64_t)(c.Kp / 2), (cuuint64_t)planes8 * c.Npad};
+    cuuint64_t strides[1] = {(cuuint64_t)(c.Kp / 2)};
+    cuuint32_t box[2] = {(cuuint32_t)(P.BK / 2), (cuuint32_t)P.BN};
+    cuuint32_t es[2] = {1, 1};
+    r = enc(&tp->p, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)wgt4, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      if (err) *err = "cuTensorMapEncodeTiled(packed B) failed with CUresult " + std::to_string((int)r);
       return -1;
     }
   }

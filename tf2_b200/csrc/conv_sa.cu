@@ -58,6 +58,8 @@ struct SaParams {
   int Npad;                 // rows per segment in the packed weight matrix
   int a_bytes, b_bytes;     // bytes one stage receives
   int ksplit;               // 1: the two half-warps take alternate 16-channel steps, partial sums via shuffles
+  const unsigned char* kmask;   // [nseg][taps * cchunks]: which 16-channel steps of a (segment, tap, chunk) hold weights;
+                                // 0 = the whole chunk is skipped by the producer and the MACs alike
 };
 
 struct SaMaps {
@@ -192,16 +194,8 @@ conv_sa_kernel(const __grid_constant__ SaParams P, const __grid_constant__ SaMap
   //      into the stage of chunk i - 1, which every warp has left once it is past the CTA barrier of chunk i.
   int p_tile = blockIdx.x, p_g = 0, p_tap = 0, p_cc = P.seg_cbeg[0], p_stage = 0;
   SaTile p_tc = sa_decode(P, p_tile < num_tiles ? p_tile : 0, BM);
-  auto produce = [&]() {
-    if (p_tile >= num_tiles) return;
-    const int fh = p_tap / c.k, fw = p_tap - fh * c.k;
-    const unsigned fb = full_bar + 8 * p_stage;
-    const unsigned sa = smem_u32(smem) + p_stage * stage_bytes;
-    mbar_expect_tx(fb, (unsigned)(P.a_bytes + P.b_bytes));
-    if (P.mode == 0) tma_load_2d(sa, &maps.a, fb, p_cc * KC, p_tc.m0);
-    else tma_load_4d(sa, &maps.a, fb, p_cc * KC, p_tc.ow0 * c.stride - c.pad + fw, p_tc.oh0 * c.stride - c.pad + fh, p_tc.b0);
-    tma_load_2d(sa + a_stage, &maps.b, fb, (p_tap * P.cchunks + p_cc) * (KC / 2), p_g * P.Npad + p_tc.n0);
-    if (++p_stage == SA_STAGES) p_stage = 0;
+  const int mask_row = P.taps * P.cchunks;
+  auto p_advance = [&]() {   // next (segment, tap, chunk) of the cursor, wrapping into the next tile
     if (++p_cc == P.seg_cend[p_g]) {
       if (++p_tap == P.taps) {
         p_tap = 0;
@@ -213,6 +207,20 @@ conv_sa_kernel(const __grid_constant__ SaParams P, const __grid_constant__ SaMap
       }
       p_cc = P.seg_cbeg[p_g];
     }
+  };
+  auto produce = [&]() {
+    // chunks without weights are never staged (the consumers skip them by the same table)
+    while (p_tile < num_tiles && P.kmask[p_g * mask_row + p_tap * P.cchunks + p_cc] == 0) p_advance();
+    if (p_tile >= num_tiles) return;
+    const int fh = p_tap / c.k, fw = p_tap - fh * c.k;
+    const unsigned fb = full_bar + 8 * p_stage;
+    const unsigned sa = smem_u32(smem) + p_stage * stage_bytes;
+    mbar_expect_tx(fb, (unsigned)(P.a_bytes + P.b_bytes));
+    if (P.mode == 0) tma_load_2d(sa, &maps.a, fb, p_cc * KC, p_tc.m0);
+    else tma_load_4d(sa, &maps.a, fb, p_cc * KC, p_tc.ow0 * c.stride - c.pad + fw, p_tc.oh0 * c.stride - c.pad + fh, p_tc.b0);
+    tma_load_2d(sa + a_stage, &maps.b, fb, (p_tap * P.cchunks + p_cc) * (KC / 2), p_g * P.Npad + p_tc.n0);
+    if (++p_stage == SA_STAGES) p_stage = 0;
+    p_advance();
   };
   if (t == 0)
     for (int i = 0; i < SA_STAGES - 1; i++) produce();
@@ -237,8 +245,11 @@ conv_sa_kernel(const __grid_constant__ SaParams P, const __grid_constant__ SaMap
       for (int j = 0; j < TN; j++) acc[i][j] = 0;
     for (int g = 0; g < P.nseg; g++) {
       const bool neg = P.seg_neg[g] != 0;
-      const int chunks_of_seg = P.taps * (P.seg_cend[g] - P.seg_cbeg[g]);
-      for (int ch = 0; ch < chunks_of_seg; ch++) {
+      const unsigned char* mrow = P.kmask + g * mask_row;
+      for (int tap = 0; tap < P.taps; tap++)
+      for (int cc = P.seg_cbeg[g]; cc < P.seg_cend[g]; cc++) {
+        const unsigned kmask = mrow[tap * P.cchunks + cc];
+        if (kmask == 0) continue;   // (warp-uniform, CTA-uniform: the producer skipped it too)
         mbar_wait(full_bar + 8 * stage, phase);
         const unsigned char* As = smem + stage * stage_bytes;
         const unsigned char* Bp = As + a_stage;
@@ -269,6 +280,7 @@ conv_sa_kernel(const __grid_constant__ SaParams P, const __grid_constant__ SaMap
         // ---- MACs: 16 channels per step as 4 x IDP.4A per (pixel, channel) pair
 #pragma unroll
         for (int ks = kh; ks < ksteps; ks += (KSPLIT ? 2 : 1)) {
+          if (!((kmask >> ks) & 1u)) continue;   // no weight of this segment in these 16 channels
           uint4 a[TM];
 #pragma unroll
           for (int i = 0; i < TM; i++) {
@@ -409,9 +421,10 @@ EncodeTiledFn sa_encode_fn(std::string* err) {
 }
 
 void sa_geometry(SaParams& P, const ConvParams& c, int nseg, const int* seg_shift, const int* seg_neg, int ksplit,
-                 const int* seg_cbeg = nullptr, const int* seg_cend = nullptr) {
+                 const int* seg_cbeg = nullptr, const int* seg_cend = nullptr, const unsigned char* kmask = nullptr) {
   memset(&P, 0, sizeof P);
   P.c = c;
+  P.kmask = kmask;
   P.ksplit = ksplit;
   const int BM = ksplit ? 64 : SA_BM;
   P.BN = c.N > 64 ? 128 : 64;
@@ -542,9 +555,10 @@ cudaError_t sa_prepare_device() {
 }
 
 cudaError_t launch_conv_sa(const ConvParams& c, int nseg, const int* seg_shift, const int* seg_neg, const int* seg_cbeg,
-                           const int* seg_cend, const void* tmaps, int ksplit, int num_sms, cudaStream_t stream) {
+                           const int* seg_cend, const unsigned char* kmask_dev, const void* tmaps, int ksplit, int num_sms,
+                           cudaStream_t stream) {
   SaParams P;
-  sa_geometry(P, c, nseg, seg_shift, seg_neg, ksplit, seg_cbeg, seg_cend);
+  sa_geometry(P, c, nseg, seg_shift, seg_neg, ksplit, seg_cbeg, seg_cend, kmask_dev);
   const int num_tiles = P.m_tiles * P.n_tiles;
   const int BM = ksplit ? 64 : SA_BM;
   const int stage_bytes = BM * P.KC + P.BN * (P.KC / 2);
