@@ -33,6 +33,12 @@ extern "C" {
 #define TF2B_VARIANT_SHIFT 1 /* CUDA-core shift-accumulate kernel for every layer (BASELINE configs[1]) */
 #define TF2B_VARIANT_MMA 2   /* force the tensor-core path on every layer it supports (configs[2]) */
 
+/* how the tensor-core kernel receives the weights of layers whose weight slab stays resident in shared memory
+ * (tf2b_set_weight_staging; the CUDA-core kernel ALWAYS reads packed 4-bit tiles and expands them on the fly) */
+#define TF2B_WEIGHTS_PLANES 0  /* int8 +-2^e planes expanded at load time (default: fastest) */
+#define TF2B_WEIGHTS_PACKED4 1 /* packed 4-bit tiles (4bit_data_format.txt's information content) fetched by TMA and */
+                               /* expanded on the fly, once per CTA, into the swizzled K-major int8 slab             */
+
 /* layouts accepted/produced at the boundary */
 #define TF2B_LAYOUT_CHW 0 /* [image][C][H][W] — the reference host order (input_loader.cpp:76-97) */
 #define TF2B_LAYOUT_HWC 1 /* [image][H][W][C] — the engine's native order */
@@ -102,6 +108,9 @@ int tf2b_load_layer_packed4(tf2b_net* net, int layer, const uint8_t* nibbles, in
 int tf2b_finalize(tf2b_net* net, int max_images);
 
 int tf2b_set_variant(tf2b_net* net, int variant);
+
+/* Weight staging of the tensor-core kernel (TF2B_WEIGHTS_*); call before tf2b_finalize. */
+int tf2b_set_weight_staging(tf2b_net* net, int mode);
 
 /* Executor: by default (on = 1) the layer sequence of a batch size is captured once into a CUDA graph (the
  * programmatic-dependent-launch edges between consecutive layers included) and replayed by every later run of

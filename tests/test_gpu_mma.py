@@ -186,3 +186,52 @@ def test_mma_modes(name, chw, spec, B, ckw, want):
         o = r.run_device(torch.from_numpy(x[:nb].copy()).cuda()).cpu().numpy()
         assert np.array_equal(o, out[:nb]), f"{name}: sub-batch of {nb} differs"
     nw.CleanUp()
+
+
+# ---- weights from packed 4-bit tiles, expanded on the fly (tf2b_set_weight_staging) ----------------------------------
+PACKED4_CASES = [
+    ("p4_halo_3x3_c64_56", (64, 56, 56), dict(N=64, k=3, pad=1), 2, {}),
+    ("p4_halo_5x5_c16_28", (16, 28, 28), dict(N=32, k=5, pad=2), 3, dict(per_c_offset=0)),
+    ("p4_flat_wres_c64_n256", (64, 28, 28), dict(N=256, k=1, relu=0), 3, {}),
+    ("p4_flat_wres_c256_n64_bk128", (256, 14, 14), dict(N=64, k=1), 3, {}),
+    ("p4_box_wres_s2_c64", (64, 28, 28), dict(N=64, k=3, pad=1, stride=2), 2, dict(per_c_offset=0)),
+    ("p4_residual_bn256", (512, 7, 7), dict(N=128, k=1), 3, dict(per_c_offset=0)),
+]
+
+
+@pytest.mark.parametrize("name,chw,spec,B,ckw", PACKED4_CASES, ids=[c[0] for c in PACKED4_CASES])
+def test_mma_packed4_weight_tiles(name, chw, spec, B, ckw):
+    """TF2B_WEIGHTS_PACKED4: the resident weight slab of the tensor-core kernel arrives as 4-bit codes through TMA and
+    every CTA expands it on the fly into the swizzled K-major int8 layout (SWIZZLE_64B and SWIZZLE_128B tiles, one
+    and two planes).  Same results as the int8 planes and as the oracle, INT32 accumulators included, and the launch
+    plan says `packed4`."""
+    import torch
+    from tf2_b200.network import NetWork, Runner
+    rng = np.random.default_rng(zlib.crc32(name.encode()))
+    net = nets.chain(chw, [dict(N=chw[0], k=1, relu=1), dict(spec)], name)
+    x = H.random_input(rng, *chw, nonneg=True, B=B)
+    old = H.random_codes
+    try:
+        if ckw:
+            H.random_codes = lambda rng_, N, C, k, **kw: old(rng_, N, C, k, **ckw)
+        model = H.random_model(net, rng, x)
+    finally:
+        H.random_codes = old
+    outs = {}
+    for staging in (capi.WEIGHTS_PLANES, capi.WEIGHTS_PACKED4):
+        nw = NetWork(net, 0)
+        nw.set_weight_staging(staging)
+        nw.InitFromCodes(model, None, max_images=B, variant=capi.VARIANT_MMA)
+        plan = nw.layer_modes(B)[1]
+        assert ("packed4" in plan) == (staging == capi.WEIGHTS_PACKED4), plan
+        assert "wres" in plan or "halo" in plan, plan
+        r = Runner(nw)
+        outs[staging] = r.run_device(torch.from_numpy(x).cuda()).cpu().numpy()
+        if staging == capi.WEIGHTS_PACKED4:
+            g = r.dump_acc(1, B).cpu().numpy()
+            for b in range(B):
+                tens, accs = H.oracle_tensors(net, model, x[b])
+                assert np.array_equal(outs[staging][b], tens[net.result_tensor()]), f"{name} [{plan}]: image {b} differs from the oracle"
+                assert np.array_equal(g[b], accs[1]), f"{name} [{plan}]: image {b} INT32 accumulators differ"
+        nw.CleanUp()
+    assert np.array_equal(outs[capi.WEIGHTS_PLANES], outs[capi.WEIGHTS_PACKED4])

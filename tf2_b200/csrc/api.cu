@@ -165,6 +165,7 @@ struct tf2b_net {
   bool lane_used[kLanes] = {true, false, false, false};
   bool multi_stream = true;
   bool permute = true;      // choose_permutations at finalize (off: natural channel order everywhere)
+  int weight_staging = TF2B_WEIGHTS_PLANES;   // tensor-core path, resident-weight layers: int8 planes or packed 4-bit tiles
   bool use_graph = true;
   struct GraphEntry { int B; int launches; cudaGraphExec_t exec; };
   std::vector<GraphEntry> graphs;
@@ -482,7 +483,8 @@ static int prepare_layer(tf2b_net* net, LayerState& S, const uint8_t* codes,
       // packed 4-bit copy of the planes for the layers that keep their weights resident in shared memory: every
       // entry of a plane is 0 or +-2^e, e <= 6 — exactly one 4-bit code (bit 3 = negative, bits 0..2 = e, 7 = zero)
       S.h_w8p.clear();
-      if (!pair && tf2b::mma_slab_bytes(k, S.Cp_m, N, np) > 0 && S.Kp_m % 32 == 0) {
+      if (net->weight_staging == TF2B_WEIGHTS_PACKED4 && !pair && tf2b::mma_slab_bytes(k, S.Cp_m, N, np) > 0 &&
+          S.Kp_m % 32 == 0) {
         S.h_w8p.assign(S.h_w8.size() / 2, 0x77);
         for (size_t i = 0; i < S.h_w8.size(); i++) {
           const int v = S.h_w8[i];
@@ -815,6 +817,14 @@ int tf2b_set_variant(tf2b_net* net, int variant) {
   return TF2B_OK;
 }
 
+int tf2b_set_weight_staging(tf2b_net* net, int mode) {
+  if (!net) return TF2B_ERR_ARG;
+  if (net->finalized) return fail(net, TF2B_ERR_STATE, "tf2b_set_weight_staging after tf2b_finalize");
+  if (mode != TF2B_WEIGHTS_PLANES && mode != TF2B_WEIGHTS_PACKED4) return fail(net, TF2B_ERR_ARG, "unknown weight staging %d", mode);
+  net->weight_staging = mode;
+  return TF2B_OK;
+}
+
 int tf2b_set_result(tf2b_net* net, int tensor) {
   if (!net) return TF2B_ERR_ARG;
   if (tensor < 0 || tensor >= (int)net->tensors.size()) return fail(net, TF2B_ERR_ARG, "tensor out of range");
@@ -961,7 +971,7 @@ static ConvParams conv_params(tf2b_net* net, const LayerState& S, int B, int8_t*
   p.w4_avail = 0;
   if (mma) {
     p.sparse2 = S.sparse2_m;
-    p.w4_avail = S.h_w8p.empty() ? 0 : 1;
+    p.w4_avail = (net->weight_staging == TF2B_WEIGHTS_PACKED4 && !S.h_w8p.empty()) ? 1 : 0;
     if (S.sparse2_m) memcpy(p.blkmask, S.h_blkmask.data(), std::min(S.h_blkmask.size(), sizeof p.blkmask));
     p.Npad = S.Npad_m; p.Kp = S.Kp_m; p.Ktot = S.Kp_m; p.planes = S.planes_m;
     for (int i = 0; i < tf2b::kMaxPlanes; i++) { p.plane_shift[i] = S.plane_shift_m[i]; p.plane_neg[i] = 0; }

@@ -1614,8 +1614,7 @@ void fill_geometry(MmaParams& P, const ConvParams& c, int planes8) {
   P.idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((unsigned)((P.BN * P.planes) >> 3) << 17) |
             ((unsigned)((P.cg2 ? 2 * MMA_M : MMA_M) >> 4) << 24);
   {
-    static const bool allow = env_int("TF2B_MMA_PACKED4", 1) != 0;
-    P.b_packed4 = (allow && c.w4_avail && P.b_resident && P.res_bytes / 2 <= P.stages * stage_bytes_final) ? 1 : 0;
+    P.b_packed4 = (c.w4_avail && P.b_resident && P.res_bytes / 2 <= P.stages * stage_bytes_final) ? 1 : 0;
   }
   P.idesc1 = (2u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(P.BN >> 3) << 17) |
              ((unsigned)((P.cg2 ? 2 * MMA_M : MMA_M) >> 4) << 24);
@@ -1671,10 +1670,14 @@ long long mma_slab_bytes(int k, int Cp, int N, int planes8) {
 }
 
 // can a two-plane layer of this shape use the sparse second plane (streamed or resident weights, not the halo tile)?
+// MEASURED AND SWITCHED OFF (profiles/r02_ab_sparse2.md): one-plane instructions (N = 128) keep the tensor pipe
+// less busy than the two-plane N = 256 ones they replace — every K-heavy layer of ResNet50 got 15-50 % slower
+// although 25-45 % fewer (block, plane) pairs were issued.  The code path stays for experiment builds.
 bool mma_sparse2_ok(const tf2b_layer_desc& L, int in_pitch, int N) {
   (void)in_pitch;
+  static const bool allow = env_int("TF2B_MMA_SPARSE2", 0) != 0;
   const int Cp = (L.C + 15) / 16 * 16;
-  return pick_bn(2, N) >= 128 && !halo_mode(L.k, L.stride, Cp, L.OW, L.OH, N, 2);
+  return allow && pick_bn(2, N) >= 128 && !halo_mode(L.k, L.stride, Cp, L.OW, L.OH, N, 2);
 }
 
 bool mma_layer_supported(const tf2b_layer_desc& L, int in_pitch, int planes8) {

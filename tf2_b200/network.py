@@ -85,6 +85,11 @@ class NetWork:
         with open(q_file, "r") as f:
             return self.InitFromMemory(blob, f.read(), max_images, variant)
 
+    def set_weight_staging(self, mode: int):
+        """capi.WEIGHTS_PLANES (default) / capi.WEIGHTS_PACKED4 for the tensor-core kernel's resident-weight layers;
+        before Init*."""
+        self._check(self._lib.tf2b_set_weight_staging(self._h, mode))
+
     def InitFromCodes(self, model, q: Optional[np.ndarray], max_images: int = 1,
                       variant: int = capi.VARIANT_AUTO):
         """`model`: per layer (codes uint8 [N][C][k][k], params int32 [N][3]) or (None, None)."""
