@@ -165,9 +165,23 @@ struct tf2b_net {
   bool lane_used[kLanes] = {true, false, false, false};
   bool multi_stream = true;
   bool permute = true;      // choose_permutations at finalize (off: natural channel order everywhere)
+  // Chunked stem (raw 3x224x224 entry point, first layer = convolution + pool): the batch goes through
+  // space-to-depth -> conv1 -> max pool in chunks of kStemChunk images whose intermediates live in two chunk-sized
+  // buffers that are REUSED by every chunk, so they stay in the 126 MB L2 (no DRAM round trip of the 64-byte/pixel
+  // tensor 0 and of conv1's 112x112x64 map).  Tensor 0 is then not materialised for the whole batch; the debug taps
+  // re-create it from the last raw input on demand.
+  static constexpr int kStemChunk = 32;
+  bool stem_chunked = false;
+  bool stem_chunk_on = true;
+  int8_t* stem_t0 = nullptr;          // [kStemChunk][114][114][64]
+  int8_t* stem_conv = nullptr;        // [kStemChunk][OH][OW][Np16]
+  std::vector<unsigned char> stem_tmaps;
+  const int8_t* last_raw = nullptr;   // raw input of the last chunked run (debug taps)
+  int last_raw_images = 0;
+  bool t0_stale = false;
   int weight_staging = TF2B_WEIGHTS_PLANES;   // tensor-core path, resident-weight layers: int8 planes or packed 4-bit tiles
   bool use_graph = true;
-  struct GraphEntry { int B; int launches; cudaGraphExec_t exec; };
+  struct GraphEntry { int B; const void* raw; int launches; cudaGraphExec_t exec; };
   std::vector<GraphEntry> graphs;
   bool profile = false;
   std::vector<cudaEvent_t> ev;  // 3 per layer: layer start, conv end, layer end
@@ -196,6 +210,7 @@ static int fail(tf2b_net* n, int code, const char* fmt, ...) {
 static thread_local std::string g_create_err;
 extern "C" {
 static int ensure_io(tf2b_net* net);
+static int build_tmaps(tf2b_net* net);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -814,6 +829,7 @@ int tf2b_set_variant(tf2b_net* net, int variant) {
     if (S.d.ipool) { S.kernel = 0; continue; }
     S.kernel = (variant != TF2B_VARIANT_SHIFT && S.mma_ok) ? 2 : 1;
   }
+  if (net->finalized && net->stem_chunked) return build_tmaps(net);   // the chunked stem's maps belong to one kernel family
   return TF2B_OK;
 }
 
@@ -889,7 +905,6 @@ int64_t tf2b_weight_blob_bytes(tf2b_net* net) {
 }
 
 static int alloc_runtime(tf2b_net* net);
-static int build_tmaps(tf2b_net* net);
 static int build_schedule(tf2b_net* net);
 
 int tf2b_finalize(tf2b_net* net, int max_images) {
@@ -1044,6 +1059,19 @@ static int alloc_runtime(tf2b_net* net) {
     int rc = ensure_io(net);
     if (rc != TF2B_OK) return rc;
   }
+  // chunk buffers of the stem (only when a run can be larger than one chunk)
+  {
+    const tf2b_layer_desc& d0 = net->layers[0].d;
+    const tf2b_tensor_desc& t0 = net->tensors[0];
+    net->stem_chunked = net->stem_chunk_on && B > tf2b_net::kStemChunk && !d0.ipool && d0.in_tensor == 0 && d0.pool && !d0.gap &&
+                        t0.C == 27 && t0.H == 114 && t0.W == 114;
+    if (net->stem_chunked) {
+      const size_t n = tf2b_net::kStemChunk;
+      CUDA_TRY(net, cudaMalloc(&net->stem_t0, n * t0.H * t0.W * net->tpitch[0] + 256));
+      CUDA_TRY(net, cudaMalloc(&net->stem_conv, n * d0.OH * d0.OW * round_up(d0.N, 16) + 256));
+      CUDA_TRY(net, cudaMemset(net->stem_t0, 0, n * t0.H * t0.W * net->tpitch[0] + 256));
+    }
+  }
   return build_tmaps(net);
 }
 
@@ -1069,6 +1097,25 @@ static int build_tmaps(tf2b_net* net) {
       S.mma_ok = false;
       net->err = "mma tensor map: " + err;
     }
+  }
+  // chunked stem: conv1's maps over the chunk buffers
+  if (net->stem_chunked) {
+    LayerState& S0 = net->layers[0];
+    const tf2b_layer_desc& d0 = S0.d;
+    const bool mma0 = S0.kernel == 2 ? S0.mma_ok : (net->variant != TF2B_VARIANT_SHIFT && S0.mma_ok);
+    ConvParams p = conv_params(net, S0, tf2b_net::kStemChunk, net->stem_conv, round_up(d0.N, 16), nullptr, 0, mma0);
+    p.x = net->stem_t0;
+    std::string err;
+    int rc;
+    if (mma0) {
+      net->stem_tmaps.assign(tf2b::mma_tmap_bytes(), 0);
+      rc = tf2b::mma_build_tmaps(net->stem_tmaps.data(), p, reinterpret_cast<const int8_t*>(net->arena + S0.off_w8),
+                                 S0.h_w8p.empty() ? nullptr : net->arena + S0.off_w8p, S0.planes_m, &err);
+    } else {
+      net->stem_tmaps.assign(tf2b::sa_tmap_bytes(), 0);
+      rc = tf2b::sa_build_tmaps(net->stem_tmaps.data(), p, net->arena + S0.off_w4, S0.nseg_s, S0.ksplit_s, &err);
+    }
+    if (rc != 0) net->stem_chunked = false;   // fall back to the whole-batch stem
   }
   // ... and those of the shift-accumulate path (every convolution has one: it is the exact fallback)
   for (auto& S : net->layers) {
@@ -1131,7 +1178,8 @@ static int build_schedule(tf2b_net* net) {
   return TF2B_OK;
 }
 
-static int run_layers(tf2b_net* net, int B, cudaStream_t st0, int only_layer, int32_t* acc_dump) {
+static int run_layers(tf2b_net* net, int B, cudaStream_t st0, int only_layer, int32_t* acc_dump,
+                      const int8_t* raw_chunked = nullptr) {
   int launches = 0;
   const bool prof = net->profile && only_layer < 0 && !net->ev.empty();
   // several lanes only for whole-network runs outside the per-layer profiler
@@ -1164,6 +1212,30 @@ static int run_layers(tf2b_net* net, int B, cudaStream_t st0, int only_layer, in
       if (prof) {
         CUDA_TRY(net, cudaEventRecord(net->ev[3 * l + 1], st));
         CUDA_TRY(net, cudaEventRecord(net->ev[3 * l + 2], st));
+      }
+      if (lanes && net->need_event[l]) CUDA_TRY(net, cudaEventRecord(net->ev_layer[l], st));
+      continue;
+    }
+    if (l == 0 && raw_chunked != nullptr) {
+      // chunked stem: space-to-depth -> conv1 -> pool per chunk through the L2-resident chunk buffers
+      const int Np16c = round_up(d.N, 16);
+      const bool mma0 = S.kernel == 2 && S.mma_ok;
+      for (int b0 = 0; b0 < B; b0 += tf2b_net::kStemChunk) {
+        const int nb = std::min(tf2b_net::kStemChunk, B - b0);
+        CUDA_TRY(net, tf2b::launch_raw224_to_s2d(raw_chunked + (size_t)b0 * 3 * 224 * 224, net->stem_t0, nb, 1, st));
+        ConvParams pc = conv_params(net, S, nb, net->stem_conv, Np16c, nullptr, 0, mma0);
+        pc.x = net->stem_t0;
+        if (mma0) {
+          const tf2b::MmaHostParams hp = {S.h_bias.data(), S.h_alpha.data(), S.h_beta.data(), S.h_nshift_m.data()};
+          CUDA_TRY(net, tf2b::launch_conv_mma(pc, hp, S.planes_m, S.plane_shift_m, net->stem_tmaps.data(), net->num_sms, st));
+        } else {
+          CUDA_TRY(net, tf2b::launch_conv_sa(pc, S.nseg_s, S.seg_shift_s, S.seg_neg_s, S.seg_cbeg_s, S.seg_cend_s,
+                                             net->arena + S.off_kmask, net->stem_tmaps.data(), S.ksplit_s, net->num_sms, st));
+        }
+        const size_t poff = (size_t)b0 * d.PH * d.PW;
+        CUDA_TRY(net, tf2b::launch_maxpool3x3(net->stem_conv, out + poff * outC, res ? res + poff * resC : nullptr, nb, d.OH, d.OW,
+                                              Np16c, d.PH, d.PW, outC, resC, d.N, d.pool_stride, d.pool_pad, d.add_relu, st));
+        launches += 3;
       }
       if (lanes && net->need_event[l]) CUDA_TRY(net, cudaEventRecord(net->ev_layer[l], st));
       continue;
@@ -1223,23 +1295,24 @@ static int run_layers(tf2b_net* net, int B, cudaStream_t st0, int only_layer, in
 // Runs the layer sequence for B images on `st`: replays the captured CUDA graph of this batch size (captured on
 // first use), or launches kernel by kernel when graphs are off, the stream cannot capture (legacy default
 // stream), or per-layer profiling is on.
-static int run_layers_exec(tf2b_net* net, int B, cudaStream_t st) {
-  if (!net->use_graph || net->profile || st == nullptr || st == cudaStreamLegacy) return run_layers(net, B, st, -1, nullptr);
+static int run_layers_exec(tf2b_net* net, int B, cudaStream_t st, const int8_t* raw_chunked = nullptr) {
+  if (!net->use_graph || net->profile || st == nullptr || st == cudaStreamLegacy)
+    return run_layers(net, B, st, -1, nullptr, raw_chunked);
   for (auto& g : net->graphs)
-    if (g.B == B) {
+    if (g.B == B && g.raw == (const void*)raw_chunked) {
       CUDA_TRY(net, cudaGraphLaunch(g.exec, st));
       net->last_launches += g.launches;
       return TF2B_OK;
     }
   cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
   if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone)
-    return run_layers(net, B, st, -1, nullptr);   // the caller is capturing already: become part of its graph
+    return run_layers(net, B, st, -1, nullptr, raw_chunked);   // the caller is capturing already: become part of its graph
   if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
     cudaGetLastError();
-    return run_layers(net, B, st, -1, nullptr);
+    return run_layers(net, B, st, -1, nullptr, raw_chunked);
   }
   const int before = net->last_launches;
-  int rc = run_layers(net, B, st, -1, nullptr);
+  int rc = run_layers(net, B, st, -1, nullptr, raw_chunked);
   cudaGraph_t graph = nullptr;
   cudaError_t ce = cudaStreamEndCapture(st, &graph);
   const int launches = net->last_launches - before;
@@ -1248,7 +1321,7 @@ static int run_layers_exec(tf2b_net* net, int B, cudaStream_t st) {
     cudaGetLastError();
     net->use_graph = false;                      // capture is not possible here: stay with plain launches
     net->last_launches = before;
-    return rc != TF2B_OK ? rc : run_layers(net, B, st, -1, nullptr);
+    return rc != TF2B_OK ? rc : run_layers(net, B, st, -1, nullptr, raw_chunked);
   }
   cudaGraphExec_t exec = nullptr;
   ce = cudaGraphInstantiate(&exec, graph, 0);
@@ -1257,14 +1330,22 @@ static int run_layers_exec(tf2b_net* net, int B, cudaStream_t st) {
     cudaGetLastError();
     net->use_graph = false;
     net->last_launches = before;
-    return run_layers(net, B, st, -1, nullptr);
+    return run_layers(net, B, st, -1, nullptr, raw_chunked);
   }
-  if (net->graphs.size() >= 8) {                 // a handful of batch sizes at most
+  if (net->graphs.size() >= 12) {                // a handful of batch sizes / input buffers at most
     cudaGraphExecDestroy(net->graphs.front().exec);
     net->graphs.erase(net->graphs.begin());
   }
-  net->graphs.push_back({B, launches, exec});
+  net->graphs.push_back({B, (const void*)raw_chunked, launches, exec});
   CUDA_TRY(net, cudaGraphLaunch(exec, st));
+  return TF2B_OK;
+}
+
+// debug taps of a chunked run: tensor 0 was never materialised for the whole batch — rebuild it from the last raw input
+static int refresh_t0(tf2b_net* net, cudaStream_t st) {
+  if (!net->t0_stale || !net->last_raw) return TF2B_OK;
+  CUDA_TRY(net, tf2b::launch_raw224_to_s2d(net->last_raw, net->tbuf[0], net->last_raw_images, 1, st));
+  net->t0_stale = false;
   return TF2B_OK;
 }
 
@@ -1312,6 +1393,7 @@ int tf2b_run(tf2b_net* net, const int8_t* in_dev, int in_layout, int n_images, i
     return fail(net, TF2B_ERR_ARG, "unknown layout %d", in_layout);
   }
   net->last_launches++;
+  net->t0_stale = false;
   rc = run_layers_exec(net, n_images, st);
   if (rc) return rc;
   return write_result(net, net->result_tensor, n_images, out_dev, out_layout, st);
@@ -1329,9 +1411,17 @@ int tf2b_run_raw224(tf2b_net* net, const int8_t* raw_dev, int n_images, int8_t* 
   CUDA_TRY(net, cudaSetDevice(net->device));
   net->last_launches = 0;
   net->last_images = n_images;
-  CUDA_TRY(net, tf2b::launch_raw224_to_s2d(raw_dev, net->tbuf[0], n_images, 1, st));
-  net->last_launches++;
-  rc = run_layers_exec(net, n_images, st);
+  if (net->stem_chunked && n_images > tf2b_net::kStemChunk && !net->profile) {
+    net->last_raw = raw_dev;
+    net->last_raw_images = n_images;
+    net->t0_stale = true;
+    rc = run_layers_exec(net, n_images, st, raw_dev);
+  } else {
+    CUDA_TRY(net, tf2b::launch_raw224_to_s2d(raw_dev, net->tbuf[0], n_images, 1, st));
+    net->last_launches++;
+    net->t0_stale = false;
+    rc = run_layers_exec(net, n_images, st);
+  }
   if (rc) return rc;
   return write_result(net, net->result_tensor, n_images, out_dev, out_layout, st);
 }
@@ -1424,6 +1514,10 @@ int tf2b_read_tensor(tf2b_net* net, int tensor, int n_images, int8_t* dst_dev, i
   if (rc) return rc;
   if (tensor < 0 || tensor >= (int)net->tensors.size() || !dst_dev) return fail(net, TF2B_ERR_ARG, "bad tensor/pointer");
   CUDA_TRY(net, cudaSetDevice(net->device));
+  if (tensor == 0) {
+    int rc0 = refresh_t0(net, (cudaStream_t)stream);
+    if (rc0) return rc0;
+  }
   return write_result(net, tensor, n_images, dst_dev, layout, (cudaStream_t)stream);
 }
 
@@ -1436,6 +1530,10 @@ int tf2b_dump_acc(tf2b_net* net, int layer, int n_images, int32_t* acc_dev, void
   // feature maps of the last run are left untouched
   LayerState& S = net->layers[layer];
   if (S.d.ipool) return fail(net, TF2B_ERR_ARG, "ipool layer has no accumulators");
+  if (S.d.in_tensor == 0) {
+    int rc0 = refresh_t0(net, (cudaStream_t)stream);
+    if (rc0) return rc0;
+  }
   size_t need = (size_t)n_images * S.d.OH * S.d.OW * round_up(S.d.N, 16);
   if (need > net->scratch_bytes) {
     // layers that normally write straight to their tensor may exceed the scratch: grow it
@@ -1646,6 +1744,8 @@ void tf2b_destroy(tf2b_net* net) {
   if (net->arena) cudaFree(net->arena);
   if (net->scratch0) cudaFree(net->scratch0);
   if (net->scratch1) cudaFree(net->scratch1);
+  if (net->stem_t0) cudaFree(net->stem_t0);
+  if (net->stem_conv) cudaFree(net->stem_conv);
   if (net->io_in) cudaFree(net->io_in);
   if (net->io_out) cudaFree(net->io_out);
   if (net->own_stream) cudaStreamDestroy(net->own_stream);

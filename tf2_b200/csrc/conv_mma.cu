@@ -470,7 +470,7 @@ __device__ __forceinline__ unsigned add_res_s8x4(unsigned y4, unsigned r4) {
 // bit2 = residual operand, bit3 = folded form: y = (tot * (alpha << nshift) + (bias*alpha +
 // ((beta + 2^14) << 20))) >> 35 with tot = plane0 + (plane1 << 7) — one IMAD.HI per output; bit4 (with
 // bit3) = every nshift >= 3, so alpha << (nshift-3) and the addend >> 3 make the high word the result.
-template <int BN, int MODE, int EPI, bool CG2 = false>
+template <int BN, int MODE, int EPI, bool CG2 = false, int GRP = 1>
 // (18 warps = 5 on one scheduler: 16 384 registers / (5 warps x 32 lanes) caps the kernel at 96 registers per thread)
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ TmapPair maps) {
@@ -878,12 +878,10 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
     constexpr bool FOLD = FAST && (EPI & 8);
     constexpr bool HI32 = FOLD && (EPI & 16);
     constexpr bool TSTORE_GLOBAL = FOLD && MODE == 0;   // every channel has nshift >= 3: y = hi32(tot*(alpha<<(nshift-3)) + (B>>3))
-#ifndef TF2B_EPI_GROUPS
-#define TF2B_EPI_GROUPS 1
-#endif
-    // epilogue groups; group g owns the tiles with local index % G == g (two groups: the TMEM reads of one tile
-    // overlap the arithmetic of the other).  Flat folded layers only; everything else runs one group.
-    constexpr int G = (FOLD && MODE == 0 && !CG2 && BN == 128) ? TF2B_EPI_GROUPS : 1;
+    // epilogue groups; group g owns the tiles with local index % G == g.  Two groups (flat folded layers with a short
+    // K loop, where the epilogue is the whole kernel): the TMEM reads and barrier waits of one tile overlap the
+    // arithmetic of the other — measured -10 % on the 64 -> 256 layers, +13 % (worse) on 256 -> 1024.
+    constexpr int G = (FOLD && MODE == 0 && !CG2 && BN == 128) ? GRP : 1;
     constexpr int SLICES = 4 / G;         // column slices of a tile (one warp per lane quarter and slice)
     constexpr int WT = BN / SLICES;       // columns per warp: 16..128
     constexpr int W = WT > 32 ? 32 : WT;  // columns per pass (staging tile width)
@@ -1832,6 +1830,7 @@ struct KernelTables {
   KernelFn single[3][2][kEpiVariants];   // [BN 64/128/256][mode][epilogue]
   KernelFn pair[2][2][2][2];             // CTA pairs: [BN 128 two planes / 256 one plane][mode][residual][hi32]
   KernelFn pair_exact[2][2];             // CTA pairs with the exact epilogue (accumulator tap)
+  KernelFn grp2[2][2][2][2];             // flat BN = 128, two epilogue groups: [planes 1/2][residual][hi32] x [fold only = 0]
 };
 const KernelTables& kernel_tables() {
 #define TF2B_EPI_ROW(BN_, MODE_)                                                                              \
@@ -1854,7 +1853,11 @@ const KernelTables& kernel_tables() {
         {{conv_mma_kernel<256, 1, 8, true>, conv_mma_kernel<256, 1, 24, true>},
          {conv_mma_kernel<256, 1, 12, true>, conv_mma_kernel<256, 1, 28, true>}}}},
       {{conv_mma_kernel<128, 0, -1, true>, conv_mma_kernel<128, 1, -1, true>},
-       {conv_mma_kernel<256, 0, -1, true>, conv_mma_kernel<256, 1, -1, true>}}};
+       {conv_mma_kernel<256, 0, -1, true>, conv_mma_kernel<256, 1, -1, true>}},
+      {{{{conv_mma_kernel<128, 0, 8, false, 2>, nullptr}, {conv_mma_kernel<128, 0, 24, false, 2>, nullptr}},
+        {{conv_mma_kernel<128, 0, 12, false, 2>, nullptr}, {conv_mma_kernel<128, 0, 28, false, 2>, nullptr}}},
+       {{{conv_mma_kernel<128, 0, 9, false, 2>, nullptr}, {conv_mma_kernel<128, 0, 25, false, 2>, nullptr}},
+        {{conv_mma_kernel<128, 0, 13, false, 2>, nullptr}, {conv_mma_kernel<128, 0, 29, false, 2>, nullptr}}}}};
 #undef TF2B_EPI_ROW
   return T;
 }
@@ -1908,7 +1911,9 @@ cudaError_t launch_conv_mma(const ConvParams& c, const MmaHostParams& /*hp*/, in
     const int bits = epi - 1;   // 8, 9, 12 or 13
     epi_idx = 17 + ((bits & 1) | ((bits & 4) >> 1));
   }
-  P.egroups = (fold && P.mode == 0 && !P.cg2 && P.BN == 128) ? TF2B_EPI_GROUPS : 1;
+  // two epilogue groups where the K loop is at most 128 channels deep
+  const bool grp2 = fold && P.mode == 0 && !P.cg2 && P.BN == 128 && P.taps * P.kchunks * P.BK <= 128;
+  P.egroups = grp2 ? 2 : 1;
   const KernelTables& T = kernel_tables();
   KernelFn kfn = T.single[P.BN == 256 ? 2 : (P.BN == 128 ? 1 : 0)][P.mode][epi_idx];
   if (P.cg2) {
@@ -1918,6 +1923,7 @@ cudaError_t launch_conv_mma(const ConvParams& c, const MmaHostParams& /*hp*/, in
     kfn = fold ? T.pair[P.BN == 256 ? 1 : 0][P.mode][c.r != nullptr ? 1 : 0][hi32 ? 1 : 0]
                : T.pair_exact[P.BN == 256 ? 1 : 0][P.mode];
   }
+  if (grp2) kfn = T.grp2[scaled_planes == 2 ? 1 : 0][c.r != nullptr ? 1 : 0][hi32 ? 1 : 0][0];
   if (!kfn) return cudaErrorInvalidValue;
   const TmapPair* tp = reinterpret_cast<const TmapPair*>(tmaps);
   P.dbg = nullptr;
