@@ -153,6 +153,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=0, help="images per GPU and step (default: the BASELINE config's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--executor", type=int, default=1, help="tf2b_set_graph: 1 graph + lanes (default), 2 graph, 3 lanes, 0 plain")
+    ap.add_argument("--stem-chunk", type=int, default=1, help="chunked L2-resident stem (default on)")
+    ap.add_argument("--weights", default="planes", choices=["planes", "packed4"], help="tensor-core weight staging")
     ap.add_argument("--layers-out", default=None, help="write per-layer device times (JSON) to this file")
     args = ap.parse_args()
 
@@ -210,6 +213,8 @@ def main():
 
     net = nets.load(args.net)
     nw = NetWork(net, device=local_rank)
+    nw.set_stem_chunk(bool(args.stem_chunk))
+    nw.set_weight_staging(capi.WEIGHTS_PACKED4 if args.weights == "packed4" else capi.WEIGHTS_PLANES)
     q = model = None
     if rank == 0:
         net, q, model = build_model(args.net)
@@ -219,6 +224,7 @@ def main():
         init_network_distributed(nw, dist, dev, model=model, q=q, max_images=B, variant=variant)
     else:
         nw.InitFromCodes(model, q, max_images=B, variant=variant)
+    nw.set_graph(args.executor)
     runner = Runner(nw)
     raw224 = cfg["raw224"]
     t0d = net.tensors[0]
@@ -396,7 +402,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int8xint4->int32", "data": "synthetic",
             "config": config,
-            "details": {"net": args.net, "kernels": {k: kernels.count(k) for k in sorted(set(kernels))},
+            "details": {"net": args.net, "executor": args.executor, "stem_chunk": args.stem_chunk, "weights": args.weights, "kernels": {k: kernels.count(k) for k in sorted(set(kernels))},
                         "l2": f"inputs rotate over {nrot} distinct batches ({nrot * in_bytes / 1e6:.0f} MB); activations per step are GBs",
                         "gmac_per_image": macs / 1e9},
             "clocks": clocks, "gpu_launches": launches,

@@ -34,7 +34,7 @@ class LayerDescC(C.Structure):
 
 # every symbol include/tf2b200.h declares (checked by tests/test_capi_symbols.py)
 SYMBOLS = [
-    "tf2b_create", "tf2b_load_layer", "tf2b_load_layer_packed4", "tf2b_finalize", "tf2b_set_variant", "tf2b_set_graph", "tf2b_set_weight_staging",
+    "tf2b_create", "tf2b_load_layer", "tf2b_load_layer_packed4", "tf2b_finalize", "tf2b_set_variant", "tf2b_set_graph", "tf2b_set_weight_staging", "tf2b_set_stem_chunk",
     "tf2b_weight_blob_bytes", "tf2b_export_weight_blob", "tf2b_import_weight_blob", "tf2b_run",
     "tf2b_run_raw224", "tf2b_run_raw224_host", "tf2b_submit_raw224_host", "tf2b_submit_host", "tf2b_wait", "tf2b_run_host", "tf2b_set_result", "tf2b_read_tensor",
     "tf2b_dump_acc", "tf2b_set_profile", "tf2b_get_profile", "tf2b_last_launches", "tf2b_layer_kernel", "tf2b_layer_mode", "tf2b_last_error", "tf2b_version",
@@ -66,6 +66,7 @@ def load() -> C.CDLL:
     lib.tf2b_set_variant.argtypes = [vp, i32]
     lib.tf2b_set_graph.argtypes = [vp, i32]
     lib.tf2b_set_weight_staging.argtypes = [vp, i32]
+    lib.tf2b_set_stem_chunk.argtypes = [vp, i32]
     lib.tf2b_weight_blob_bytes.argtypes = [vp]
     lib.tf2b_weight_blob_bytes.restype = i64
     lib.tf2b_export_weight_blob.argtypes = [vp, vp, vp]
@@ -93,7 +94,7 @@ def load() -> C.CDLL:
     lib.tf2b_destroy.argtypes = [vp]
     lib.tf2b_destroy.restype = None
     for name in ("tf2b_create", "tf2b_load_layer", "tf2b_load_layer_packed4", "tf2b_finalize",
-                 "tf2b_set_variant", "tf2b_set_graph", "tf2b_set_weight_staging", "tf2b_export_weight_blob", "tf2b_import_weight_blob", "tf2b_run",
+                 "tf2b_set_variant", "tf2b_set_graph", "tf2b_set_weight_staging", "tf2b_set_stem_chunk", "tf2b_export_weight_blob", "tf2b_import_weight_blob", "tf2b_run",
                  "tf2b_run_raw224", "tf2b_run_raw224_host", "tf2b_submit_raw224_host", "tf2b_submit_host", "tf2b_wait", "tf2b_run_host", "tf2b_set_result",
                  "tf2b_read_tensor", "tf2b_dump_acc", "tf2b_last_launches", "tf2b_set_profile", "tf2b_get_profile"):
         getattr(lib, name).restype = i32

@@ -841,6 +841,13 @@ int tf2b_set_weight_staging(tf2b_net* net, int mode) {
   return TF2B_OK;
 }
 
+int tf2b_set_stem_chunk(tf2b_net* net, int on) {
+  if (!net) return TF2B_ERR_ARG;
+  if (net->finalized) return fail(net, TF2B_ERR_STATE, "tf2b_set_stem_chunk after tf2b_finalize");
+  net->stem_chunk_on = on != 0;
+  return TF2B_OK;
+}
+
 int tf2b_set_result(tf2b_net* net, int tensor) {
   if (!net) return TF2B_ERR_ARG;
   if (tensor < 0 || tensor >= (int)net->tensors.size()) return fail(net, TF2B_ERR_ARG, "tensor out of range");

@@ -146,7 +146,8 @@ struct MmaParams {
 struct TmapPair {
   CUtensorMap a;
   CUtensorMap b;
-  CUtensorMap r;   // residual operand (flat layers): [pixels][channels], 128 x 128-byte boxes; CTA pairs: weight half tile
+  CUtensorMap r;   // residual operand (flat layers): [pixels][channels], 128 x 128-byte boxes
+  CUtensorMap h;   // CTA pairs: the half weight tile one CTA of the pair stages
   CUtensorMap y;   // output of flat layers with the folded epilogue: [pixels][channels], per-warp 32-row boxes (TMA store)
   CUtensorMap p;   // packed 4-bit weight planes [planes * Npad][Kp / 2] (resident-weight layers)
 };
@@ -682,7 +683,7 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
           const unsigned fb = full_bar + 8 * stage;
           const unsigned sa = smem_base + stage * stage_bytes;
           // sparse second plane: which planes hold weights anywhere in this (tap, K chunk)
-          const unsigned cmask = P.sparse2 ? (unsigned)P.c.blkmask[tap * P.kchunks + kc] : 0xffu;
+          const unsigned cmask = (kExp && P.sparse2) ? (unsigned)P.c.blkmask[tap * P.kchunks + kc] : 0xffu;
           const bool ld0 = (cmask & 0x55u) != 0, ld1 = (cmask & 0xaau) != 0;
           if constexpr (cg2) {
             // Pair mode: both producers signal the LEADER's full barrier (its MMA warp drives both SMs).
@@ -690,7 +691,7 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
             // `rank` of a two-plane layer, or rows rank*128.. of a 256-wide single plane — or, with the sparse
             // second plane, rows rank*64.. of EACH plane that holds weights in this chunk (one-plane MMAs, N = BN,
             // take half of their rows from either CTA).
-            if (P.sparse2) {
+            if (kExp && P.sparse2) {
               if (elect_one()) {
                 const unsigned half = (unsigned)(64 * P.BK);
                 const unsigned bbytes = (ld0 ? half : 0u) + (ld1 ? half : 0u);
@@ -698,8 +699,8 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
                 else mbar_arrive_leader(fb);
                 if (MODE == 0) tma_load_2d_cg2(sa, &maps.a, fb, kc * P.BK, t.m0);
                 else tma_load_4d_cg2(sa, &maps.a, fb, kc * P.BK, t.ow0 * P.c.stride - P.c.pad + fw, t.oh0 * P.c.stride - P.c.pad + fh, t.b0);
-                if (ld0) tma_load_2d_cg2(sa + a_stage, &maps.r, fb, tap * P.Cpm + kc * P.BK, t.n0 + (int)cta_rank * 64);
-                if (ld1) tma_load_2d_cg2(sa + a_stage + half, &maps.r, fb, tap * P.Cpm + kc * P.BK, P.Npad + t.n0 + (int)cta_rank * 64);
+                if (ld0) tma_load_2d_cg2(sa + a_stage, &maps.h, fb, tap * P.Cpm + kc * P.BK, t.n0 + (int)cta_rank * 64);
+                if (ld1) tma_load_2d_cg2(sa + a_stage + half, &maps.h, fb, tap * P.Cpm + kc * P.BK, P.Npad + t.n0 + (int)cta_rank * 64);
               }
             } else if (elect_one()) {
               if (cta_rank == 0) mbar_expect_tx(fb, 2u * (unsigned)(P.a_bytes + P.b_stage_bytes));
@@ -711,10 +712,10 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
                                 t.oh0 * P.c.stride - P.c.pad + fh, t.b0);
               }
               const int brow = P.planes == 2 ? (int)cta_rank * P.Npad + t.n0 : t.n0 + (int)cta_rank * (BN / 2);
-              tma_load_2d_cg2(sa + a_stage, &maps.r, fb, tap * P.Cpm + kc * P.BK, brow);
+              tma_load_2d_cg2(sa + a_stage, &maps.h, fb, tap * P.Cpm + kc * P.BK, brow);
             }
           } else if (elect_one()) {
-            const int nld = P.sparse2 ? (int)ld0 + (int)ld1 : P.planes;
+            const int nld = (kExp && P.sparse2) ? (int)ld0 + (int)ld1 : P.planes;
             mbar_expect_tx(fb, (unsigned)(P.a_bytes + (P.b_resident ? 0 : nld * P.b_bytes)));
             if (MODE == 0) {
               tma_load_2d(sa, &maps.a, fb, kc * P.BK, t.m0);
@@ -727,7 +728,7 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
             }
             if (!P.b_resident)
               for (int pl = 0; pl < P.planes; pl++)
-                if (!P.sparse2 || (pl == 0 ? ld0 : ld1))
+                if (!(kExp && P.sparse2) || (pl == 0 ? ld0 : ld1))
                   tma_load_2d(sa + a_stage + pl * b_plane, &maps.b, fb, tap * P.Cpm + kc * P.BK, pl * P.Npad + t.n0);
           }
           __syncwarp();
@@ -797,7 +798,7 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
           const unsigned bsrc = P.b_resident ? smem_res + it * P.planes * b_plane : sa + a_stage;
           const unsigned long long db = make_smem_desc(bsrc, P.sbo16, P.layout_type);
           const unsigned acc0 = it > 0 ? 1u : 0u;
-          if (P.sparse2) {
+          if (kExp && P.sparse2) {
             // Sparse second plane: one-plane instructions (N = BN) into each plane's own TMEM columns, issued only
             // for the (32-channel block, plane) combinations that hold weights.  The first instruction a plane
             // sees in a tile overwrites its accumulator.
@@ -847,7 +848,7 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
             umma_i8(d_tmem, da, db, P.idesc, acc0);
             umma_i8(d_tmem, da + 2ull, db + 2ull, P.idesc, 1u);
           }
-          if (!cg2 && !P.sparse2) {
+          if (!cg2 && !(kExp && P.sparse2)) {
             umma_commit(empty_bar + 8 * stage);             // frees the smem stage when the MMAs retire
             if (it == kiters - 1) umma_commit(tfull_bar + 8 * buf);   // accumulators complete -> epilogue
           }
@@ -1558,21 +1559,30 @@ void fill_geometry(MmaParams& P, const ConvParams& c, int planes8) {
     P.b_resident = P.halo || (allow && slab <= 96 * 1024 && P.taps * P.kchunks * planes8 <= 64 && P.n_tiles <= 16);
     P.res_bytes = P.b_resident ? (int)slab : 0;
   }
-  const int stage_bytes = P.a_stage_bytes + (P.b_resident ? 0 : planes8 * P.b_bytes);
+  // CTA-pair mode for streaming-weight layers whose MMA is 256 wide: one SM ingests ~64 B/clk, an
+  // M128 x N256 x K32 step needs 12 KB per 128 clk (96 B/clk); the pair's M256 x N256 step needs 8 KB per SM.
+  P.b_stage_bytes = planes8 * P.b_bytes;
+  P.cg2 = 0;
+  {
+    static const bool allow = env_int("TF2B_MMA_CG2", 1) != 0;
+    if (allow && !P.halo && !P.pair && !P.b_resident && planes8 * P.BN == 256 && planes8 <= 2 &&
+        P.m_tiles >= 4 && P.BK == 128 && fold_applies(c, planes8)) {
+      P.cg2 = 1;
+      P.b_stage_bytes = 128 * P.BK;   // half of the 256 weight rows
+    }
+  }
+  const int stage_bytes = P.a_stage_bytes + (P.b_resident ? 0 : P.b_stage_bytes);
   {
     static const bool allow = env_int("TF2B_MMA_RESTMA", 1) != 0;
     P.res_tma = allow && c.r != nullptr && P.mode == 0 && P.BN >= 128 && (c.rC % 16 == 0);
     P.res_bufs = 2;
     if (P.res_tma) {
-      // The residual operand streams from HBM once; what hides its latency is the number of tiles in
-      // flight (measured: with two buffers the producer idles on the ring).  Split shared memory into
-      // whole tiles in flight: (activation stages of one tile + one residual tile) each.
+      // The residual operand streams from HBM once through a ring of whole tiles (128 rows x BN bytes); the
+      // epilogue reads it with 16-byte shared loads instead of per-lane global loads.  Depth: whatever shared
+      // memory leaves after three pipeline stages, at most TF2B_RBUFS_CAP (measured: 2 and 4 perform alike).
 #ifndef TF2B_RBUFS_CAP
 #define TF2B_RBUFS_CAP 4
 #endif
-      // ring depth: the residual tile streams from HBM, and a slot is re-requested only when the epilogue has
-      // consumed it, so depth x tile bytes in flight have to cover the DRAM latency (with the lean epilogue the
-      // per-tile time of the 64 -> 256 layers was (latency + epilogue) / depth)
       static const int cap = env_int("TF2B_MMA_RBUFS", TF2B_RBUFS_CAP);
       const int budget = 224 * 1024 - EPI_BYTES - P.res_bytes;
       const int per_tile = P.kchunks * stage_bytes + P.BN * 128;
@@ -1587,18 +1597,6 @@ void fill_geometry(MmaParams& P, const ConvParams& c, int planes8) {
     }
   }
   const int rres_bytes = P.res_tma ? P.res_bufs * P.BN * 128 : 0;
-  // CTA-pair mode for streaming-weight layers whose MMA is 256 wide: one SM ingests ~64 B/clk, an
-  // M128 x N256 x K32 step needs 12 KB per 128 clk (96 B/clk); the pair's M256 x N256 step needs 8 KB per SM.
-  P.b_stage_bytes = planes8 * P.b_bytes;
-  P.cg2 = 0;
-  {
-    static const bool allow = env_int("TF2B_MMA_CG2", 1) != 0;
-    if (allow && !P.halo && !P.pair && !P.b_resident && !P.res_tma && planes8 * P.BN == 256 && planes8 <= 2 &&
-        P.m_tiles >= 4 && P.BK == 128 && fold_applies(c, planes8)) {
-      P.cg2 = 1;
-      P.b_stage_bytes = 128 * P.BK;   // half of the 256 weight rows
-    }
-  }
   const int stage_bytes_final = P.a_stage_bytes + (P.b_resident ? 0 : P.b_stage_bytes);
   int st = (224 * 1024 - EPI_BYTES - P.res_bytes - rres_bytes) / stage_bytes_final;
   P.stages = st > MAX_STAGES ? MAX_STAGES : (st < 2 ? 2 : st);
@@ -1616,7 +1614,7 @@ void fill_geometry(MmaParams& P, const ConvParams& c, int planes8) {
   }
   P.idesc1 = (2u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(P.BN >> 3) << 17) |
              ((unsigned)((P.cg2 ? 2 * MMA_M : MMA_M) >> 4) << 24);
-  P.sparse2 = (c.sparse2 && planes8 == 2 && !P.halo && !P.pair && P.BN >= 128) ? 1 : 0;
+  P.sparse2 = (kExp && c.sparse2 && planes8 == 2 && !P.halo && !P.pair && P.BN >= 128) ? 1 : 0;   // experiment builds only
   P.p1mul = 1u << (c.plane_shift[1] & 31);
   P.layout_type = (P.BK == 128) ? 2u : 4u;
   P.sbo16 = (unsigned)(8 * P.BK) >> 4;
@@ -1767,12 +1765,13 @@ int mma_build_tmaps(void* host_tmaps, const ConvParams& c, const int8_t* wgt8, c
     return -1;
   }
   memset(&tp->r, 0, sizeof tp->r);
+  memset(&tp->h, 0, sizeof tp->h);
   if (P.cg2) {
     cuuint64_t dims[2] = {(cuuint64_t)c.Kp, (cuuint64_t)planes8 * c.Npad};
     cuuint64_t strides[1] = {(cuuint64_t)c.Kp};
     cuuint32_t box[2] = {(cuuint32_t)P.BK, (cuuint32_t)(P.sparse2 ? 64 : 128)};   // sparse second plane: half of EACH plane
     cuuint32_t es[2] = {1, 1};
-    r = enc(&tp->r, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)wgt8, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    r = enc(&tp->h, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)wgt8, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
             sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
       if (err) *err = "cuTensorMapEncodeTiled(B half) failed with CUresult " + std::to_string((int)r);

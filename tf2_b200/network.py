@@ -85,6 +85,10 @@ class NetWork:
         with open(q_file, "r") as f:
             return self.InitFromMemory(blob, f.read(), max_images, variant)
 
+    def set_stem_chunk(self, on: bool):
+        """Chunked L2-resident stem on (default) / off; before Init*."""
+        self._check(self._lib.tf2b_set_stem_chunk(self._h, 1 if on else 0))
+
     def set_weight_staging(self, mode: int):
         """capi.WEIGHTS_PLANES (default) / capi.WEIGHTS_PACKED4 for the tensor-core kernel's resident-weight layers;
         before Init*."""
