@@ -154,7 +154,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="images per GPU and step (default: the BASELINE config's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--executor", type=int, default=1, help="tf2b_set_graph: 1 graph + lanes (default), 2 graph, 3 lanes, 0 plain")
-    ap.add_argument("--stem-chunk", type=int, default=1, help="chunked L2-resident stem (default on)")
+    ap.add_argument("--stem-chunk", type=int, default=0, help="chunked L2-resident stem (default off: measured slower)")
     ap.add_argument("--weights", default="planes", choices=["planes", "packed4"], help="tensor-core weight staging")
     ap.add_argument("--layers-out", default=None, help="write per-layer device times (JSON) to this file")
     args = ap.parse_args()

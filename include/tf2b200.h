@@ -109,7 +109,7 @@ int tf2b_finalize(tf2b_net* net, int max_images);
 
 int tf2b_set_variant(tf2b_net* net, int variant);
 
-/* Chunked stem (default on): with the raw 3x224x224 entry points and a first layer that is convolution + pool
+/* Chunked stem (default OFF — measured 4 % slower on ResNet50 B=256, kept as an option): with the raw 3x224x224 entry points and a first layer that is convolution + pool
  * (input_loader.cpp:27-73's transformed stem), batches of more than 32 images go through space-to-depth -> conv1 ->
  * max pool in chunks of 32 whose intermediates stay in the L2 cache.  Tensor 0 is then not kept for the whole batch;
  * tf2b_read_tensor(0) / tf2b_dump_acc(layer 0) re-create it from the last raw input (which must still be valid).

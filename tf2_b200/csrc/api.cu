@@ -172,7 +172,8 @@ struct tf2b_net {
   // re-create it from the last raw input on demand.
   static constexpr int kStemChunk = 32;
   bool stem_chunked = false;
-  bool stem_chunk_on = true;
+  bool stem_chunk_on = false;   // measured (profiles/r02_ab_options.md): 21 more launches of smaller kernels cost more than the
+                                // saved DRAM round trips — 100.6 k images/s with the chunked stem, 104.6 k without
   int8_t* stem_t0 = nullptr;          // [kStemChunk][114][114][64]
   int8_t* stem_conv = nullptr;        // [kStemChunk][OH][OW][Np16]
   std::vector<unsigned char> stem_tmaps;

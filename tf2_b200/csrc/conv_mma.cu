@@ -1464,14 +1464,18 @@ int pick_bn(int planes8, int N);
 // Halo mode: k x k, stride 1, the whole weight slab of an n-tile resident in shared memory and a
 // position-space row (OW + k - 1) that fits the 128 accumulator rows.  One TMA box per tile instead
 // of one per filter tap; measured: the 64-channel layers were bound by the number of TMA boxes/rows.
+// output columns per halo tile: the whole row when it fits the accumulator rows together with its halo
+int halo_tw(int OW, int k) { return OW + k - 1 <= MMA_M ? OW : MMA_M - (k - 1); }
+
 bool halo_mode(int k, int stride, int Cp, int OW, int OH, int N, int planes8) {
   static const bool allow = env_int("TF2B_MMA_HALO", 1) != 0;
-  if (!allow || k < 2 || stride != 1 || OW + k - 1 > MMA_M) return false;
+  if (!allow || k < 2 || stride != 1 || k > 7) return false;
   const int BK = pick_bk(Cp), BN = pick_bn(planes8, N);
   const int kchunks = (Cp + BK - 1) / BK, n_tiles = (N + BN - 1) / BN;
   const long long slab = (long long)k * k * kchunks * planes8 * BN * BK;
   if (slab > 112 * 1024 || n_tiles > 16) return false;
-  const int Wp = OW + k - 1;
+  // rows wider than the 128 accumulator rows are tiled in W: 128 - (k - 1) output columns + the halo
+  const int Wp = halo_tw(OW, k) + k - 1;
   int th = MMA_M / Wp;
   if (th > OH) th = OH;
   const int rows = std::max(Wp * (th + k - 1), MMA_M + (k - 1) * (Wp + 1));
@@ -1505,7 +1509,7 @@ void fill_geometry(MmaParams& P, const ConvParams& c, int planes8) {
   P.c = c;
   P.planes = planes8;
   P.halo = halo_mode(c.k, c.stride, c.Cp, c.OW, c.OH, c.N, planes8) ? 1 : 0;
-  P.Wp = c.OW + c.k - 1;
+  P.Wp = halo_tw(c.OW, c.k) + c.k - 1;
   P.pair = (!P.halo && pair_mode(c.k, c.stride, c.pad, c.Cp, c.xC, c.OW)) ? 1 : 0;
   if (P.pair) {
     P.BK = 128;
@@ -1529,7 +1533,7 @@ void fill_geometry(MmaParams& P, const ConvParams& c, int planes8) {
     P.m_tiles = (int)((M + MMA_M - 1) / MMA_M);
     P.a_bytes = MMA_M * P.BK;
   } else {
-    P.tw = c.OW < MMA_M ? c.OW : MMA_M;
+    P.tw = P.halo ? halo_tw(c.OW, c.k) : (c.OW < MMA_M ? c.OW : MMA_M);
     P.th = P.pair ? 1 : MMA_M / (P.halo ? P.Wp : P.tw);
     if (P.th > c.OH) P.th = c.OH;
     // balance rows over the tiles of one image (14 rows -> 7+7 rather than 9+5)

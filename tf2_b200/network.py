@@ -86,7 +86,7 @@ class NetWork:
             return self.InitFromMemory(blob, f.read(), max_images, variant)
 
     def set_stem_chunk(self, on: bool):
-        """Chunked L2-resident stem on (default) / off; before Init*."""
+        """Chunked L2-resident stem on / off (default off: measured slower); before Init*."""
         self._check(self._lib.tf2b_set_stem_chunk(self._h, 1 if on else 0))
 
     def set_weight_staging(self, mode: int):
