@@ -407,7 +407,7 @@ def main():
                         "gmac_per_image": macs / 1e9},
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": total_images / e2e_s, "unit": "images/sec",
-                    "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": int(np.prod(out_shape)),
+                    "h2d_bytes_per_step": in_bytes * world, "d2h_bytes_per_step": int(np.prod(out_shape)) * world,
                     "api": ("tf2b_submit_raw224_host" if raw224 else "tf2b_submit_host") + " + tf2b_wait (2 slots, pinned host buffers)",
                     "sync_call_value": B * args.steps / e2e_sync_s},
             "roofline": roofline,
