@@ -31,6 +31,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <type_traits>
 
 #include "../../include/tf2b200.h"
 #include "common.cuh"
@@ -987,6 +988,10 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
     if constexpr (FOLD && MODE == 0) {
       if (P.tstore != 0 && (!CT_RES || res_tma) && !(kExp && (P.noepi != 0 || P.dbg != nullptr))) {
         lean_done = true;
+        // the two ReLU flags are layer constants: four copies of the loop, picked once, instead of branches per 4 outputs
+        auto lean_loop = [&](auto crelu_c, auto arelu_c) {
+          constexpr bool CRELU = decltype(crelu_c)::value;
+          constexpr bool ARELU = decltype(arelu_c)::value;
         const unsigned t_row_w = tmem_base + ((unsigned)(quarter * 32) << 16) + slice * WT;
         const int res_bufs = P.res_bufs;
         int lrb = group % res_bufs;
@@ -1079,8 +1084,8 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
                   yy[u] = HI32 ? (int)(tq >> 32) : (int)(tq >> 35);
                 }
                 unsigned y4 = pack_sat4(yy[0], yy[1], yy[2], yy[3]);
-                if (conv_relu) y4 = relu_s8x4(y4);
-                if (CT_RES) y4 = add_relu ? add_res_s8x4<true>(y4, rw[j4]) : add_res_s8x4<false>(y4, rw[j4]);
+                if (CRELU) y4 = relu_s8x4(y4);
+                if (CT_RES) y4 = add_res_s8x4<ARELU>(y4, rw[j4]);
                 packed[j4] = y4;
               }
               const int chunk = (W == 32) ? ((cc >> 4) ^ ((lane >> 2) & 1)) : 0;
@@ -1101,6 +1106,14 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
             if (lrb >= res_bufs) { lrb -= res_bufs; lrph ^= 1u; }
           }
           tsel = (tsel + PASSES) & 1;
+        }
+        };
+        if (conv_relu) {
+          if (add_relu) lean_loop(std::true_type{}, std::true_type{});
+          else lean_loop(std::true_type{}, std::false_type{});
+        } else {
+          if (add_relu) lean_loop(std::false_type{}, std::true_type{});
+          else lean_loop(std::false_type{}, std::false_type{});
         }
       }
     }
@@ -1467,10 +1480,27 @@ int pick_bn(int planes8, int N);
 // output columns per halo tile: the whole row when it fits the accumulator rows together with its halo
 int halo_tw(int OW, int k) { return OW + k - 1 <= MMA_M ? OW : MMA_M - (k - 1); }
 
+bool halo_fits(int k, int stride, int Cp, int OW, int OH, int N, int planes8, int BN);
+
+// N tile of a layer: pick_bn(), narrowed to 64 when only that lets a k x k / stride-1 layer with 64 input
+// channels keep its weight slab resident and run on halo tiles (VGG16's 64 -> 128 3x3 on 112 x 112 maps: the
+// activation tile is fetched once per 64 output channels, still 9 x fewer TMA boxes than one per tap)
+int layer_bn(int k, int stride, int Cp, int OW, int OH, int N, int planes8) {
+  const int bn = pick_bn(planes8, N);
+  if (bn > 64 && k >= 2 && stride == 1 && Cp <= 64 && !halo_fits(k, stride, Cp, OW, OH, N, planes8, bn) &&
+      halo_fits(k, stride, Cp, OW, OH, N, planes8, 64))
+    return 64;
+  return bn;
+}
+
 bool halo_mode(int k, int stride, int Cp, int OW, int OH, int N, int planes8) {
+  return halo_fits(k, stride, Cp, OW, OH, N, planes8, layer_bn(k, stride, Cp, OW, OH, N, planes8));
+}
+
+bool halo_fits(int k, int stride, int Cp, int OW, int OH, int N, int planes8, int BN) {
   static const bool allow = env_int("TF2B_MMA_HALO", 1) != 0;
   if (!allow || k < 2 || stride != 1 || k > 7) return false;
-  const int BK = pick_bk(Cp), BN = pick_bn(planes8, N);
+  const int BK = pick_bk(Cp);
   const int kchunks = (Cp + BK - 1) / BK, n_tiles = (N + BN - 1) / BN;
   const long long slab = (long long)k * k * kchunks * planes8 * BN * BK;
   if (slab > 112 * 1024 || n_tiles > 16) return false;
@@ -1522,7 +1552,7 @@ void fill_geometry(MmaParams& P, const ConvParams& c, int planes8) {
     P.kchunks = P.Cpm / P.BK;
     P.taps = c.k * c.k;
   }
-  P.BN = pick_bn(planes8, c.N);
+  P.BN = layer_bn(c.k, c.stride, c.Cp, c.OW, c.OH, c.N, planes8);
   P.Npad = c.Npad;
   P.n_tiles = (c.N + P.BN - 1) / P.BN;
   P.mode = (c.k == 1 && c.stride == 1 && c.pad == 0) ? 0 : 1;
