@@ -136,10 +136,18 @@ MODE_CASES = [
     ("pair_flat_p1_c512_n256", (512, 14, 14), dict(N=256, k=1), 5, dict(per_c_offset=0), "ctapair"),
     ("pair_flat_p2_c512_n128", (512, 28, 28), dict(N=128, k=1), 1, dict(per_c_offset=4, per_n_offset=5), "ctapair"),
     ("pair_flat_odd_tiles", (1024, 9, 9), dict(N=256, k=1), 7, dict(per_c_offset=0), "ctapair"),   # 567 pixels: 5 m-tiles
-    ("pair_box_p1_c256_14", (256, 14, 14), dict(N=256, k=3, pad=1), 9, dict(per_c_offset=0), "box"),
-    ("pair_box_p2_c128_28", (128, 28, 28), dict(N=128, k=3, pad=1), 3, dict(shift_lo=1, per_c_offset=4, per_n_offset=0), "box"),
     ("pair_box_s2_c256", (256, 28, 28), dict(N=256, k=3, pad=1, stride=2), 5, dict(per_c_offset=0), "box"),
-    ("pair_box_residual", (256, 14, 14), dict(N=256, k=3, pad=1, relu=0, add=0, add_relu=1), 6, dict(per_c_offset=0), "ctapair"),
+    ("pair_box_c512_7", (512, 7, 7), dict(N=256, k=3, pad=1), 16, dict(per_c_offset=0), "box"),     # 49 of 128 rows: stays on boxes
+    # CTA pairs on halo tiles with streamed weights (stride-1 k x k, C >= 128): one activation box per tile and chunk
+    ("pair_hs_p1_c256_14", (256, 14, 14), dict(N=256, k=3, pad=1), 9, dict(per_c_offset=0), "halo wstream"),
+    ("pair_hs_p2_c128_28", (128, 28, 28), dict(N=128, k=3, pad=1), 3, dict(shift_lo=1, per_c_offset=4, per_n_offset=0), "halo wstream"),
+    ("pair_hs_residual", (256, 14, 14), dict(N=256, k=3, pad=1, relu=0, add=0, add_relu=1), 6, dict(per_c_offset=0), "halo wstream"),
+    ("pair_hs_p2_c256_n256_two_ntiles", (256, 14, 14), dict(N=256, k=3, pad=1), 5, dict(shift_lo=1, per_c_offset=4, per_n_offset=0), "halo wstream"),
+    ("pair_hs_ragged_rows_c128_13", (128, 13, 13), dict(N=128, k=3, pad=1), 3, dict(per_c_offset=4, per_n_offset=0), "halo wstream"),
+    ("pair_hs_5x5_c128_20", (128, 20, 20), dict(N=256, k=5, pad=2), 2, dict(per_c_offset=0), "halo wstream"),
+    ("pair_hs_nopad_c128_30", (128, 30, 30), dict(N=128, k=3, pad=0), 2, dict(per_c_offset=4, per_n_offset=0), "halo wstream"),
+    ("pair_hs_wide_c128_150", (128, 20, 150), dict(N=128, k=3, pad=1), 1, dict(per_c_offset=4, per_n_offset=0), "halo wstream"),   # W tiled: 126 + 24 columns
+    ("pair_hs_c384_n200_28", (384, 28, 28), dict(N=200, k=3, pad=1), 1, dict(per_c_offset=4, per_n_offset=0), "halo wstream"),    # 3 chunks, ragged N
     # halo tiles: one TMA box per tile, taps as row-shifted descriptor views
     ("halo_3x3_c64_56", (64, 56, 56), dict(N=64, k=3, pad=1), 2, {}, "halo"),
     ("halo_3x3_c64_56_p1", (64, 56, 56), dict(N=64, k=3, pad=1), 2, dict(per_c_offset=0), "halo"),

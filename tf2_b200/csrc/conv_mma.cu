@@ -127,6 +127,11 @@ struct MmaParams {
                             // order; every filter tap is a row-shifted view of it (UMMA descriptor start
                             // address + (fh * Wp + fw) * BK: the swizzle is a function of the address bits)
   int Wp;                   // halo mode: row width of the position space = tw + k - 1
+  int hstream;              // halo tiles with STREAMED weights (CTA pairs, K-heavy k x k / stride-1 layers): the halo
+                            // tile of a channel chunk sits in its own ring (a_bufs x a_ring_bytes) and is fetched once
+                            // per tile and chunk instead of once per tap; the pipeline stages carry weights only
+  int a_bufs, a_ring_bytes; // halo-tile ring of that mode
+  int lean_roles;           // producer / MMA roles run as lean single-thread loops (CTA pairs, resident-weight halo tiles)
   int a_stage_bytes;        // bytes reserved per pipeline stage for the activation tile
   int idx32;                // output / residual tensors are smaller than 2 GiB: 32-bit byte offsets
   int cg2;                  // CTA-pair mode: clusters of two CTAs, tcgen05.mma.cta_group::2 (M = 256 over two
@@ -182,6 +187,15 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
   if (mbar_try_wait(bar, parity)) return;
   long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000ll) __trap();
+  }
+}
+// converged-warp wait whose loop branch is a vote: provably uniform, so the compiler keeps the surrounding loop state
+// (ring addresses, descriptors) in uniform registers
+__device__ __forceinline__ void mbar_wait_u(unsigned bar, unsigned parity) {
+  if (__any_sync(0xffffffffu, mbar_try_wait(bar, parity))) return;
+  long long t0 = clock64();
+  while (!__any_sync(0xffffffffu, mbar_try_wait(bar, parity))) {
     if (clock64() - t0 > 4000000000ll) __trap();
   }
 }
@@ -487,9 +501,10 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
   // as a cluster of CTA pairs
   constexpr bool cg2 = CG2;
   unsigned cta_rank = 0u;
-  if constexpr (CG2) cta_rank = cluster_ctarank();
+  if constexpr (CG2) cta_rank = __shfl_sync(0xffffffffu, cluster_ctarank(), 0);   // (shuffle: provably warp-uniform)
   const int res_tile = BN * 128;   // one residual tile: 128 rows x BN bytes as BN/128 SWIZZLE_128B sub-tiles
   const unsigned smem_rres = smem_base + (unsigned)(P.stages * stage_bytes + EPI_BYTES);   // residual ring
+  const unsigned smem_aring = smem_rres;   // streamed-weight halo mode (box layers have no residual ring): halo-tile ring
 
   __shared__ __align__(8) unsigned long long bars[2 * MAX_STAGES + 5 + 2 * MAX_RBUFS];
   __shared__ unsigned tmem_base_slot;
@@ -505,11 +520,11 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
   // Warp roles.  The SM's issue arbiter favours higher warp ids, so the two single-issuer warps that
   // feed the tensor pipe sit at the top and are never starved by the ALU-heavy epilogue warps:
   //   hardware warps 0..15 -> epilogue (role ids 2..17), warp 16 -> TMA producer (role 0), warp 17 -> MMA (role 1)
-  const int hw_warp = threadIdx.x >> 5;
+  const int hw_warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // canonical warp index: warp-uniform for the compiler
   const int warp = (kExp && P.roles_top) ? (hw_warp < NUM_EPI_WARPS ? hw_warp + 2 : hw_warp - NUM_EPI_WARPS) : hw_warp;
   const int lane = threadIdx.x & 31;
   const int num_tiles = P.m_tiles * P.n_tiles;
-  const int kiters = P.halo ? P.kchunks : P.taps * P.kchunks;   // pipeline stages consumed per tile
+  const int kiters = (P.halo && !P.hstream) ? P.kchunks : P.taps * P.kchunks;   // pipeline stages consumed per tile
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&maps.a);
@@ -524,8 +539,10 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
     }
     mbar_init(bres_bar, 1);
     for (int b = 0; b < MAX_RBUFS; b++) {
-      mbar_init(rfull_bar + 8 * b, 1);
-      mbar_init(rempty_bar + 8 * b, NUM_EPI_WARPS / P.egroups);
+      // residual ring (flat layers) or halo-tile ring (streamed-weight halo mode: filled by both producers of the
+      // pair, released by the MMA warp's commit)
+      mbar_init(rfull_bar + 8 * b, P.hstream ? (cg2 ? 2 : 1) : 1);
+      mbar_init(rempty_bar + 8 * b, P.hstream ? 1 : NUM_EPI_WARPS / P.egroups);
     }
     fence_barrier_init();
   }
@@ -625,6 +642,98 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
     }
     int rb = 0;
     unsigned rphase = 0;
+    // Lean form of this role (CTA pairs and resident-weight halo tiles): ONE thread runs the whole loop — no election,
+    // no warp re-convergence per stage, tile-constant coordinates hoisted, ring addresses advanced by additions.
+    // Measured with the role counters (profiles/r02_mma_roles.md): the generic warp-wide loop spent 500-800 clk per
+    // pipeline stage in its own instructions, more than the 512 clk the stage's four M256 x N256 x K32 MMAs take.
+    if (P.lean_roles) {
+      // (all 32 lanes walk the loop so that every address stays in uniform registers; one elected lane issues)
+      const int nst = P.stages, BK = P.BK, kch = P.kchunks, kk = P.c.k, pad = P.c.pad;
+      const unsigned a_bytes = (unsigned)P.a_bytes;
+      unsigned sa = smem_base, fb = full_bar, eb = empty_bar;
+      auto advance = [&]() {
+        if (++stage == nst) { stage = 0; phase ^= 1; sa = smem_base; fb = full_bar; eb = empty_bar; }
+        else { sa += (unsigned)stage_bytes; fb += 8; eb += 8; }
+      };
+      for (int q = q_first; q < q_count; q += q_step) {
+        const TileCoord t = decode_tile(P, tile_of(q));
+        if constexpr (cg2) {
+          const int brow = P.planes == 2 ? (int)cta_rank * P.Npad + t.n0 : t.n0 + (int)cta_rank * (BN / 2);
+          if (MODE == 0 && P.res_tma) {
+            mbar_wait_u(rempty_bar + 8 * rb, rphase ^ 1);
+            if (elect_one()) {
+              mbar_expect_tx(rfull_bar + 8 * rb, (unsigned)res_tile);
+              for (int j = 0; j < BN / 128; j++)
+                tma_load_2d(smem_rres + rb * res_tile + j * (128 * 128), &maps.r, rfull_bar + 8 * rb, t.n0 + j * 128, t.m0);
+            }
+            if (++rb == P.res_bufs) { rb = 0; rphase ^= 1; }
+          }
+          if (MODE == 0) {
+            const unsigned tx = 2u * (a_bytes + (unsigned)P.b_stage_bytes);
+            for (int kc = 0, c0 = 0; kc < kch; kc++, c0 += BK) {
+              mbar_wait_u(eb, phase ^ 1);
+              if (elect_one()) {
+                if (cta_rank == 0) mbar_expect_tx(fb, tx);
+                else mbar_arrive_leader(fb);
+                tma_load_2d_cg2(sa, &maps.a, fb, c0, t.m0);
+                tma_load_2d_cg2(sa + a_stage, &maps.h, fb, c0, brow);
+              }
+              advance();
+            }
+          } else if (P.hstream) {
+            const unsigned txa = 2u * a_bytes, txb = 2u * (unsigned)P.b_stage_bytes;
+            const int x0 = t.ow0 - pad, y0 = t.oh0 - pad, ntap = P.taps, Cpm = P.Cpm;
+            for (int kc = 0, c0 = 0; kc < kch; kc++, c0 += BK) {
+              mbar_wait_u(rempty_bar + 8 * rb, rphase ^ 1);
+              if (elect_one()) {
+                const unsigned ab = rfull_bar + 8 * rb;
+                if (cta_rank == 0) mbar_expect_tx(ab, txa);
+                else mbar_arrive_leader(ab);
+                tma_load_4d_cg2(smem_aring + rb * P.a_ring_bytes, &maps.a, ab, c0, x0, y0, t.b0);
+              }
+              if (++rb == P.a_bufs) { rb = 0; rphase ^= 1; }
+              for (int tap = 0, kcol = c0; tap < ntap; tap++, kcol += Cpm) {
+                mbar_wait_u(eb, phase ^ 1);
+                if (elect_one()) {
+                  if (cta_rank == 0) mbar_expect_tx(fb, txb);
+                  else mbar_arrive_leader(fb);
+                  tma_load_2d_cg2(sa, &maps.h, fb, kcol, brow);
+                }
+                advance();
+              }
+            }
+          } else {
+            const unsigned tx = 2u * (a_bytes + (unsigned)P.b_stage_bytes);
+            const int x0 = t.ow0 * P.c.stride - pad, y0 = t.oh0 * P.c.stride - pad, Cpm = P.Cpm;
+            int kcol = 0;
+            for (int fh = 0; fh < kk; fh++)
+              for (int fw = 0; fw < kk; fw++, kcol += Cpm)
+                for (int kc = 0, c0 = 0; kc < kch; kc++, c0 += BK) {
+                  mbar_wait_u(eb, phase ^ 1);
+                  if (elect_one()) {
+                    if (cta_rank == 0) mbar_expect_tx(fb, tx);
+                    else mbar_arrive_leader(fb);
+                    tma_load_4d_cg2(sa, &maps.a, fb, c0, x0 + fw, y0 + fh, t.b0);
+                    tma_load_2d_cg2(sa + a_stage, &maps.h, fb, kcol + c0, brow);
+                  }
+                  advance();
+                }
+          }
+        } else {
+          // halo tiles, resident weights: one box per tile and channel chunk
+          const int x0 = t.ow0 - pad, y0 = t.oh0 - pad;
+          for (int kc = 0, c0 = 0; kc < kch; kc++, c0 += BK) {
+            mbar_wait_u(eb, phase ^ 1);
+            if (elect_one()) {
+              mbar_expect_tx(fb, a_bytes);
+              tma_load_4d(sa, &maps.a, fb, c0, x0, y0, t.b0);
+            }
+            advance();
+          }
+        }
+      }
+      __syncwarp();
+    } else
     for (int q = q_first; q < q_count; q += q_step) {
       const int tile = tile_of(q);
       const TileCoord t = decode_tile(P, tile);
@@ -663,6 +772,36 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
         }
         __syncwarp();
         if (++rb == P.res_bufs) { rb = 0; rphase ^= 1; }
+      }
+      if constexpr (cg2) {
+        if (P.hstream) {
+          // halo tiles, streamed weights: per channel chunk ONE box with the tile's whole input window into the
+          // halo ring, then the chunk's k*k half weight tiles through the pipeline stages
+          for (int kc = 0; kc < P.kchunks; kc++) {
+            mbar_wait_timed(rempty_bar + 8 * rb, rphase ^ 1, w_empty, dbg, (kExp ? P.poll_lane0 : 0));
+            if (elect_one()) {
+              const unsigned ab = rfull_bar + 8 * rb;
+              if (cta_rank == 0) mbar_expect_tx(ab, 2u * (unsigned)P.a_bytes);
+              else mbar_arrive_leader(ab);
+              tma_load_4d_cg2(smem_aring + rb * P.a_ring_bytes, &maps.a, ab, kc * P.BK, t.ow0 - P.c.pad, t.oh0 - P.c.pad, t.b0);
+            }
+            __syncwarp();
+            if (++rb == P.a_bufs) { rb = 0; rphase ^= 1; }
+            const int brow = P.planes == 2 ? (int)cta_rank * P.Npad + t.n0 : t.n0 + (int)cta_rank * (BN / 2);
+            for (int tap = 0; tap < P.taps; tap++) {
+              mbar_wait_timed(empty_bar + 8 * stage, phase ^ 1, w_empty, dbg, (kExp ? P.poll_lane0 : 0));
+              if (elect_one()) {
+                const unsigned fb = full_bar + 8 * stage;
+                if (cta_rank == 0) mbar_expect_tx(fb, 2u * (unsigned)P.b_stage_bytes);
+                else mbar_arrive_leader(fb);
+                tma_load_2d_cg2(smem_base + stage * stage_bytes, &maps.h, fb, tap * P.Cpm + kc * P.BK, brow);
+              }
+              __syncwarp();
+              if (++stage == P.stages) { stage = 0; phase ^= 1; }
+            }
+          }
+          continue;
+        }
       }
       if (P.halo) {
         for (int kc = 0; kc < P.kchunks; kc++) {
@@ -749,6 +888,116 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
     long long w_full = 0, w_tempty = 0, t_issue = 0, t_start = clock64();
     if (P.b_resident && (int)blockIdx.x < num_tiles) mbar_wait_warp(bres_bar, 0, (kExp ? P.poll_lane0 : 0));
     int li = 0;   // CTA-local tile index: TMEM buffer li & 1, its phase (li >> 1) & 1
+    int ab = 0, hs_tap = 0, hs_fh = 0, hs_fw = 0;   // streamed-weight halo mode: ring slot, filter tap of the next stage
+    unsigned aphase = 0;
+    // experiment builds: where a steady-state stage of CTA 0's MMA thread spends its cycles
+    long long fa[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = 0;
+    const bool ftr = dbg && blockIdx.x == 0;
+#define TF2B_TICK(i) do { if (kExp && ftr) { const long long t_ = clock64(); fa[i] += t_ - tprev; tprev = t_; } } while (0)
+    // Lean form (see the producer): one thread, descriptors advanced by additions, nothing between the stage's
+    // barrier and its MMAs.  No tcgen05 fence after the full barrier: the operands arrive through TMA (async proxy,
+    // completion on the mbarrier), not through tcgen05 operations of other threads.
+    if (P.lean_roles) {
+      if (!cg2 || cta_rank == 0) {
+        const int nst = P.stages, kch = P.kchunks, kk = P.c.k;
+        const unsigned idesc = P.idesc;
+        const unsigned long long d0 = make_smem_desc(smem_base, P.sbo16, P.layout_type);
+        const unsigned long long dstep = (unsigned long long)((unsigned)stage_bytes >> 4);
+        const unsigned long long px16 = (unsigned long long)(P.BK >> 4);              // one pixel of a halo tile
+        const unsigned long long row16 = (unsigned long long)((P.Wp * P.BK) >> 4);   // one raster row of it
+        unsigned long long ds = d0;
+        unsigned fb = full_bar, eb = empty_bar;
+        auto advance = [&]() {
+          if (++stage == nst) { stage = 0; phase ^= 1; ds = d0; fb = full_bar; eb = empty_bar; }
+          else { ds += dstep; fb += 8; eb += 8; }
+        };
+        for (int q = q_first; q < q_count; q += q_step, li++) {
+          const int buf = li & 1;
+          mbar_wait_u(tempty_bar + 8 * buf, ((unsigned)(li >> 1) & 1u) ^ 1u);   // epilogue has drained this accumulator
+          tc_fence_after();
+          const unsigned d_tmem = tmem_base + buf * acc_cols;
+          unsigned acc = 0u;
+          if constexpr (cg2) {
+            if (P.hstream) {
+              const unsigned long long dring0 = make_smem_desc(smem_aring, P.sbo16, P.layout_type);
+              const unsigned long long ring16 = (unsigned long long)((unsigned)P.a_ring_bytes >> 4);
+              for (int kc = 0; kc < kch; kc++) {
+                mbar_wait_u(rfull_bar + 8 * ab, aphase);
+                unsigned long long da_row = dring0 + (unsigned long long)ab * ring16;
+                for (int fh = 0; fh < kk; fh++) {
+                  unsigned long long dat = da_row;
+                  for (int fw = 0; fw < kk; fw++) {
+                    mbar_wait_u(fb, phase);
+                    if (elect_one()) {
+                      umma_i8_cg2(d_tmem, dat, ds, idesc, acc);
+                      umma_i8_cg2(d_tmem, dat + 2ull, ds + 2ull, idesc, 1u);
+                      umma_i8_cg2(d_tmem, dat + 4ull, ds + 4ull, idesc, 1u);
+                      umma_i8_cg2(d_tmem, dat + 6ull, ds + 6ull, idesc, 1u);
+                      umma_commit_cg2(eb);
+                    }
+                    acc = 1u;
+                    dat += px16;
+                    advance();
+                  }
+                  da_row += row16;
+                }
+                if (elect_one()) umma_commit_cg2(rempty_bar + 8 * ab);   // halo tile of this chunk consumed
+                if (++ab == P.a_bufs) { ab = 0; aphase ^= 1; }
+              }
+            } else {
+              const unsigned long long boff = (unsigned long long)((unsigned)a_stage >> 4);
+              for (int it = 0; it < kiters; it++) {
+                mbar_wait_u(fb, phase);
+                if (elect_one()) {
+                  const unsigned long long db = ds + boff;
+                  umma_i8_cg2(d_tmem, ds, db, idesc, acc);
+                  umma_i8_cg2(d_tmem, ds + 2ull, db + 2ull, idesc, 1u);
+                  umma_i8_cg2(d_tmem, ds + 4ull, db + 4ull, idesc, 1u);
+                  umma_i8_cg2(d_tmem, ds + 6ull, db + 6ull, idesc, 1u);
+                  umma_commit_cg2(eb);
+                }
+                acc = 1u;
+                advance();
+              }
+            }
+            if (elect_one()) umma_commit_cg2(tfull_bar + 8 * buf);
+          } else {
+            // halo tiles, resident weights: every tap of a channel chunk is a row-shifted view of the chunk's tile
+            const unsigned long long dres = make_smem_desc(smem_res, P.sbo16, P.layout_type);
+            const unsigned long long b_kc16 = (unsigned long long)((unsigned)(P.planes * b_plane) >> 4);
+            const unsigned long long b_tap16 = (unsigned long long)kch * b_kc16;
+            const bool k128 = P.BK == 128;
+            unsigned long long db_kc = dres;
+            for (int kc = 0; kc < kch; kc++, db_kc += b_kc16) {
+              mbar_wait_u(fb, phase);
+              if (elect_one()) {
+                unsigned long long da_row = ds, db = db_kc;
+                for (int fh = 0; fh < kk; fh++) {
+                  unsigned long long dat = da_row;
+                  for (int fw = 0; fw < kk; fw++) {
+                    umma_i8(d_tmem, dat, db, idesc, acc);
+                    umma_i8(d_tmem, dat + 2ull, db + 2ull, idesc, 1u);
+                    if (k128) {
+                      umma_i8(d_tmem, dat + 4ull, db + 4ull, idesc, 1u);
+                      umma_i8(d_tmem, dat + 6ull, db + 6ull, idesc, 1u);
+                    }
+                    acc = 1u;
+                    dat += px16;
+                    db += b_tap16;
+                  }
+                  da_row += row16;
+                }
+                umma_commit(eb);
+              }
+              acc = 1u;
+              advance();
+            }
+            if (elect_one()) umma_commit(tfull_bar + 8 * buf);
+          }
+        }
+      }
+      __syncwarp();
+    } else
     for (int q = q_first; q < q_count && (!cg2 || cta_rank == 0); q += q_step, li++) {   // pair mode: the leader issues
       const int buf = li & 1;
       mbar_wait_timed(tempty_bar + 8 * buf, ((unsigned)(li >> 1) & 1u) ^ 1u, w_tempty, dbg, (kExp ? P.poll_lane0 : 0));   // epilogue has drained this accumulator
@@ -756,13 +1005,49 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
       const unsigned d_tmem = tmem_base + buf * acc_cols;
       unsigned touched0 = 0u, touched1 = 0u;   // sparse second plane: has the plane's accumulator been written in this tile
       for (int it = 0; it < kiters; it++) {
-        mbar_wait_timed(full_bar + 8 * stage, phase, w_full, dbg, (kExp ? P.poll_lane0 : 0));
+        long long tr0 = 0;
+        if (dbg) tr0 = clock64();
+        if (kExp && ftr) tprev = clock64();
+        if (kExp && ftr) mbar_wait_warp(full_bar + 8 * stage, phase, 0);
+        else mbar_wait_timed(full_bar + 8 * stage, phase, w_full, dbg, (kExp ? P.poll_lane0 : 0));
+        TF2B_TICK(0);
+#ifndef TF2B_NO_STAGE_FENCE
         tc_fence_after();
+#endif
+        TF2B_TICK(1);
+        long long tr1 = 0;
+        if (dbg) tr1 = clock64();
         const unsigned sa = smem_base + stage * stage_bytes;
         const unsigned long long da = make_smem_desc(sa, P.sbo16, P.layout_type);
         long long ti0 = 0;
         if (dbg) ti0 = clock64();
-        if (P.halo) {
+        if (cg2 && P.hstream) {
+          if constexpr (cg2) {
+            // this stage = the half weight tiles of one (channel chunk, tap); the activations are the tap's
+            // row-shifted view of the chunk's halo tile
+            if (hs_tap == 0) {
+              mbar_wait_timed(rfull_bar + 8 * ab, aphase, w_full, dbg, (kExp ? P.poll_lane0 : 0));
+              tc_fence_after();
+            }
+            if (elect_one()) {
+              const unsigned long long dah = make_smem_desc(smem_aring + ab * P.a_ring_bytes, P.sbo16, P.layout_type) +
+                                             (unsigned long long)(((hs_fh * P.Wp + hs_fw) * P.BK) >> 4);
+              const unsigned long long db = make_smem_desc(sa, P.sbo16, P.layout_type);
+              umma_i8_cg2(d_tmem, dah, db, P.idesc, it > 0 ? 1u : 0u);
+              umma_i8_cg2(d_tmem, dah + 2ull, db + 2ull, P.idesc, 1u);
+              umma_i8_cg2(d_tmem, dah + 4ull, db + 4ull, P.idesc, 1u);
+              umma_i8_cg2(d_tmem, dah + 6ull, db + 6ull, P.idesc, 1u);
+              umma_commit_cg2(empty_bar + 8 * stage);
+              if (hs_tap == P.taps - 1) umma_commit_cg2(rempty_bar + 8 * ab);   // halo tile of this chunk consumed
+              if (it == kiters - 1) umma_commit_cg2(tfull_bar + 8 * buf);
+            }
+            if (++hs_fw == P.c.k) { hs_fw = 0; hs_fh++; }
+            if (++hs_tap == P.taps) {
+              hs_tap = hs_fh = hs_fw = 0;
+              if (++ab == P.a_bufs) { ab = 0; aphase ^= 1; }
+            }
+          }
+        } else if (P.halo) {
           if (elect_one()) {
             // all taps of this channel chunk read the same halo tile through row-shifted descriptors.
             // Only the 14-bit start-address field differs between taps, so the descriptors advance by
@@ -832,14 +1117,18 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
           // advance both descriptors by 32 bytes of K inside the swizzled row
           if constexpr (cg2) {
             // one M = 256 instruction spans both SMs: A = the two CTAs' activation tiles, B = their halves
+            TF2B_TICK(2);
             umma_i8_cg2(d_tmem, da, db, P.idesc, acc0);
+            TF2B_TICK(3);
             umma_i8_cg2(d_tmem, da + 2ull, db + 2ull, P.idesc, 1u);
             if (P.BK == 128) {
               umma_i8_cg2(d_tmem, da + 4ull, db + 4ull, P.idesc, 1u);
               umma_i8_cg2(d_tmem, da + 6ull, db + 6ull, P.idesc, 1u);
             }
+            TF2B_TICK(4);
             umma_commit_cg2(empty_bar + 8 * stage);
             if (it == kiters - 1) umma_commit_cg2(tfull_bar + 8 * buf);
+            TF2B_TICK(5);
           } else if (P.BK == 128) {
             umma_i8(d_tmem, da, db, P.idesc, acc0);
             umma_i8(d_tmem, da + 2ull, db + 2ull, P.idesc, 1u);
@@ -855,10 +1144,22 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
           }
         }
         __syncwarp();
+        TF2B_TICK(6);
+        if (kExp && ftr) fa[7] += 1;
         if (dbg) t_issue += clock64() - ti0;
+        if (dbg && blockIdx.x == 0 && lane == 0 && it < 64) {
+          // stage-position profile of CTA 0: cycles waiting for the stage, and from wait start to issue end
+          const long long tr2 = clock64();
+          P.dbg[8 * 148 + 3 * it + 0] += tr1 - tr0;
+          P.dbg[8 * 148 + 3 * it + 1] += tr2 - tr0;
+          P.dbg[8 * 148 + 3 * it + 2] += 1;
+        }
         if (++stage == P.stages) { stage = 0; phase ^= 1; }
       }
     }
+    if (kExp && ftr && lane == 0)
+      for (int i = 0; i < 8; i++) P.dbg[8 * 148 + 3 * 64 + i] = fa[i];
+#undef TF2B_TICK
     if (dbg && lane == 0) {
       P.dbg[blockIdx.x * 8 + 2] = w_full;
       P.dbg[blockIdx.x * 8 + 3] = w_tempty;
@@ -1556,6 +1857,35 @@ void fill_geometry(MmaParams& P, const ConvParams& c, int planes8) {
   P.Npad = c.Npad;
   P.n_tiles = (c.N + P.BN - 1) / P.BN;
   P.mode = (c.k == 1 && c.stride == 1 && c.pad == 0) ? 0 : 1;
+  // Halo tiles with streamed weights: k x k / stride-1 layers that would otherwise run as CTA pairs with one
+  // activation box PER TAP.  One box per tile and channel chunk instead: k*k times fewer activation bytes cross
+  // L2 -> shared memory (the pair's feed drops from 64 to ~36 B/clk per SM on 256 -> 256 3x3 at 14 x 14).  The
+  // price is the padded raster: tw * th of the 128 accumulator rows are real outputs, so narrow maps stay on boxes.
+  P.hstream = 0;
+  P.a_bufs = 0;
+  P.a_ring_bytes = 0;
+  {
+    static const bool allow = env_int("TF2B_MMA_HSTREAM", 1) != 0;
+    static const bool allow_cg2 = env_int("TF2B_MMA_CG2", 1) != 0;
+    if (allow && allow_cg2 && !P.halo && !P.pair && P.mode == 1 && c.k >= 2 && c.k <= 7 && c.stride == 1 &&
+        P.BK == 128 && planes8 * P.BN == 256 && planes8 <= 2 && fold_applies(c, planes8)) {
+      const int tw = halo_tw(c.OW, c.k);
+      int th = MMA_M / P.Wp;
+      if (th > c.OH) th = c.OH;
+      const int th_tiles = (c.OH + th - 1) / th;
+      th = (c.OH + th_tiles - 1) / th_tiles;
+      const int rows = std::max(P.Wp * (th + c.k - 1), MMA_M + (c.k - 1) * (P.Wp + 1));
+      const int ring = (rows * P.BK + 1023) / 1024 * 1024;
+      const int budget = 224 * 1024 - EPI_BYTES;
+      const int bufs = (budget - 3 * ring) / (128 * P.BK) >= 4 ? 3 : 2;
+      // (nothing here may depend on the batch of a particular run: the tensor maps are built once, for max_images)
+      if (tw * th * 100 >= 70 * MMA_M && (budget - bufs * ring) / (128 * P.BK) >= 3) {
+        P.hstream = P.halo = 1;
+        P.a_bufs = bufs;
+        P.a_ring_bytes = ring;
+      }
+    }
+  }
   if (P.mode == 0) {
     P.tw = P.th = P.tn = 0;
     P.tiles_w = P.tiles_h = P.tiles_b = 0;
@@ -1585,12 +1915,14 @@ void fill_geometry(MmaParams& P, const ConvParams& c, int planes8) {
     const int rows = std::max(P.Wp * (P.th + c.k - 1), MMA_M + (c.k - 1) * (P.Wp + 1));
     P.a_stage_bytes = (rows * P.BK + 1023) / 1024 * 1024;
   }
+  if (P.hstream) P.a_stage_bytes = 0;   // the halo tiles have their own ring; the stages carry weights only
   P.b_bytes = P.BN * P.BK;
   // weight-stationary when the CTA's slab is small and the grid can be a multiple of n_tiles
   {
     static const bool allow = env_int("TF2B_MMA_BRES", 1) != 0;
     const long long slab = (long long)P.taps * P.kchunks * planes8 * P.b_bytes;
-    P.b_resident = P.halo || (allow && slab <= 96 * 1024 && P.taps * P.kchunks * planes8 <= 64 && P.n_tiles <= 16);
+    P.b_resident = !P.hstream &&
+                   (P.halo || (allow && slab <= 96 * 1024 && P.taps * P.kchunks * planes8 <= 64 && P.n_tiles <= 16));
     P.res_bytes = P.b_resident ? (int)slab : 0;
   }
   // CTA-pair mode for streaming-weight layers whose MMA is 256 wide: one SM ingests ~64 B/clk, an
@@ -1599,8 +1931,8 @@ void fill_geometry(MmaParams& P, const ConvParams& c, int planes8) {
   P.cg2 = 0;
   {
     static const bool allow = env_int("TF2B_MMA_CG2", 1) != 0;
-    if (allow && !P.halo && !P.pair && !P.b_resident && planes8 * P.BN == 256 && planes8 <= 2 &&
-        P.m_tiles >= 4 && P.BK == 128 && fold_applies(c, planes8)) {
+    if (allow && (!P.halo || P.hstream) && !P.pair && !P.b_resident && planes8 * P.BN == 256 && planes8 <= 2 &&
+        (P.m_tiles >= 4 || P.hstream) && P.BK == 128 && fold_applies(c, planes8)) {
       P.cg2 = 1;
       P.b_stage_bytes = 128 * P.BK;   // half of the 256 weight rows
     }
@@ -1630,7 +1962,7 @@ void fill_geometry(MmaParams& P, const ConvParams& c, int planes8) {
       if (stages_with(P.res_bufs) < 3) P.res_tma = 0;   // a single buffer would serialise the producer
     }
   }
-  const int rres_bytes = P.res_tma ? P.res_bufs * P.BN * 128 : 0;
+  const int rres_bytes = P.res_tma ? P.res_bufs * P.BN * 128 : (P.hstream ? P.a_bufs * P.a_ring_bytes : 0);
   const int stage_bytes_final = P.a_stage_bytes + (P.b_resident ? 0 : P.b_stage_bytes);
   int st = (224 * 1024 - EPI_BYTES - P.res_bytes - rres_bytes) / stage_bytes_final;
   P.stages = st > MAX_STAGES ? MAX_STAGES : (st < 2 ? 2 : st);
@@ -1664,6 +1996,10 @@ void fill_geometry(MmaParams& P, const ConvParams& c, int planes8) {
     P.noepi = noepi;
     static const int l2pf = env_int("TF2B_MMA_L2PF", 0);
     P.l2_prefetch = l2pf;
+  }
+  {
+    static const bool allow = env_int("TF2B_MMA_LEANROLES", 1) != 0;
+    P.lean_roles = (allow && (P.cg2 || (P.halo && !P.hstream && !P.pair)) && !P.sparse2 && P.l2_prefetch == 0) ? 1 : 0;
   }
   P.n_tile0 = 0;
   // per-warp TMA stores: flat layers whose run-time epilogue is the folded one (the accumulator tap runs the exact
@@ -1734,7 +2070,8 @@ std::string mma_describe(const ConvParams& c, int planes8) {
   fill_geometry(P, c, planes8);
   char b[192];
   snprintf(b, sizeof b, "mma BN%d BK%d planes%d %s%s%s%s%s%s%s%s stages%d", P.BN, P.BK, planes8,
-           P.mode == 0 ? "flat" : (P.halo ? "halo" : (P.pair ? "pixelpair" : "box")), P.b_resident ? " wres" : "",
+           P.mode == 0 ? "flat" : (P.hstream ? "halo wstream" : (P.halo ? "halo" : (P.pair ? "pixelpair" : "box"))),
+           P.b_resident ? " wres" : "",
            P.res_tma ? " restma" : "", fold_applies(c, planes8) ? (c.fast_requant >= 3 ? " fold hi32" : " fold") : "",
            P.tstore ? " tmastore" : "", P.cg2 ? " ctapair" : "", P.sparse2 ? " sparse2" : "", P.b_packed4 ? " packed4" : "", P.stages);
   return std::string(b);
@@ -1922,7 +2259,7 @@ cudaError_t launch_conv_mma(const ConvParams& c, const MmaHostParams& /*hp*/, in
   for (int i = 0; i < kMaxPlanes; i++) P.plane8_shift[i] = plane8_shift[i];
   const int stage_bytes = P.a_stage_bytes + (P.b_resident ? 0 : P.b_stage_bytes);
   const size_t smem = (size_t)P.res_bytes + (size_t)P.stages * stage_bytes + EPI_BYTES +
-                      (P.res_tma ? (size_t)P.res_bufs * P.BN * 128 : 0) + 1024;
+                      (P.res_tma ? (size_t)P.res_bufs * P.BN * 128 : 0) + (size_t)P.a_bufs * P.a_ring_bytes + 1024;
   // the fast requantisation needs at most two scaled planes (+ the optional low plane); the INT32
   // accumulator tap lives in the exact epilogue (EPI < 0), which sees the very TMEM accumulators the
   // fast forms would
@@ -1963,9 +2300,10 @@ cudaError_t launch_conv_mma(const ConvParams& c, const MmaHostParams& /*hp*/, in
   static const bool debug = env_int("TF2B_MMA_DEBUG", 0) != 0;
   static long long* dbg_dev = nullptr;
   if (debug) {
-    if (!dbg_dev) cudaMalloc(&dbg_dev, sizeof(long long) * 8 * 148);
-    cudaMemsetAsync(dbg_dev, 0, sizeof(long long) * 8 * 148, stream);
+    if (!dbg_dev) cudaMalloc(&dbg_dev, sizeof(long long) * (8 * 148 + 3 * 64 + 8));
+    cudaMemsetAsync(dbg_dev, 0, sizeof(long long) * (8 * 148 + 3 * 64 + 8), stream);
     P.dbg = dbg_dev;
+    P.lean_roles = 0;   // the role counters live in the generic loops
   }
   int grid = 0, num_tiles = 0;
   {
@@ -2008,7 +2346,7 @@ cudaError_t launch_conv_mma(const ConvParams& c, const MmaHostParams& /*hp*/, in
     if (le != cudaSuccess) return le;
   }
   if (debug) {
-    long long h[8 * 148];
+    long long h[8 * 148 + 3 * 64 + 8];
     cudaStreamSynchronize(stream);
     cudaMemcpy(h, dbg_dev, sizeof h, cudaMemcpyDeviceToHost);
     double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -2022,6 +2360,20 @@ cudaError_t launch_conv_mma(const ConvParams& c, const MmaHostParams& /*hp*/, in
             c.Cp, c.N, c.k, c.stride, c.OH, P.mode, P.BK, P.BN, P.planes, P.stages, tiles_per_cta,
             P.taps * P.kchunks, a[1] / tiles_per_cta, a[0] / tiles_per_cta, a[4] / tiles_per_cta, a[2] / tiles_per_cta,
             a[3] / tiles_per_cta, a[7] / tiles_per_cta, a[6] / tiles_per_cta, a[5] / tiles_per_cta);
+    static const bool trace = env_int("TF2B_MMA_TRACE", 0) != 0;
+    if (trace) {
+      fprintf(stderr, "[mma trace] CTA 0, per stage position: wait / wait+issue clk:");
+      for (int it = 0; it < 64 && it < P.taps * P.kchunks; it++) {
+        const long long n = h[8 * 148 + 3 * it + 2];
+        if (n > 0) fprintf(stderr, " %lld/%lld", h[8 * 148 + 3 * it] / n, h[8 * 148 + 3 * it + 1] / n);
+      }
+      fprintf(stderr, "\n");
+      const long long* f = h + 8 * 148 + 3 * 64;
+      if (f[7] > 0)
+        fprintf(stderr, "[mma ticks] per stage of CTA 0 (%lld stages): wait %lld | fence %lld | desc+elect %lld | mma#1 %lld | mma#2-4 %lld | "
+                        "commit %lld | syncwarp %lld\n", f[7], f[0] / f[7], f[1] / f[7], f[2] / f[7], f[3] / f[7], f[4] / f[7],
+                f[5] / f[7], f[6] / f[7]);
+    }
   }
   return cudaGetLastError();
 }
