@@ -131,7 +131,8 @@ struct MmaParams {
                             // tile of a channel chunk sits in its own ring (a_bufs x a_ring_bytes) and is fetched once
                             // per tile and chunk instead of once per tap; the pipeline stages carry weights only
   int a_bufs, a_ring_bytes; // halo-tile ring of that mode
-  int lean_roles;           // producer / MMA roles run as lean single-thread loops (CTA pairs, resident-weight halo tiles)
+  int lean_roles;           // producer / MMA roles run their lean loops (always in product builds; experiment builds
+                            // keep the generic loops for the role counters and switches)
   int a_stage_bytes;        // bytes reserved per pipeline stage for the activation tile
   int idx32;                // output / residual tensors are smaller than 2 GiB: 32-bit byte offsets
   int cg2;                  // CTA-pair mode: clusters of two CTAs, tcgen05.mma.cta_group::2 (M = 256 over two
@@ -642,11 +643,12 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
     }
     int rb = 0;
     unsigned rphase = 0;
-    // Lean form of this role (CTA pairs and resident-weight halo tiles): ONE thread runs the whole loop — no election,
-    // no warp re-convergence per stage, tile-constant coordinates hoisted, ring addresses advanced by additions.
-    // Measured with the role counters (profiles/r02_mma_roles.md): the generic warp-wide loop spent 500-800 clk per
-    // pipeline stage in its own instructions, more than the 512 clk the stage's four M256 x N256 x K32 MMAs take.
-    if (P.lean_roles) {
+    // Lean form of this role: tile-constant coordinates hoisted, ring addresses advanced by additions, no per-stage
+    // division / descriptor rebuild / warp barrier, and waits whose loop branch is a warp vote — with provably uniform
+    // control flow the compiler keeps the loop state in uniform registers and issues UTMALDG / UTCIMMA back to back.
+    // Measured with the role counters (profiles/r02_mma_roles.md): the generic loop spent 500-800 clk per pipeline
+    // stage in its own instructions, more than the 512 clk the stage's four M256 x N256 x K32 MMAs take.
+    if (!kExp || P.lean_roles) {
       // (all 32 lanes walk the loop so that every address stays in uniform registers; one elected lane issues)
       const int nst = P.stages, BK = P.BK, kch = P.kchunks, kk = P.c.k, pad = P.c.pad;
       const unsigned a_bytes = (unsigned)P.a_bytes;
@@ -657,17 +659,18 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
       };
       for (int q = q_first; q < q_count; q += q_step) {
         const TileCoord t = decode_tile(P, tile_of(q));
+        if (MODE == 0 && P.res_tma) {
+          // residual operand of this tile: full 128-byte lines, no L1, latency hidden by the run-ahead
+          mbar_wait_u(rempty_bar + 8 * rb, rphase ^ 1);
+          if (elect_one()) {
+            mbar_expect_tx(rfull_bar + 8 * rb, (unsigned)res_tile);
+            for (int j = 0; j < BN / 128; j++)
+              tma_load_2d(smem_rres + rb * res_tile + j * (128 * 128), &maps.r, rfull_bar + 8 * rb, t.n0 + j * 128, t.m0);
+          }
+          if (++rb == P.res_bufs) { rb = 0; rphase ^= 1; }
+        }
         if constexpr (cg2) {
           const int brow = P.planes == 2 ? (int)cta_rank * P.Npad + t.n0 : t.n0 + (int)cta_rank * (BN / 2);
-          if (MODE == 0 && P.res_tma) {
-            mbar_wait_u(rempty_bar + 8 * rb, rphase ^ 1);
-            if (elect_one()) {
-              mbar_expect_tx(rfull_bar + 8 * rb, (unsigned)res_tile);
-              for (int j = 0; j < BN / 128; j++)
-                tma_load_2d(smem_rres + rb * res_tile + j * (128 * 128), &maps.r, rfull_bar + 8 * rb, t.n0 + j * 128, t.m0);
-            }
-            if (++rb == P.res_bufs) { rb = 0; rphase ^= 1; }
-          }
           if (MODE == 0) {
             const unsigned tx = 2u * (a_bytes + (unsigned)P.b_stage_bytes);
             for (int kc = 0, c0 = 0; kc < kch; kc++, c0 += BK) {
@@ -719,7 +722,7 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
                   advance();
                 }
           }
-        } else {
+        } else if (P.halo) {
           // halo tiles, resident weights: one box per tile and channel chunk
           const int x0 = t.ow0 - pad, y0 = t.oh0 - pad;
           for (int kc = 0, c0 = 0; kc < kch; kc++, c0 += BK) {
@@ -730,10 +733,59 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
             }
             advance();
           }
+        } else {
+          // single CTA, flat rows or one box per tap; weights resident or streamed with the activations
+          const bool bres = P.b_resident != 0;
+          const int npl = P.planes, Npad = P.Npad;
+          const unsigned tx = a_bytes + (bres ? 0u : (unsigned)(npl * P.b_bytes));
+          if (MODE == 0) {
+            for (int kc = 0, c0 = 0; kc < kch; kc++, c0 += BK) {
+              mbar_wait_u(eb, phase ^ 1);
+              if (elect_one()) {
+                mbar_expect_tx(fb, tx);
+                tma_load_2d(sa, &maps.a, fb, c0, t.m0);
+                if (!bres)
+                  for (int pl = 0; pl < npl; pl++) tma_load_2d(sa + a_stage + pl * b_plane, &maps.b, fb, c0, pl * Npad + t.n0);
+              }
+              advance();
+            }
+          } else if (P.pair) {
+            // pixel pairs: tap = filter row, chunk kc = horizontal taps 2kc, 2kc+1 = pixels ow+2kc, ow+2kc+1 of one 128-byte row
+            const int Cpm = P.Cpm, ntap = P.taps;
+            int row = (t.b0 * P.c.IH + t.oh0) * P.c.IW + t.ow0;
+            for (int tap = 0, kcol = 0; tap < ntap; tap++, kcol += Cpm, row += P.c.IW)
+              for (int kc = 0, c0 = 0; kc < kch; kc++, c0 += BK) {
+                mbar_wait_u(eb, phase ^ 1);
+                if (elect_one()) {
+                  mbar_expect_tx(fb, tx);
+                  tma_load_2d(sa, &maps.a, fb, 0, row + 2 * kc);
+                  if (!bres)
+                    for (int pl = 0; pl < npl; pl++)
+                      tma_load_2d(sa + a_stage + pl * b_plane, &maps.b, fb, kcol + c0, pl * Npad + t.n0);
+                }
+                advance();
+              }
+          } else {
+            const int x0 = t.ow0 * P.c.stride - pad, y0 = t.oh0 * P.c.stride - pad, Cpm = P.Cpm;
+            int kcol = 0;
+            for (int fh = 0; fh < kk; fh++)
+              for (int fw = 0; fw < kk; fw++, kcol += Cpm)
+                for (int kc = 0, c0 = 0; kc < kch; kc++, c0 += BK) {
+                  mbar_wait_u(eb, phase ^ 1);
+                  if (elect_one()) {
+                    mbar_expect_tx(fb, tx);
+                    tma_load_4d(sa, &maps.a, fb, c0, x0 + fw, y0 + fh, t.b0);
+                    if (!bres)
+                      for (int pl = 0; pl < npl; pl++)
+                        tma_load_2d(sa + a_stage + pl * b_plane, &maps.b, fb, kcol + c0, pl * Npad + t.n0);
+                  }
+                  advance();
+                }
+          }
         }
       }
       __syncwarp();
-    } else
+    } else if constexpr (kExp)   // the generic loop (role counters, experiment switches) exists in experiment builds only
     for (int q = q_first; q < q_count; q += q_step) {
       const int tile = tile_of(q);
       const TileCoord t = decode_tile(P, tile);
@@ -894,10 +946,9 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
     long long fa[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = 0;
     const bool ftr = dbg && blockIdx.x == 0;
 #define TF2B_TICK(i) do { if (kExp && ftr) { const long long t_ = clock64(); fa[i] += t_ - tprev; tprev = t_; } } while (0)
-    // Lean form (see the producer): one thread, descriptors advanced by additions, nothing between the stage's
-    // barrier and its MMAs.  No tcgen05 fence after the full barrier: the operands arrive through TMA (async proxy,
+    // Lean form (see the producer): descriptors advanced by additions, nothing between the stage's barrier and its MMAs.  No tcgen05 fence after the full barrier: the operands arrive through TMA (async proxy,
     // completion on the mbarrier), not through tcgen05 operations of other threads.
-    if (P.lean_roles) {
+    if (!kExp || P.lean_roles) {
       if (!cg2 || cta_rank == 0) {
         const int nst = P.stages, kch = P.kchunks, kk = P.c.k;
         const unsigned idesc = P.idesc;
@@ -961,6 +1012,29 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
               }
             }
             if (elect_one()) umma_commit_cg2(tfull_bar + 8 * buf);
+          } else if (!P.halo) {
+            // single CTA, flat rows or one box per tap: the planes of a chunk lie back to back, ONE N = planes * BN
+            // instruction per 32 channels covers them
+            const bool bres = P.b_resident != 0, k128 = P.BK == 128;
+            const unsigned long long boff = (unsigned long long)((unsigned)a_stage >> 4);
+            const unsigned long long b_it16 = (unsigned long long)((unsigned)(P.planes * b_plane) >> 4);
+            unsigned long long db_res = make_smem_desc(smem_res, P.sbo16, P.layout_type);
+            for (int it = 0; it < kiters; it++, db_res += b_it16) {
+              mbar_wait_u(fb, phase);
+              if (elect_one()) {
+                const unsigned long long db = bres ? db_res : ds + boff;
+                umma_i8(d_tmem, ds, db, idesc, acc);
+                umma_i8(d_tmem, ds + 2ull, db + 2ull, idesc, 1u);
+                if (k128) {
+                  umma_i8(d_tmem, ds + 4ull, db + 4ull, idesc, 1u);
+                  umma_i8(d_tmem, ds + 6ull, db + 6ull, idesc, 1u);
+                }
+                umma_commit(eb);
+              }
+              acc = 1u;
+              advance();
+            }
+            if (elect_one()) umma_commit(tfull_bar + 8 * buf);
           } else {
             // halo tiles, resident weights: every tap of a channel chunk is a row-shifted view of the chunk's tile
             const unsigned long long dres = make_smem_desc(smem_res, P.sbo16, P.layout_type);
@@ -997,7 +1071,7 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
         }
       }
       __syncwarp();
-    } else
+    } else if constexpr (kExp)
     for (int q = q_first; q < q_count && (!cg2 || cta_rank == 0); q += q_step, li++) {   // pair mode: the leader issues
       const int buf = li & 1;
       mbar_wait_timed(tempty_bar + 8 * buf, ((unsigned)(li >> 1) & 1u) ^ 1u, w_tempty, dbg, (kExp ? P.poll_lane0 : 0));   // epilogue has drained this accumulator
@@ -1999,7 +2073,7 @@ void fill_geometry(MmaParams& P, const ConvParams& c, int planes8) {
   }
   {
     static const bool allow = env_int("TF2B_MMA_LEANROLES", 1) != 0;
-    P.lean_roles = (allow && (P.cg2 || (P.halo && !P.hstream && !P.pair)) && !P.sparse2 && P.l2_prefetch == 0) ? 1 : 0;
+    P.lean_roles = (!kExp || (allow && !P.sparse2 && P.l2_prefetch == 0)) ? 1 : 0;
   }
   P.n_tile0 = 0;
   // per-warp TMA stores: flat layers whose run-time epilogue is the folded one (the accumulator tap runs the exact
