@@ -393,7 +393,7 @@ def main():
                 "share_of_step": share,
                 "step_ms_profiled_pass": prof_step_ms,
                 "traffic": traffic,
-                "staging_modes": {k: sum(1 for m in modes if k in m) for k in ("flat", "box", "halo", "ctapair", "fold", "wres")},
+                "staging_modes": {k: sum(1 for m in modes if k in m) for k in ("flat", "box", "halo", "wstream", "ctapair", "fold", "wres")},
                 "hbm_view": {"algorithmic_bytes_per_image": abytes,
                              "achieved_gbs": abytes * B / (step_ms * 1e-3) / 1e9,
                              "peak_gbs": peaks["hbm_gbs"]}}

@@ -120,13 +120,17 @@ def test_shipped_networks_weight_preparation(name, seed, tmp_path):
                                                                       # reports "fold": 53 — conv1's low plane keeps the literal form)
         assert sum(r["fast_requant"] == 3 for r in rows) >= 40        # most layers: every base shift >= 3 -> hi32
         # the launch plan at the BASELINE batch (what tf2b_layer_mode reports on the GPU) is the one the committed
-        # bench line was measured with (profiles/r01_bench_auto_v5.json: roofline.staging_modes)
+        # bench line was measured with (profiles/r02_bench_resnet50_v3.json: roofline.staging_modes)
         import collections
         import json
         plan = collections.Counter(tok for r in rows for tok in r["mode"].split("_"))
-        with open(os.path.join(ROOT, "profiles", "r01_bench_auto_v5.json")) as f:
-            measured = json.load(f)["roofline"]["staging_modes"]
+        with open(os.path.join(ROOT, "profiles", "r02_bench_resnet50_v3.json")) as f:
+            measured = json.loads(f.read().strip().splitlines()[-1])["roofline"]["staging_modes"]
         assert {k: plan[k] for k in measured} == measured, (dict(plan), measured)
+        # stride-1 3x3 layers with C >= 128 on 28 x 28 / 14 x 14 maps: CTA pairs on halo tiles with streamed weights;
+        # the 7 x 7 ones (49 of 128 accumulator rows) and the strided ones stay on one box per tap
+        assert all("halo_wstream" in rows[l]["mode"] and "ctapair" in rows[l]["mode"] for l in (16, 19, 22, 29, 32, 35, 38, 41))
+        assert all("box" in rows[l]["mode"] for l in (13, 26, 45, 48, 51))
         assert rows[0]["mode"] == "mma_BN64_BK64_planes2_halo_wres_stages4"                  # conv1: halo tile, literal epilogue
         assert rows[1]["mode"] == "mma_BN128_BK64_planes2_flat_wres_fold_hi32_tmastore_stages8"
         assert plan["tmastore"] >= 30 and plan["sparse2"] == 0 and plan["packed4"] == 0      # both measured and left off

@@ -200,6 +200,13 @@ __device__ __forceinline__ void mbar_wait_u(unsigned bar, unsigned parity) {
     if (clock64() - t0 > 4000000000ll) __trap();
   }
 }
+// same, accumulating the cycles spent waiting (experiment builds, TF2B_MMA_DEBUG)
+__device__ __forceinline__ void mbar_wait_ut(unsigned bar, unsigned parity, long long& acc, bool on) {
+  if (!on) { mbar_wait_u(bar, parity); return; }
+  long long t0 = clock64();
+  mbar_wait_u(bar, parity);
+  acc += clock64() - t0;
+}
 // warp-collective wait: lane 0 polls, __syncwarp releases the others
 __device__ __forceinline__ void mbar_wait_warp(unsigned bar, unsigned parity, int lane0_only) {
   if (lane0_only) {
@@ -618,6 +625,21 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
     fence_proxy_async();
     __syncthreads();   // slab complete; the ring is free for the activation tiles from here on
   }
+  // Weight-stationary layers: every tile of this CTA has the same n-tile (the grid is a multiple of n_tiles), so its
+  // whole weight slab is fetched once — and BEFORE the wait on the previous layer: weights do not depend on it, so the
+  // fetch overlaps that layer's tail on every SM that CTA has already left.
+  if (warp == 0 && P.b_resident && !P.b_packed4 && (int)blockIdx.x < num_tiles) {
+    const int n0 = decode_tile(P, blockIdx.x).n0;
+    if (elect_one()) {
+      mbar_expect_tx(bres_bar, (unsigned)P.res_bytes);
+      for (int tap = 0; tap < P.taps; tap++)
+        for (int kc = 0; kc < P.kchunks; kc++)
+          for (int pl = 0; pl < P.planes; pl++)
+            tma_load_2d(smem_res + ((tap * P.kchunks + kc) * P.planes + pl) * b_plane, &maps.b, bres_bar,
+                        tap * P.Cpm + kc * P.BK, pl * P.Npad + n0);
+    }
+    __syncwarp();
+  }
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
@@ -627,20 +649,6 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
     unsigned phase = 0;
     const bool dbg = kExp && P.dbg != nullptr;
     long long w_empty = 0, t_start = clock64();
-    if (P.b_resident && !P.b_packed4 && (int)blockIdx.x < num_tiles) {
-      // weight-stationary: every tile of this CTA has the same n-tile (grid is a multiple of
-      // n_tiles), so its whole weight slab is fetched once
-      const int n0 = decode_tile(P, blockIdx.x).n0;
-      if (elect_one()) {
-        mbar_expect_tx(bres_bar, (unsigned)P.res_bytes);
-        for (int tap = 0; tap < P.taps; tap++)
-          for (int kc = 0; kc < P.kchunks; kc++)
-            for (int pl = 0; pl < P.planes; pl++)
-              tma_load_2d(smem_res + ((tap * P.kchunks + kc) * P.planes + pl) * b_plane, &maps.b, bres_bar,
-                          tap * P.Cpm + kc * P.BK, pl * P.Npad + n0);
-      }
-      __syncwarp();
-    }
     int rb = 0;
     unsigned rphase = 0;
     // Lean form of this role: tile-constant coordinates hoisted, ring addresses advanced by additions, no per-stage
@@ -674,7 +682,7 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
           if (MODE == 0) {
             const unsigned tx = 2u * (a_bytes + (unsigned)P.b_stage_bytes);
             for (int kc = 0, c0 = 0; kc < kch; kc++, c0 += BK) {
-              mbar_wait_u(eb, phase ^ 1);
+              mbar_wait_ut(eb, phase ^ 1, w_empty, kExp && dbg);
               if (elect_one()) {
                 if (cta_rank == 0) mbar_expect_tx(fb, tx);
                 else mbar_arrive_leader(fb);
@@ -696,7 +704,7 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
               }
               if (++rb == P.a_bufs) { rb = 0; rphase ^= 1; }
               for (int tap = 0, kcol = c0; tap < ntap; tap++, kcol += Cpm) {
-                mbar_wait_u(eb, phase ^ 1);
+                mbar_wait_ut(eb, phase ^ 1, w_empty, kExp && dbg);
                 if (elect_one()) {
                   if (cta_rank == 0) mbar_expect_tx(fb, txb);
                   else mbar_arrive_leader(fb);
@@ -712,7 +720,7 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
             for (int fh = 0; fh < kk; fh++)
               for (int fw = 0; fw < kk; fw++, kcol += Cpm)
                 for (int kc = 0, c0 = 0; kc < kch; kc++, c0 += BK) {
-                  mbar_wait_u(eb, phase ^ 1);
+                  mbar_wait_ut(eb, phase ^ 1, w_empty, kExp && dbg);
                   if (elect_one()) {
                     if (cta_rank == 0) mbar_expect_tx(fb, tx);
                     else mbar_arrive_leader(fb);
@@ -726,7 +734,7 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
           // halo tiles, resident weights: one box per tile and channel chunk
           const int x0 = t.ow0 - pad, y0 = t.oh0 - pad;
           for (int kc = 0, c0 = 0; kc < kch; kc++, c0 += BK) {
-            mbar_wait_u(eb, phase ^ 1);
+            mbar_wait_ut(eb, phase ^ 1, w_empty, kExp && dbg);
             if (elect_one()) {
               mbar_expect_tx(fb, a_bytes);
               tma_load_4d(sa, &maps.a, fb, c0, x0, y0, t.b0);
@@ -740,7 +748,7 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
           const unsigned tx = a_bytes + (bres ? 0u : (unsigned)(npl * P.b_bytes));
           if (MODE == 0) {
             for (int kc = 0, c0 = 0; kc < kch; kc++, c0 += BK) {
-              mbar_wait_u(eb, phase ^ 1);
+              mbar_wait_ut(eb, phase ^ 1, w_empty, kExp && dbg);
               if (elect_one()) {
                 mbar_expect_tx(fb, tx);
                 tma_load_2d(sa, &maps.a, fb, c0, t.m0);
@@ -755,7 +763,7 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
             int row = (t.b0 * P.c.IH + t.oh0) * P.c.IW + t.ow0;
             for (int tap = 0, kcol = 0; tap < ntap; tap++, kcol += Cpm, row += P.c.IW)
               for (int kc = 0, c0 = 0; kc < kch; kc++, c0 += BK) {
-                mbar_wait_u(eb, phase ^ 1);
+                mbar_wait_ut(eb, phase ^ 1, w_empty, kExp && dbg);
                 if (elect_one()) {
                   mbar_expect_tx(fb, tx);
                   tma_load_2d(sa, &maps.a, fb, 0, row + 2 * kc);
@@ -771,7 +779,7 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
             for (int fh = 0; fh < kk; fh++)
               for (int fw = 0; fw < kk; fw++, kcol += Cpm)
                 for (int kc = 0, c0 = 0; kc < kch; kc++, c0 += BK) {
-                  mbar_wait_u(eb, phase ^ 1);
+                  mbar_wait_ut(eb, phase ^ 1, w_empty, kExp && dbg);
                   if (elect_one()) {
                     mbar_expect_tx(fb, tx);
                     tma_load_4d(sa, &maps.a, fb, c0, x0 + fw, y0 + fh, t.b0);
@@ -964,7 +972,7 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
         };
         for (int q = q_first; q < q_count; q += q_step, li++) {
           const int buf = li & 1;
-          mbar_wait_u(tempty_bar + 8 * buf, ((unsigned)(li >> 1) & 1u) ^ 1u);   // epilogue has drained this accumulator
+          mbar_wait_ut(tempty_bar + 8 * buf, ((unsigned)(li >> 1) & 1u) ^ 1u, w_tempty, kExp && dbg);   // epilogue has drained this accumulator
           tc_fence_after();
           const unsigned d_tmem = tmem_base + buf * acc_cols;
           unsigned acc = 0u;
@@ -973,12 +981,12 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
               const unsigned long long dring0 = make_smem_desc(smem_aring, P.sbo16, P.layout_type);
               const unsigned long long ring16 = (unsigned long long)((unsigned)P.a_ring_bytes >> 4);
               for (int kc = 0; kc < kch; kc++) {
-                mbar_wait_u(rfull_bar + 8 * ab, aphase);
+                mbar_wait_ut(rfull_bar + 8 * ab, aphase, w_full, kExp && dbg);
                 unsigned long long da_row = dring0 + (unsigned long long)ab * ring16;
                 for (int fh = 0; fh < kk; fh++) {
                   unsigned long long dat = da_row;
                   for (int fw = 0; fw < kk; fw++) {
-                    mbar_wait_u(fb, phase);
+                    mbar_wait_ut(fb, phase, w_full, kExp && dbg);
                     if (elect_one()) {
                       umma_i8_cg2(d_tmem, dat, ds, idesc, acc);
                       umma_i8_cg2(d_tmem, dat + 2ull, ds + 2ull, idesc, 1u);
@@ -998,7 +1006,7 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
             } else {
               const unsigned long long boff = (unsigned long long)((unsigned)a_stage >> 4);
               for (int it = 0; it < kiters; it++) {
-                mbar_wait_u(fb, phase);
+                mbar_wait_ut(fb, phase, w_full, kExp && dbg);
                 if (elect_one()) {
                   const unsigned long long db = ds + boff;
                   umma_i8_cg2(d_tmem, ds, db, idesc, acc);
@@ -1020,7 +1028,7 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
             const unsigned long long b_it16 = (unsigned long long)((unsigned)(P.planes * b_plane) >> 4);
             unsigned long long db_res = make_smem_desc(smem_res, P.sbo16, P.layout_type);
             for (int it = 0; it < kiters; it++, db_res += b_it16) {
-              mbar_wait_u(fb, phase);
+              mbar_wait_ut(fb, phase, w_full, kExp && dbg);
               if (elect_one()) {
                 const unsigned long long db = bres ? db_res : ds + boff;
                 umma_i8(d_tmem, ds, db, idesc, acc);
@@ -1043,7 +1051,7 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
             const bool k128 = P.BK == 128;
             unsigned long long db_kc = dres;
             for (int kc = 0; kc < kch; kc++, db_kc += b_kc16) {
-              mbar_wait_u(fb, phase);
+              mbar_wait_ut(fb, phase, w_full, kExp && dbg);
               if (elect_one()) {
                 unsigned long long da_row = ds, db = db_kc;
                 for (int fh = 0; fh < kk; fh++) {
@@ -2377,7 +2385,6 @@ cudaError_t launch_conv_mma(const ConvParams& c, const MmaHostParams& /*hp*/, in
     if (!dbg_dev) cudaMalloc(&dbg_dev, sizeof(long long) * (8 * 148 + 3 * 64 + 8));
     cudaMemsetAsync(dbg_dev, 0, sizeof(long long) * (8 * 148 + 3 * 64 + 8), stream);
     P.dbg = dbg_dev;
-    P.lean_roles = 0;   // the role counters live in the generic loops
   }
   int grid = 0, num_tiles = 0;
   {
