@@ -2364,7 +2364,10 @@ cudaError_t launch_conv_mma(const ConvParams& c, const MmaHostParams& /*hp*/, in
     epi_idx = 17 + ((bits & 1) | ((bits & 4) >> 1));
   }
   // two epilogue groups where the K loop is at most 128 channels deep
-  const bool grp2 = fold && P.mode == 0 && !P.cg2 && P.BN == 128 && P.taps * P.kchunks * P.BK <= 128;
+#ifndef TF2B_GRP2_MAXK
+#define TF2B_GRP2_MAXK 128
+#endif
+  const bool grp2 = fold && P.mode == 0 && !P.cg2 && P.BN == 128 && P.taps * P.kchunks * P.BK <= TF2B_GRP2_MAXK;
   P.egroups = grp2 ? 2 : 1;
   const KernelTables& T = kernel_tables();
   KernelFn kfn = T.single[P.BN == 256 ? 2 : (P.BN == 128 ? 1 : 0)][P.mode][epi_idx];
