@@ -499,6 +499,11 @@ template <int BN, int MODE, int EPI, bool CG2 = false, int GRP = 1>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ TmapPair maps) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
+  // experiment builds: phase time stamps of CTA 0 (entry, prologue done, previous layer done, first operands landed,
+  // last MMA issued, last tile stored, teardown) -> dbg[kTlBase ..]
+  long long tl_entry = 0;
+  if (kExp && P.dbg != nullptr && blockIdx.x == 0) tl_entry = clock64();
+#define TF2B_TL(i) do { if (kExp && P.dbg != nullptr && blockIdx.x == 0 && (threadIdx.x & 31) == 0) P.dbg[8 * 148 + 3 * 64 + 8 + (i)] = clock64() - tl_entry; } while (0)
   // carve: [resident weight slab] [stages][A | B planes] (1024-aligned) [epilogue scratch]
   const unsigned smem_res = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const unsigned smem_base = smem_res + (unsigned)P.res_bytes;
@@ -640,8 +645,10 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
     }
     __syncwarp();
   }
+  if (threadIdx.x == 32) TF2B_TL(0);
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (threadIdx.x == 32) TF2B_TL(1);
 
   if (warp == 0) {
     // ===================================================== TMA producer (whole warp, one elected lane issues)
@@ -970,6 +977,8 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
           if (++stage == nst) { stage = 0; phase ^= 1; ds = d0; fb = full_bar; eb = empty_bar; }
           else { ds += dstep; fb += 8; eb += 8; }
         };
+        bool tl_first = true;
+        auto tl_mark = [&]() { if (kExp && tl_first) { tl_first = false; TF2B_TL(2); } };
         for (int q = q_first; q < q_count; q += q_step, li++) {
           const int buf = li & 1;
           mbar_wait_ut(tempty_bar + 8 * buf, ((unsigned)(li >> 1) & 1u) ^ 1u, w_tempty, kExp && dbg);   // epilogue has drained this accumulator
@@ -986,7 +995,7 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
                 for (int fh = 0; fh < kk; fh++) {
                   unsigned long long dat = da_row;
                   for (int fw = 0; fw < kk; fw++) {
-                    mbar_wait_ut(fb, phase, w_full, kExp && dbg);
+                    mbar_wait_ut(fb, phase, w_full, kExp && dbg); tl_mark();
                     if (elect_one()) {
                       umma_i8_cg2(d_tmem, dat, ds, idesc, acc);
                       umma_i8_cg2(d_tmem, dat + 2ull, ds + 2ull, idesc, 1u);
@@ -1006,7 +1015,7 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
             } else {
               const unsigned long long boff = (unsigned long long)((unsigned)a_stage >> 4);
               for (int it = 0; it < kiters; it++) {
-                mbar_wait_ut(fb, phase, w_full, kExp && dbg);
+                mbar_wait_ut(fb, phase, w_full, kExp && dbg); tl_mark();
                 if (elect_one()) {
                   const unsigned long long db = ds + boff;
                   umma_i8_cg2(d_tmem, ds, db, idesc, acc);
@@ -1028,7 +1037,7 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
             const unsigned long long b_it16 = (unsigned long long)((unsigned)(P.planes * b_plane) >> 4);
             unsigned long long db_res = make_smem_desc(smem_res, P.sbo16, P.layout_type);
             for (int it = 0; it < kiters; it++, db_res += b_it16) {
-              mbar_wait_ut(fb, phase, w_full, kExp && dbg);
+              mbar_wait_ut(fb, phase, w_full, kExp && dbg); tl_mark();
               if (elect_one()) {
                 const unsigned long long db = bres ? db_res : ds + boff;
                 umma_i8(d_tmem, ds, db, idesc, acc);
@@ -1051,7 +1060,7 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
             const bool k128 = P.BK == 128;
             unsigned long long db_kc = dres;
             for (int kc = 0; kc < kch; kc++, db_kc += b_kc16) {
-              mbar_wait_ut(fb, phase, w_full, kExp && dbg);
+              mbar_wait_ut(fb, phase, w_full, kExp && dbg); tl_mark();
               if (elect_one()) {
                 unsigned long long da_row = ds, db = db_kc;
                 for (int fh = 0; fh < kk; fh++) {
@@ -1246,6 +1255,7 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
       P.dbg[blockIdx.x * 8 + 2] = w_full;
       P.dbg[blockIdx.x * 8 + 3] = w_tempty;
       P.dbg[blockIdx.x * 8 + 4] = clock64() - t_start;
+      TF2B_TL(3);
       P.dbg[blockIdx.x * 8 + 7] = t_issue;
     }
   } else {
@@ -1818,12 +1828,14 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
     if (dbg && lane == 0) {
       P.dbg[blockIdx.x * 8 + 5] = w_tfull;
       P.dbg[blockIdx.x * 8 + 6] = clock64() - t_start;
+      TF2B_TL(4);
     }
   }
 
   tc_fence_before();
   __syncthreads();
   if constexpr (cg2) cluster_sync_all();   // neither CTA may leave while its peer can still signal its barriers / read its smem
+  if (threadIdx.x == 32) TF2B_TL(5);
   if (warp == 1) {
     tc_fence_after();
     if constexpr (cg2) tmem_dealloc_cg2(tmem_base, TMEM_COLS);
@@ -2385,8 +2397,8 @@ cudaError_t launch_conv_mma(const ConvParams& c, const MmaHostParams& /*hp*/, in
   static const bool debug = env_int("TF2B_MMA_DEBUG", 0) != 0;
   static long long* dbg_dev = nullptr;
   if (debug) {
-    if (!dbg_dev) cudaMalloc(&dbg_dev, sizeof(long long) * (8 * 148 + 3 * 64 + 8));
-    cudaMemsetAsync(dbg_dev, 0, sizeof(long long) * (8 * 148 + 3 * 64 + 8), stream);
+    if (!dbg_dev) cudaMalloc(&dbg_dev, sizeof(long long) * (8 * 148 + 3 * 64 + 16));
+    cudaMemsetAsync(dbg_dev, 0, sizeof(long long) * (8 * 148 + 3 * 64 + 16), stream);
     P.dbg = dbg_dev;
   }
   int grid = 0, num_tiles = 0;
@@ -2430,7 +2442,7 @@ cudaError_t launch_conv_mma(const ConvParams& c, const MmaHostParams& /*hp*/, in
     if (le != cudaSuccess) return le;
   }
   if (debug) {
-    long long h[8 * 148 + 3 * 64 + 8];
+    long long h[8 * 148 + 3 * 64 + 16];
     cudaStreamSynchronize(stream);
     cudaMemcpy(h, dbg_dev, sizeof h, cudaMemcpyDeviceToHost);
     double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -2444,6 +2456,11 @@ cudaError_t launch_conv_mma(const ConvParams& c, const MmaHostParams& /*hp*/, in
             c.Cp, c.N, c.k, c.stride, c.OH, P.mode, P.BK, P.BN, P.planes, P.stages, tiles_per_cta,
             P.taps * P.kchunks, a[1] / tiles_per_cta, a[0] / tiles_per_cta, a[4] / tiles_per_cta, a[2] / tiles_per_cta,
             a[3] / tiles_per_cta, a[7] / tiles_per_cta, a[6] / tiles_per_cta, a[5] / tiles_per_cta);
+    {
+      const long long* tl = h + 8 * 148 + 3 * 64 + 8;
+      fprintf(stderr, "[mma timeline] CTA 0 clk since entry: prologue done %lld | previous layer done %lld | first operands %lld | "
+                      "last MMA issued %lld | last tile stored %lld | teardown sync %lld\n", tl[0], tl[1], tl[2], tl[3], tl[4], tl[5]);
+    }
     static const bool trace = env_int("TF2B_MMA_TRACE", 0) != 0;
     if (trace) {
       fprintf(stderr, "[mma trace] CTA 0, per stage position: wait / wait+issue clk:");
