@@ -542,6 +542,9 @@ conv_mma_kernel(const __grid_constant__ MmaParams P, const __grid_constant__ Tma
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&maps.a);
     tma_prefetch_desc(&maps.b);
+    if (cg2) tma_prefetch_desc(&maps.h);
+    if (MODE == 0 && P.res_tma) tma_prefetch_desc(&maps.r);
+    if (MODE == 0 && P.tstore) tma_prefetch_desc(&maps.y);
     for (int s = 0; s < P.stages; s++) {
       mbar_init(full_bar + 8 * s, cg2 ? 2 : 1);   // pair mode: the producers of both CTAs arrive on the leader's
       mbar_init(empty_bar + 8 * s, 1);
