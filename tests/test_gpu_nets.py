@@ -48,3 +48,31 @@ def test_network_matches_oracle(name, variant):
     kinds = set(nw.layer_kernels())
     assert ("mma" in kinds) == (variant != capi.VARIANT_SHIFT)
     nw.CleanUp()
+
+
+def test_raw224_input_at_an_unaligned_device_address():
+    """The space-to-depth kernel stages the raw image with 16-byte loads; a caller's buffer at an odd address takes
+    the byte-load path.  Same results, and tensor 0 (27 transformed channels, input_loader.cpp:27-73) equals
+    feature_trans of the quantised image either way."""
+    import torch
+    from tf2_b200.network import NetWork, Runner
+    net, q, model = _model("googlenet")
+    B = 2
+    imgs = synth.synth_images(B, seed=23)
+    raw, t0 = formats.prepare_input(net, imgs, q)
+    nw = NetWork(net, 0)
+    nw.InitFromCodes(model, q, max_images=B, variant=capi.VARIANT_AUTO)
+    r = Runner(nw)
+    x = torch.from_numpy(raw).cuda()
+    a = r.run_device(x, raw224=True).cpu().numpy()
+    ta = r.read_tensor(0, B).cpu().numpy()
+    assert np.array_equal(ta[:, :t0.shape[1]], t0), "tensor 0 differs from feature_trans"
+    flat = torch.empty(x.numel() + 16, dtype=torch.int8, device="cuda")
+    for off in (1, 7):
+        y = flat[off:off + x.numel()].view(x.shape)
+        y.copy_(x)
+        assert y.data_ptr() % 16 != 0
+        b = r.run_device(y, raw224=True).cpu().numpy()
+        assert np.array_equal(a, b), off
+        assert np.array_equal(r.read_tensor(0, B).cpu().numpy(), ta), off
+    nw.CleanUp()

@@ -77,78 +77,132 @@ __global__ void hwc_repitch_kernel(const int8_t* __restrict__ src, int8_t* __res
 // channels 27..31 are zero.  Quantise-then-permute equals the reference's permute-then-quantise
 // (runner.cpp:158-164 is elementwise and maps the padding zeros to zero).
 // With dual != 0 the pixel is 64 bytes: channels 32..58 hold the int8-negated copy (pe.cl:32-34).
-__global__ void raw224_to_s2d_kernel(const int8_t* __restrict__ raw, int8_t* __restrict__ dst,
-                                     int B, int dual) {
+// One CTA per (image, output row): the nine source rows (3 colour planes x raw rows 2r-3 .. 2r-1) are staged in
+// shared memory with 16-byte coalesced loads (zero borders included), every thread then assembles one output pixel
+// from shared bytes and writes its 32 / 64 bytes with 16-byte stores (a warp covers 2 KB contiguous).
+constexpr int kS2dPitch = 240;   // 224 source bytes at offset 8 (column -3 lands on index 5), zero borders
+__global__ void __launch_bounds__(128) raw224_to_s2d_kernel(const int8_t* __restrict__ raw, int8_t* __restrict__ dst,
+                                                            int B, int dual) {
   const int OD = 114, ID = 224;
-  size_t total = (size_t)B * OD * OD;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
-       i += (size_t)gridDim.x * blockDim.x) {
-    int c = (int)(i % OD);
-    size_t t = i / OD;
-    int r = (int)(t % OD);
-    int b = (int)(t / OD);
-    __align__(16) unsigned char out[32];
-#pragma unroll
-    for (int e = 27; e < 32; e++) out[e] = 0;
-#pragma unroll
-    for (int ci = 0; ci < 3; ci++) {
-      const int8_t* plane = raw + ((size_t)b * 3 + ci) * ID * ID;
-#pragma unroll
-      for (int d = 0; d < 9; d++) {
-        int row = (d < 6) ? (2 * r + (d & 1)) : (2 * r + 2);
-        int col = 2 * c + ((d < 6) ? (d >> 1) : (d - 6));
-        row -= 3;
-        col -= 3;
-        unsigned char v = 0;
-        if (row >= 0 && row < ID && col >= 0 && col < ID) v = (unsigned char)plane[row * ID + col];
-        out[ci * 9 + d] = v;
+  __shared__ __align__(16) unsigned char rows[9][kS2dPitch];
+  const int r = blockIdx.x, b = blockIdx.y;
+  (void)B;
+  // 9 rows x 15 16-byte words: words 0 and 14 are borders (columns < 0 / >= 224), word 1 + j holds source bytes 16j..
+  for (int i = threadIdx.x; i < 9 * 15; i += blockDim.x) {
+    const int q = i / 15, wd = i - q * 15;
+    const int ci = q / 3, rs = q - ci * 3;
+    const int row = 2 * r + rs - 3;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (wd >= 1 && wd <= 14 && row >= 0 && row < ID) {
+      const int8_t* sp = raw + (((size_t)b * 3 + ci) * ID + row) * ID + (wd - 1) * 16;
+      if (dual & 2) {   // caller's buffer is not 16-byte aligned: byte loads
+        unsigned ww[4] = {0, 0, 0, 0};
+        for (int e = 0; e < 16; e++) ww[e >> 2] |= (unsigned)(unsigned char)sp[e] << (8 * (e & 3));
+        v = make_uint4(ww[0], ww[1], ww[2], ww[3]);
+      } else {
+        v = *reinterpret_cast<const uint4*>(sp);
       }
     }
-    uint4* o = reinterpret_cast<uint4*>(dst + i * (dual ? 64 : 32));
-    uint4 v0 = *reinterpret_cast<const uint4*>(out);
-    uint4 v1 = *reinterpret_cast<const uint4*>(out + 16);
-    o[0] = v0;
-    o[1] = v1;
-    if (dual) {
-      o[2] = make_uint4(__vneg4(v0.x), __vneg4(v0.y), __vneg4(v0.z), __vneg4(v0.w));
-      o[3] = make_uint4(__vneg4(v1.x), __vneg4(v1.y), __vneg4(v1.z), __vneg4(v1.w));
+    // word wd sits at byte offset 16*wd - 8: the 8 leading bytes are the left border
+    if (wd == 0) {
+      *reinterpret_cast<uint2*>(&rows[q][0]) = make_uint2(0, 0);
+    } else if (wd <= 14) {
+      *reinterpret_cast<uint2*>(&rows[q][16 * wd - 8]) = make_uint2(v.x, v.y);
+      *reinterpret_cast<uint2*>(&rows[q][16 * wd]) = make_uint2(v.z, v.w);
+    }
+    if (wd == 14) *reinterpret_cast<uint2*>(&rows[q][kS2dPitch - 8]) = make_uint2(0, 0);
+  }
+  __syncthreads();
+  const int c = threadIdx.x;
+  if (c >= OD) return;
+  // source column 2c - 3 + k lives at index 2c + 5 + k
+  unsigned w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+  for (int ci = 0; ci < 3; ci++) {
+#pragma unroll
+    for (int d = 0; d < 9; d++) {
+      const int rs = (d < 6) ? (d & 1) : 2;
+      const int k = (d < 6) ? (d >> 1) : (d - 6);
+      const unsigned v = rows[ci * 3 + rs][2 * c + 5 + k];
+      const int e = ci * 9 + d;
+      w[e >> 2] |= v << (8 * (e & 3));
     }
   }
+  uint4* o = reinterpret_cast<uint4*>(dst + (((size_t)b * OD + r) * OD + c) * ((dual & 1) ? 64 : 32));
+  o[0] = make_uint4(w[0], w[1], w[2], w[3]);
+  o[1] = make_uint4(w[4], w[5], w[6], w[7]);
+  if (dual & 1) {
+    o[2] = make_uint4(__vneg4(w[0]), __vneg4(w[1]), __vneg4(w[2]), __vneg4(w[3]));
+    o[3] = make_uint4(__vneg4(w[4]), __vneg4(w[5]), __vneg4(w[6]), __vneg4(w[7]));
+  }
+}
+
+// four packed int8 -> two s16x2 words (sign-extending PRMT), and back (values are int8 again after max)
+__device__ __forceinline__ void s8x4_to_s16x2(unsigned v, unsigned& lo, unsigned& hi) {
+  asm("prmt.b32 %0, %1, %1, 0x9180;" : "=r"(lo) : "r"(v));
+  asm("prmt.b32 %0, %1, %1, 0xb3a2;" : "=r"(hi) : "r"(v));
+}
+__device__ __forceinline__ unsigned max_s16x2(unsigned a, unsigned b) {
+  unsigned d;
+  asm("max.s16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
 }
 
 // pool.cl:178-260 + pool_tail.cl:91-216: 3x3 max, window of output j starts at j*ps - ppad, taps
 // outside the map contribute 0; optional residual add (feature_writer.cl:124-127).
-// One thread per (output pixel, 16-channel chunk).
+// One thread per (output pixel, 16-channel chunk); grid = (row chunks, output rows, images), so the only division is
+// pixel / chunk inside a row.  The maximum runs in int16 lanes (PRMT sign extension + VIMNMX.S16x2: 4 instructions
+// per 4 values and tap; the packed-byte __vmaxs4 is emulated with ~20).
 __global__ void maxpool3x3_kernel(const int8_t* __restrict__ src, int8_t* __restrict__ dst,
                                   const int8_t* __restrict__ res, int B, int H, int W, int sC,
                                   int PH, int PW, int dC, int rC, int C, int ps, int ppad,
                                   int add_relu) {
+  (void)B;
   const int chunks = (C + 15) / 16;
-  size_t total = (size_t)B * PH * PW * chunks;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
-       i += (size_t)gridDim.x * blockDim.x) {
-    int ck = (int)(i % chunks);
-    size_t pix = i / chunks;
-    int pw = (int)(pix % PW);
-    size_t t = pix / PW;
-    int ph = (int)(t % PH);
-    int b = (int)(t / PH);
-    // identity of signed max is -128 in every byte
-    uint4 m = make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u);
+  const int row_items = PW * chunks;
+  const int ph = blockIdx.y, b = blockIdx.z;
+  const int h0 = ph * ps - ppad;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < row_items; t += gridDim.x * blockDim.x) {
+    const int pw = t / chunks, ck = t - pw * chunks;
+    const int w0 = pw * ps - ppad;
+    // identity of the signed maximum: -128 in every lane
+    unsigned lo[4] = {0xff80ff80u, 0xff80ff80u, 0xff80ff80u, 0xff80ff80u};
+    unsigned hi[4] = {0xff80ff80u, 0xff80ff80u, 0xff80ff80u, 0xff80ff80u};
+    bool outside = false;
 #pragma unroll
     for (int dh = 0; dh < 3; dh++) {
+      const int h = h0 + dh;
+      const bool hv = h >= 0 && h < H;
+      const int8_t* rowp = src + (((size_t)b * H + (hv ? h : 0)) * W) * sC + ck * 16;
 #pragma unroll
       for (int dw = 0; dw < 3; dw++) {
-        int h = ph * ps - ppad + dh, w = pw * ps - ppad + dw;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (h >= 0 && h < H && w >= 0 && w < W)
-          v = *reinterpret_cast<const uint4*>(src + (((size_t)b * H + h) * W + w) * sC + ck * 16);
-        m.x = __vmaxs4(m.x, v.x);
-        m.y = __vmaxs4(m.y, v.y);
-        m.z = __vmaxs4(m.z, v.z);
-        m.w = __vmaxs4(m.w, v.w);
+        const int w = w0 + dw;
+        if (hv && w >= 0 && w < W) {
+          const uint4 v = *reinterpret_cast<const uint4*>(rowp + (size_t)w * sC);
+          const unsigned vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            unsigned l, hh;
+            s8x4_to_s16x2(vv[q], l, hh);
+            lo[q] = max_s16x2(lo[q], l);
+            hi[q] = max_s16x2(hi[q], hh);
+          }
+        } else {
+          outside = true;
+        }
       }
     }
+    unsigned mm[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      if (outside) {   // taps outside the map contribute 0
+        lo[q] = max_s16x2(lo[q], 0u);
+        hi[q] = max_s16x2(hi[q], 0u);
+      }
+      asm("prmt.b32 %0, %1, %2, 0x6420;" : "=r"(mm[q]) : "r"(lo[q]), "r"(hi[q]));
+    }
+    uint4 m = make_uint4(mm[0], mm[1], mm[2], mm[3]);
+    const size_t pix = ((size_t)b * PH + ph) * PW + pw;
     if (res != nullptr) {
       uint4 rv = *reinterpret_cast<const uint4*>(res + pix * rC + ck * 16);
       m.x = add_res4(m.x, rv.x, add_relu);
@@ -161,8 +215,8 @@ __global__ void maxpool3x3_kernel(const int8_t* __restrict__ src, int8_t* __rest
     if (nvalid == 16) {
       *reinterpret_cast<uint4*>(d) = m;
     } else {
-      const unsigned char* mb = reinterpret_cast<const unsigned char*>(&m);
-      for (int e = 0; e < nvalid; e++) d[e] = (int8_t)mb[e];
+      const unsigned mw[4] = {m.x, m.y, m.z, m.w};
+      for (int e = 0; e < nvalid; e++) d[e] = (int8_t)((mw[e >> 2] >> (8 * (e & 3))) & 0xffu);
     }
   }
 }
@@ -213,16 +267,24 @@ cudaError_t launch_hwc_repitch(const int8_t* src, int8_t* dst, size_t npix, int 
   return cudaGetLastError();
 }
 cudaError_t launch_raw224_to_s2d(const int8_t* raw, int8_t* dst, int B, int dual, cudaStream_t s) {
-  size_t total = (size_t)B * 114 * 114;
-  raw224_to_s2d_kernel<<<grid_for(total, 128), 128, 0, s>>>(raw, dst, B, dual);
+  if (B <= 0) return cudaSuccess;
+  if (B > 65535) return cudaErrorInvalidValue;
+  // bit 0 of the kernel's flag word: 64-byte pixels with the negated copy; bit 1: source not 16-byte aligned
+  const int flags = (dual ? 1 : 0) | ((reinterpret_cast<uintptr_t>(raw) & 15u) ? 2 : 0);
+  raw224_to_s2d_kernel<<<dim3(114, B), 128, 0, s>>>(raw, dst, B, flags);
   return cudaGetLastError();
 }
 cudaError_t launch_maxpool3x3(const int8_t* src, int8_t* dst, const int8_t* res, int B, int H, int W,
                               int sC, int PH, int PW, int dC, int rC, int C, int ps, int ppad,
                               int add_relu, cudaStream_t s) {
-  size_t total = (size_t)B * PH * PW * ((C + 15) / 16);
-  maxpool3x3_kernel<<<grid_for(total, 256), 256, 0, s>>>(src, dst, res, B, H, W, sC, PH, PW, dC, rC,
-                                                        C, ps, ppad, add_relu);
+  const int row_items = PW * ((C + 15) / 16);
+  if (B <= 0 || PH <= 0 || row_items <= 0) return cudaSuccess;
+  if (B > 65535 || PH > 65535) return cudaErrorInvalidValue;
+  const int block = row_items >= 256 ? 256 : (row_items + 31) / 32 * 32;
+  int gx = (row_items + block - 1) / block;
+  if (gx > 64) gx = 64;   // (grid-stride within the row beyond that)
+  maxpool3x3_kernel<<<dim3(gx, PH, B), block, 0, s>>>(src, dst, res, B, H, W, sC, PH, PW, dC, rC, C, ps, ppad,
+                                                      add_relu);
   return cudaGetLastError();
 }
 cudaError_t launch_gap(const int8_t* src, int8_t* dst, int B, int HW, int sC, int dC, int C,
