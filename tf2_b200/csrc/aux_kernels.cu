@@ -128,13 +128,16 @@ __global__ void __launch_bounds__(128) raw224_to_s2d_kernel(const int8_t* __rest
       w[e >> 2] |= v << (8 * (e & 3));
     }
   }
-  uint4* o = reinterpret_cast<uint4*>(dst + (((size_t)b * OD + r) * OD + c) * ((dual & 1) ? 64 : 32));
-  o[0] = make_uint4(w[0], w[1], w[2], w[3]);
-  o[1] = make_uint4(w[4], w[5], w[6], w[7]);
-  if (dual & 1) {
-    o[2] = make_uint4(__vneg4(w[0]), __vneg4(w[1]), __vneg4(w[2]), __vneg4(w[3]));
-    o[3] = make_uint4(__vneg4(w[4]), __vneg4(w[5]), __vneg4(w[6]), __vneg4(w[7]));
-  }
+  // one whole 32-byte sector per lane and store (two 16-byte stores per sector doubled the L1 -> L2 write sectors)
+  int8_t* o = dst + (((size_t)b * OD + r) * OD + c) * ((dual & 1) ? 64 : 32);
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(o), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]),
+               "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+               : "memory");
+  if (dual & 1)
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(o + 32), "r"(__vneg4(w[0])), "r"(__vneg4(w[1])),
+                 "r"(__vneg4(w[2])), "r"(__vneg4(w[3])), "r"(__vneg4(w[4])), "r"(__vneg4(w[5])), "r"(__vneg4(w[6])),
+                 "r"(__vneg4(w[7]))
+                 : "memory");
 }
 
 // four packed int8 -> two s16x2 words (sign-extending PRMT), and back (values are int8 again after max)
@@ -169,26 +172,39 @@ __global__ void maxpool3x3_kernel(const int8_t* __restrict__ src, int8_t* __rest
     unsigned lo[4] = {0xff80ff80u, 0xff80ff80u, 0xff80ff80u, 0xff80ff80u};
     unsigned hi[4] = {0xff80ff80u, 0xff80ff80u, 0xff80ff80u, 0xff80ff80u};
     bool outside = false;
+    auto take = [&](const int8_t* p) {
+      const uint4 v = *reinterpret_cast<const uint4*>(p);
+      const unsigned vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-    for (int dh = 0; dh < 3; dh++) {
-      const int h = h0 + dh;
-      const bool hv = h >= 0 && h < H;
-      const int8_t* rowp = src + (((size_t)b * H + (hv ? h : 0)) * W) * sC + ck * 16;
+      for (int q = 0; q < 4; q++) {
+        unsigned l, hh;
+        s8x4_to_s16x2(vv[q], l, hh);
+        lo[q] = max_s16x2(lo[q], l);
+        hi[q] = max_s16x2(hi[q], hh);
+      }
+    };
+    if (h0 >= 0 && h0 + 2 < H && w0 >= 0 && w0 + 2 < W) {
+      // interior window (almost every thread): nine unconditional loads off one base pointer
+      const int8_t* p0 = src + (((size_t)b * H + h0) * W + w0) * sC + ck * 16;
+      const int rs = W * sC;
 #pragma unroll
-      for (int dw = 0; dw < 3; dw++) {
-        const int w = w0 + dw;
-        if (hv && w >= 0 && w < W) {
-          const uint4 v = *reinterpret_cast<const uint4*>(rowp + (size_t)w * sC);
-          const unsigned vv[4] = {v.x, v.y, v.z, v.w};
+      for (int dh = 0; dh < 3; dh++) {
+        const int8_t* pr = p0 + dh * rs;
+        take(pr);
+        take(pr + sC);
+        take(pr + 2 * sC);
+      }
+    } else {
 #pragma unroll
-          for (int q = 0; q < 4; q++) {
-            unsigned l, hh;
-            s8x4_to_s16x2(vv[q], l, hh);
-            lo[q] = max_s16x2(lo[q], l);
-            hi[q] = max_s16x2(hi[q], hh);
-          }
-        } else {
-          outside = true;
+      for (int dh = 0; dh < 3; dh++) {
+        const int h = h0 + dh;
+        const bool hv = h >= 0 && h < H;
+        const int8_t* rowp = src + (((size_t)b * H + (hv ? h : 0)) * W) * sC + ck * 16;
+#pragma unroll
+        for (int dw = 0; dw < 3; dw++) {
+          const int w = w0 + dw;
+          if (hv && w >= 0 && w < W) take(rowp + (size_t)w * sC);
+          else outside = true;
         }
       }
     }
