@@ -120,11 +120,11 @@ def test_shipped_networks_weight_preparation(name, seed, tmp_path):
                                                                       # reports "fold": 53 — conv1's low plane keeps the literal form)
         assert sum(r["fast_requant"] == 3 for r in rows) >= 40        # most layers: every base shift >= 3 -> hi32
         # the launch plan at the BASELINE batch (what tf2b_layer_mode reports on the GPU) is the one the committed
-        # bench line was measured with (profiles/r02_bench_resnet50_v3.json: roofline.staging_modes)
+        # bench line was measured with (profiles/r02_bench_resnet50_v4.json: roofline.staging_modes)
         import collections
         import json
         plan = collections.Counter(tok for r in rows for tok in r["mode"].split("_"))
-        with open(os.path.join(ROOT, "profiles", "r02_bench_resnet50_v3.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_bench_resnet50_v4.json")) as f:
             measured = json.loads(f.read().strip().splitlines()[-1])["roofline"]["staging_modes"]
         assert {k: plan[k] for k in measured} == measured, (dict(plan), measured)
         # stride-1 3x3 layers with C >= 128 on 28 x 28 / 14 x 14 maps: CTA pairs on halo tiles with streamed weights;
