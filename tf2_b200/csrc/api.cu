@@ -734,6 +734,8 @@ int tf2b_create(const tf2b_tensor_desc* tensors, int n_tensors, const tf2b_layer
       if (eh != to.H || ew != to.W) return bad("output tensor size mismatch");
       if (!d.pool && (d.PH != d.OH || d.PW != d.OW)) return bad("PH/PW must equal OH/OW without pool");
     }
+    if ((d.pool || d.ipool) && d.pool_stride != 1 && d.pool_stride != 2)
+      return bad("pool stride must be 1 or 2 (pool.cl / pool_tail.cl)");
     if (d.add_tensor >= 0) {
       const tf2b_tensor_desc& tr = tensors[d.add_tensor];
       if (tr.H != d.PH || tr.W != d.PW || tr.C < d.N) return bad("residual tensor shape mismatch");
