@@ -94,6 +94,13 @@ def test_errors_do_not_exit():
     with pytest.raises(Tf2bError):
         Runner(nw).run_host(np.zeros((2, 16, 8, 8), np.int8))  # more images than max_images
     nw.CleanUp()
+    # pool.cl / pool_tail.cl know stride 1 and 2 only: anything else is refused when the tables are handed over
+    import dataclasses
+    bad = nets.chain((16, 12, 12), [dict(N=16, k=1, pool=1, pool_stride=2, pool_pad=0, PH=5, PW=5)])
+    bad.layers[0] = dataclasses.replace(bad.layers[0], pool_stride=3)
+    with pytest.raises(Tf2bError) as ei:
+        NetWork(bad, 0)
+    assert "pool stride" in str(ei.value)
 
 
 def test_weight_blob_roundtrip():
