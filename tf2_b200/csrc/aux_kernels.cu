@@ -159,14 +159,21 @@ __device__ __forceinline__ unsigned max_s16x2(unsigned a, unsigned b) {
 __global__ void maxpool3x3_kernel(const int8_t* __restrict__ src, int8_t* __restrict__ dst,
                                   const int8_t* __restrict__ res, int B, int H, int W, int sC,
                                   int PH, int PW, int dC, int rC, int C, int ps, int ppad,
-                                  int add_relu) {
+                                  int add_relu, int chunk_shift) {
   (void)B;
   const int chunks = (C + 15) / 16;
   const int row_items = PW * chunks;
   const int ph = blockIdx.y, b = blockIdx.z;
   const int h0 = ph * ps - ppad;
+  // one 64-bit product per block; everything inside an image is 32-bit (the launcher checks the sizes)
+  const int8_t* img = src + (size_t)b * H * W * sC;
+  int8_t* dimg = dst + (size_t)b * PH * PW * dC;
+  const int8_t* rimg = res != nullptr ? res + (size_t)b * PH * PW * rC : nullptr;
+  const int rs = W * sC;
+  const bool rows_in = h0 >= 0 && h0 + 2 < H;
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < row_items; t += gridDim.x * blockDim.x) {
-    const int pw = t / chunks, ck = t - pw * chunks;
+    const int pw = chunk_shift >= 0 ? (t >> chunk_shift) : t / chunks;
+    const int ck = t - pw * chunks;
     const int w0 = pw * ps - ppad;
     // identity of the signed maximum: -128 in every lane
     unsigned lo[4] = {0xff80ff80u, 0xff80ff80u, 0xff80ff80u, 0xff80ff80u};
@@ -183,10 +190,9 @@ __global__ void maxpool3x3_kernel(const int8_t* __restrict__ src, int8_t* __rest
         hi[q] = max_s16x2(hi[q], hh);
       }
     };
-    if (h0 >= 0 && h0 + 2 < H && w0 >= 0 && w0 + 2 < W) {
+    if (rows_in && w0 >= 0 && w0 + 2 < W) {
       // interior window (almost every thread): nine unconditional loads off one base pointer
-      const int8_t* p0 = src + (((size_t)b * H + h0) * W + w0) * sC + ck * 16;
-      const int rs = W * sC;
+      const int8_t* p0 = img + ((h0 * W + w0) * sC + ck * 16);
 #pragma unroll
       for (int dh = 0; dh < 3; dh++) {
         const int8_t* pr = p0 + dh * rs;
@@ -199,11 +205,11 @@ __global__ void maxpool3x3_kernel(const int8_t* __restrict__ src, int8_t* __rest
       for (int dh = 0; dh < 3; dh++) {
         const int h = h0 + dh;
         const bool hv = h >= 0 && h < H;
-        const int8_t* rowp = src + (((size_t)b * H + (hv ? h : 0)) * W) * sC + ck * 16;
+        const int8_t* rowp = img + ((hv ? h : 0) * rs + ck * 16);
 #pragma unroll
         for (int dw = 0; dw < 3; dw++) {
           const int w = w0 + dw;
-          if (hv && w >= 0 && w < W) take(rowp + (size_t)w * sC);
+          if (hv && w >= 0 && w < W) take(rowp + w * sC);
           else outside = true;
         }
       }
@@ -218,15 +224,15 @@ __global__ void maxpool3x3_kernel(const int8_t* __restrict__ src, int8_t* __rest
       asm("prmt.b32 %0, %1, %2, 0x6420;" : "=r"(mm[q]) : "r"(lo[q]), "r"(hi[q]));
     }
     uint4 m = make_uint4(mm[0], mm[1], mm[2], mm[3]);
-    const size_t pix = ((size_t)b * PH + ph) * PW + pw;
-    if (res != nullptr) {
-      uint4 rv = *reinterpret_cast<const uint4*>(res + pix * rC + ck * 16);
+    const int pix = ph * PW + pw;   // inside the image
+    if (rimg != nullptr) {
+      uint4 rv = *reinterpret_cast<const uint4*>(rimg + (pix * rC + ck * 16));
       m.x = add_res4(m.x, rv.x, add_relu);
       m.y = add_res4(m.y, rv.y, add_relu);
       m.z = add_res4(m.z, rv.z, add_relu);
       m.w = add_res4(m.w, rv.w, add_relu);
     }
-    int8_t* d = dst + pix * dC + ck * 16;
+    int8_t* d = dimg + (pix * dC + ck * 16);
     int nvalid = min(16, C - ck * 16);
     if (nvalid == 16) {
       *reinterpret_cast<uint4*>(d) = m;
@@ -299,8 +305,14 @@ cudaError_t launch_maxpool3x3(const int8_t* src, int8_t* dst, const int8_t* res,
   const int block = row_items >= 256 ? 256 : (row_items + 31) / 32 * 32;
   int gx = (row_items + block - 1) / block;
   if (gx > 64) gx = 64;   // (grid-stride within the row beyond that)
+  // offsets inside one image are 32-bit in the kernel
+  if ((long long)H * W * sC >= (1ll << 31) || (long long)PH * PW * (dC > rC ? dC : rC) >= (1ll << 31)) return cudaErrorInvalidValue;
+  const int chunks = (C + 15) / 16;
+  int chunk_shift = -1;
+  for (int sh = 0; sh < 16; sh++)
+    if ((1 << sh) == chunks) chunk_shift = sh;
   maxpool3x3_kernel<<<dim3(gx, PH, B), block, 0, s>>>(src, dst, res, B, H, W, sC, PH, PW, dC, rC, C, ps, ppad,
-                                                      add_relu);
+                                                      add_relu, chunk_shift);
   return cudaGetLastError();
 }
 cudaError_t launch_gap(const int8_t* src, int8_t* dst, int B, int HW, int sC, int dC, int C,
